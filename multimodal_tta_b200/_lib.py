@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI in include/tta_b200.h (libtta_b200.so, built in-tree by nvcc).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised -- the product path never routes through PyTorch ops or the oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtta_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+TTA_F16, TTA_BF16 = 0, 1
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu into libtta_b200.so for sm_100a (cross-compiles without a GPU)."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh")))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(p) for p in deps)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *srcs, "-lcuda"] if _has_libcuda() else \
+          [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *srcs]
+    if verbose:
+        print(" ".join(cmd))
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+    return LIB_PATH
+
+
+def _has_libcuda() -> bool:
+    # the driver API entry points (cuTensorMapEncodeTiled) are resolved at run time through
+    # cudaGetDriverEntryPoint, so libcuda is never needed at link time.
+    return False
+
+
+_lib = None
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+
+_SIGNATURES = {
+    "tta_last_error": (c_char_p, []),
+    "tta_abi_version": (I, []),
+    "tta_device_sm": (I, []),
+    "tta_norm_workspace_floats": (L, [I, I, L]),
+    "tta_norm_stats": (I, [P, L, I, I, L, I, F, P, P, P, P]),
+    "tta_norm_apply": (I, [P, L, I, I, L, P, P, P, P, I, I, P, P, L, P, P, L, I, P]),
+    "tta_norm_bwd_reduce": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, I, P, P, P, P, P]),
+    "tta_norm_bwd_apply": (I, [P, L, P, L, P, L, I, I, L, P, P, P, P, I, I, P, P, P, L, P, P, L, I, P]),
+    "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
+    "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, P]),
+    "tta_head_entropy_blocks": (I, [I, L]),
+    "tta_head_entropy": (I, [P, L, I, I, L, I, F, P, P, P, P, L, P, P, P]),
+    "tta_adam_step": (I, [P, P, P, P, I, F, F, F, F, F, P, P]),
+    "tta_sw_blend": (I, [P, I, I, I, I, I, P, P, P, P, P, F, P, P, I, I, I, I, P]),
+    "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),
+    "tta_dice_counts": (I, [P, P, I, L, F, P, P]),
+    "tta_conv_simt": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, P]),
+    "tta_conv_tc_supported": (I, [I, I, I, I, I]),
+    "tta_conv_tc_ntile": (I, [I]),
+    "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),
+    "tta_conv_tc": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, I, P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "multimodal_tta_b200 has no CPU or PyTorch fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().tta_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libtta_b200 {what} failed (status {rc}): {msg}")

@@ -1,0 +1,110 @@
+// Shared device/host helpers for the B200 TTA kernels (sm_100a only).
+//
+// Data layout in HBM:
+//   * channel-blocked "chunk" layout  [N][C8][D][H][W][8]   (C8 = ceil(C/8), pad channels are 0)
+//   * conv RESULTS   are fp32   : one voxel-chunk = 32 B
+//   * conv OPERANDS  are split  : two 16-bit planes hi/lo (fp16 in forward, bf16 in backward),
+//                                 x ~= hi + lo, one voxel-chunk = 16 B per plane
+//   A tensor "view" is (base pointer, n_stride in ELEMENTS, C8, D, H, W): a channel slice of a
+//   concat buffer is just a pointer offset with the parent's n_stride -> torch.cat is free.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define TTA_OK 0
+#define TTA_ERR_ARG 1
+#define TTA_ERR_CUDA 2
+#define TTA_ERR_UNSUPPORTED 3
+
+// dtype tags of the 16-bit operand planes
+#define TTA_F16 0
+#define TTA_BF16 1
+
+void tta_set_error(const char* fmt, ...);
+int tta_check_launch(const char* what);
+
+#define TTA_REQUIRE(cond, ...)              \
+  do {                                      \
+    if (!(cond)) {                          \
+      tta_set_error(__VA_ARGS__);           \
+      return TTA_ERR_ARG;                   \
+    }                                       \
+  } while (0)
+
+namespace tta {
+
+struct alignas(16) U16x8 {
+  uint16_t v[8];
+};
+struct alignas(16) F32x4 {
+  float v[4];
+};
+
+__device__ __forceinline__ void load_f32x8(const float* __restrict__ p, float (&o)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void store_f32x8(float* __restrict__ p, const float (&o)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+template <int DT>
+__device__ __forceinline__ float u16_to_f32(uint16_t u) {
+  if (DT == TTA_F16) return __half2float(__ushort_as_half(u));
+  return __bfloat162float(__ushort_as_bfloat16(u));
+}
+template <int DT>
+__device__ __forceinline__ uint16_t f32_to_u16(float f) {
+  if (DT == TTA_F16) {
+    // saturate instead of producing inf: fp16 max is 65504
+    f = fminf(fmaxf(f, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(f));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+
+// x -> (hi, lo) with hi = rn16(x), lo = rn16(x - hi)
+template <int DT>
+__device__ __forceinline__ void split8(const float (&x)[8], U16x8& hi, U16x8& lo) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint16_t h = f32_to_u16<DT>(x[i]);
+    hi.v[i] = h;
+    lo.v[i] = f32_to_u16<DT>(x[i] - u16_to_f32<DT>(h));
+  }
+}
+template <int DT>
+__device__ __forceinline__ void store_split8(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                             long long off, const float (&x)[8]) {
+  U16x8 h, l;
+  split8<DT>(x, h, l);
+  *reinterpret_cast<U16x8*>(hi + off) = h;
+  *reinterpret_cast<U16x8*>(lo + off) = l;
+}
+template <int DT>
+__device__ __forceinline__ void load_split8(const uint16_t* __restrict__ hi,
+                                            const uint16_t* __restrict__ lo, long long off,
+                                            float (&x)[8]) {
+  const U16x8 h = *reinterpret_cast<const U16x8*>(hi + off);
+  const U16x8 l = *reinterpret_cast<const U16x8*>(lo + off);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = u16_to_f32<DT>(h.v[i]) + u16_to_f32<DT>(l.v[i]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace tta

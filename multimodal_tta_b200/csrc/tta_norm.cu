@@ -1,0 +1,414 @@
+// Instance/Batch-norm statistics, fused normalise+affine+ReLU(+residual)+split, and the norm
+// backward (affine gradients + input gradient) for the TTA step.  All HBM-streaming kernels:
+// one thread handles one voxel-chunk (8 channels = 32 B fp32 / 16 B per 16-bit plane), a warp
+// reads 1 KB contiguous, reductions are warp-shuffle -> smem -> per-block partials -> a tiny
+// fp64 finalize kernel (deterministic, no atomics).
+//
+// Reference semantics restated:
+//   nn.InstanceNorm3d(eps=1e-5): per-(n,c) mean / biased variance over D*H*W
+//   nn.BatchNorm3d in TENT mode : per-c statistics over (n, D*H*W), no running stats
+//   backward: dbeta = sum dz, dgamma = sum dz*xhat,
+//             dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dz = g * [z > 0]
+#include "tta_common.cuh"
+
+namespace tta {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- block reduction of 16 values
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* __restrict__ dst) {
+  __shared__ float red[kThreads / 32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------- forward statistics
+// partial[((n*C8 + chunk)*splits + split)*16 + {0..7: sum, 8..15: sumsq}]
+__global__ void __launch_bounds__(kThreads)
+norm_stats_partial_kernel(const float* __restrict__ y, long long n_stride, int C8, long long V,
+                          int splits, float* __restrict__ partial) {
+  const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  const float* base = y + (long long)n * n_stride + (long long)chunk * V * 8;
+  const long long per = (V + splits - 1) / splits;
+  const long long v0 = (long long)split * per;
+  const long long v1 = min(V, v0 + per);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (long long v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float x[8];
+    load_f32x8(base + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += x[i];
+      acc[8 + i] = fmaf(x[i], x[i], acc[8 + i]);
+    }
+  }
+  block_reduce_store<16>(acc, partial + ((long long)(n * C8 + chunk) * splits + split) * 16);
+}
+
+// one thread per (n, channel): combine splits (and n for batch mode) in fp64.
+// mean/rstd are written per (n, c) in both modes so consumers are mode-agnostic.
+__global__ void norm_stats_finalize_kernel(const float* __restrict__ partial, int N, int C8,
+                                           int splits, long long V, int batch_mode, float eps,
+                                           float* __restrict__ mean, float* __restrict__ rstd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = C8 * 8;
+  if (idx >= N * C) return;
+  const int n = idx / C, c = idx % C, chunk = c >> 3, j = c & 7;
+  double s = 0.0, q = 0.0;
+  const int n0 = batch_mode ? 0 : n, n1 = batch_mode ? N : n + 1;
+  for (int nn = n0; nn < n1; ++nn) {
+    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
+    for (int sp = 0; sp < splits; ++sp) {
+      s += (double)p[sp * 16 + j];
+      q += (double)p[sp * 16 + 8 + j];
+    }
+  }
+  const double M = (double)V * (batch_mode ? N : 1);
+  const double mu = s / M;
+  double var = q / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[idx] = (float)mu;
+  rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------- forward apply
+// out = relu?(gamma*(y-mean)*rstd + beta) (+ residual), written as split 16-bit planes.
+// RES: 0 none, 1 fp32 view, 2 split-plane view (dtype ODT)
+template <int RES, int ODT>
+__global__ void __launch_bounds__(kThreads)
+norm_apply_kernel(const float* __restrict__ y, long long y_ns, int C8, long long V,
+                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                  const float* __restrict__ res_f32, const uint16_t* __restrict__ res_hi,
+                  const uint16_t* __restrict__ res_lo, long long res_ns,
+                  uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, long long out_ns) {
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const int C = C8 * 8;
+  float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[n * C + chunk * 8 + i];
+    rs[i] = rstd[n * C + chunk * 8 + i];
+    ga[i] = gamma[chunk * 8 + i];
+    be[i] = beta[chunk * 8 + i];
+  }
+  const long long slab = (long long)chunk * V * 8;
+  const float* yb = y + (long long)n * y_ns + slab;
+  const long long ob = (long long)n * out_ns + slab;
+  const long long rb = (long long)n * res_ns + slab;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
+       v += (long long)gridDim.x * kThreads) {
+    float x[8];
+    load_f32x8(yb + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float z = (x[i] - mu[i]) * rs[i];
+      z = fmaf(z, ga[i], be[i]);
+      x[i] = relu ? fmaxf(z, 0.f) : z;
+    }
+    if (RES == 1) {
+      float r[8];
+      load_f32x8(res_f32 + rb + v * 8, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += r[i];
+    } else if (RES == 2) {
+      float r[8];
+      load_split8<ODT>(res_hi, res_lo, rb + v * 8, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += r[i];
+    }
+    store_split8<ODT>(out_hi, out_lo, ob + v * 8, x);
+  }
+}
+
+// ---------------------------------------------------------------- backward reductions
+// partial[..][0..7] = sum dz, [8..15] = sum dz*xhat     (dz = (g0+g1) * [z>0])
+__global__ void __launch_bounds__(kThreads)
+norm_bwd_partial_kernel(const float* __restrict__ g0, long long g0_ns,
+                        const float* __restrict__ g1, long long g1_ns,
+                        const float* __restrict__ y, long long y_ns, int C8, long long V,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                        int splits, float* __restrict__ partial) {
+  const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  const int C = C8 * 8;
+  float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[n * C + chunk * 8 + i];
+    rs[i] = rstd[n * C + chunk * 8 + i];
+    ga[i] = gamma[chunk * 8 + i];
+    be[i] = beta[chunk * 8 + i];
+  }
+  const long long slab = (long long)chunk * V * 8;
+  const float* yb = y + (long long)n * y_ns + slab;
+  const float* g0b = g0 + (long long)n * g0_ns + slab;
+  const float* g1b = g1 ? g1 + (long long)n * g1_ns + slab : nullptr;
+  const long long per = (V + splits - 1) / splits;
+  const long long v0 = (long long)split * per;
+  const long long v1 = min(V, v0 + per);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (long long v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float x[8], g[8];
+    load_f32x8(yb + v * 8, x);
+    load_f32x8(g0b + v * 8, g);
+    if (g1b) {
+      float h[8];
+      load_f32x8(g1b + v * 8, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += h[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (x[i] - mu[i]) * rs[i];
+      const float z = fmaf(xh, ga[i], be[i]);
+      const float dz = (relu && !(z > 0.f)) ? 0.f : g[i];
+      acc[i] += dz;
+      acc[8 + i] = fmaf(dz, xh, acc[8 + i]);
+    }
+  }
+  block_reduce_store<16>(acc, partial + ((long long)(n * C8 + chunk) * splits + split) * 16);
+}
+
+// sums[(n*C + c)*2 + {0,1}] = {sum dz, sum dz*xhat} over the normalisation group (per n for IN,
+// over all n for BN, broadcast to every n);  dgamma[c], dbeta[c] = sums over n (IN) / the group (BN).
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int N, int C8, int Creal,
+                                         int splits, int batch_mode, float* __restrict__ sums,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = C8 * 8;
+  if (c >= C) return;
+  const int chunk = c >> 3, j = c & 7;
+  double t1 = 0.0, t2 = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = partial + (long long)(n * C8 + chunk) * splits * 16;
+    double s1 = 0.0, s2 = 0.0;
+    for (int sp = 0; sp < splits; ++sp) {
+      s1 += (double)p[sp * 16 + j];
+      s2 += (double)p[sp * 16 + 8 + j];
+    }
+    t1 += s1;
+    t2 += s2;
+    if (!batch_mode) {
+      sums[(n * C + c) * 2 + 0] = (float)s1;
+      sums[(n * C + c) * 2 + 1] = (float)s2;
+    }
+  }
+  if (batch_mode) {
+    for (int n = 0; n < N; ++n) {
+      sums[(n * C + c) * 2 + 0] = (float)t1;
+      sums[(n * C + c) * 2 + 1] = (float)t2;
+    }
+  }
+  if (c < Creal) {
+    dgamma[c] = (float)t2;
+    dbeta[c] = (float)t1;
+  }
+}
+
+// dy = gamma*rstd*(dz - S1/M - xhat*S2/M) -> split planes (ODT);  optionally also the summed
+// incoming gradient itself as split planes (aux), which feeds the shortcut conv's dgrad.
+template <int ODT>
+__global__ void __launch_bounds__(kThreads)
+norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float* __restrict__ g1,
+                      long long g1_ns, const float* __restrict__ y, long long y_ns, int C8,
+                      long long V, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                      const float* __restrict__ sums, float inv_m, uint16_t* __restrict__ dy_hi,
+                      uint16_t* __restrict__ dy_lo, long long dy_ns, uint16_t* __restrict__ aux_hi,
+                      uint16_t* __restrict__ aux_lo, long long aux_ns) {
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const int C = C8 * 8;
+  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = chunk * 8 + i;
+    mu[i] = mean[n * C + c];
+    rs[i] = rstd[n * C + c];
+    ga[i] = gamma[c];
+    be[i] = beta[c];
+    m1[i] = sums[(n * C + c) * 2 + 0] * inv_m;
+    m2[i] = sums[(n * C + c) * 2 + 1] * inv_m;
+  }
+  const long long slab = (long long)chunk * V * 8;
+  const float* yb = y + (long long)n * y_ns + slab;
+  const float* g0b = g0 + (long long)n * g0_ns + slab;
+  const float* g1b = g1 ? g1 + (long long)n * g1_ns + slab : nullptr;
+  const long long ob = (long long)n * dy_ns + slab;
+  const long long ab = (long long)n * aux_ns + slab;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
+       v += (long long)gridDim.x * kThreads) {
+    float x[8], g[8];
+    load_f32x8(yb + v * 8, x);
+    load_f32x8(g0b + v * 8, g);
+    if (g1b) {
+      float h[8];
+      load_f32x8(g1b + v * 8, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += h[i];
+    }
+    if (aux_hi) store_split8<ODT>(aux_hi, aux_lo, ab + v * 8, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (x[i] - mu[i]) * rs[i];
+      const float z = fmaf(xh, ga[i], be[i]);
+      const float dz = (relu && !(z > 0.f)) ? 0.f : g[i];
+      x[i] = ga[i] * rs[i] * (dz - m1[i] - xh * m2[i]);
+    }
+    store_split8<ODT>(dy_hi, dy_lo, ob + v * 8, x);
+  }
+}
+
+// plain fp32 (sum of up to two views) -> split planes; used where a gradient feeds a conv
+// directly without a norm in between.
+template <int ODT>
+__global__ void __launch_bounds__(kThreads)
+split_f32_kernel(const float* __restrict__ g0, long long g0_ns, const float* __restrict__ g1,
+                 long long g1_ns, int C8, long long V, uint16_t* __restrict__ hi,
+                 uint16_t* __restrict__ lo, long long o_ns) {
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const long long slab = (long long)chunk * V * 8;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
+       v += (long long)gridDim.x * kThreads) {
+    float g[8];
+    load_f32x8(g0 + (long long)n * g0_ns + slab + v * 8, g);
+    if (g1) {
+      float h[8];
+      load_f32x8(g1 + (long long)n * g1_ns + slab + v * 8, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += h[i];
+    }
+    store_split8<ODT>(hi, lo, (long long)n * o_ns + slab + v * 8, g);
+  }
+}
+
+static inline int pick_splits(int N, int C8, long long V) {
+  // enough CTAs for ~4 waves of 148 SMs, at least 2048 voxels per CTA
+  long long want = (4LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
+  long long maxs = (V + 2047) / 2048;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  return (int)want;
+}
+static inline int pick_xblocks(int N, int C8, long long V) {
+  long long full = (V + kThreads - 1) / kThreads;
+  long long want = (8LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
+  if (want > full) want = full;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace tta
+
+using namespace tta;
+
+extern "C" {
+
+// Workspace (floats) needed by tta_norm_stats / tta_norm_bwd_reduce for a given shape.
+long long tta_norm_workspace_floats(int N, int C8, long long V) {
+  return (long long)N * C8 * pick_splits(N, C8, V) * 16;
+}
+
+int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, int batch_mode,
+                   float eps, float* mean, float* rstd, float* workspace, cudaStream_t stream) {
+  TTA_REQUIRE(y && mean && rstd && workspace, "tta_norm_stats: null pointer");
+  TTA_REQUIRE(N > 0 && C8 > 0 && V > 0, "tta_norm_stats: empty shape N=%d C8=%d V=%lld", N, C8, V);
+  const int splits = pick_splits(N, C8, V);
+  norm_stats_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(y, y_ns, C8, V, splits,
+                                                                         workspace);
+  const int tot = N * C8 * 8;
+  norm_stats_finalize_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(workspace, N, C8, splits, V,
+                                                                    batch_mode, eps, mean, rstd);
+  return tta_check_launch("tta_norm_stats");
+}
+
+int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, const float* mean,
+                   const float* rstd, const float* gamma, const float* beta, int relu,
+                   int res_kind, const void* res_a, const void* res_b, long long res_ns,
+                   uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int out_dtype,
+                   cudaStream_t stream) {
+  TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_apply: null pointer");
+  TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_apply: res_kind %d", res_kind);
+  TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_apply: bad dtype");
+  const dim3 grid(pick_xblocks(N, C8, V), C8, N);
+#define LAUNCH(RES, DT)                                                                        \
+  norm_apply_kernel<RES, DT><<<grid, kThreads, 0, stream>>>(                                   \
+      y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
+      (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns)
+  if (out_dtype == TTA_F16) {
+    if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
+  } else {
+    if (res_kind == 0) LAUNCH(0, TTA_BF16); else if (res_kind == 1) LAUNCH(1, TTA_BF16); else LAUNCH(2, TTA_BF16);
+  }
+#undef LAUNCH
+  return tta_check_launch("tta_norm_apply");
+}
+
+int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long long g1_ns,
+                        const float* y, long long y_ns, int N, int C8, int Creal, long long V,
+                        const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, int relu, int batch_mode, float* sums, float* dgamma,
+                        float* dbeta, float* workspace, cudaStream_t stream) {
+  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dgamma && dbeta && workspace,
+              "tta_norm_bwd_reduce: null pointer");
+  const int splits = pick_splits(N, C8, V);
+  norm_bwd_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(
+      g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace);
+  const int C = C8 * 8;
+  norm_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(workspace, N, C8, Creal, splits,
+                                                             batch_mode, sums, dgamma, dbeta);
+  return tta_check_launch("tta_norm_bwd_reduce");
+}
+
+int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long long g1_ns,
+                       const float* y, long long y_ns, int N, int C8, long long V,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       int relu, int batch_mode, const float* sums, uint16_t* dy_hi,
+                       uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi, uint16_t* aux_lo,
+                       long long aux_ns, int out_dtype, cudaStream_t stream) {
+  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dy_hi && dy_lo,
+              "tta_norm_bwd_apply: null pointer");
+  const float inv_m = (float)(1.0 / ((double)V * (batch_mode ? N : 1)));
+  const dim3 grid(pick_xblocks(N, C8, V), C8, N);
+  if (out_dtype == TTA_F16)
+    norm_bwd_apply_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(
+        g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
+  else
+    norm_bwd_apply_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(
+        g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
+  return tta_check_launch("tta_norm_bwd_apply");
+}
+
+int tta_split_f32(const float* g0, long long g0_ns, const float* g1, long long g1_ns, int N, int C8,
+                  long long V, uint16_t* hi, uint16_t* lo, long long o_ns, int out_dtype,
+                  cudaStream_t stream) {
+  TTA_REQUIRE(g0 && hi && lo, "tta_split_f32: null pointer");
+  const dim3 grid(pick_xblocks(N, C8, V), C8, N);
+  if (out_dtype == TTA_F16)
+    split_f32_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
+  else
+    split_f32_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
+  return tta_check_launch("tta_split_f32");
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+// HBM-streaming kernels of the TTA step that are not norms:
+//   * window gather / input pack   (NCDHW fp32 volume -> split fp16 operand planes, zero pad,
+//                                   optional per-(window,channel) modality scale)
+//   * fused head: logits (NCDHW fp32) + per-voxel entropy loss + dlogits in ONE pass
+//   * Adam on the flat [gamma || beta] buffer (single CTA, device-side step counter so the
+//     whole step can be replayed from a CUDA graph)
+//   * sliding-window Gaussian blend (deterministic gather form) + normalise
+//   * sigmoid/threshold/Dice counts (reference: src/evaluation/seg_eval.py:41-68,304-308)
+#include "tta_common.cuh"
+
+namespace tta {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- gather / pack
+// win[b*4 + {0,1,2,3}] = {volume index, d0, h0, w0} of window b (origins may be negative or
+// run past the volume: those voxels read 0 = MONAI's constant pad).
+__global__ void __launch_bounds__(kThreads)
+gather_pack_kernel(const float* __restrict__ vol, int C, int Ds, int Hs, int Ws,
+                   const int* __restrict__ win, const float* __restrict__ chan_scale, int D, int H,
+                   int W, int C8, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                   long long o_ns) {
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
+  const long long V = (long long)D * H * W;
+  const long long Vs = (long long)Ds * Hs * Ws;
+  const float* src = vol + (long long)vi * C * Vs;
+  float sc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = chunk * 8 + i;
+    sc[i] = (c < C) ? (chan_scale ? chan_scale[b * C + c] : 1.f) : 0.f;
+  }
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
+       v += (long long)gridDim.x * kThreads) {
+    const int w = (int)(v % W);
+    const int h = (int)((v / W) % H);
+    const int d = (int)(v / ((long long)W * H));
+    const int sd = d + d0, sh = h + h0, sw = w + w0;
+    float x[8];
+    const bool inside = sd >= 0 && sd < Ds && sh >= 0 && sh < Hs && sw >= 0 && sw < Ws;
+    const long long so = ((long long)sd * Hs + sh) * Ws + sw;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = chunk * 8 + i;
+      x[i] = (inside && c < C) ? src[(long long)c * Vs + so] * sc[i] : 0.f;
+    }
+    store_split8<TTA_F16>(hi, lo, (long long)b * o_ns + ((long long)chunk * V + v) * 8, x);
+  }
+}
+
+// ---------------------------------------------------------------- fused head
+// One pass: read the last conv's fp32 result (chunk 0, R <= 8 real channels), write logits in
+// the reference's NCDHW fp32 layout, the per-voxel entropy (block partial sums) and
+// dlogits = sample_w[n] * inv_count * dH/dz as split bf16 planes for the first dgrad conv.
+//   mode 0: softmax entropy   H = lse(z) - sum_c p_c z_c ;  dH/dz_k = -p_k (z_k - sum_c p_c z_c)
+//   mode 1: Bernoulli entropy H = sum_c softplus(z_c) - p_c z_c ; dH/dz_c = -z_c p_c (1 - p_c)
+__global__ void __launch_bounds__(kThreads)
+head_entropy_kernel(const float* __restrict__ y, long long y_ns, int R, long long V, int mode,
+                    float inv_count, const float* __restrict__ sample_w,
+                    float* __restrict__ logits, uint16_t* __restrict__ dz_hi,
+                    uint16_t* __restrict__ dz_lo, long long dz_ns, float* __restrict__ partial) {
+  const int n = blockIdx.y;
+  const float sw = sample_w ? sample_w[n] : 1.f;
+  const float gs = sw * inv_count;
+  float hsum = 0.f;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
+       v += (long long)gridDim.x * kThreads) {
+    float z[8], g[8];
+    load_f32x8(y + (long long)n * y_ns + v * 8, z);
+    if (logits) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < R) logits[((long long)n * R + c) * V + v] = z[c];
+    }
+    float Hv = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    if (mode == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < R) {
+          const float zi = z[i];
+          const float p = 1.f / (1.f + expf(-zi));
+          const float sp = fmaxf(zi, 0.f) + log1pf(expf(-fabsf(zi)));
+          Hv += sp - p * zi;
+          g[i] = -zi * p * (1.f - p) * gs;
+        }
+      }
+    } else {
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < R) m = fmaxf(m, z[i]);
+      float e[8], S = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        e[i] = (i < R) ? expf(z[i] - m) : 0.f;
+        S += e[i];
+      }
+      const float invS = 1.f / S;
+      float pz = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < R) pz = fmaf(e[i] * invS, z[i], pz);
+      Hv = (m + logf(S)) - pz;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < R) g[i] = -(e[i] * invS) * (z[i] - pz) * gs;
+    }
+    hsum += Hv * sw;
+    if (dz_hi) store_split8<TTA_BF16>(dz_hi, dz_lo, (long long)n * dz_ns + v * 8, g);
+  }
+  __shared__ float red[kThreads / 32];
+  hsum = warp_sum(hsum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = hsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+    partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+__global__ void loss_finalize_kernel(const float* __restrict__ partial, int count, float inv_count,
+                                     float* __restrict__ loss) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += 32) s += (double)partial[i];
+  s = warp_sum_d(s);
+  if (threadIdx.x == 0) *loss = (float)(s * (double)inv_count);
+}
+
+// ---------------------------------------------------------------- Adam (torch.optim.Adam math)
+__global__ void __launch_bounds__(1024)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float gscale,
+            int* __restrict__ step_dev) {
+  const int t = *step_dev + 1;
+  __syncthreads();
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  const float step_size = (float)((double)lr / bc1);
+  const float sq_bc2 = (float)sqrt(bc2);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sq_bc2 + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+  if (threadIdx.x == 0) *step_dev = t;
+}
+
+// ---------------------------------------------------------------- sliding-window blend
+// Deterministic gather form: one thread per volume voxel loops over the windows of this batch
+// in order and accumulates  acc += w * logit,  wsum += w  with
+// w = max(gd[d]*gh[h]*gw[w], wmin)  (MONAI gaussian importance map, clamped).
+__global__ void __launch_bounds__(kThreads)
+sw_blend_kernel(const float* __restrict__ logits, int NB, int R, int D, int H, int W,
+                const int* __restrict__ win, const float* __restrict__ sample_w,
+                const float* __restrict__ gd, const float* __restrict__ gh,
+                const float* __restrict__ gw, float wmin, float* __restrict__ acc,
+                float* __restrict__ wsum, int Ds, int Hs, int Ws) {
+  const long long Vs = (long long)Ds * Hs * Ws;
+  const long long V = (long long)D * H * W;
+  const int vi = blockIdx.y;
+  for (long long s = (long long)blockIdx.x * kThreads + threadIdx.x; s < Vs;
+       s += (long long)gridDim.x * kThreads) {
+    const int sw_ = (int)(s % Ws);
+    const int sh = (int)((s / Ws) % Hs);
+    const int sd = (int)(s / ((long long)Ws * Hs));
+    float wacc = 0.f;
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    bool touched = false;
+    for (int b = 0; b < NB; ++b) {
+      if (win[b * 4 + 0] != vi) continue;
+      if (sample_w && sample_w[b] == 0.f) continue;
+      const int d = sd - win[b * 4 + 1], h = sh - win[b * 4 + 2], w = sw_ - win[b * 4 + 3];
+      if (d < 0 || d >= D || h < 0 || h >= H || w < 0 || w >= W) continue;
+      const float wt = fmaxf(gd[d] * gh[h] * gw[w], wmin);
+      const long long o = ((long long)d * H + h) * W + w;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < R) a[c] = fmaf(wt, logits[((long long)b * R + c) * V + o], a[c]);
+      wacc += wt;
+      touched = true;
+    }
+    if (touched) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < R) acc[((long long)vi * R + c) * Vs + s] += a[c];
+      wsum[(long long)vi * Vs + s] += wacc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+sw_normalise_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, int R,
+                    long long Vs, float* __restrict__ out) {
+  const int vi = blockIdx.y;
+  for (long long s = (long long)blockIdx.x * kThreads + threadIdx.x; s < Vs;
+       s += (long long)gridDim.x * kThreads) {
+    const float w = wsum[(long long)vi * Vs + s];
+    for (int c = 0; c < R; ++c) {
+      const long long o = ((long long)vi * R + c) * Vs + s;
+      out[o] = acc[o] / w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Dice counts
+// counts[(b*R + r)*3 + {0,1,2}] += {sum pred*gt, sum pred, sum gt} with
+// pred = sigmoid(z) >= thr, gt = label > 0.5 (integer atomics: order-independent, exact).
+__global__ void __launch_bounds__(kThreads)
+dice_counts_kernel(const float* __restrict__ logits, const float* __restrict__ label, long long V,
+                   float thr, unsigned long long* __restrict__ counts) {
+  const int br = blockIdx.y;
+  const float* z = logits + (long long)br * V;
+  const float* y = label + (long long)br * V;
+  unsigned int inter = 0, ps = 0, gs = 0;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
+       v += (long long)gridDim.x * kThreads) {
+    const float p = 1.f / (1.f + expf(-z[v]));
+    const unsigned int pr = p >= thr, gt = y[v] > 0.5f;
+    inter += pr & gt;
+    ps += pr;
+    gs += gt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&counts[br * 3 + 0], (unsigned long long)inter);
+    atomicAdd(&counts[br * 3 + 1], (unsigned long long)ps);
+    atomicAdd(&counts[br * 3 + 2], (unsigned long long)gs);
+  }
+}
+
+static inline int xblocks(long long V, long long rows) {
+  long long full = (V + kThreads - 1) / kThreads;
+  long long want = (8LL * 148 + rows - 1) / rows;
+  if (want > full) want = full;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace tta
+
+using namespace tta;
+
+extern "C" {
+
+int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                    const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi,
+                    uint16_t* lo, long long o_ns, int C8, cudaStream_t stream) {
+  TTA_REQUIRE(vol && win && hi && lo, "tta_gather_pack: null pointer");
+  TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
+  const long long V = (long long)D * H * W;
+  gather_pack_kernel<<<dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream>>>(
+      vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns);
+  return tta_check_launch("tta_gather_pack");
+}
+
+int tta_head_entropy_blocks(int N, long long V) { return xblocks(V, N); }
+
+int tta_head_entropy(const float* y, long long y_ns, int N, int R, long long V, int mode,
+                     float inv_count, const float* sample_w, float* logits, uint16_t* dz_hi,
+                     uint16_t* dz_lo, long long dz_ns, float* partial, float* loss,
+                     cudaStream_t stream) {
+  TTA_REQUIRE(y && partial && loss, "tta_head_entropy: null pointer");
+  TTA_REQUIRE(R >= 1 && R <= 8, "tta_head_entropy: R=%d unsupported (1..8 region channels)", R);
+  TTA_REQUIRE(mode == 0 || mode == 1, "tta_head_entropy: mode %d", mode);
+  TTA_REQUIRE(!(mode == 0 && R < 2), "tta_head_entropy: softmax entropy is degenerate for R=1");
+  const int xb = xblocks(V, N);
+  head_entropy_kernel<<<dim3(xb, N), kThreads, 0, stream>>>(y, y_ns, R, V, mode, inv_count,
+                                                           sample_w, logits, dz_hi, dz_lo, dz_ns,
+                                                           partial);
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(partial, xb * N, inv_count, loss);
+  return tta_check_launch("tta_head_entropy");
+}
+
+int tta_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float b1,
+                  float b2, float eps, float gscale, int* step_dev, cudaStream_t stream) {
+  TTA_REQUIRE(p && g && m && v && step_dev, "tta_adam_step: null pointer");
+  TTA_REQUIRE(n >= 0, "tta_adam_step: n=%d", n);
+  if (n == 0) return TTA_OK;
+  adam_kernel<<<1, 1024, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, gscale, step_dev);
+  return tta_check_launch("tta_adam_step");
+}
+
+int tta_sw_blend(const float* logits, int NB, int R, int D, int H, int W, const int* win,
+                 const float* sample_w, const float* gd, const float* gh, const float* gw,
+                 float wmin, float* acc, float* wsum, int n_vol, int Ds, int Hs, int Ws,
+                 cudaStream_t stream) {
+  TTA_REQUIRE(logits && win && gd && gh && gw && acc && wsum, "tta_sw_blend: null pointer");
+  TTA_REQUIRE(R >= 1 && R <= 8, "tta_sw_blend: R=%d unsupported", R);
+  const long long Vs = (long long)Ds * Hs * Ws;
+  sw_blend_kernel<<<dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream>>>(
+      logits, NB, R, D, H, W, win, sample_w, gd, gh, gw, wmin, acc, wsum, Ds, Hs, Ws);
+  return tta_check_launch("tta_sw_blend");
+}
+
+int tta_sw_normalise(const float* acc, const float* wsum, int n_vol, int R, long long Vs, float* out,
+                     cudaStream_t stream) {
+  TTA_REQUIRE(acc && wsum && out, "tta_sw_normalise: null pointer");
+  sw_normalise_kernel<<<dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream>>>(acc, wsum, R, Vs, out);
+  return tta_check_launch("tta_sw_normalise");
+}
+
+int tta_dice_counts(const float* logits, const float* label, int BR, long long V, float thr,
+                    unsigned long long* counts, cudaStream_t stream) {
+  TTA_REQUIRE(logits && label && counts, "tta_dice_counts: null pointer");
+  dice_counts_kernel<<<dim3(xblocks(V, BR), BR), kThreads, 0, stream>>>(logits, label, V, thr, counts);
+  return tta_check_launch("tta_dice_counts");
+}
+
+}  // extern "C"

@@ -1,0 +1,605 @@
+"""Execution engine: turns the ``UNetB200`` module tree into a static list of C-ABI kernel
+launches (forward, fused head, backward, Adam) over pre-allocated HBM buffers, optionally
+replayed as one CUDA graph.
+
+Path covered: MONAI-UNet forward (a2-a6), entropy loss + dlogits, backward
+(dgrad only -- TENT freezes conv weights, so there is no wgrad), norm-affine gradients, Adam
+(a10) on the flat [gamma || beta] buffer.
+
+Layouts: activations that feed a conv are split 16-bit planes
+(fp16 forward / bf16 backward, x ~= hi + lo) in the channel-blocked layout [N][C8][D][H][W][8];
+conv results are fp32 in the same blocked layout.  ``torch.cat`` of the skip connection is free:
+producers write into channel slices of one buffer.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import TTA_BF16, TTA_F16, check
+from .layout import pack_bias, pack_weights_simt, pack_weights_tc, wg_dgrad, wg_forward
+from .unet_b200 import (ConvHolder, ConvolutionH, NormHolder, ResidualUnitH, SkipConnectionH, UNetB200)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------ tensors
+class Act:
+    """Conv-operand activation: split fp16 planes [2][N][C8][D][H][W][8] (+ fp32 grad)."""
+
+    def __init__(self, N, C, D, H, W, device, needs_grad: bool, name: str = ""):
+        self.N, self.C, self.C8, self.D, self.H, self.W = N, C, (C + 7) // 8, D, H, W
+        self.V = D * H * W
+        self.name, self.needs_grad = name, needs_grad
+        self.planes = torch.zeros((2, N, self.C8, D, H, W, 8), dtype=torch.int16, device=device)
+        self.grad = (torch.zeros((N, self.C8, D, H, W, 8), dtype=torch.float32, device=device)
+                     if needs_grad else None)
+        self.ns = self.C8 * self.V * 8  # elements between samples
+        self.written: set = set()       # chunks of .grad written so far in this backward
+        self.extra: List["ActView"] = []  # identity-residual gradient contributions
+
+    def view(self, c8_off: int = 0, c8_len: Optional[int] = None) -> "ActView":
+        return ActView(self, c8_off, self.C8 - c8_off if c8_len is None else c8_len)
+
+
+@dataclass
+class ActView:
+    parent: Act
+    c8_off: int
+    C8: int
+
+    @property
+    def dims(self):
+        return self.parent.D, self.parent.H, self.parent.W
+
+    @property
+    def hi(self) -> int:
+        return self.parent.planes[0].data_ptr() + self.c8_off * self.parent.V * 8 * 2
+
+    @property
+    def lo(self) -> int:
+        return self.parent.planes[1].data_ptr() + self.c8_off * self.parent.V * 8 * 2
+
+    @property
+    def g(self) -> int:
+        return self.parent.grad.data_ptr() + self.c8_off * self.parent.V * 8 * 4
+
+    @property
+    def ns(self) -> int:
+        return self.parent.ns
+
+
+class Res:
+    """fp32 conv result [N][C8][D][H][W][8] (+ its bf16 split gradient planes dY)."""
+
+    def __init__(self, N, C, D, H, W, device, name: str = ""):
+        self.N, self.C, self.C8, self.D, self.H, self.W = N, C, (C + 7) // 8, D, H, W
+        self.V = D * H * W
+        self.name = name
+        self.data = torch.zeros((N, self.C8, D, H, W, 8), dtype=torch.float32, device=device)
+        self.ns = self.C8 * self.V * 8
+        self.dy: Optional[torch.Tensor] = None
+        self.device = device
+
+    def alloc_dy(self):
+        if self.dy is None:
+            self.dy = torch.zeros((2, self.N, self.C8, self.D, self.H, self.W, 8), dtype=torch.int16,
+                                  device=self.device)
+
+    @property
+    def ptr(self) -> int:
+        return self.data.data_ptr()
+
+
+# ------------------------------------------------------------------------------ layers
+class ConvLayer:
+    def __init__(self, holder: ConvHolder, name: str, fold_identity: bool = False):
+        self.h, self.name, self.fold_identity = holder, name, fold_identity
+        self.K, self.stride = holder.k, holder.stride
+        self.mode = 1 if holder.transposed else 0
+        self.cin, self.cout = holder.cin, holder.cout
+        self.packed = {}
+
+    def pack(self, device, want_tc: bool):
+        """(Re)pack weights: fp32 for the CUDA-core kernel, split fp16/bf16 for tcgen05."""
+        w = self.h.weight.detach().to(device=device, dtype=torch.float32)
+        wf = wg_forward(w, self.h.transposed)
+        wd = wg_dgrad(w, self.h.transposed)
+        if self.fold_identity:
+            c = self.K ** 3 // 2
+            eye = torch.eye(self.cin, device=device)
+            wf = wf.clone(); wd = wd.clone()
+            wf[c] += eye
+            wd[c] += eye
+        self.packed = {
+            "simt_fwd": pack_weights_simt(wf), "simt_bwd": pack_weights_simt(wd),
+            "bias": pack_bias(self.h.bias.detach().to(device=device, dtype=torch.float32)),
+        }
+        if want_tc:
+            lib = _lib.lib()
+            if lib.tta_conv_tc_supported(self.mode, self.K, self.stride, self.cin, self.cout):
+                self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16)
+            bmode = 1 - self.mode
+            if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.cin):
+                self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, TTA_BF16)
+
+
+class NormLayer:
+    def __init__(self, holder: NormHolder, name: str, off: int):
+        self.h, self.name, self.off = holder, name, off
+        self.C, self.C8 = holder.num_features, (holder.num_features + 7) // 8
+        self.batch = 1 if holder.kind == "batch" else 0
+
+
+# ------------------------------------------------------------------------------ plan
+@dataclass
+class Plan:
+    N: int
+    dims: Tuple[int, int, int]
+    x: Act
+    logits: torch.Tensor
+    loss: torch.Tensor
+    fwd: List[Callable[[], None]] = field(default_factory=list)
+    head_infer: Optional[Callable[[], None]] = None
+    head_train: Optional[Callable[[], None]] = None
+    bwd: List[Callable[[], None]] = field(default_factory=list)
+    keep: list = field(default_factory=list)
+    launches_fwd: int = 0
+    launches_bwd: int = 0
+    conv_backends: dict = field(default_factory=dict)
+    graph: Optional[torch.cuda.CUDAGraph] = None
+    graph_key: Optional[tuple] = None
+    sample_w: Optional[torch.Tensor] = None
+    win: Optional[torch.Tensor] = None
+    chan_scale: Optional[torch.Tensor] = None
+    x_static: Optional[torch.Tensor] = None
+    stats_ops: list = field(default_factory=list)
+
+
+class TTAEngine:
+    """Owns packed weights, the flat norm-affine parameter/optimizer state and per-shape plans."""
+
+    def __init__(self, model: UNetB200):
+        self.model = model
+        self.lib = _lib.lib()  # raises if the CUDA library is missing
+        self.plans = {}
+        self.device: Optional[torch.device] = None
+        self.conv_layers = {}
+        self.norm_layers: List[NormLayer] = []
+        self.P = 0
+        self.gb = self.dgb = self.m = self.v = self.step_dev = None
+        self.entropy_mode = 1
+        self.adam = dict(lr=1e-3, b1=0.9, b2=0.999, eps=1e-8)
+        self._collect()
+
+    # ---------------------------------------------------------------- structure
+    def _collect(self):
+        fold = set()
+        for m in self.model.modules():
+            if isinstance(m, ResidualUnitH):
+                last = list(m.conv.children())[-1]
+                if last.conv_only:
+                    if not isinstance(m.residual, nn.Identity):
+                        raise ValueError("unet_b200: conv-only residual unit with a conv shortcut is unsupported")
+                    fold.add(id(last.conv))
+        for name, m in self.model.named_modules():
+            if isinstance(m, ConvHolder):
+                self.conv_layers[id(m)] = ConvLayer(m, name, fold_identity=id(m) in fold)
+        off = 0
+        for name, m in self.model.named_modules():
+            if isinstance(m, NormHolder):
+                nl = NormLayer(m, name, off)
+                self.norm_layers.append(nl)
+                off += nl.C8 * 8
+        self.P = off
+
+    def invalidate(self):
+        self.model._params_dirty = True
+
+    @property
+    def n_adaptable(self) -> int:
+        return 2 * sum(n.C for n in self.norm_layers)
+
+    def _ensure_device(self, device: torch.device, dry: bool = False):
+        """``dry=True`` (tests only) builds buffers on the CPU to inspect the op graph; nothing can
+        be launched from such a plan."""
+        if device.type != "cuda" and not dry:
+            raise RuntimeError("multimodal_tta_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.device is not None and self.device != device:
+            self.plans.clear()
+            self.gb = None
+        self.device = device
+        if self.gb is None:
+            P = self.P
+            self.gb = torch.zeros(2 * P, dtype=torch.float32, device=device)
+            self.dgb = torch.zeros(2 * P, dtype=torch.float32, device=device)
+            self.m = torch.zeros(2 * P, dtype=torch.float32, device=device)
+            self.v = torch.zeros(2 * P, dtype=torch.float32, device=device)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)
+            self.model._params_dirty = True
+        if self.model._params_dirty:
+            self._bind_params()
+            want_tc = self.model.conv_backend in ("auto", "tc")
+            for cl in self.conv_layers.values():
+                cl.pack(device, want_tc)
+            self.model._params_dirty = False
+
+    def _bind_params(self):
+        """Copy norm affine values into the flat [gamma || beta] buffer and rebind the holders'
+        Parameters as views of it, so ``state_dict()`` always shows the adapted values."""
+        P = self.P
+        for nl in self.norm_layers:
+            g = self.gb[nl.off: nl.off + nl.C]
+            b = self.gb[P + nl.off: P + nl.off + nl.C]
+            if nl.h.weight is not None:
+                if nl.h.weight.data_ptr() != g.data_ptr():
+                    g.copy_(nl.h.weight.detach().to(self.device))
+                    b.copy_(nl.h.bias.detach().to(self.device))
+                    nl.h.weight.data = g
+                    nl.h.bias.data = b
+            else:
+                g.fill_(1.0)
+                b.zero_()
+
+    def flat_params(self) -> torch.Tensor:
+        """Compact [gamma_0..gamma_L || beta_0..beta_L] copy (real channels only)."""
+        P = self.P
+        gs = [self.gb[nl.off: nl.off + nl.C] for nl in self.norm_layers]
+        bs = [self.gb[P + nl.off: P + nl.off + nl.C] for nl in self.norm_layers]
+        return torch.cat(gs + bs)
+
+    def flat_grads(self) -> torch.Tensor:
+        P = self.P
+        gs = [self.dgb[nl.off: nl.off + nl.C] for nl in self.norm_layers]
+        bs = [self.dgb[P + nl.off: P + nl.off + nl.C] for nl in self.norm_layers]
+        return torch.cat(gs + bs)
+
+    def reset_optimizer(self):
+        self.m.zero_(); self.v.zero_(); self.step_dev.zero_()
+
+    # ---------------------------------------------------------------- op emitters
+    def _conv_call(self, plan: Plan, cl: ConvLayer, backward: bool, src, src_dtype, N, cin8, idims,
+                   dst_ptr, dst_ns, cout8, odims, accumulate: bool):
+        """Returns a closure launching one conv (tcgen05 kernel when the geometry is supported,
+        otherwise the fp32 CUDA-core kernel)."""
+        lib = self.lib
+        mode = (1 - cl.mode) if backward else cl.mode
+        key = "bwd" if backward else "fwd"
+        bias = 0 if backward else cl.packed["bias"].data_ptr()
+        hi, lo, ns = src
+        use_tc = ("tc_" + key) in cl.packed and self.model.conv_backend in ("auto", "tc")
+        if self.model.conv_backend == "tc" and not use_tc:
+            raise RuntimeError(f"conv_backend=tc but {cl.name} ({key}) is not supported by the tcgen05 kernel")
+        plan.conv_backends[f"{cl.name}:{key}"] = "tc" if use_tc else "simt"
+        if use_tc:
+            wp = cl.packed["tc_" + key]
+            plan.keep.append(wp)
+            args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
+                    *odims, mode, cl.K, cl.stride, int(accumulate), 0)
+
+            def run():
+                check(lib.tta_conv_tc(*args, _stream()), f"conv_tc {cl.name}")
+        else:
+            wp = cl.packed["simt_" + key]
+            plan.keep.append(wp)
+            args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
+                    *odims, mode, cl.K, cl.stride, int(accumulate))
+
+            def run():
+                check(lib.tta_conv_simt(*args, _stream()), f"conv_simt {cl.name}")
+        return run
+
+    def build_plan(self, N: int, D: int, H: int, W: int) -> Plan:
+        dev = self.device
+        lib = self.lib
+        model = self.model
+        P = self.P
+        R = model.out_channels
+        x = Act(N, model.in_channels, D, H, W, dev, needs_grad=False, name="x")
+        plan = Plan(N=N, dims=(D, H, W), x=x,
+                    logits=torch.zeros((N, R, D, H, W), dtype=torch.float32, device=dev),
+                    loss=torch.zeros(1, dtype=torch.float32, device=dev))
+        ops: list = []  # forward op records, replayed in reverse to emit the backward
+        max_ws = [1]
+
+        def conv(cl: ConvLayer, inp: ActView) -> Res:
+            d, h, w = inp.dims
+            s = cl.stride
+            if cl.mode == 0:
+                od, oh, ow = (d - 1) // s + 1, (h - 1) // s + 1, (w - 1) // s + 1
+            else:
+                od, oh, ow = d * s, h * s, w * s
+            if inp.C8 != (cl.cin + 7) // 8:
+                raise ValueError(f"{cl.name}: input has {inp.C8} channel chunks, layer expects {cl.cin} channels")
+            y = Res(N, cl.cout, od, oh, ow, dev, name=cl.name)
+            plan.keep.append(y)
+            run = self._conv_call(plan, cl, False, (inp.hi, inp.lo, inp.ns), TTA_F16, N, inp.C8, inp.dims,
+                                  y.ptr, y.ns, y.C8, (od, oh, ow), False)
+            plan.fwd.append(run)
+            ops.append(("conv", cl, inp, y))
+            return y
+
+        def normact(nl: NormLayer, y: Res, relu: bool, residual, out: Optional[ActView]) -> ActView:
+            if out is None:
+                a = Act(N, y.C, y.D, y.H, y.W, dev, needs_grad=True, name=nl.name)
+                plan.keep.append(a)
+                out = a.view()
+            if (out.C8, *out.dims) != (y.C8, y.D, y.H, y.W):
+                raise ValueError(f"{nl.name}: output view shape mismatch")
+            mean = torch.zeros(N * y.C8 * 8, dtype=torch.float32, device=dev)
+            rstd = torch.zeros_like(mean)
+            sums = torch.zeros(N * y.C8 * 8 * 2, dtype=torch.float32, device=dev)
+            plan.keep += [mean, rstd, sums]
+            max_ws[0] = max(max_ws[0], lib.tta_norm_workspace_floats(N, y.C8, y.V))
+            gptr = self.gb.data_ptr() + nl.off * 4
+            bptr = self.gb.data_ptr() + (P + nl.off) * 4
+            rec = dict(nl=nl, y=y, relu=relu, residual=residual, out=out, mean=mean, rstd=rstd, sums=sums,
+                       gptr=gptr, bptr=bptr)
+            if residual is None:
+                rk, ra, rb, rns = 0, 0, 0, 0
+            elif isinstance(residual, Res):
+                rk, ra, rb, rns = 1, residual.ptr, 0, residual.ns
+            else:
+                rk, ra, rb, rns = 2, residual.hi, residual.lo, residual.ns
+            st_args = (y.ptr, y.ns, N, y.C8, y.V, nl.batch, float(nl.h.eps), mean.data_ptr(), rstd.data_ptr())
+            ap_args = (y.ptr, y.ns, N, y.C8, y.V, mean.data_ptr(), rstd.data_ptr(), gptr, bptr, int(relu),
+                       rk, ra, rb, rns, out.hi, out.lo, out.ns, TTA_F16)
+            plan.stats_ops.append((nl, mean, rstd, y))
+
+            def run():
+                if not (nl.batch and not model.training and nl.h.track_running_stats):
+                    check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), _stream()), "norm_stats")
+                check(lib.tta_norm_apply(*ap_args, _stream()), "norm_apply")
+            plan.fwd.append(run)
+            ops.append(("norm", rec))
+            return out
+
+        def convolution(cv: ConvolutionH, inp: ActView, out: Optional[ActView]):
+            y = conv(self.conv_layers[id(cv.conv)], inp)
+            if cv.conv_only:
+                return y
+            return normact(self._nl(cv.adn.N), y, True, None, out)
+
+        def residual_unit(ru: ResidualUnitH, inp: ActView, out: Optional[ActView]):
+            if isinstance(ru.residual, ConvHolder):
+                res = conv(self.conv_layers[id(ru.residual)], inp)
+            else:
+                res = inp
+            cur = inp
+            units = list(ru.conv.children())
+            for i, u in enumerate(units):
+                last = i == len(units) - 1
+                y = conv(self.conv_layers[id(u.conv)], cur)
+                if u.conv_only:
+                    return y  # identity shortcut folded into the centre tap (ConvLayer.fold_identity)
+                cur = normact(self._nl(u.adn.N), y, True, res if last else None, out if last else None)
+            return cur
+
+        def layer(mod, inp: ActView, out: Optional[ActView]):
+            if isinstance(mod, ResidualUnitH):
+                return residual_unit(mod, inp, out)
+            if isinstance(mod, ConvolutionH):
+                return convolution(mod, inp, out)
+            if isinstance(mod, nn.Sequential):  # up path: Sequential(convT-Convolution, ResidualUnit)
+                cur = inp
+                mods = list(mod.children())
+                for i, sm in enumerate(mods):
+                    cur = layer(sm, cur, out if i == len(mods) - 1 else None)
+                return cur
+            raise TypeError(type(mod))
+
+        def out_channels(mod) -> int:
+            if isinstance(mod, ResidualUnitH):
+                return list(mod.conv.children())[-1].conv.cout
+            if isinstance(mod, ConvolutionH):
+                return mod.conv.cout
+            return out_channels(list(mod.children())[-1])
+
+        def block(seq: nn.Sequential, inp: ActView, out: Optional[ActView]):
+            down, skip, up = seq[0], seq[1], seq[2]
+            sub = skip.submodule
+            c, cs = out_channels(down), out_channels(sub)
+            if c % 8 or cs % 8:
+                raise ValueError("unet_b200: skip-connection channel counts must be multiples of 8")
+            d, h, w = inp.dims
+            if isinstance(down, ResidualUnitH):
+                s = list(down.conv.children())[0].conv.stride
+            else:
+                s = down.conv.stride
+            if d % s or h % s or w % s:
+                raise ValueError(f"unet_b200: spatial size {(d, h, w)} not divisible by stride {s} "
+                                 "(the skip concat would mismatch, as in the reference)")
+            od, oh, ow = d // s, h // s, w // s
+            cat = Act(N, c + cs, od, oh, ow, dev, needs_grad=True, name="cat")
+            plan.keep.append(cat)
+            dv = cat.view(0, c // 8)
+            layer(down, inp, dv)
+            sv = cat.view(c // 8, cs // 8)
+            if isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], SkipConnectionH):
+                block(sub, dv, sv)
+            else:
+                layer(sub, dv, sv)
+            return layer(up, cat.view(), out)
+
+        final = block(model.model, x.view(), None)
+        if not isinstance(final, Res):
+            raise ValueError("unet_b200: the top-level up layer must end in a conv (MONAI UNet does)")
+        plan.ws = torch.zeros(max_ws[0], dtype=torch.float32, device=dev)
+        final.alloc_dy()
+        nblk = lib.tta_head_entropy_blocks(N, final.V)
+        plan.partial = torch.zeros(nblk * N, dtype=torch.float32, device=dev)
+        plan.sample_w = torch.ones(N, dtype=torch.float32, device=dev)
+        plan.inv_count = 1.0 / (N * final.V)
+
+        def head(train: bool):
+            def run():
+                check(lib.tta_head_entropy(
+                    final.ptr, final.ns, N, R, final.V, self.entropy_mode, float(plan.inv_count),
+                    plan.sample_w.data_ptr(), plan.logits.data_ptr(),
+                    final.dy[0].data_ptr() if train else 0, final.dy[1].data_ptr() if train else 0, final.ns,
+                    plan.partial.data_ptr(), plan.loss.data_ptr(), _stream()), "head_entropy")
+            return run
+        plan.head_infer, plan.head_train = head(False), head(True)
+
+        # ------------------------------------------------------------ backward emission
+        bwd_apply_flags = []
+        for op in reversed(ops):
+            if op[0] == "conv":
+                _, cl, inp, y = op
+                if not inp.parent.needs_grad:
+                    continue
+                par = inp.parent
+                chunks = set(range(inp.c8_off, inp.c8_off + inp.C8))
+                done = chunks & par.written
+                if done and done != chunks:
+                    raise RuntimeError("partial gradient accumulation state")
+                acc = bool(done)
+                par.written |= chunks
+                y.alloc_dy()
+                plan.bwd.append(self._conv_call(
+                    plan, cl, True, (y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns), TTA_BF16, N, y.C8,
+                    (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc))
+            else:
+                rec = op[1]
+                nl, y, out = rec["nl"], rec["y"], rec["out"]
+                par = out.parent
+                chunks = set(range(out.c8_off, out.c8_off + out.C8))
+                srcs = []
+                if chunks <= par.written:
+                    srcs.append((out.g, out.ns))
+                for ev in par.extra:
+                    if (ev[2], ev[3]) == (out.c8_off, out.C8):
+                        srcs.append((ev[0], ev[1]))
+                if not srcs or len(srcs) > 2:
+                    raise RuntimeError(f"{nl.name}: {len(srcs)} gradient sources (supported: 1 or 2)")
+                g0, g0ns = srcs[0]
+                g1, g1ns = srcs[1] if len(srcs) > 1 else (0, 0)
+                conv_in_needs = self._producer_input_needs_grad(ops, y)
+                res = rec["residual"]
+                aux = None
+                if isinstance(res, Res) and self._producer_input_needs_grad(ops, res):
+                    res.alloc_dy()
+                    aux = res
+                elif isinstance(res, ActView):
+                    # identity shortcut: this op's incoming gradient also flows into `res`
+                    if len(srcs) != 1:
+                        raise RuntimeError("identity residual with two incoming gradients is unsupported")
+                    res.parent.extra.append((g0, g0ns, res.c8_off, res.C8))
+                dg = self.dgb.data_ptr() + nl.off * 4
+                db = self.dgb.data_ptr() + (P + nl.off) * 4
+                rd_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, nl.C, y.V, rec["mean"].data_ptr(),
+                           rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
+                           rec["sums"].data_ptr(), dg, db)
+                do_apply = conv_in_needs or aux is not None
+                bwd_apply_flags.append(do_apply)
+                if do_apply:
+                    y.alloc_dy()
+                    ap_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, y.V, rec["mean"].data_ptr(),
+                               rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
+                               rec["sums"].data_ptr(), y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns,
+                               aux.dy[0].data_ptr() if aux else 0, aux.dy[1].data_ptr() if aux else 0,
+                               aux.ns if aux else 0, TTA_BF16)
+
+                def run(rd_args=rd_args, ap_args=ap_args if do_apply else None):
+                    check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), _stream()), "norm_bwd_reduce")
+                    if ap_args is not None:
+                        check(lib.tta_norm_bwd_apply(*ap_args, _stream()), "norm_bwd_apply")
+                plan.bwd.append(run)
+        n_conv = sum(1 for o in ops if o[0] == "conv")
+        n_norm = sum(1 for o in ops if o[0] == "norm")
+        plan.launches_fwd = 1 + n_conv + 3 * n_norm + 2          # gather + convs + (2 stats + apply) + head
+        plan.launches_bwd = sum(1 for o in ops if o[0] == "conv" and o[2].parent.needs_grad) + \
+            sum(3 if a else 2 for a in bwd_apply_flags) + 1       # dgrads + norm bwd + adam
+        return plan
+
+    def _nl(self, holder: NormHolder) -> NormLayer:
+        for nl in self.norm_layers:
+            if nl.h is holder:
+                return nl
+        raise KeyError("norm holder not registered")
+
+    @staticmethod
+    def _producer_input_needs_grad(ops, y: Res) -> bool:
+        for op in ops:
+            if op[0] == "conv" and op[3] is y:
+                return op[2].parent.needs_grad
+        raise KeyError("no producer conv for result tensor")
+
+    # ---------------------------------------------------------------- execution
+    def get_plan(self, N, D, H, W) -> Plan:
+        key = (N, D, H, W)
+        if key not in self.plans:
+            self.plans[key] = self.build_plan(N, D, H, W)
+        return self.plans[key]
+
+    def _load_running_stats(self, plan: Plan):
+        """eval()-mode BatchNorm: statistics come from the running buffers, not the batch."""
+        for nl, mean, rstd, y in plan.stats_ops:
+            if nl.batch and not self.model.training and nl.h.track_running_stats:
+                C8 = nl.C8 * 8
+                mu = torch.zeros(C8, device=self.device); mu[:nl.C] = nl.h.running_mean.to(self.device)
+                rs = torch.zeros(C8, device=self.device)
+                rs[:nl.C] = torch.rsqrt(nl.h.running_var.to(self.device) + nl.h.eps)
+                mean.copy_(mu.repeat(plan.N)); rstd.copy_(rs.repeat(plan.N))
+
+    def _pack_input(self, plan: Plan, x: torch.Tensor, win: Optional[torch.Tensor] = None,
+                    chan_scale: Optional[torch.Tensor] = None, vol_dims=None, n_vol=None):
+        N = plan.N
+        D, H, W = plan.dims
+        if win is None:
+            if plan.win is None:
+                w = torch.zeros((N, 4), dtype=torch.int32)
+                w[:, 0] = torch.arange(N, dtype=torch.int32)
+                plan.win = w.to(self.device)
+            win = plan.win
+            vol_dims, n_vol = (D, H, W), N
+        a = plan.x
+        check(self.lib.tta_gather_pack(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
+                                       chan_scale.data_ptr() if chan_scale is not None else 0, N, D, H, W,
+                                       a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8, _stream()),
+              "gather_pack")
+
+    def _check_input(self, x: torch.Tensor):
+        if x.dim() != 5:
+            raise ValueError(f"expected [B,C,D,H,W], got {tuple(x.shape)}")
+        if x.shape[1] != self.model.in_channels:
+            raise ValueError(f"expected {self.model.in_channels} input channels, got {x.shape[1]}")
+        if not x.is_cuda:
+            raise RuntimeError("multimodal_tta_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.contiguous().float()
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self._check_input(x)
+        self._ensure_device(x.device)
+        plan = self.get_plan(*[int(s) for s in (x.shape[0], *x.shape[2:])])
+        self._load_running_stats(plan)
+        self._pack_input(plan, x)
+        for op in plan.fwd:
+            op()
+        plan.head_infer()
+        return plan.logits.clone()
+
+    def run_step(self, plan: Plan, adam: bool = True, gscale: float = 1.0):
+        """forward + fused head + backward (+ Adam) on whatever is in plan.x."""
+        for op in plan.fwd:
+            op()
+        plan.head_train()
+        for op in plan.bwd:
+            op()
+        if adam:
+            self.adam_step(gscale)
+
+    def adam_step(self, gscale: float = 1.0):
+        a = self.adam
+        check(self.lib.tta_adam_step(self.gb.data_ptr(), self.dgb.data_ptr(), self.m.data_ptr(),
+                                     self.v.data_ptr(), 2 * self.P, a["lr"], a["b1"], a["b2"], a["eps"],
+                                     float(gscale), self.step_dev.data_ptr(), _stream()), "adam")

@@ -1,0 +1,123 @@
+"""HBM layouts of the B200 TTA path and the host-side weight packers.
+
+* activations / results : channel-blocked ``[N][C8][D][H][W][8]`` (pad channels are zero)
+* conv operands         : two 16-bit planes hi/lo (fp16 forward, bf16 backward), x ~= hi + lo
+* canonical weights     : ``Wg[tap][ci][co]`` with tap = (kd*K + kh)*K + kw, see
+                          csrc/tta_conv_simt.cu for the gather semantics of mode 0/1.
+The torch ops here run once per weight load (plumbing), never inside the timed step.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import TTA_BF16, TTA_F16
+
+
+def wg_forward(w: torch.Tensor, transposed: bool) -> torch.Tensor:
+    """nn.Conv3d weight [co][ci][k,k,k] or nn.ConvTranspose3d weight [ci][co][k,k,k] -> Wg[T][ci][co]."""
+    k = w.shape[-1]
+    if transposed:
+        return w.permute(2, 3, 4, 0, 1).reshape(k ** 3, w.shape[0], w.shape[1]).contiguous()
+    return w.permute(2, 3, 4, 1, 0).reshape(k ** 3, w.shape[1], w.shape[0]).contiguous()
+
+
+def wg_dgrad(w: torch.Tensor, transposed: bool) -> torch.Tensor:
+    """Weights of the input-gradient conv.  dgrad(Conv3d) is a mode-1 (transposed) conv with
+    Wg[k][ci=cout][co=cin] = w[cout][cin][k]; dgrad(ConvTranspose3d) is a mode-0 conv with
+    Wg[k][ci=cout_f][co=cin_f] = w[cin_f][cout_f][k]."""
+    k = w.shape[-1]
+    if transposed:
+        return w.permute(2, 3, 4, 1, 0).reshape(k ** 3, w.shape[1], w.shape[0]).contiguous()
+    return w.permute(2, 3, 4, 0, 1).reshape(k ** 3, w.shape[0], w.shape[1]).contiguous()
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def pack_weights_simt(wg: torch.Tensor) -> torch.Tensor:
+    """Wg[T][ci][co] -> Wp[T][C8in][C8out][8 ci][8 co] fp32 (zero padded)."""
+    T, ci, co = wg.shape
+    cip, cop = _pad8(ci), _pad8(co)
+    p = torch.zeros((T, cip, cop), dtype=torch.float32, device=wg.device)
+    p[:, :ci, :co] = wg
+    return p.reshape(T, cip // 8, 8, cop // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def pack_bias(b: torch.Tensor) -> torch.Tensor:
+    p = torch.zeros(_pad8(b.numel()), dtype=torch.float32, device=b.device)
+    p[: b.numel()] = b
+    return p
+
+
+def split_planes(x: torch.Tensor, dtype_tag: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> (hi, lo) 16-bit planes stored as int16, hi = rn16(x), lo = rn16(x - hi)."""
+    dt = torch.float16 if dtype_tag == TTA_F16 else torch.bfloat16
+    if dtype_tag == TTA_F16:
+        x = x.clamp(-65504.0, 65504.0)
+    hi = x.to(dt)
+    lo = (x - hi.float()).to(dt)
+    return hi.view(torch.int16), lo.view(torch.int16)
+
+
+def join_planes(hi: torch.Tensor, lo: torch.Tensor, dtype_tag: int) -> torch.Tensor:
+    dt = torch.float16 if dtype_tag == TTA_F16 else torch.bfloat16
+    return hi.view(dt).float() + lo.view(dt).float()
+
+
+def to_chunked(x: torch.Tensor) -> torch.Tensor:
+    """NCDHW fp32 -> [N][C8][D][H][W][8] fp32 (zero padded channels)."""
+    N, C, D, H, W = x.shape
+    Cp = _pad8(C)
+    xp = torch.zeros((N, Cp, D, H, W), dtype=x.dtype, device=x.device)
+    xp[:, :C] = x
+    return xp.reshape(N, Cp // 8, 8, D, H, W).permute(0, 1, 3, 4, 5, 2).contiguous()
+
+
+def from_chunked(x: torch.Tensor, C: int) -> torch.Tensor:
+    """[N][C8][D][H][W][8] -> NCDHW (first C channels)."""
+    N, C8, D, H, W, _ = x.shape
+    return x.permute(0, 1, 5, 2, 3, 4).reshape(N, C8 * 8, D, H, W)[:, :C].contiguous()
+
+
+# ---------------------------------------------------------------------------- tcgen05 packing
+# Geometry tables shared with csrc/tta_conv_tc.cu (tta_conv_tc_plan): for every pipeline
+# "group" g the kernel consumes, in order, the taps listed here.
+def tc_groups(mode: int, K: int, stride: int) -> list[list[int]]:
+    """Tap indices (kd*K*K + kh*K + kw) per pipeline group, in the kernel's MMA issue order."""
+    if K == 1:
+        return [[0]]
+    taps = lambda kds: [kd * 9 + kh * 3 + kw for kd in kds for kh in range(3) for kw in range(3)]
+    if mode == 0:                      # conv s1 / s2: one group per kd
+        return [taps([0]), taps([1]), taps([2])]
+    if stride == 1:                    # transposed s1: same structure, offsets mirrored in-kernel
+        return [taps([0]), taps([1]), taps([2])]
+    # transposed s2: group jd=0 holds kd in {1 (even out planes), 2 (odd)}, jd=1 holds kd=0
+    return [taps([1, 2]), taps([0])]
+
+
+def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int) -> torch.Tensor:
+    """Wg[T][ci][co] -> per-(n_tile, cblk, group) contiguous blobs
+    [ntile][cblk][group][hi|lo][entry][kchunk 2][n_tile rows][8 ci] of 16-bit values.
+    A blob is what one pipeline stage of the tcgen05 kernel bulk-copies into shared memory as
+    its B operand (K-major, no swizzle: 8 rows x 16 B core matrices, LBO = n_tile*16 B)."""
+    from . import _lib
+    T, ci, co = wg.shape
+    lib = _lib.lib()
+    ntile = lib.tta_conv_tc_ntile(co)
+    cip = (ci + 15) // 16 * 16
+    cop = (co + ntile - 1) // ntile * ntile
+    w = torch.zeros((T, cip, cop), dtype=torch.float32, device=wg.device)
+    w[:, :ci, :co] = wg
+    hi, lo = split_planes(w, dtype_tag)
+    groups = tc_groups(mode, K, stride)
+    gmax = max(len(g) for g in groups)
+    ncb, nnt = cip // 16, cop // ntile
+    out = torch.zeros((nnt, ncb, len(groups), 2, gmax, 2, ntile, 8), dtype=torch.int16, device=wg.device)
+    for gi, taps in enumerate(groups):
+        idx = torch.tensor(taps, device=wg.device)
+        for pi, plane in enumerate((hi, lo)):
+            sel = plane[idx]                                       # [E][cip][cop]
+            sel = sel.reshape(len(taps), ncb, 2, 8, nnt, ntile)    # [E][cb][kc][8][nt][n]
+            out[:, :, gi, pi, : len(taps)] = sel.permute(4, 1, 0, 2, 5, 3)
+    return out.contiguous()

@@ -1,0 +1,210 @@
+"""``unet_b200`` -- drop-in for the reference's ``@register_model("unet")`` class
+(/root/reference/src/models/unet.py:14-69) whose arithmetic runs in hand-written sm_100a CUDA.
+
+Contract kept from the reference:
+  * constructor ``cls(cfg)`` reading the same fields/defaults as src/models/unet.py:27-48;
+  * ``forward(x[B,C,D,H,W] fp32 cuda) -> logits[B,R,D,H,W] fp32``;
+  * ``state_dict()`` keys equal MONAI's (``model.0.conv.unit0.conv.weight`` ...), so checkpoints
+    written by the reference's CheckpointHook (src/core/hooks.py:53-59) load unchanged
+    (a ``module.`` DataParallel prefix is stripped).
+The module tree below only HOLDS parameters under MONAI's names; no torch conv/norm op is ever
+called -- ``forward`` goes through ``TTAEngine`` (engine.py) and fails loudly without CUDA.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Mapping, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .config import DictConfig, create, get_config
+from .registry import register_model
+
+
+class ConvHolder(nn.Module):
+    """Parameters of nn.Conv3d / nn.ConvTranspose3d (same shapes, same default init)."""
+
+    def __init__(self, cin: int, cout: int, k: int, stride: int, transposed: bool):
+        super().__init__()
+        self.cin, self.cout, self.k, self.stride, self.transposed = cin, cout, k, stride, transposed
+        shape = (cin, cout, k, k, k) if transposed else (cout, cin, k, k, k)
+        self.weight = nn.Parameter(torch.empty(shape))
+        self.bias = nn.Parameter(torch.empty(cout))
+        # identical call sequence to torch.nn.modules.conv._ConvNd.reset_parameters
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        fan_in, _ = nn.init._calculate_fan_in_and_fan_out(self.weight)
+        bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+        nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("ConvHolder only stores parameters; use UNetB200.forward")
+
+
+class NormHolder(nn.Module):
+    """Parameters/buffers of nn.InstanceNorm3d(affine=False) or nn.BatchNorm3d(affine=True)."""
+
+    def __init__(self, channels: int, kind: str):
+        super().__init__()
+        self.num_features, self.kind, self.eps, self.momentum = channels, kind, 1e-5, 0.1
+        if kind == "batch":
+            self.weight = nn.Parameter(torch.ones(channels))
+            self.bias = nn.Parameter(torch.zeros(channels))
+            self.register_buffer("running_mean", torch.zeros(channels))
+            self.register_buffer("running_var", torch.ones(channels))
+            self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+            self.track_running_stats = True
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+            self.track_running_stats = False
+
+    def materialize_affine(self) -> None:
+        """TENT needs gamma/beta on every norm; InstanceNorm3d(affine=False) gets gamma=1, beta=0
+        (forward-identical, checkpoint-compatible)."""
+        if self.weight is None:
+            dev = next((b.device for b in self.buffers()), None) or torch.device("cpu")
+            self.weight = nn.Parameter(torch.ones(self.num_features, device=dev))
+            self.bias = nn.Parameter(torch.zeros(self.num_features, device=dev))
+
+
+def _adn(channels: int, norm: str, act: str, dropout: Optional[float]) -> nn.Sequential:
+    n = str(norm).upper()
+    if n not in ("INSTANCE", "BATCH"):
+        raise ValueError(f"unet_b200: norm {norm!r} unsupported (INSTANCE or BATCH)")
+    if str(act).upper() != "RELU":
+        raise ValueError(f"unet_b200: act {act!r} unsupported (RELU)")
+    seq = nn.Sequential()
+    seq.add_module("N", NormHolder(channels, "instance" if n == "INSTANCE" else "batch"))
+    if dropout is not None:
+        if float(dropout) != 0.0:
+            raise ValueError("unet_b200: dropout > 0 unsupported (reference configs use 0.0)")
+        seq.add_module("D", nn.Dropout(0.0))
+    seq.add_module("A", nn.ReLU())
+    return seq
+
+
+class ConvolutionH(nn.Sequential):
+    def __init__(self, cin, cout, stride, k, norm, act, dropout, conv_only=False, transposed=False):
+        super().__init__()
+        self.add_module("conv", ConvHolder(cin, cout, k, stride, transposed))
+        self.conv_only = conv_only
+        if not conv_only:
+            self.add_module("adn", _adn(cout, norm, act, dropout))
+
+
+class ResidualUnitH(nn.Module):
+    def __init__(self, cin, cout, stride, k, subunits, norm, act, dropout, last_conv_only=False):
+        super().__init__()
+        self.conv = nn.Sequential()
+        self.residual: nn.Module = nn.Identity()
+        sch, sst = cin, stride
+        subunits = max(1, subunits)
+        for su in range(subunits):
+            co = last_conv_only and su == subunits - 1
+            self.conv.add_module(f"unit{su:d}", ConvolutionH(sch, cout, sst, k, norm, act, dropout, conv_only=co))
+            sch, sst = cout, 1
+        if stride != 1 or cin != cout:
+            rk = k if stride != 1 else 1
+            self.residual = ConvHolder(cin, cout, rk, stride, False)
+
+
+class SkipConnectionH(nn.Module):
+    def __init__(self, submodule: nn.Module):
+        super().__init__()
+        self.submodule = submodule
+
+
+@register_model("unet_b200")
+class UNetB200(nn.Module):
+    def __init__(self, cfg: DictConfig | Dict[str, Any], in_channels: Optional[int] = None,
+                 eps: Optional[float] = None):
+        super().__init__()
+        if not isinstance(cfg, DictConfig):
+            cfg = create(dict(cfg))
+        c_in_cfg = get_config(cfg, "in_channels", 3)
+        c_in = in_channels if in_channels is not None else (None if c_in_cfg == "auto" else int(c_in_cfg))
+        if c_in is None:
+            raise ValueError("[UNet] in_channels is 'auto'; please pass in_channels at construction time.")
+        self.in_channels = c_in
+        self.out_channels = int(get_config(cfg, "num_classes", 1))
+        self.channels = [int(c) for c in get_config(cfg, "channels", [32, 64, 128, 256, 512])]
+        self.strides = [int(s) for s in get_config(cfg, "strides", [2, 2, 2, 2])]
+        self.num_res_units = int(get_config(cfg, "num_res_units", 0))
+        self.act = get_config(cfg, "act", "relu")
+        self.norm = get_config(cfg, "norm", "BATCH")
+        self.dropout = float(get_config(cfg, "dropout", 0.0))
+        if int(get_config(cfg, "spatial_dims", 3)) != 3:
+            raise ValueError("unet_b200 implements the 3-D path only")
+        if len(self.channels) < 2:
+            raise ValueError("the length of `channels` should be no less than 2.")
+        if len(self.strides) < len(self.channels) - 1:
+            raise ValueError("the length of `strides` should equal to `len(channels) - 1`.")
+        for s in self.strides:
+            if s not in (1, 2):
+                raise ValueError(f"unet_b200: stride {s} unsupported (1 or 2)")
+        # backend options (not in the reference): conv kernel family and whole-step CUDA graph
+        self.conv_backend = str(get_config(cfg, "conv_backend", "auto"))
+        self.use_cuda_graph = bool(get_config(cfg, "cuda_graph", True))
+        k, nru, norm, act, dr = 3, self.num_res_units, self.norm, self.act, self.dropout
+
+        def down(cin, cout, stride):
+            if nru > 0:
+                return ResidualUnitH(cin, cout, stride, k, nru, norm, act, dr)
+            return ConvolutionH(cin, cout, stride, k, norm, act, dr)
+
+        def up(cin, cout, stride, is_top):
+            conv: nn.Module = ConvolutionH(cin, cout, stride, k, norm, act, dr,
+                                           conv_only=is_top and nru == 0, transposed=True)
+            if nru > 0:
+                conv = nn.Sequential(conv, ResidualUnitH(cout, cout, 1, k, 1, norm, act, dr, last_conv_only=is_top))
+            return conv
+
+        def block(inc, outc, chs, sts, is_top):
+            c, s = chs[0], sts[0]
+            if len(chs) > 2:
+                sub, upc = block(c, c, chs[1:], sts[1:], False), c * 2
+            else:
+                sub, upc = down(c, chs[1], 1), c + chs[1]
+            return nn.Sequential(down(inc, c, s), SkipConnectionH(sub), up(upc, outc, s, is_top))
+
+        self.model = block(self.in_channels, self.out_channels, self.channels, self.strides, True)
+        self._engine = None
+        self._params_dirty = True
+
+    # ------------------------------------------------------------------ plumbing
+    def norm_holders(self) -> List[NormHolder]:
+        return [m for m in self.modules() if isinstance(m, NormHolder)]
+
+    def conv_holders(self) -> List[ConvHolder]:
+        return [m for m in self.modules() if isinstance(m, ConvHolder)]
+
+    def _apply(self, fn, *a, **k):
+        self._params_dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
+        """Accepts reference checkpoints: plain MONAI keys or ``module.``-prefixed DataParallel
+        keys (src/core/experiment_manager.py:95-96); norm affine keys materialise gamma/beta."""
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        for name, m in self.named_modules():
+            if isinstance(m, NormHolder) and f"{name}.weight" in sd:
+                m.materialize_affine()
+        self._params_dirty = True
+        out = super().load_state_dict(sd, strict=strict, assign=assign)
+        if self._engine is not None:
+            self._engine.invalidate()
+        return out
+
+    @property
+    def engine(self):
+        from .engine import TTAEngine
+
+        if self._engine is None:
+            self._engine = TTAEngine(self)
+        return self._engine
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Raw logits [B,R,D,H,W].  train(): test-batch norm statistics; eval(): BatchNorm uses its
+        running statistics (InstanceNorm always uses instance statistics, as in the reference)."""
+        return self.engine.forward(x)

@@ -1,0 +1,208 @@
+"""Op-level parity: every C-ABI kernel against the CPU oracle / plain torch fp32 on seeded inputs.
+Tolerances are stated per test; integer work (Dice counts) is bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, check
+from multimodal_tta_b200.layout import (from_chunked, join_planes, pack_bias, pack_weights_simt, to_chunked,
+                                        wg_dgrad, wg_forward)
+from tests.util import planes_from, rel_l2, stream
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = [  # (cin, cout, K, stride, transposed, dims)
+    (4, 32, 3, 2, False, (12, 10, 16)),
+    (32, 32, 3, 1, False, (6, 9, 12)),
+    (16, 24, 3, 1, False, (5, 5, 5)),
+    (64, 16, 3, 2, True, (4, 5, 6)),
+    (24, 3, 3, 2, True, (6, 6, 8)),
+    (3, 3, 3, 1, False, (8, 8, 8)),
+    (40, 48, 1, 1, False, (4, 6, 8)),
+    (2, 32, 3, 2, False, (8, 8, 8)),
+]
+
+
+def _run_conv(lib, which, hi, lo, dt, N, cin, idims, wp, bias, cout, odims, mode, K, s, acc=None):
+    dev = hi.device
+    out = torch.zeros((N, (cout + 7) // 8, *odims, 8), device=dev) if acc is None else acc
+    c8i, c8o = (cin + 7) // 8, (cout + 7) // 8
+    ins = c8i * idims[0] * idims[1] * idims[2] * 8
+    ons = c8o * odims[0] * odims[1] * odims[2] * 8
+    args = [hi.data_ptr(), lo.data_ptr(), ins, dt, N, c8i, *idims, wp.data_ptr(),
+            bias.data_ptr() if bias is not None else 0, out.data_ptr(), ons, c8o, *odims, mode, K, s,
+            int(acc is not None)]
+    if which == "simt":
+        check(lib.tta_conv_simt(*args, stream()), "conv_simt")
+    else:
+        check(lib.tta_conv_tc(*args, 0, stream()), "conv_tc")
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,K,s,tr,dims", GEOMS)
+def test_conv_simt_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
+    torch.manual_seed(1)
+    N = 2
+    x = torch.randn(N, cin, *dims)
+    w = torch.randn((cin, cout, K, K, K) if tr else (cout, cin, K, K, K)) * 0.1
+    b = torch.randn(cout)
+    pad = (K - 1) // 2
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    xr = xv.cpu().requires_grad_(True)
+    if tr:
+        ref = F.conv_transpose3d(xr, w, b, stride=s, padding=pad, output_padding=s - 1)
+    else:
+        ref = F.conv3d(xr, w, b, stride=s, padding=pad)
+    odims = tuple(ref.shape[2:])
+    wp = pack_weights_simt(wg_forward(w.to(cuda), tr))
+    out = _run_conv(lib, "simt", hi, lo, TTA_F16, N, cin, dims, wp, pack_bias(b.to(cuda)), cout, odims,
+                    1 if tr else 0, K, s)
+    got = from_chunked(out, cout).cpu()
+    assert rel_l2(got, ref.detach()) < 2e-6          # fp32 FMA order only
+    # dgrad: conv of dy with the dgrad weights must equal autograd's input gradient
+    dy = torch.randn_like(ref)
+    dhi, dlo, dyv = planes_from(dy.to(cuda), TTA_BF16)
+    wpd = pack_weights_simt(wg_dgrad(w.to(cuda), tr))
+    gx = _run_conv(lib, "simt", dhi, dlo, TTA_BF16, N, cout, odims, wpd, None, cin, dims, 0 if tr else 1, K, s)
+    # reference computed on the bf16x2-rounded dy the kernel actually saw
+    xr2 = xv.cpu().requires_grad_(True)
+    ref2 = F.conv_transpose3d(xr2, w, b, stride=s, padding=pad, output_padding=s - 1) if tr else \
+        F.conv3d(xr2, w, b, stride=s, padding=pad)
+    (g2,) = torch.autograd.grad(ref2, xr2, dyv.cpu())
+    assert rel_l2(from_chunked(gx, cin).cpu(), g2) < 2e-6
+    # accumulate flag adds onto the existing output
+    gx2 = _run_conv(lib, "simt", dhi, dlo, TTA_BF16, N, cout, odims, wpd, None, cin, dims, 0 if tr else 1, K, s,
+                    acc=gx.clone())
+    assert rel_l2(from_chunked(gx2, cin).cpu(), 2 * g2) < 2e-6
+
+
+@pytest.mark.parametrize("batch_mode", [0, 1])
+@pytest.mark.parametrize("C,dims", [(32, (8, 9, 10)), (3, (16, 16, 16)), (20, (5, 7, 3))])
+def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
+    torch.manual_seed(2)
+    N = 2
+    V = dims[0] * dims[1] * dims[2]
+    C8 = (C + 7) // 8
+    y = (torch.randn(N, C, *dims) * 1.7 + 0.4)
+    gamma = torch.rand(C) + 0.5
+    beta = torch.randn(C) * 0.2
+    resid = torch.randn(N, C, *dims)
+    g_in = torch.randn(N, C, *dims)
+    # oracle (CPU fp32 autograd)
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    if batch_mode:
+        z = F.batch_norm(yr, None, None, gr, br, training=True, eps=1e-5)
+    else:
+        z = F.instance_norm(yr, weight=gr, bias=br, eps=1e-5)
+    a = torch.relu(z) + resid
+    a.backward(g_in)
+    # device
+    ych = to_chunked(y.to(cuda))
+    mean = torch.zeros(N * C8 * 8, device=cuda); rstd = torch.zeros_like(mean)
+    ws = torch.zeros(lib.tta_norm_workspace_floats(N, C8, V), device=cuda)
+    gp = torch.zeros(C8 * 8, device=cuda); gp[:C] = gamma.to(cuda)
+    bp = torch.zeros(C8 * 8, device=cuda); bp[:C] = beta.to(cuda)
+    ns = C8 * V * 8
+    check(lib.tta_norm_stats(ych.data_ptr(), ns, N, C8, V, batch_mode, 1e-5, mean.data_ptr(), rstd.data_ptr(),
+                             ws.data_ptr(), stream()))
+    rch = to_chunked(resid.to(cuda))
+    ohi = torch.zeros((N, C8, *dims, 8), dtype=torch.int16, device=cuda); olo = torch.zeros_like(ohi)
+    check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
+                             bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi.data_ptr(), olo.data_ptr(), ns,
+                             TTA_F16, stream()))
+    got = from_chunked(join_planes(ohi, olo, TTA_F16), C).cpu()
+    assert (got - a.detach()).abs().max() < 2e-5      # fp16x2 storage (22 bits) + fp32 stats
+    # backward
+    gch = to_chunked(g_in.to(cuda))
+    sums = torch.zeros(N * C8 * 8 * 2, device=cuda)
+    dg = torch.zeros(C8 * 8, device=cuda); db = torch.zeros(C8 * 8, device=cuda)
+    check(lib.tta_norm_bwd_reduce(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, C, V, mean.data_ptr(),
+                                  rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
+                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), stream()))
+    assert rel_l2(dg[:C].cpu(), gr.grad) < 1e-5
+    assert rel_l2(db[:C].cpu(), br.grad) < 1e-5
+    dhi = torch.zeros_like(ohi); dlo = torch.zeros_like(ohi); ahi = torch.zeros_like(ohi); alo = torch.zeros_like(ohi)
+    check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
+                                 rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
+                                 dhi.data_ptr(), dlo.data_ptr(), ns, ahi.data_ptr(), alo.data_ptr(), ns, TTA_BF16,
+                                 stream()))
+    dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu()
+    assert rel_l2(dy, yr.grad) < 3e-5                 # bf16x2 storage (~16 bits)
+    aux = from_chunked(join_planes(ahi, alo, TTA_BF16), C).cpu()
+    assert rel_l2(aux, g_in) < 2e-5
+
+
+@pytest.mark.parametrize("mode,R", [(1, 3), (1, 1), (0, 3), (0, 2)])
+def test_head_entropy(lib, cuda, mode, R):
+    from oracle.tent_oracle import entropy_loss
+    torch.manual_seed(3)
+    N, dims = 2, (6, 7, 9)
+    V = dims[0] * dims[1] * dims[2]
+    z = torch.randn(N, R, *dims) * 3
+    zr = z.clone().requires_grad_(True)
+    loss = entropy_loss(zr, "sigmoid" if mode == 1 else "softmax")
+    loss.backward()
+    ych = to_chunked(z.to(cuda))
+    logits = torch.zeros(N, R, *dims, device=cuda)
+    dhi = torch.zeros((N, 1, *dims, 8), dtype=torch.int16, device=cuda); dlo = torch.zeros_like(dhi)
+    nb = lib.tta_head_entropy_blocks(N, V)
+    part = torch.zeros(nb * N, device=cuda); lossd = torch.zeros(1, device=cuda)
+    check(lib.tta_head_entropy(ych.data_ptr(), V * 8, N, R, V, mode, 1.0 / (N * V), 0, logits.data_ptr(),
+                               dhi.data_ptr(), dlo.data_ptr(), V * 8, part.data_ptr(), lossd.data_ptr(), stream()))
+    assert torch.equal(logits.cpu(), z)               # pure layout change: bit exact
+    assert abs(float(lossd) - float(loss)) < 1e-6 * max(1.0, abs(float(loss)))
+    dz = from_chunked(join_planes(dhi, dlo, TTA_BF16), R).cpu()
+    assert rel_l2(dz, zr.grad) < 2e-5                 # bf16x2 storage
+    assert float(join_planes(dhi, dlo, TTA_BF16)[..., R:].abs().max()) == 0.0 if R < 8 else True
+
+
+def test_adam_matches_torch(lib, cuda):
+    torch.manual_seed(4)
+    n = 4870
+    p0 = torch.randn(n)
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    pd = p0.clone().to(cuda); m = torch.zeros(n, device=cuda); v = torch.zeros(n, device=cuda)
+    step = torch.zeros(1, dtype=torch.int32, device=cuda)
+    for it in range(5):
+        g = torch.randn(n) * (10.0 ** -it)
+        p.grad = g.clone()
+        opt.step()
+        gd = g.to(cuda)
+        check(lib.tta_adam_step(pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8,
+                                1.0, step.data_ptr(), stream()))
+        assert (pd.cpu() - p.detach()).abs().max() < 5e-7, it
+    assert int(step) == 5
+
+
+def test_gather_pack_windows_and_padding(lib, cuda):
+    torch.manual_seed(5)
+    vol = torch.randn(2, 3, 9, 10, 11)
+    wins = torch.tensor([[0, 0, 0, 0], [1, 3, 2, 5], [1, -2, -1, 4]], dtype=torch.int32)
+    roi = (6, 8, 6)
+    scale = torch.tensor([[1., 1., 1.], [1., 0., 1.], [0., 1., 1.]])
+    hi = torch.zeros((3, 1, *roi, 8), dtype=torch.int16, device=cuda); lo = torch.zeros_like(hi)
+    check(lib.tta_gather_pack(vol.to(cuda).data_ptr(), 2, 3, 9, 10, 11, wins.to(cuda).data_ptr(),
+                              scale.to(cuda).data_ptr(), 3, *roi, hi.data_ptr(), lo.data_ptr(),
+                              roi[0] * roi[1] * roi[2] * 8, 1, stream()))
+    got = from_chunked(join_planes(hi, lo, TTA_F16), 3).cpu()
+    pv = F.pad(vol, (8, 8, 8, 8, 8, 8))
+    for b, (vi, d0, h0, w0) in enumerate(wins.tolist()):
+        ref = pv[vi, :, d0 + 8:d0 + 8 + roi[0], h0 + 8:h0 + 8 + roi[1], w0 + 8:w0 + 8 + roi[2]] * scale[b].view(3, 1, 1, 1)
+        assert (got[b] - ref).abs().max() < 1e-6      # fp16x2 storage of O(1) values
+
+
+def test_dice_counts_match_reference_golden(lib, cuda):
+    import os
+    from multimodal_tta_b200.evaluation import device_dice_counts, dice_iou_from_counts
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "dice_golden.npz"))
+    for i in range(4):
+        pred, gt = torch.from_numpy(gold[f"pred{i}"]), torch.from_numpy(gold[f"gt{i}"])
+        logits = (pred.float() * 2 - 1) * 3.0          # sigmoid(+-3) on either side of 0.5
+        counts = device_dice_counts(logits.to(cuda), gt.float().to(cuda), 0.5).cpu()
+        dice, iou, valid = dice_iou_from_counts(counts)
+        assert torch.equal(dice, torch.from_numpy(gold[f"dice{i}"]))     # bit exact
+        assert torch.equal(iou, torch.from_numpy(gold[f"iou{i}"]))
+        assert torch.equal(valid, torch.from_numpy(gold[f"valid{i}"]))

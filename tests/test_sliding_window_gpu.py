@@ -1,0 +1,38 @@
+"""Sliding-window TTA: on-device gather / TENT step / Gaussian blend against the CPU oracle."""
+import pytest
+import torch
+
+from multimodal_tta_b200 import SlidingWindowTTA, TentB200
+from multimodal_tta_b200.synthetic import brats_volume, hecktor_volume
+from oracle.sliding_window_oracle import sliding_window_oracle
+from oracle.tent_oracle import TentOracle, flat_gamma_beta
+from oracle.unet_oracle import BRATS_MODEL_CFG, HECKTOR_MODEL_CFG
+from tests.util import make_pair, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dims,roi,swb", [((40, 48, 36), (32, 32, 32), 2), ((24, 40, 32), (32, 32, 32), 1)])
+def test_sliding_window_tta_matches_oracle(cuda, dims, roi, swb):
+    oracle, prod = make_pair(BRATS_MODEL_CFG, seed=31)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"cuda_graph": True})
+    vol = brats_volume(1, dims, seed=77)
+    ref = sliding_window_oracle(vol, roi, swb, lambda w: to.step(w)[0], overlap=0.5)
+    sw = SlidingWindowTTA(tp, roi, sw_batch=swb, overlap=0.5)
+    got = sw(vol.cuda()).cpu()
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < 1e-3
+    assert ((got >= 0) == (ref >= 0)).float().mean().item() >= 0.9999
+    # parameters adapted through the same number of steps
+    p_o, p_p = flat_gamma_beta(to.model), prod.engine.flat_params().cpu()
+    assert (p_p - p_o).abs().median() < 1e-5
+
+
+def test_missing_modality_dropout(cuda):
+    oracle, prod = make_pair(HECKTOR_MODEL_CFG, seed=32)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"cuda_graph": False})
+    vol, keep = hecktor_volume(2, (32, 48, 32), seed=5, p_drop=1.0)
+    ref = sliding_window_oracle(vol * keep.view(2, 2, 1, 1, 1), (32, 32, 32), 2, lambda w: to.step(w)[0], overlap=0.5)
+    sw = SlidingWindowTTA(tp, (32, 32, 32), sw_batch=2, overlap=0.5)
+    got = sw(vol.cuda(), chan_scale_per_volume=keep).cpu()
+    assert rel_l2(got, ref) < 1e-3

@@ -1,0 +1,138 @@
+"""Step-level parity of the CUDA TTA path against the CPU oracle at the north-star tolerances
+(BASELINE.json): logits <= 1e-3 relative, adapted gamma/beta <= 1e-4 after N steps, voxel
+(per-channel threshold) agreement >= 99.99 %, Dice equal to 1e-3.
+
+Adam's first update is -lr*sign(g) for every scalar, so a gradient whose magnitude is below the
+fp32 noise floor of the oracle ITSELF can flip sign (the fp32 oracle run with 3 vs 8 CPU threads
+already flips 1 of 4870 -- DESIGN.md section 6).  The parameter check is therefore stated on the
+scalars whose oracle gradient is above that floor (|g| > 1e-3 * median|g|), and the fraction of
+excluded scalars is itself bounded (< 0.5 %); the gradient itself is checked in relative L2.
+"""
+import copy
+
+import pytest
+import torch
+
+from multimodal_tta_b200 import TentB200
+from oracle.dice_oracle import evaluate_logits
+from oracle.tent_oracle import TentOracle, flat_gamma_beta
+from oracle.unet_oracle import BARE_DEFAULT_MODEL_CFG, BRATS_MODEL_CFG, HECKTOR_MODEL_CFG
+from multimodal_tta_b200.synthetic import brats_volume, region_labels
+from tests.util import make_pair, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_step(cfg, x, mode, steps, use_graph, backend="auto"):
+    cfg = dict(cfg, conv_backend=backend)
+    oracle, prod = make_pair(cfg, seed=11)
+    to = TentOracle(oracle, mode=mode)
+    tp = TentB200(prod, {"entropy": mode, "cuda_graph": use_graph})
+    xd = x.cuda()
+    for it in range(steps):
+        lo, loss_o = to.step(x)
+        lp = tp.step(xd).cpu()
+        g_o, g_p = to.last_grads, prod.engine.flat_grads().cpu()
+        # --- logits (north star: 1e-3 relative)
+        assert rel_l2(lp, lo) < 1e-3, (it, rel_l2(lp, lo))
+        assert float((lp - lo).abs().max() / lo.abs().max()) < 1e-3
+        assert abs(float(tp.last_loss) - loss_o) < 1e-4 * max(1.0, abs(loss_o))
+        # --- per-channel threshold agreement (sigmoid heads) / argmax agreement (softmax heads)
+        if mode == "sigmoid":
+            agree = ((lp >= 0) == (lo >= 0)).float().mean().item()
+        else:
+            agree = (lp.argmax(1) == lo.argmax(1)).float().mean().item()
+        assert agree >= 0.9999, agree
+        # --- gradients
+        assert rel_l2(g_p, g_o) < 2e-3, (it, rel_l2(g_p, g_o))
+        # --- adapted parameters (north star: 1e-4 after N steps)
+        p_o, p_p = flat_gamma_beta(to.model), prod.engine.flat_params().cpu()
+        floor = 1e-3 * g_o.abs().median()
+        well = g_o.abs() > floor
+        if it == 0:
+            assert well.float().mean() > 0.995
+            sign_ok = (torch.sign(g_p[well]) == torch.sign(g_o[well])).float().mean().item()
+            assert sign_ok == 1.0, sign_ok
+        assert float((p_p - p_o)[well].abs().max()) < 1e-4, (it, float((p_p - p_o)[well].abs().max()))
+    return to, tp, prod
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_brats_resunit_instance_norm_sigmoid(cuda, use_graph):
+    x = brats_volume(2, (32, 32, 32), seed=42)
+    _check_step(BRATS_MODEL_CFG, x, "sigmoid", steps=3, use_graph=use_graph)
+
+
+def test_brats_softmax_entropy(cuda):
+    x = brats_volume(1, (32, 48, 32), seed=43)
+    _check_step(BRATS_MODEL_CFG, x, "softmax", steps=2, use_graph=False)
+
+
+def test_hecktor_single_channel_head(cuda):
+    torch.manual_seed(5)
+    x = torch.randn(1, 2, 48, 32, 32)
+    _check_step(HECKTOR_MODEL_CFG, x, "sigmoid", steps=2, use_graph=True)
+
+
+def test_bare_default_batchnorm_no_res_units(cuda):
+    cfg = dict(BARE_DEFAULT_MODEL_CFG, in_channels=4)
+    x = brats_volume(2, (32, 32, 32), seed=44)
+    _check_step(cfg, x, "sigmoid", steps=3, use_graph=True)
+
+
+def test_simt_backend_alone(cuda):
+    x = brats_volume(1, (32, 32, 32), seed=45)
+    _check_step(BRATS_MODEL_CFG, x, "sigmoid", steps=1, use_graph=False, backend="simt")
+
+
+def test_inference_forward_matches_oracle_eval_and_train(cuda):
+    for cfg in (BRATS_MODEL_CFG, dict(BARE_DEFAULT_MODEL_CFG, in_channels=4)):
+        oracle, prod = make_pair(cfg, seed=3)
+        x = brats_volume(1, (32, 32, 32), seed=1)
+        for train in (True, False):
+            oracle.train(train); prod.train(train)
+            with torch.no_grad():
+                ref = oracle(x)
+            got = prod(x.cuda()).cpu()
+            assert rel_l2(got, ref) < 1e-3 and got.shape == ref.shape
+
+
+def test_dice_identical_after_adaptation(cuda):
+    from multimodal_tta_b200.evaluation import device_dice_counts, dice_iou_from_counts
+    oracle, prod = make_pair(BRATS_MODEL_CFG, seed=21)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"cuda_graph": True})
+    xs = [brats_volume(1, (32, 32, 32), seed=s) for s in (1, 2, 3)]
+    ys = [region_labels(1, 3, (32, 32, 32), seed=s) for s in (1, 2, 3)]
+    lo = [to.step(x)[0] for x in xs]
+    lp = [tp.step(x.cuda()).clone() for x in xs]
+    ref = evaluate_logits(lo, ys)
+    sd, cnt = torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64)
+    for l, y in zip(lp, ys):
+        d, _, v = dice_iou_from_counts(device_dice_counts(l, y.cuda(), 0.5).cpu())
+        sd += (d[0] * v[0]).double(); cnt += v[0].double()
+    md = sd / cnt.clamp_min(1)
+    for i, n in enumerate(["et", "tc", "wt"]):
+        assert abs(float(md[i]) - ref[f"{n}_dc"]) < 1e-3
+
+
+def test_episodic_reset_and_state_dict_view(cuda):
+    oracle, prod = make_pair(BRATS_MODEL_CFG, seed=5)
+    tp = TentB200(prod, {"episodic": True, "cuda_graph": False})
+    x = brats_volume(1, (32, 32, 32), seed=9).cuda()
+    l1 = tp.step(x).clone()
+    sd = prod.state_dict()
+    k = "model.0.conv.unit0.adn.N.weight"
+    assert k in sd and float((sd[k] - 1).abs().max()) > 0      # adapted values visible in state_dict
+    l2 = tp.step(x).clone()
+    assert torch.equal(l1, l2)                                 # episodic: same start every batch
+
+
+def test_rejects_bad_inputs(cuda):
+    _, prod = make_pair(BRATS_MODEL_CFG, seed=5)
+    tp = TentB200(prod, {})
+    with pytest.raises(ValueError):
+        tp.step(torch.zeros(1, 3, 32, 32, 32, device="cuda"))      # wrong channel count
+    with pytest.raises(ValueError):
+        tp.step(torch.zeros(1, 4, 24, 32, 32, device="cuda"))      # 24 not divisible by 16
+    with pytest.raises(RuntimeError):
+        tp.step(torch.zeros(1, 4, 32, 32, 32))                     # CPU tensor: no fallback
