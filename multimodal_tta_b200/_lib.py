@@ -69,7 +69,9 @@ _SIGNATURES = {
     "tta_dice_counts": (I, [P, P, I, L, F, P, P]),
     "tta_conv_simt": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, P]),
     "tta_conv_tc_supported": (I, [I, I, I, I, I]),
-    "tta_conv_tc_ntile": (I, [I]),
+    "tta_conv_tc_ntile": (I, [I, I, I, I]),
+    "tta_conv_tc_gmax": (I, [I, I, I]),
+    "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),
     "tta_conv_tc": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, I, P]),
 }

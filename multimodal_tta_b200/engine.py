@@ -549,6 +549,21 @@ class TTAEngine:
                 rs[:nl.C] = torch.rsqrt(nl.h.running_var.to(self.device) + nl.h.eps)
                 mean.copy_(mu.repeat(plan.N)); rstd.copy_(rs.repeat(plan.N))
 
+    def _update_running_stats(self, plan: Plan):
+        """train()-mode BatchNorm outside TENT keeps nn.BatchNorm3d's side effect: running stats
+        move by ``momentum`` towards the batch statistics (unbiased variance)."""
+        if not self.model.training:
+            return
+        for nl, mean, rstd, y in plan.stats_ops:
+            h = nl.h
+            if nl.batch and h.track_running_stats:
+                M = plan.N * y.V
+                mu = mean[:nl.C]
+                var = (1.0 / (rstd[:nl.C] * rstd[:nl.C]) - h.eps) * (M / max(M - 1, 1))
+                h.running_mean.mul_(1 - h.momentum).add_(mu.to(h.running_mean.device), alpha=h.momentum)
+                h.running_var.mul_(1 - h.momentum).add_(var.to(h.running_var.device), alpha=h.momentum)
+                h.num_batches_tracked += 1
+
     def _pack_input(self, plan: Plan, x: torch.Tensor, win: Optional[torch.Tensor] = None,
                     chan_scale: Optional[torch.Tensor] = None, vol_dims=None, n_vol=None):
         N = plan.N
@@ -586,6 +601,7 @@ class TTAEngine:
         for op in plan.fwd:
             op()
         plan.head_infer()
+        self._update_running_stats(plan)
         return plan.logits.clone()
 
     def run_step(self, plan: Plan, adam: bool = True, gscale: float = 1.0):

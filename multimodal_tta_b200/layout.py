@@ -104,7 +104,7 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
     from . import _lib
     T, ci, co = wg.shape
     lib = _lib.lib()
-    ntile = lib.tta_conv_tc_ntile(co)
+    ntile = lib.tta_conv_tc_ntile(mode, K, stride, co)
     cip = (ci + 15) // 16 * 16
     cop = (co + ntile - 1) // ntile * ntile
     w = torch.zeros((T, cip, cop), dtype=torch.float32, device=wg.device)

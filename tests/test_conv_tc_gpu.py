@@ -1,0 +1,118 @@
+"""tcgen05 implicit-GEMM conv (tta_conv_tc) against torch fp32 conv on the CPU, every geometry
+family the UNet uses (s1, s2, transposed s2, 1x1, and their input-gradient duals), ragged tile
+edges (dims not multiples of the 16x8 tile), channel counts that need zero-padded k-chunks and
+n-tiles, concat-slice views, and the accumulate epilogue.
+
+Tolerance: operands are split 16-bit planes and the kernel drops the lo*lo term, so products
+carry ~2^-22 (fp16 planes) / ~2^-16 (bf16 planes) relative error against a reference computed
+from the SAME split-rounded inputs: rel-L2 <= 2e-5 (fp16 planes; measured 2e-6 .. 7e-6, growing
+with K = 27*Cin because the tensor core's fp32 accumulator truncates) / 1e-4 (bf16 planes)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, check
+from multimodal_tta_b200.layout import (from_chunked, join_planes, pack_bias, pack_weights_tc, split_planes,
+                                        to_chunked, wg_dgrad, wg_forward)
+from tests.util import planes_from, rel_l2, stream
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = [  # cin, cout, K, stride, transposed, dims
+    (32, 32, 3, 1, False, (4, 16, 8)),      # exact tiles
+    (32, 32, 3, 1, False, (5, 20, 12)),     # ragged h/w/d
+    (4, 32, 3, 2, False, (8, 32, 16)),      # stem: cin 4 -> one chunk + OOB k-chunk
+    (32, 64, 3, 2, False, (8, 16, 16)),
+    (64, 128, 3, 2, False, (4, 12, 12)),
+    (128, 256, 3, 1, False, (2, 6, 6)),     # n-tiles = 2, tiny spatial
+    (48, 16, 3, 2, True, (3, 10, 6)),       # transposed s2, ragged
+    (64, 3, 3, 2, True, (4, 16, 8)),        # head convT: cout 3 -> N=16 tile
+    (3, 3, 3, 1, False, (8, 16, 16)),       # head conv 3->3
+    (256, 512, 1, 1, False, (4, 8, 8)),     # 1x1 shortcut
+    (96, 40, 3, 1, False, (3, 9, 9)),       # odd chunk counts
+]
+
+
+def _tc(lib, hi, lo, ns, dt, N, c8i, idims, wp, bias, out, ons, c8o, odims, mode, K, s, acc=0, flags=0):
+    check(lib.tta_conv_tc(hi.data_ptr(), lo.data_ptr(), ns, dt, N, c8i, *idims, wp.data_ptr(),
+                          bias.data_ptr() if bias is not None else 0, out.data_ptr(), ons, c8o, *odims, mode, K, s,
+                          acc, flags, stream()), "conv_tc")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("cin,cout,K,s,tr,dims", GEOMS)
+def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
+    torch.manual_seed(7)
+    N = 2
+    x = torch.randn(N, cin, *dims)
+    w = torch.randn((cin, cout, K, K, K) if tr else (cout, cin, K, K, K)) * 0.1
+    b = torch.randn(cout)
+    pad = (K - 1) // 2
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    # reference on the rounded operands: weights also go through the fp16 hi/lo split
+    whi, wlo = split_planes(w, TTA_F16)
+    wv = join_planes(whi, wlo, TTA_F16)
+    xr = xv.cpu().requires_grad_(True)
+    ref = F.conv_transpose3d(xr, wv, b, stride=s, padding=pad, output_padding=s - 1) if tr else \
+        F.conv3d(xr, wv, b, stride=s, padding=pad)
+    odims = tuple(ref.shape[2:])
+    c8i, c8o = (cin + 7) // 8, (cout + 7) // 8
+    mode = 1 if tr else 0
+    wp = pack_weights_tc(wg_forward(w.to(cuda), tr), mode, K, s, TTA_F16)
+    out = torch.zeros((N, c8o, *odims, 8), device=cuda)
+    _tc(lib, hi, lo, c8i * xv[0, 0].numel() * 8, TTA_F16, N, c8i, dims, wp, pack_bias(b.to(cuda)), out,
+        c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s)
+    got = from_chunked(out, cout).cpu()
+    assert rel_l2(got, ref.detach()) < 2e-5, rel_l2(got, ref.detach())
+    # pad channels of the last chunk stay exactly zero (+ bias pad 0)
+    if cout % 8:
+        assert float(out[:, -1, ..., cout % 8:].abs().max()) == 0.0
+    # ---- dgrad in bf16 planes, written into a channel SLICE of a wider (concat) gradient buffer
+    dy = torch.randn_like(ref)
+    dhi, dlo, dyv = planes_from(dy.to(cuda), TTA_BF16)
+    bhi, blo = split_planes(w, TTA_BF16)
+    wvb = join_planes(bhi, blo, TTA_BF16)
+    xr2 = xv.cpu().requires_grad_(True)
+    ref2 = F.conv_transpose3d(xr2, wvb, None, stride=s, padding=pad, output_padding=s - 1) if tr else \
+        F.conv3d(xr2, wvb, None, stride=s, padding=pad)
+    (g2,) = torch.autograd.grad(ref2, xr2, dyv.cpu())
+    wpd = pack_weights_tc(wg_dgrad(w.to(cuda), tr), 1 - mode, K, s, TTA_BF16)
+    extra = 2
+    gbuf = torch.full((N, c8i + extra, *dims, 8), 7.0, device=cuda)
+    Vi = dims[0] * dims[1] * dims[2]
+    gview_ptr_off = extra * Vi * 8
+    gflat = gbuf.view(-1)
+    sub = gflat[gview_ptr_off:]
+    check(lib.tta_conv_tc(dhi.data_ptr(), dlo.data_ptr(), c8o * ref[0, 0].numel() * 8, TTA_BF16, N, c8o, *odims,
+                          wpd.data_ptr(), 0, sub.data_ptr(), (c8i + extra) * Vi * 8, c8i, *dims, 1 - mode, K, s, 0, 0,
+                          stream()), "conv_tc dgrad")
+    torch.cuda.synchronize()
+    gx = from_chunked(gbuf[:, extra:], cin).cpu()
+    assert rel_l2(gx, g2) < 1e-4, rel_l2(gx, g2)
+    assert float((gbuf[:, :extra] - 7.0).abs().max()) == 0.0       # neighbouring slice untouched
+    # accumulate epilogue
+    check(lib.tta_conv_tc(dhi.data_ptr(), dlo.data_ptr(), c8o * ref[0, 0].numel() * 8, TTA_BF16, N, c8o, *odims,
+                          wpd.data_ptr(), 0, sub.data_ptr(), (c8i + extra) * Vi * 8, c8i, *dims, 1 - mode, K, s, 1, 0,
+                          stream()), "conv_tc dgrad acc")
+    torch.cuda.synchronize()
+    assert rel_l2(from_chunked(gbuf[:, extra:], cin).cpu(), 2 * g2) < 1e-4
+
+
+def test_conv_tc_reads_concat_slice_view(lib, cuda):
+    """Input is the SECOND half of a concat buffer (c8 pitch > view chunks)."""
+    torch.manual_seed(8)
+    N, ctot, c0, cin, cout, dims = 2, 48, 16, 32, 32, (4, 16, 8)
+    xfull = torch.randn(N, ctot, *dims)
+    w = torch.randn(cout, cin, 3, 3, 3) * 0.1
+    hi, lo, xv = planes_from(xfull.to(cuda), TTA_F16)
+    V = dims[0] * dims[1] * dims[2]
+    whi, wlo = split_planes(w, TTA_F16)
+    ref = F.conv3d(xv.cpu()[:, c0:c0 + cin], join_planes(whi, wlo, TTA_F16), None, padding=1)
+    wp = pack_weights_tc(wg_forward(w.to(cuda), False), 0, 3, 1, TTA_F16)
+    out = torch.zeros((N, cout // 8, *dims, 8), device=cuda)
+    off = (c0 // 8) * V * 8
+    check(lib.tta_conv_tc(hi.view(-1)[off:].data_ptr(), lo.view(-1)[off:].data_ptr(), (ctot // 8) * V * 8, TTA_F16,
+                          N, cin // 8, *dims, wp.data_ptr(), 0, out.data_ptr(), (cout // 8) * V * 8, cout // 8, *dims,
+                          0, 3, 1, 0, 0, stream()), "conv_tc view")
+    torch.cuda.synchronize()
+    assert rel_l2(from_chunked(out, cout).cpu(), ref) < 2e-5

@@ -29,6 +29,7 @@ def _check_step(cfg, x, mode, steps, use_graph, backend="auto"):
     to = TentOracle(oracle, mode=mode)
     tp = TentB200(prod, {"entropy": mode, "cuda_graph": use_graph})
     xd = x.cuda()
+    well = None
     for it in range(steps):
         lo, loss_o = to.step(x)
         lp = tp.step(xd).cpu()
@@ -48,9 +49,11 @@ def _check_step(cfg, x, mode, steps, use_graph, backend="auto"):
         # --- adapted parameters (north star: 1e-4 after N steps)
         p_o, p_p = flat_gamma_beta(to.model), prod.engine.flat_params().cpu()
         floor = 1e-3 * g_o.abs().median()
-        well = g_o.abs() > floor
+        # a scalar stays in the check only while its oracle gradient has been above the fp32 noise
+        # floor at EVERY step so far (an early sign flip persists in Adam's moments)
+        well = (g_o.abs() > floor) if well is None else (well & (g_o.abs() > floor))
+        assert well.float().mean() > 0.99, well.float().mean()
         if it == 0:
-            assert well.float().mean() > 0.995
             sign_ok = (torch.sign(g_p[well]) == torch.sign(g_o[well])).float().mean().item()
             assert sign_ok == 1.0, sign_ok
         assert float((p_p - p_o)[well].abs().max()) < 1e-4, (it, float((p_p - p_o)[well].abs().max()))
