@@ -53,6 +53,7 @@ struct TcParams {
   int a_plane_bytes, b_bytes, stage_bytes, tmem_cols;
   int c8_view;  // chunk pitch of the merged (n, chunk) tensor-map dimension
   int out_mul, Do, Ho, Wo, C8out, accumulate, idesc, gmax;
+  int ksplit, cb_per_split;
   signed char acc_pd[kMaxAcc], acc_qd[kMaxAcc], acc_qh[kMaxAcc], acc_qw[kMaxAcc];
   long long out_ns;
   const uint16_t* wpacked;
@@ -136,6 +137,94 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 
 // ---------------------------------------------------------------- the kernel
+enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2 };
+
+// One k-step (16 channels) of one tap for one accumulator: hi*hi + hi*lo + lo*hi.
+__device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_w1, uint32_t b_hi,
+                                     uint32_t b_lo, uint32_t b_w1, uint32_t idesc, uint32_t& touched, int acc) {
+  // descriptor words: w0 = (addr>>4) | lbo16<<16 ; w1 = sbo16 | version(1)<<14
+  const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | a_hi, ad_lo = ((uint64_t)a_w1 << 32) | a_lo;
+  const uint64_t bd_hi = ((uint64_t)b_w1 << 32) | b_hi, bd_lo = ((uint64_t)b_w1 << 32) | b_lo;
+  umma_f16(d, ad_hi, bd_hi, idesc, (touched >> acc) & 1u);
+  touched |= 1u << acc;
+  umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+  umma_f16(d, ad_lo, bd_hi, idesc, 1u);
+}
+
+// All MMAs of pipeline group g for one smem stage; tap geometry is compile-time arithmetic so the
+// single issuing thread spends a handful of integer instructions per MMA (no table loads).
+template <int GEOM>
+__device__ __forceinline__ void issue_group(const TcParams& P, int g, uint32_t stage, uint32_t tmem_base,
+                                            uint32_t& touched) {
+  const uint32_t nt = P.ntile;
+  const uint32_t a_hi0 = stage >> 4, a_lo0 = (stage + P.a_plane_bytes) >> 4;
+  const uint32_t b_w0 = ((stage + 2 * P.a_plane_bytes) >> 4) | (nt << 16);   // lbo16 = NT
+  const uint32_t b_pl = (uint32_t)P.b_bytes >> 4;                            // hi -> lo plane, 16 B units
+  const uint32_t b_ent = 2u * nt;                                            // entry pitch, 16 B units
+  const uint32_t b_w1 = 8u | (1u << 14);                                     // sbo16 = 8 (128 B)
+  const uint32_t idesc = P.idesc;
+  if (GEOM == GEOM_S1 || GEOM == GEOM_S1T) {
+    const int td = P.td;
+    const uint32_t a_w1 = 10u | (1u << 14);
+    const uint32_t lbo = (uint32_t)(td * 180) << 16;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int rh = GEOM == GEOM_S1 ? kh : 2 - kh, rw = GEOM == GEOM_S1 ? kw : 2 - kw;
+        const uint32_t bo = b_w0 + (uint32_t)(kh * 3 + kw) * b_ent;
+        for (int p = 0; p < td; ++p) {
+          const uint32_t ao = (uint32_t)(rh * 10 + rw + p * 180);
+          mma3(tmem_base + p * nt, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, bo + b_pl, b_w1, idesc,
+               touched, p);
+        }
+      }
+  } else if (GEOM == GEOM_K1) {
+    const int td = P.td;
+    const uint32_t a_w1 = 8u | (1u << 14);
+    const uint32_t lbo = (uint32_t)(td * 128) << 16;
+    for (int p = 0; p < td; ++p) {
+      const uint32_t ao = (uint32_t)(p * 128);
+      mma3(tmem_base + p * nt, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, b_w0, b_w0 + b_pl, b_w1, idesc,
+           touched, p);
+    }
+  } else if (GEOM == GEOM_S2) {
+    // parity sub-tiles [ph][pw] at fixed 128-aligned offsets: 16x8, 16x9, 17x8, 17x9 voxels x 32 B
+    constexpr int off16[4] = {0, 4096 / 16, 8704 / 16, 13056 / 16};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ph = kh != 1, pw = kw != 1, rh = kh == 2, rw = kw == 2, m = ph * 2 + pw;
+        const int wx = pw ? 9 : 8, hx = ph ? 17 : 16;
+        const uint32_t a_w1 = (uint32_t)wx | (1u << 14);
+        const uint32_t lbo = (uint32_t)(hx * wx) << 16;
+        const uint32_t ao = (uint32_t)(off16[m] + rh * wx + rw);
+        const uint32_t bo = b_w0 + (uint32_t)(kh * 3 + kw) * b_ent;
+        mma3(tmem_base, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, bo + b_pl, b_w1, idesc, touched, 0);
+      }
+  } else {  // GEOM_T2: group 0 = input plane d0 (kd = 1 -> even, kd = 2 -> odd out planes), group 1 = d0+1 (kd = 0)
+    const uint32_t a_w1 = 9u | (1u << 14);
+    const uint32_t lbo = (uint32_t)(17 * 9) << 16;
+    const int nk = g == 0 ? 2 : 1;
+    for (int ki = 0; ki < nk; ++ki) {
+      const int qd = (g == 0 && ki == 0) ? 0 : 1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int qh = kh != 1, jh = kh == 0, qw = kw != 1, jw = kw == 0;
+          const int acc = qd * 4 + qh * 2 + qw;
+          const uint32_t ao = (uint32_t)(jh * 9 + jw);
+          const uint32_t bo = b_w0 + (uint32_t)(ki * 9 + kh * 3 + kw) * b_ent;
+          mma3(tmem_base + acc * nt, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, bo + b_pl, b_w1, idesc,
+               touched, acc);
+        }
+    }
+  }
+}
+
+template <int GEOM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -148,8 +237,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   const int tile = blockIdx.x;
   const int tw = tile % P.tiles_w, th = (tile / P.tiles_w) % P.tiles_h, tdi = tile / (P.tiles_w * P.tiles_h);
   const int w0 = tw * 8, h0 = th * 16, d0 = tdi * P.td;
-  const int nt = blockIdx.y, n = blockIdx.z;
-  const int total_it = P.ncblk * P.ngroups;
+  const int nt = blockIdx.y / P.ksplit, ks = blockIdx.y % P.ksplit, n = blockIdx.z;
+  const int cb0 = ks * P.cb_per_split;
+  const int cb1 = min(P.ncblk, cb0 + P.cb_per_split);
+  const int total_it = (cb1 - cb0) * P.ngroups;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) {
@@ -178,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       for (int it = 0; it < total_it; ++it) {
         const int s = it % P.nstages, ph = (it / P.nstages) & 1;
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-        const int g = it % P.ngroups, cb = it / P.ngroups;
+        const int g = it % P.ngroups, cb = cb0 + it / P.ngroups;
         const TcGroup& G = P.grp[g];
         const uint32_t full = smem_u32(&bar_full[s]);
         const uint32_t stage = smem_base + s * P.stage_bytes;
@@ -201,34 +292,11 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       uint32_t touched = 0;
-      const int nplanes = P.td;
       for (int it = 0; it < total_it; ++it) {
         const int s = it % P.nstages, ph = (it / P.nstages) & 1;
         mbar_wait(smem_u32(&bar_full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const TcGroup& G = P.grp[it % P.ngroups];
-        const uint32_t a_hi = smem_base + s * P.stage_bytes;
-        const uint32_t a_lo = a_hi + P.a_plane_bytes;
-        const uint32_t b_hi = a_hi + 2 * P.a_plane_bytes;
-        const uint32_t b_lo = b_hi + P.b_bytes;
-        const uint32_t b_lbo16 = P.ntile;      // k-chunk pitch = NT rows * 16 B
-        const uint32_t b_entry_bytes = 2u * P.ntile * 16u;
-        for (int m = 0; m < G.nmma; ++m) {
-          const TcMma M = G.mma[m];
-          const uint64_t bd_hi = make_desc(b_hi + M.b_entry * b_entry_bytes, b_lbo16, 8);
-          const uint64_t bd_lo = make_desc(b_lo + M.b_entry * b_entry_bytes, b_lbo16, 8);
-          for (int p = 0; p < nplanes; ++p) {
-            const int acc = M.acc + p;
-            const uint32_t aoff = (uint32_t)(M.a_off16 + p * P.plane_stride16) * 16u;
-            const uint64_t ad_hi = make_desc(a_hi + aoff, M.lbo16, M.sbo16);
-            const uint64_t ad_lo = make_desc(a_lo + aoff, M.lbo16, M.sbo16);
-            const uint32_t d = tmem_base + acc * P.ntile;
-            umma_f16(d, ad_hi, bd_hi, P.idesc, (touched >> acc) & 1u);
-            touched |= 1u << acc;
-            umma_f16(d, ad_hi, bd_lo, P.idesc, 1u);
-            umma_f16(d, ad_lo, bd_hi, P.idesc, 1u);
-          }
-        }
+        issue_group<GEOM>(P, it % P.ngroups, smem_base + s * P.stage_bytes, tmem_base, touched);
         umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
       }
       umma_commit(smem_u32(&bar_acc));         // accumulators complete
@@ -242,6 +310,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     const int hh = row >> 3, ww = row & 7;
     const long long Vo = (long long)P.Do * P.Ho * P.Wo;
     const int nchunks = P.ntile >> 3;
+    const bool add_bias = P.bias != nullptr && ks == 0;
     for (int acc = 0; acc < P.nacc; ++acc) {
       const int od = P.out_mul * (d0 + P.acc_pd[acc]) + P.acc_qd[acc];
       const int oh = P.out_mul * (h0 + hh) + P.acc_qh[acc];
@@ -254,17 +323,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
         const int co_chunk = nt * nchunks + ch;
         if (valid && co_chunk < P.C8out) {
           float* dst = P.out + (long long)n * P.out_ns + ((long long)co_chunk * Vo + vox) * 8;
-          if (P.bias) {
+          if (add_bias) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += P.bias[co_chunk * 8 + i];
           }
-          if (P.accumulate) {
-            float o[8];
-            load_f32x8(dst, o);
+          if (P.ksplit > 1) {
+            // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
+            atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+          } else {
+            if (P.accumulate) {
+              float o[8];
+              load_f32x8(dst, o);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += o[i];
+              for (int i = 0; i < 8; ++i) v[i] += o[i];
+            }
+            store_f32x8(dst, v);
           }
-          store_f32x8(dst, v);
         }
       }
     }
@@ -294,8 +369,6 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-
-enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2 };
 
 static int geom_of(int mode, int K, int stride) {
   if (K == 1 && stride == 1) return GEOM_K1;  // 1x1: conv and its dgrad are both plain GEMMs
@@ -379,30 +452,47 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   // tile space
   int Td, Th, Tw;  // extents of the tile space
   if (geom == GEOM_T2) { Td = Di; Th = Hi; Tw = Wi; } else { Td = Do; Th = Ho; Tw = Wo; }
-  const int smem_budget = 200 * 1024;
-  // choose TD (conv d-planes per CTA)
-  int td = 1;
+  // ---- shape the CTA: TD d-planes per CTA (B-operand reuse), pipeline depth, CTAs per SM.
+  // Two co-resident CTAs per SM let one CTA's epilogue overlap the other's main loop, so a
+  // configuration with >= 2 stages at occupancy 2 is preferred over a deeper single-CTA pipeline.
+  int td_max = 1;
   if (geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1) {
-    td = 512 / P.ntile;
-    if (td > 4) td = 4;
-    if (td > Td) td = Td;
-    if (flags & 1) td = 1;
+    td_max = 512 / P.ntile;
+    if (td_max > 4) td_max = 4;
+    if (td_max > Td) td_max = Td;
+    if (flags & 1) td_max = 1;
   }
   int hx, wx;  // halo extents for the single-box geometries
-  for (;; --td) {
-    if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else { hx = 18; wx = 10; }
+  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else { hx = 18; wx = 10; }
+  P.gmax = tta_conv_tc_gmax(mode, K, stride);
+  P.ngroups = tta_conv_tc_ngroups(mode, K, stride);
+  P.b_bytes = P.gmax * 2 * P.ntile * 16;
+  auto stage_bytes_of = [&](int td_) {
     int a_bytes;
-    if (geom == GEOM_S2) a_bytes = round128(16 * 8 * 32) + round128(16 * 9 * 32) + round128(17 * 8 * 32) + round128(17 * 9 * 32);
-    else a_bytes = round128(hx * wx * td * 32);
-    P.gmax = tta_conv_tc_gmax(mode, K, stride);
-    P.a_plane_bytes = a_bytes;
-    P.b_bytes = P.gmax * 2 * P.ntile * 16;
-    P.stage_bytes = round128(2 * P.a_plane_bytes + 2 * P.b_bytes);
-    P.nstages = smem_budget / P.stage_bytes;
-    if (P.nstages >= 2 || td == 1) break;
+    if (geom == GEOM_S2) a_bytes = 18048;  // 4096 + 4608 + 4352 + 4992 (128-aligned parity sub-tiles)
+    else a_bytes = round128(hx * wx * td_ * 32);
+    return round128(2 * a_bytes + 2 * P.b_bytes);
+  };
+  const int total_it_full = P.ncblk * P.ngroups;
+  int td = 1, occ = 1;
+  bool found = false;
+  for (int o = 2; o >= 1 && !found; --o) {
+    const int budget = (227 * 1024) / o - 2048;
+    for (int t = td_max; t >= 1; --t) {
+      if (o == 2 && 2 * (geom == GEOM_T2 ? 8 : t) * P.ntile > 512) continue;  // TMEM columns for 2 CTAs
+      const int ns = budget / stage_bytes_of(t);
+      if (ns >= 2 || (ns >= 1 && total_it_full == 1)) { td = t; occ = o; found = true; break; }
+    }
   }
-  TTA_REQUIRE(P.nstages >= 1, "tta_conv_tc: stage of %d bytes does not fit shared memory", P.stage_bytes);
-  if (P.nstages > kMaxStages) P.nstages = kMaxStages;
+  TTA_REQUIRE(found, "tta_conv_tc: stage of %d bytes does not fit shared memory", stage_bytes_of(1));
+  {
+    const int budget = (227 * 1024) / occ - 2048;
+    P.stage_bytes = stage_bytes_of(td);
+    P.a_plane_bytes = geom == GEOM_S2 ? 18048 : round128(hx * wx * td * 32);
+    P.nstages = budget / P.stage_bytes;
+    if (P.nstages > 4) P.nstages = 4;
+    if (P.nstages > total_it_full) P.nstages = total_it_full;
+  }
   P.td = td;
   P.nacc = geom == GEOM_T2 ? 8 : td;
   int cols = 32;
@@ -410,7 +500,18 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   TTA_REQUIRE(cols <= 512, "tta_conv_tc: %d accumulator columns exceed TMEM", P.nacc * P.ntile);
   P.tmem_cols = cols;
   P.tiles_w = (Tw + 7) / 8; P.tiles_h = (Th + 15) / 16; P.tiles_d = (Td + td - 1) / td;
-  P.ngroups = tta_conv_tc_ngroups(mode, K, stride);
+  // ---- split-K over channel blocks when the tile grid cannot fill the 148 SMs
+  {
+    const long long ctas = (long long)P.tiles_w * P.tiles_h * P.tiles_d * P.n_ntiles * N;
+    int ks = 1;
+    if (!(flags & 2) && ctas < 148 && P.ncblk >= 4) {
+      ks = (int)((2 * 148 + ctas - 1) / ctas);
+      if (ks > P.ncblk / 2) ks = P.ncblk / 2;
+      if (ks < 1) ks = 1;
+    }
+    P.cb_per_split = (P.ncblk + ks - 1) / ks;
+    P.ksplit = (P.ncblk + P.cb_per_split - 1) / P.cb_per_split;
+  }
 
   // ---- tensor maps
   auto encode = [&](CUtensorMap* m, const uint16_t* base, int par_h, int par_w, int s, int bw, int bh, int bd) -> bool {
@@ -519,18 +620,36 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   }
 
   const size_t smem = (size_t)P.nstages * P.stage_bytes + 1024;
-  static bool configured = false;
-  if (!configured) {
-    // 227 KB per CTA includes the kernel's static shared memory (barriers, TMEM base)
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, conv_tc_kernel) != cudaSuccess) return tta_check_launch("tta_conv_tc(attrs)");
-    const int max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess)
-      return tta_check_launch("tta_conv_tc(cudaFuncSetAttribute)");
-    configured = true;
+  if (P.ksplit > 1 && !accumulate) {
+    // partial sums are combined with float4 atomics: start from zero
+    const long long Vo = (long long)Do * Ho * Wo;
+    for (int nn = 0; nn < N; ++nn)
+      if (cudaMemsetAsync(out + nn * out_ns, 0, (size_t)C8out * Vo * 8 * sizeof(float), stream) != cudaSuccess)
+        return tta_check_launch("tta_conv_tc(memset)");
   }
-  const dim3 grid(P.tiles_w * P.tiles_h * P.tiles_d, P.n_ntiles, N);
-  conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(P);
+  const dim3 grid(P.tiles_w * P.tiles_h * P.tiles_d, P.n_ntiles * P.ksplit, N);
+#define TTA_TC_LAUNCH(G)                                                                                   \
+  do {                                                                                                     \
+    static bool configured = false;                                                                        \
+    if (!configured) {                                                                                     \
+      cudaFuncAttributes fa;                                                                               \
+      if (cudaFuncGetAttributes(&fa, conv_tc_kernel<G>) != cudaSuccess) return tta_check_launch("tta_conv_tc(attrs)"); \
+      const int max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;                                            \
+      if (cudaFuncSetAttribute(conv_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != \
+          cudaSuccess)                                                                                     \
+        return tta_check_launch("tta_conv_tc(cudaFuncSetAttribute)");                                      \
+      configured = true;                                                                                   \
+    }                                                                                                      \
+    conv_tc_kernel<G><<<grid, kTcThreads, smem, stream>>>(P);                                              \
+  } while (0)
+  switch (geom) {
+    case GEOM_S1: TTA_TC_LAUNCH(GEOM_S1); break;
+    case GEOM_S1T: TTA_TC_LAUNCH(GEOM_S1T); break;
+    case GEOM_K1: TTA_TC_LAUNCH(GEOM_K1); break;
+    case GEOM_S2: TTA_TC_LAUNCH(GEOM_S2); break;
+    default: TTA_TC_LAUNCH(GEOM_T2); break;
+  }
+#undef TTA_TC_LAUNCH
   return tta_check_launch("tta_conv_tc");
 }
 

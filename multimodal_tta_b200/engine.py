@@ -282,7 +282,7 @@ class TTAEngine:
             wp = cl.packed["tc_" + key]
             plan.keep.append(wp)
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
-                    *odims, mode, cl.K, cl.stride, int(accumulate), 0)
+                    *odims, mode, cl.K, cl.stride, int(accumulate), 2 if self.model.deterministic else 0)
 
             def run():
                 check(lib.tta_conv_tc(*args, _stream()), f"conv_tc {cl.name}")

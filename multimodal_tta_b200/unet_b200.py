@@ -146,6 +146,8 @@ class UNetB200(nn.Module):
         # backend options (not in the reference): conv kernel family and whole-step CUDA graph
         self.conv_backend = str(get_config(cfg, "conv_backend", "auto"))
         self.use_cuda_graph = bool(get_config(cfg, "cuda_graph", True))
+        # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
+        self.deterministic = bool(get_config(cfg, "deterministic", False))
         k, nru, norm, act, dr = 3, self.num_res_units, self.norm, self.act, self.dropout
 
         def down(cin, cout, stride):
