@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-TTA_F16, TTA_BF16 = 0, 1
+TTA_F16, TTA_BF16, TTA_F16_HI = 0, 1, 2
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -62,14 +62,14 @@ _SIGNATURES = {
     "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
     "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, P]),
     "tta_head_entropy_blocks": (I, [I, L]),
-    "tta_head_entropy": (I, [P, L, I, I, L, I, F, P, P, P, P, L, P, P, P]),
+    "tta_head_entropy": (I, [P, L, I, I, L, I, F, F, I, P, P, P, P, L, P, P, P]),
     "tta_adam_step": (I, [P, P, P, P, I, F, F, F, F, F, P, P]),
     "tta_sw_blend": (I, [P, I, I, I, I, I, P, P, P, P, P, F, P, P, I, I, I, I, P]),
     "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),
     "tta_dice_counts": (I, [P, P, I, L, F, P, P]),
     "tta_conv_simt": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, P]),
     "tta_conv_tc_supported": (I, [I, I, I, I, I]),
-    "tta_conv_tc_ntile": (I, [I, I, I, I]),
+    "tta_conv_tc_ntile": (I, [I, I, I, I, I]),
     "tta_conv_tc_gmax": (I, [I, I, I]),
     "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),

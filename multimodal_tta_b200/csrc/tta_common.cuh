@@ -21,6 +21,7 @@
 // dtype tags of the 16-bit operand planes
 #define TTA_F16 0
 #define TTA_BF16 1
+#define TTA_F16_HI 2  // single fp16 plane (no lo plane is written or read): scaled gradients in backward
 
 void tta_set_error(const char* fmt, ...);
 int tta_check_launch(const char* what);
@@ -55,12 +56,12 @@ __device__ __forceinline__ void store_f32x8(float* __restrict__ p, const float (
 
 template <int DT>
 __device__ __forceinline__ float u16_to_f32(uint16_t u) {
-  if (DT == TTA_F16) return __half2float(__ushort_as_half(u));
+  if (DT == TTA_F16 || DT == TTA_F16_HI) return __half2float(__ushort_as_half(u));
   return __bfloat162float(__ushort_as_bfloat16(u));
 }
 template <int DT>
 __device__ __forceinline__ uint16_t f32_to_u16(float f) {
-  if (DT == TTA_F16) {
+  if (DT == TTA_F16 || DT == TTA_F16_HI) {
     // saturate instead of producing inf: fp16 max is 65504
     f = fminf(fmaxf(f, -65504.f), 65504.f);
     return __half_as_ushort(__float2half_rn(f));
@@ -81,6 +82,13 @@ __device__ __forceinline__ void split8(const float (&x)[8], U16x8& hi, U16x8& lo
 template <int DT>
 __device__ __forceinline__ void store_split8(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                              long long off, const float (&x)[8]) {
+  if (DT == TTA_F16_HI) {
+    U16x8 h;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h.v[i] = f32_to_u16<DT>(x[i]);
+    *reinterpret_cast<U16x8*>(hi + off) = h;
+    return;
+  }
   U16x8 h, l;
   split8<DT>(x, h, l);
   *reinterpret_cast<U16x8*>(hi + off) = h;
@@ -91,6 +99,11 @@ __device__ __forceinline__ void load_split8(const uint16_t* __restrict__ hi,
                                             const uint16_t* __restrict__ lo, long long off,
                                             float (&x)[8]) {
   const U16x8 h = *reinterpret_cast<const U16x8*>(hi + off);
+  if (DT == TTA_F16_HI) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = u16_to_f32<DT>(h.v[i]);
+    return;
+  }
   const U16x8 l = *reinterpret_cast<const U16x8*>(lo + off);
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = u16_to_f32<DT>(h.v[i]) + u16_to_f32<DT>(l.v[i]);

@@ -151,11 +151,11 @@ extern "C" int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long 
                              const float* Wp, const float* bias, float* out, long long out_ns,
                              int C8out, int Do, int Ho, int Wo, int mode, int K, int stride,
                              int accumulate, cudaStream_t stream) {
-  TTA_REQUIRE(in_hi && in_lo && Wp && out, "tta_conv_simt: null pointer");
+  TTA_REQUIRE(in_hi && (in_lo || in_dtype == TTA_F16_HI) && Wp && out, "tta_conv_simt: null pointer");
   TTA_REQUIRE(mode == 0 || mode == 1, "tta_conv_simt: mode %d", mode);
   TTA_REQUIRE(K == 1 || K == 3, "tta_conv_simt: kernel size %d unsupported (1 or 3)", K);
   TTA_REQUIRE(stride == 1 || stride == 2, "tta_conv_simt: stride %d unsupported (1 or 2)", stride);
-  TTA_REQUIRE(in_dtype == TTA_F16 || in_dtype == TTA_BF16, "tta_conv_simt: bad dtype");
+  TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_simt: bad dtype");
   const int pad = (K - 1) / 2;
   if (mode == 0) {
     TTA_REQUIRE(Do == (Di + 2 * pad - K) / stride + 1 && Ho == (Hi + 2 * pad - K) / stride + 1 &&
@@ -174,6 +174,8 @@ extern "C" int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long 
   const size_t smem = (size_t)K * K * K * 64 * sizeof(float);
   if (in_dtype == TTA_F16)
     conv_simt_kernel<TTA_F16><<<grid, kConvThreads, smem, stream>>>(in_hi, in_lo, Wp, bias, out, g, accumulate);
+  else if (in_dtype == TTA_F16_HI)
+    conv_simt_kernel<TTA_F16_HI><<<grid, kConvThreads, smem, stream>>>(in_hi, in_lo, Wp, bias, out, g, accumulate);
   else
     conv_simt_kernel<TTA_BF16><<<grid, kConvThreads, smem, stream>>>(in_hi, in_lo, Wp, bias, out, g, accumulate);
   return tta_check_launch("tta_conv_simt");

@@ -1,12 +1,12 @@
 // tcgen05 / TMEM / TMA implicit-GEMM 3-D convolution for sm_100a (forward AND input-gradient).
 //
-// GEMM view per CTA:  D[128 voxels x NT couts] += A[128 voxels x 16 cin] * B[16 cin x NT couts]
+// GEMM view per work item:  D[128 voxels x NT couts] += A[128 voxels x 16 cin] * B[16 cin x NT]
 // for every (16-channel block, tap).  M = 128 rows = a 16(h) x 8(w) patch of one d-plane of the
-// "tile space"; a CTA owns up to 8 such accumulators in TMEM (TD consecutive d-planes for convs,
-// the 8 output-parity classes for stride-2 transposed convs).
+// "tile space"; one work item owns up to 8 such accumulators in TMEM (TD consecutive d-planes for
+// convs, the 8 output-parity classes for stride-2 transposed convs).
 //
-//  * A operand: the input HALO tile is loaded ONCE per (channel block, tap group) by TMA from the
-//    channel-blocked layout [N][C8][D][H][W][8] into smem as [kchunk][d][h][w][8ch] with NO swizzle.
+//  * A operand: the input HALO tile is loaded once per (channel block, tap group) by TMA from the
+//    channel-blocked layout [N][C8][D][H][W][8] into smem as [kchunk][d][h][w][8ch], NO swizzle.
 //    In the UMMA K-major no-swizzle canonical layout a core matrix is 8 rows x 16 B contiguous --
 //    exactly 8 consecutive-w voxels x 8 channels -- so every filter tap is just a different
 //    descriptor START ADDRESS into the same halo tile (SBO = halo row pitch, LBO = k-chunk pitch):
@@ -14,13 +14,16 @@
 //    Stride-2 convs read 4 (h,w)-parity sub-tiles through strided tensor maps; stride-2 transposed
 //    convs are 8 output-parity sub-convolutions over the same halo tile.
 //  * B operand: weights pre-packed on the host per (n-tile, channel block, tap group) as
-//    [tap][kchunk 2][NT][8ch] blobs, one cp.async.bulk per stage.
-//  * Precision: operands are split 16-bit planes (x = hi + lo); 3 MMAs per k-step
-//    (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator give ~fp32-equivalent products
-//    (fp16 planes: 22 bits in forward; bf16 planes: 16 bits in backward, where range matters).
-//  * Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issue,
-//    warps 2..5 = epilogue (tcgen05.ld -> +bias (+= existing) -> 32 B vector stores).
-//    mbarrier ring (full/empty) between producer and MMA, tcgen05.commit releases stages.
+//    [tap][kchunk 2][hi NT rows | lo NT rows][8ch] blobs: ONE cp.async.bulk per stage.
+//  * Precision: operands are split 16-bit planes (x = hi + lo; fp16 forward, bf16 backward).
+//    Per k-step TWO MMAs:  A_hi x [B_hi | B_lo]  (N = 2*NT: the stacked B reads A_hi once) and
+//    A_lo x B_hi (N = NT); the epilogue adds the two column halves.  That is hi*hi + hi*lo + lo*hi
+//    in fp32 -- ~fp32-equivalent products -- for 2/3 of the shared-memory operand traffic of three
+//    separate MMAs (small-N MMAs are bound by the 4 KB A-tile read, not by tensor math).
+//  * Persistent CTAs: grid = min(work items, #SMs); warp 0 = TMA producer, warp 1 = TMEM alloc +
+//    single-thread MMA issue, warps 2..5 = epilogue.  The smem stage ring (full/empty mbarriers)
+//    runs across work items; TMEM accumulators are double buffered when they fit, so the epilogue
+//    of item i overlaps the main loop of item i+1.
 #include <cuda.h>
 
 #include "tta_common.cuh"
@@ -30,33 +33,31 @@ namespace tta {
 constexpr int kTcThreads = 192;
 constexpr int kMaxGroups = 3;
 constexpr int kMaxLoads = 4;
-constexpr int kMaxMma = 18;
 constexpr int kMaxAcc = 8;
 constexpr int kMaxStages = 6;
 
+enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2 };
+
 struct TcLoad {
-  int map, dw, dh, dd, smem_off, bytes;
-};
-struct TcMma {
-  short a_off16, sbo16, lbo16, b_entry, acc, pad;
+  int map, dw, dh, dd, smem_off, bytes, chunk_pitch, pad;  // bytes / pitch are per k-chunk (8 channels)
 };
 struct TcGroup {
-  int nloads, nmma, tx_bytes, pad;
+  int nloads, nmma, tx_bytes, pad;  // tx_bytes: A bytes of both planes for ONE k-chunk
   TcLoad ld[kMaxLoads];
-  TcMma mma[kMaxMma];
 };
 struct TcParams {
-  CUtensorMap amap[8];  // [box shape 0..3][hi, lo]
+  CUtensorMap amap[8];  // stride-2: [parity class 0..3][hi, lo]; otherwise [0] = hi, [1] = lo
   TcGroup grp[kMaxGroups];
-  int ngroups, ncblk, nstages, ntile, n_ntiles, nacc, td, plane_stride16;
+  int ngroups, ncblk, nstages, ntile, n_ntiles, nacc, td, nbuf;
   int tiles_w, tiles_h, tiles_d, d_mul;
-  int a_plane_bytes, b_bytes, stage_bytes, tmem_cols;
-  int c8_view;  // chunk pitch of the merged (n, chunk) tensor-map dimension
-  int out_mul, Do, Ho, Wo, C8out, accumulate, idesc, gmax;
-  int ksplit, cb_per_split;
+  int a_plane_bytes, b_entry_bytes, b_blob_bytes, stage_bytes;
+  int c8_view, c8in, single_chunk, tmem_cols;
+  int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n;
+  int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
+  int lbo16[4];  // k-chunk pitch (16 B units, 128 B aligned) per A sub-tile
   signed char acc_pd[kMaxAcc], acc_qd[kMaxAcc], acc_qh[kMaxAcc], acc_qw[kMaxAcc];
   long long out_ns;
-  const uint16_t* wpacked;
+  const uint8_t* wpacked;
   const float* bias;
   float* out;
 };
@@ -70,6 +71,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -89,7 +93,7 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 22)) asm volatile("trap;");
+    if (++spins > (1u << 24)) asm volatile("trap;");
   }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
@@ -100,16 +104,18 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
-  // K-major, SWIZZLE_NONE: ((8,m),(8 elems,2)) : ((16 B, SBO), (1, LBO)); version 1 (sm_100)
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) |
-         ((uint64_t)(sbo16 & 0x3FFFu) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -126,86 +132,109 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred;
 }
 
-// ---------------------------------------------------------------- the kernel
-enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2 };
-
-// One k-step (16 channels) of one tap for one accumulator: hi*hi + hi*lo + lo*hi.
-__device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_w1, uint32_t b_hi,
-                                     uint32_t b_lo, uint32_t b_w1, uint32_t idesc, uint32_t& touched, int acc) {
-  // descriptor words: w0 = (addr>>4) | lbo16<<16 ; w1 = sbo16 | version(1)<<14
+// One k-step (16 channels) of one tap for one accumulator:
+//   D[0:2NT] (+)= A_hi * [B_hi | B_lo]   and   D[0:NT] += A_lo * B_hi
+// descriptor words: w0 = (addr >> 4) | lbo16 << 16 ; w1 = sbo16 | version(1) << 14.
+// Called by ALL lanes of the MMA warp with warp-uniform arguments (so the descriptor arithmetic
+// stays in the uniform datapath); only the elected lane issues the two tcgen05.mma.
+// SPLIT = 0 (single-plane operands, e.g. scaled-fp16 gradients): one MMA, D[0:NT] (+)= A * B.
+template <int SPLIT>
+__device__ __forceinline__ void mma_pair(uint32_t leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_w1,
+                                         uint32_t b_w0, uint32_t b_w1, uint32_t idesc_2n, uint32_t idesc_n,
+                                         uint32_t accumulate) {
   const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | a_hi, ad_lo = ((uint64_t)a_w1 << 32) | a_lo;
-  const uint64_t bd_hi = ((uint64_t)b_w1 << 32) | b_hi, bd_lo = ((uint64_t)b_w1 << 32) | b_lo;
-  umma_f16(d, ad_hi, bd_hi, idesc, (touched >> acc) & 1u);
-  touched |= 1u << acc;
-  umma_f16(d, ad_hi, bd_lo, idesc, 1u);
-  umma_f16(d, ad_lo, bd_hi, idesc, 1u);
+  const uint64_t bd = ((uint64_t)b_w1 << 32) | b_w0;
+  if (leader) {
+    if (SPLIT) {
+      umma_f16(d, ad_hi, bd, idesc_2n, accumulate);
+      umma_f16(d, ad_lo, bd, idesc_n, 1u);
+    } else {
+      umma_f16(d, ad_hi, bd, idesc_n, accumulate);
+    }
+  }
 }
 
-// All MMAs of pipeline group g for one smem stage; tap geometry is compile-time arithmetic so the
-// single issuing thread spends a handful of integer instructions per MMA (no table loads).
-template <int GEOM>
-__device__ __forceinline__ void issue_group(const TcParams& P, int g, uint32_t stage, uint32_t tmem_base,
-                                            uint32_t& touched) {
+// All MMAs of pipeline group g for one smem stage.  Tap geometry and TD are compile-time, so per
+// MMA the warp spends a couple of uniform integer adds; `first` = first stage of the work item
+// (the first MMA into each accumulator overwrites instead of accumulating).
+template <int GEOM, int TD, int SPLIT>
+__device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, int g, uint32_t stage,
+                                            uint32_t tmem_acc0, bool first) {
   const uint32_t nt = P.ntile;
+  const uint32_t acc_cols = SPLIT ? 2u * nt : nt;
   const uint32_t a_hi0 = stage >> 4, a_lo0 = (stage + P.a_plane_bytes) >> 4;
-  const uint32_t b_w0 = ((stage + 2 * P.a_plane_bytes) >> 4) | (nt << 16);   // lbo16 = NT
-  const uint32_t b_pl = (uint32_t)P.b_bytes >> 4;                            // hi -> lo plane, 16 B units
-  const uint32_t b_ent = 2u * nt;                                            // entry pitch, 16 B units
-  const uint32_t b_w1 = 8u | (1u << 14);                                     // sbo16 = 8 (128 B)
-  const uint32_t idesc = P.idesc;
+  const uint32_t b_w0 = ((stage + P.b_off) >> 4) | (acc_cols << 16);  // lbo16 = B rows per k-chunk
+  const uint32_t b_ent = (uint32_t)P.b_entry_bytes >> 4;                          // entry pitch, 16 B units
+  const uint32_t b_w1 = 8u | (1u << 14);                                          // sbo16 = 8 (128 B)
+  const uint32_t i2n = P.idesc_2n, in_ = P.idesc_n;
   if (GEOM == GEOM_S1 || GEOM == GEOM_S1T) {
-    const int td = P.td;
     const uint32_t a_w1 = 10u | (1u << 14);
-    const uint32_t lbo = (uint32_t)(td * 180) << 16;
+    const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
+    const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;   // address field never carries into lbo
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int rh = GEOM == GEOM_S1 ? kh : 2 - kh, rw = GEOM == GEOM_S1 ? kw : 2 - kw;
         const uint32_t bo = b_w0 + (uint32_t)(kh * 3 + kw) * b_ent;
-        for (int p = 0; p < td; ++p) {
+        const uint32_t accum = (first && g == 0 && kh == 0 && kw == 0) ? 0u : 1u;
+#pragma unroll
+        for (int p = 0; p < TD; ++p) {
           const uint32_t ao = (uint32_t)(rh * 10 + rw + p * 180);
-          mma3(tmem_base + p * nt, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, bo + b_pl, b_w1, idesc,
-               touched, p);
+          mma_pair<SPLIT>(leader, tmem_acc0 + p * acc_cols, ah + ao, al + ao, a_w1, bo, b_w1, i2n, in_, accum);
         }
       }
   } else if (GEOM == GEOM_K1) {
-    const int td = P.td;
     const uint32_t a_w1 = 8u | (1u << 14);
-    const uint32_t lbo = (uint32_t)(td * 128) << 16;
-    for (int p = 0; p < td; ++p) {
+    const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
+    const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;
+#pragma unroll
+    for (int p = 0; p < TD; ++p) {
       const uint32_t ao = (uint32_t)(p * 128);
-      mma3(tmem_base + p * nt, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, b_w0, b_w0 + b_pl, b_w1, idesc,
-           touched, p);
+      mma_pair<SPLIT>(leader, tmem_acc0 + p * acc_cols, ah + ao, al + ao, a_w1, b_w0, b_w1, i2n, in_, first ? 0u : 1u);
     }
   } else if (GEOM == GEOM_S2) {
-    // parity sub-tiles [ph][pw] at fixed 128-aligned offsets: 16x8, 16x9, 17x8, 17x9 voxels x 32 B
+    // parity sub-tiles [ph][pw] at fixed 128-aligned offsets: 16x8, 16x9, 17x8, 17x9 voxels
     constexpr int off16[4] = {0, 4096 / 16, 8704 / 16, 13056 / 16};
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int ph = kh != 1, pw = kw != 1, rh = kh == 2, rw = kw == 2, m = ph * 2 + pw;
-        const int wx = pw ? 9 : 8, hx = ph ? 17 : 16;
+        const int wx = pw ? 9 : 8;
         const uint32_t a_w1 = (uint32_t)wx | (1u << 14);
-        const uint32_t lbo = (uint32_t)(hx * wx) << 16;
+        const uint32_t lbo = (uint32_t)P.lbo16[m] << 16;
         const uint32_t ao = (uint32_t)(off16[m] + rh * wx + rw);
         const uint32_t bo = b_w0 + (uint32_t)(kh * 3 + kw) * b_ent;
-        mma3(tmem_base, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, bo + b_pl, b_w1, idesc, touched, 0);
+        const uint32_t accum = (first && g == 0 && kh == 0 && kw == 0) ? 0u : 1u;
+        mma_pair<SPLIT>(leader, tmem_acc0, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, b_w1, i2n, in_, accum);
       }
   } else {  // GEOM_T2: group 0 = input plane d0 (kd = 1 -> even, kd = 2 -> odd out planes), group 1 = d0+1 (kd = 0)
     const uint32_t a_w1 = 9u | (1u << 14);
-    const uint32_t lbo = (uint32_t)(17 * 9) << 16;
+    const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
+    const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;
     const int nk = g == 0 ? 2 : 1;
     for (int ki = 0; ki < nk; ++ki) {
       const int qd = (g == 0 && ki == 0) ? 0 : 1;
@@ -214,40 +243,63 @@ __device__ __forceinline__ void issue_group(const TcParams& P, int g, uint32_t s
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const int qh = kh != 1, jh = kh == 0, qw = kw != 1, jw = kw == 0;
-          const int acc = qd * 4 + qh * 2 + qw;
+          const uint32_t acc = (uint32_t)(qd * 4 + qh * 2 + qw);
           const uint32_t ao = (uint32_t)(jh * 9 + jw);
           const uint32_t bo = b_w0 + (uint32_t)(ki * 9 + kh * 3 + kw) * b_ent;
-          mma3(tmem_base + acc * nt, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, bo + b_pl, b_w1, idesc,
-               touched, acc);
+          // each parity accumulator is first written in group 0 by its (kh < 2, kw < 2) tap
+          const uint32_t accum = (first && g == 0 && kh < 2 && kw < 2) ? 0u : 1u;
+          mma_pair<SPLIT>(leader, tmem_acc0 + acc * acc_cols, ah + ao, al + ao, a_w1, bo, b_w1, i2n, in_, accum);
         }
     }
   }
 }
 
-template <int GEOM>
+struct WorkItem {
+  int n, nt, ks, w0, h0, d0, cb0, nit;
+};
+// item = ((n * tiles + tile) * n_ntiles + nt) * ksplit + ks : neighbouring CTAs share the A tile in L2
+__device__ __forceinline__ WorkItem decode_item(const TcParams& P, int item) {
+  WorkItem w;
+  const int per_tile = P.n_ntiles * P.ksplit;
+  const int ntks = item % per_tile;
+  int t = item / per_tile;
+  const int tiles = P.tiles_w * P.tiles_h * P.tiles_d;
+  w.n = t / tiles;
+  t -= w.n * tiles;
+  w.nt = ntks / P.ksplit;
+  w.ks = ntks - w.nt * P.ksplit;
+  const int tw = t % P.tiles_w, th = (t / P.tiles_w) % P.tiles_h, tdi = t / (P.tiles_w * P.tiles_h);
+  w.w0 = tw * 8;
+  w.h0 = th * 16;
+  w.d0 = tdi * P.td;
+  w.cb0 = w.ks * P.cb_per_split;
+  const int cb1 = min(P.ncblk, w.cb0 + P.cb_per_split);
+  w.nit = (cb1 - w.cb0) * P.ngroups;
+  return w;
+}
+
+template <int GEOM, int TD, int SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
-  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int tw = tile % P.tiles_w, th = (tile / P.tiles_w) % P.tiles_h, tdi = tile / (P.tiles_w * P.tiles_h);
-  const int w0 = tw * 8, h0 = th * 16, d0 = tdi * P.td;
-  const int nt = blockIdx.y / P.ksplit, ks = blockIdx.y % P.ksplit, n = blockIdx.z;
-  const int cb0 = ks * P.cb_per_split;
-  const int cb1 = min(P.ncblk, cb0 + P.cb_per_split);
-  const int total_it = (cb1 - cb0) * P.ngroups;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_acc), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -257,91 +309,157 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (P.single_chunk) {
+    // 1-chunk inputs (stem, head): the second k-chunk of every A tile is never loaded -> zero it once
+    const int n16 = (P.nstages * P.stage_bytes) >> 4;
+    for (int i = threadIdx.x; i < n16; i += kTcThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t acc_cols = SPLIT ? 2u * P.ntile : (uint32_t)P.ntile;
+  const uint32_t buf_cols = (uint32_t)P.nacc * acc_cols;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int it = 0; it < total_it; ++it) {
-        const int s = it % P.nstages, ph = (it / P.nstages) & 1;
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-        const int g = it % P.ngroups, cb = cb0 + it / P.ngroups;
-        const TcGroup& G = P.grp[g];
-        const uint32_t full = smem_u32(&bar_full[s]);
-        const uint32_t stage = smem_base + s * P.stage_bytes;
-        mbar_expect_tx(full, (uint32_t)G.tx_bytes);
-        const int c4 = n * P.c8_view + cb * 2;
-        for (int l = 0; l < G.nloads; ++l) {
-          const TcLoad& L = G.ld[l];
-          const int cw = w0 + L.dw, chh = h0 + L.dh, cd = d0 * P.d_mul + L.dd;
-          tma_load_5d(stage + L.smem_off, &P.amap[L.map * 2 + 0], full, 0, cw, chh, cd, c4);
-          tma_load_5d(stage + P.a_plane_bytes + L.smem_off, &P.amap[L.map * 2 + 1], full, 0, cw, chh, cd, c4);
+      uint32_t ring = 0;  // stage-ring position, continues across work items
+      for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
+        const WorkItem wi = decode_item(P, item);
+        for (int it = 0; it < wi.nit; ++it, ++ring) {
+          const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          const int g = it % P.ngroups, cb = wi.cb0 + it / P.ngroups;
+          const TcGroup& G = P.grp[g];
+          const uint32_t full = smem_u32(&bar_full[s]);
+          const uint32_t stage = smem_base + s * P.stage_bytes;
+          const int c4 = wi.n * P.c8_view + cb * 2;
+          const int nkc = (cb * 2 + 1 < P.c8in || !P.single_chunk) ? 2 : 1;
+          const uint32_t bbytes = (uint32_t)G.nmma * P.b_entry_bytes;
+          mbar_expect_tx(full, (uint32_t)((SPLIT ? G.tx_bytes : G.tx_bytes / 2) * nkc) + bbytes);
+          for (int l = 0; l < G.nloads; ++l) {
+            const TcLoad& L = G.ld[l];
+            const int cw = wi.w0 + L.dw, chh = wi.h0 + L.dh, cd = wi.d0 * P.d_mul + L.dd;
+            for (int kc = 0; kc < nkc; ++kc) {
+              const uint32_t dst = stage + L.smem_off + kc * L.chunk_pitch;
+              if (GEOM == GEOM_S2) {
+                tma_load_5d(dst, &P.amap[L.map * 2 + 0], full, 0, cw, chh, cd, c4 + kc);
+                if (SPLIT)
+                  tma_load_5d(dst + P.a_plane_bytes, &P.amap[L.map * 2 + 1], full, 0, cw, chh, cd, c4 + kc);
+              } else {
+                tma_load_4d(dst, &P.amap[0], full, cw * 8, chh, cd, c4 + kc);
+                if (SPLIT) tma_load_4d(dst + P.a_plane_bytes, &P.amap[1], full, cw * 8, chh, cd, c4 + kc);
+              }
+            }
+          }
+          // every (nt, cb, g) blob reserves gmax entries; only this group's nmma entries are copied
+          const long long blob = ((long long)wi.nt * P.ncblk + cb) * P.ngroups + g;
+          bulk_load(stage + P.b_off, P.wpacked + blob * P.b_blob_bytes, bbytes, full);
         }
-        const uint32_t bbytes = (uint32_t)G.nmma * 2u * P.ntile * 16u;
-        const uint16_t* wsrc =
-            P.wpacked + ((((long long)nt * P.ncblk + cb) * P.ngroups + g) * 2) * (long long)(P.b_bytes / 2);
-        bulk_load(stage + 2 * P.a_plane_bytes, wsrc, bbytes, full);
-        bulk_load(stage + 2 * P.a_plane_bytes + P.b_bytes, wsrc + P.b_bytes / 2, bbytes, full);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      uint32_t touched = 0;
-      for (int it = 0; it < total_it; ++it) {
-        const int s = it % P.nstages, ph = (it / P.nstages) & 1;
+    // ===================== MMA issuer (whole warp runs uniform code, one elected lane issues) =====
+    const uint32_t leader = elect_one();
+    uint32_t ring = 0, local = 0;
+    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
+      const WorkItem wi = decode_item(P, item);
+      const uint32_t buf = local % P.nbuf, use = local / P.nbuf;
+      mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);  // epilogue drained this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc0 = tmem_base + buf * buf_cols;
+      for (int it = 0; it < wi.nit; ++it, ++ring) {
+        const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
         mbar_wait(smem_u32(&bar_full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_group<GEOM>(P, it % P.ngroups, smem_base + s * P.stage_bytes, tmem_base, touched);
-        umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
+        issue_group<GEOM, TD, SPLIT>(P, leader, it % P.ngroups, smem_base + s * P.stage_bytes, acc0, it == 0);
+        __syncwarp();
+        if (leader) umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
       }
-      umma_commit(smem_u32(&bar_acc));         // accumulators complete
+      if (leader) umma_commit(smem_u32(&bar_acc_full[buf]));  // accumulators of this item complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    mbar_wait(smem_u32(&bar_acc), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
+    const int et = threadIdx.x - 64;  // 0..127
     const long long Vo = (long long)P.Do * P.Ho * P.Wo;
     const int nchunks = P.ntile >> 3;
-    const bool add_bias = P.bias != nullptr && ks == 0;
-    for (int acc = 0; acc < P.nacc; ++acc) {
-      const int od = P.out_mul * (d0 + P.acc_pd[acc]) + P.acc_qd[acc];
-      const int oh = P.out_mul * (h0 + hh) + P.acc_qh[acc];
-      const int ow = P.out_mul * (w0 + ww) + P.acc_qw[acc];
-      const bool valid = od < P.Do && oh < P.Ho && ow < P.Wo;
-      const long long vox = ((long long)od * P.Ho + oh) * P.Wo + ow;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        float v[8];
-        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + acc * P.ntile + ch * 8, v);
-        const int co_chunk = nt * nchunks + ch;
-        if (valid && co_chunk < P.C8out) {
-          float* dst = P.out + (long long)n * P.out_ns + ((long long)co_chunk * Vo + vox) * 8;
-          if (add_bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += P.bias[co_chunk * 8 + i];
-          }
-          if (P.ksplit > 1) {
-            // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
-            atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
-            atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+    uint32_t local = 0;
+    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
+      const WorkItem wi = decode_item(P, item);
+      const uint32_t buf = local % P.nbuf, use = local / P.nbuf;
+      // bias of this n-tile -> smem (only split 0 adds it)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers are done with bias_s
+      if (et < P.ntile) {
+        const int c = wi.nt * P.ntile + et;
+        bias_s[et] = (P.bias != nullptr && wi.ks == 0 && c < P.C8out * 8) ? P.bias[c] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16);
+      for (int acc = 0; acc < P.nacc; ++acc) {
+        const int od = P.out_mul * (wi.d0 + P.acc_pd[acc]) + P.acc_qd[acc];
+        const int oh = P.out_mul * (wi.h0 + hh) + P.acc_qh[acc];
+        const int ow = P.out_mul * (wi.w0 + ww) + P.acc_qw[acc];
+        const bool valid = od < P.Do && oh < P.Ho && ow < P.Wo;
+        const long long vox = ((long long)od * P.Ho + oh) * P.Wo + ow;
+        float* obase = P.out + (long long)wi.n * P.out_ns + vox * 8;
+        const uint32_t tacc = tbase + acc * acc_cols;
+        for (int c16 = 0; c16 < (P.ntile >> 4); ++c16) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16_nowait(tacc + c16 * 16, ra);            // hi*hi + lo*hi columns
+          if (SPLIT) {
+            tmem_ld16_nowait(tacc + P.ntile + c16 * 16, rb);  // hi*lo columns
           } else {
-            if (P.accumulate) {
-              float o[8];
-              load_f32x8(dst, o);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += o[i];
+            for (int i = 0; i < 16; ++i) rb[i] = 0u;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int co_chunk = wi.nt * nchunks + c16 * 2 + hlf;
+            if (valid && co_chunk < P.C8out) {
+              float* dst = obase + (long long)co_chunk * Vo * 8;
+              const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
+              const int o = hlf * 8;
+              float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
+                                      __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
+                                      __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
+                                      __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
+              float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
+                                      __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
+                                      __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
+                                      __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
+              if (P.ksplit > 1) {
+                // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
+                atomicAdd(reinterpret_cast<float4*>(dst), r0);
+                atomicAdd(reinterpret_cast<float4*>(dst + 4), r1);
+              } else {
+                if (P.accumulate) {
+                  const float4 o0 = *reinterpret_cast<const float4*>(dst);
+                  const float4 o1 = *reinterpret_cast<const float4*>(dst + 4);
+                  r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w;
+                  r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+                }
+                *reinterpret_cast<float4*>(dst) = r0;
+                *reinterpret_cast<float4*>(dst + 4) = r1;
+              }
             }
-            store_f32x8(dst, v);
           }
         }
       }
+      // this warp's TMEM reads are complete: hand the accumulator buffer back to the MMA thread
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -377,13 +495,25 @@ static int geom_of(int mode, int K, int stride) {
   return stride == 1 ? GEOM_S1T : (stride == 2 ? GEOM_T2 : GEOM_NONE);
 }
 
-static int ntile_of(int geom, int cout) {
+// n-tile: couts per work item.  Each accumulator takes 2*NT TMEM columns (stacked hi|lo halves).
+static int ntile_of(int geom, int cout, int split) {
   const int c16 = (cout + 15) / 16 * 16;
-  const int cap = geom == GEOM_T2 ? 64 : 128;
+  // T2: 8 parity accumulators x (split ? 2 : 1)*NT <= 512 TMEM columns
+  const int cap = geom == GEOM_T2 ? (split ? 32 : 64) : 128;
   return c16 < cap ? c16 : cap;
 }
 
 static int round128(int x) { return (x + 127) / 128 * 128; }
+
+static int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
 
 }  // namespace tta
 
@@ -397,8 +527,8 @@ int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout) {
   return geom_of(mode, K, stride) != GEOM_NONE;
 }
 
-int tta_conv_tc_ntile(int mode, int K, int stride, int cout) {
-  return ntile_of(geom_of(mode, K, stride), cout);
+int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split) {
+  return ntile_of(geom_of(mode, K, stride), cout, split);
 }
 
 int tta_conv_tc_gmax(int mode, int K, int stride) {
@@ -411,16 +541,18 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
   return g == GEOM_K1 ? 1 : (g == GEOM_T2 ? 2 : 3);
 }
 
-// in: split planes view [N][C8in (pitch c8_pitch)][Di][Hi][Wi][8];  out fp32 view; Wpacked from
-// layout.pack_weights_tc.  flags bit0: force TD=1 (testing).
+// in: split planes view [N][C8in (pitch from in_ns)][Di][Hi][Wi][8];  out: fp32 view; wpacked from
+// layout.pack_weights_tc.  flags bit0: force TD=1, bit1: no split-K (deterministic), bit2: one
+// work item per CTA (non-persistent; testing).
 int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
                 int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
                 int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
                 cudaStream_t stream) {
-  TTA_REQUIRE(in_hi && in_lo && wpacked && out, "tta_conv_tc: null pointer");
+  const int split = in_dtype == TTA_F16_HI ? 0 : 1;
+  TTA_REQUIRE(in_hi && (in_lo || !split) && wpacked && out, "tta_conv_tc: null pointer");
   const int geom = geom_of(mode, K, stride);
   TTA_REQUIRE(geom != GEOM_NONE, "tta_conv_tc: unsupported geometry mode=%d K=%d stride=%d", mode, K, stride);
-  TTA_REQUIRE(in_dtype == TTA_F16 || in_dtype == TTA_BF16, "tta_conv_tc: bad dtype");
+  TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_tc: bad dtype");
   const long long Vi = (long long)Di * Hi * Wi;
   TTA_REQUIRE(in_ns % (Vi * 8) == 0, "tta_conv_tc: n_stride must be a whole number of channel chunks");
   const int c8_pitch = (int)(in_ns / (Vi * 8));
@@ -438,93 +570,109 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   TcParams P;
   memset(&P, 0, sizeof(P));
   const int cout_pad = C8out * 8;
-  P.ntile = ntile_of(geom, cout_pad);
+  P.ntile = ntile_of(geom, cout_pad, split);
   P.n_ntiles = (cout_pad + P.ntile - 1) / P.ntile;
   P.ncblk = (C8in + 1) / 2;
   P.c8_view = c8_pitch;
+  P.c8in = C8in;
+  P.single_chunk = C8in == 1;
   P.out_mul = geom == GEOM_T2 ? 2 : 1;
   P.d_mul = geom == GEOM_S2 ? 2 : 1;
   P.Do = Do; P.Ho = Ho; P.Wo = Wo; P.C8out = C8out; P.accumulate = accumulate;
-  P.out_ns = out_ns; P.wpacked = (const uint16_t*)wpacked; P.bias = bias; P.out = out;
-  const int fmt = in_dtype == TTA_F16 ? 0 : 1;
-  P.idesc = (1 << 4) | (fmt << 7) | (fmt << 10) | ((P.ntile >> 3) << 17) | ((128 >> 4) << 24);
+  P.out_ns = out_ns; P.wpacked = (const uint8_t*)wpacked; P.bias = bias; P.out = out;
+  const int fmt = in_dtype == TTA_BF16 ? 1 : 0;
+  const int idesc0 = (1 << 4) | (fmt << 7) | (fmt << 10) | ((128 >> 4) << 24);
+  P.idesc_n = idesc0 | ((P.ntile >> 3) << 17);
+  P.idesc_2n = idesc0 | (((2 * P.ntile) >> 3) << 17);
 
-  // tile space
   int Td, Th, Tw;  // extents of the tile space
   if (geom == GEOM_T2) { Td = Di; Th = Hi; Tw = Wi; } else { Td = Do; Th = Ho; Tw = Wo; }
-  // ---- shape the CTA: TD d-planes per CTA (B-operand reuse), pipeline depth, CTAs per SM.
-  // Two co-resident CTAs per SM let one CTA's epilogue overlap the other's main loop, so a
-  // configuration with >= 2 stages at occupancy 2 is preferred over a deeper single-CTA pipeline.
+  int hx, wx;      // halo extents of the single-box geometries
+  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else { hx = 18; wx = 10; }
+  const int gmax = tta_conv_tc_gmax(mode, K, stride);
+  P.ngroups = tta_conv_tc_ngroups(mode, K, stride);
+  const int acc_cols = split ? 2 * P.ntile : P.ntile;
+  P.b_entry_bytes = 2 * acc_cols * 16;  // [kchunk 2][hi NT (| lo NT) rows][16 B]
+  P.b_blob_bytes = gmax * P.b_entry_bytes;
+
+  // ---- shape the work item: TD d-planes (B-operand reuse), TMEM double buffering, pipeline depth.
+  // TMEM columns: nbuf * nacc * 2*NT <= 512.
+  const bool conv_like = geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1;
   int td_max = 1;
-  if (geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1) {
-    td_max = 512 / P.ntile;
+  if (conv_like) {
+    td_max = 512 / acc_cols;
     if (td_max > 4) td_max = 4;
     if (td_max > Td) td_max = Td;
+    if (td_max < 1) td_max = 1;
     if (flags & 1) td_max = 1;
   }
-  int hx, wx;  // halo extents for the single-box geometries
-  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else { hx = 18; wx = 10; }
-  P.gmax = tta_conv_tc_gmax(mode, K, stride);
-  P.ngroups = tta_conv_tc_ngroups(mode, K, stride);
-  P.b_bytes = P.gmax * 2 * P.ntile * 16;
-  auto stage_bytes_of = [&](int td_) {
-    int a_bytes;
-    if (geom == GEOM_S2) a_bytes = 18048;  // 4096 + 4608 + 4352 + 4992 (128-aligned parity sub-tiles)
-    else a_bytes = round128(hx * wx * td_ * 32);
-    return round128(2 * a_bytes + 2 * P.b_bytes);
-  };
-  const int total_it_full = P.ncblk * P.ngroups;
-  int td = 1, occ = 1;
-  bool found = false;
-  for (int o = 2; o >= 1 && !found; --o) {
-    const int budget = (227 * 1024) / o - 2048;
-    for (int t = td_max; t >= 1; --t) {
-      if (o == 2 && 2 * (geom == GEOM_T2 ? 8 : t) * P.ntile > 512) continue;  // TMEM columns for 2 CTAs
-      const int ns = budget / stage_bytes_of(t);
-      if (ns >= 2 || (ns >= 1 && total_it_full == 1)) { td = t; occ = o; found = true; break; }
+  auto a_plane_of = [&](int td_) { return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * 16); };
+  const int a_planes = split ? 2 : 1;
+  auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + P.b_blob_bytes); };
+  const int smem_budget = 227 * 1024 - 4096;
+  int td = td_max;
+  while (td > 1 && smem_budget / stage_bytes_of(td) < 2) --td;
+  int nacc = geom == GEOM_T2 ? 8 : td;
+  int nbuf = (2 * nacc * acc_cols <= 512) ? 2 : 1;
+  {
+    // many work items: trade TD for the second accumulator buffer (epilogue/main-loop overlap)
+    const long long tiles_now = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td - 1) / td);
+    if (nbuf == 1 && conv_like && td > 1 && tiles_now * N * P.n_ntiles > 2LL * num_sms()) {
+      const int t2 = td / 2;
+      if (2 * t2 * acc_cols <= 512) { td = t2; nacc = td; nbuf = 2; }
     }
   }
-  TTA_REQUIRE(found, "tta_conv_tc: stage of %d bytes does not fit shared memory", stage_bytes_of(1));
-  {
-    const int budget = (227 * 1024) / occ - 2048;
-    P.stage_bytes = stage_bytes_of(td);
-    P.a_plane_bytes = geom == GEOM_S2 ? 18048 : round128(hx * wx * td * 32);
-    P.nstages = budget / P.stage_bytes;
-    if (P.nstages > 4) P.nstages = 4;
-    if (P.nstages > total_it_full) P.nstages = total_it_full;
-  }
-  P.td = td;
-  P.nacc = geom == GEOM_T2 ? 8 : td;
+  P.td = td; P.nacc = nacc; P.nbuf = nbuf;
+  P.a_plane_bytes = a_plane_of(td);
+  P.stage_bytes = stage_bytes_of(td);
+  P.b_off = a_planes * P.a_plane_bytes;
+  P.lbo16[0] = round128(hx * wx * td * 16) / 16;
+  P.nstages = smem_budget / P.stage_bytes;
+  TTA_REQUIRE(P.nstages >= 1, "tta_conv_tc: stage of %d bytes does not fit shared memory", P.stage_bytes);
+  if (P.nstages > kMaxStages) P.nstages = kMaxStages;
   int cols = 32;
-  while (cols < P.nacc * P.ntile) cols *= 2;
-  TTA_REQUIRE(cols <= 512, "tta_conv_tc: %d accumulator columns exceed TMEM", P.nacc * P.ntile);
+  while (cols < nbuf * nacc * acc_cols) cols *= 2;
+  TTA_REQUIRE(cols <= 512, "tta_conv_tc: %d accumulator columns exceed TMEM", nbuf * nacc * acc_cols);
   P.tmem_cols = cols;
   P.tiles_w = (Tw + 7) / 8; P.tiles_h = (Th + 15) / 16; P.tiles_d = (Td + td - 1) / td;
-  // ---- split-K over channel blocks when the tile grid cannot fill the 148 SMs
+
+  // ---- split-K over channel blocks when the tile grid cannot fill the SMs
   {
-    const long long ctas = (long long)P.tiles_w * P.tiles_h * P.tiles_d * P.n_ntiles * N;
+    const long long items = (long long)P.tiles_w * P.tiles_h * P.tiles_d * P.n_ntiles * N;
     int ks = 1;
-    if (!(flags & 2) && ctas < 148 && P.ncblk >= 4) {
-      ks = (int)((2 * 148 + ctas - 1) / ctas);
+    if (!(flags & 2) && items < num_sms() && P.ncblk >= 4) {
+      ks = (int)((num_sms() + items - 1) / items);
       if (ks > P.ncblk / 2) ks = P.ncblk / 2;
       if (ks < 1) ks = 1;
     }
     P.cb_per_split = (P.ncblk + ks - 1) / ks;
     P.ksplit = (P.ncblk + P.cb_per_split - 1) / P.cb_per_split;
+    P.work_items = (int)(items * P.ksplit);
   }
 
-  // ---- tensor maps
-  auto encode = [&](CUtensorMap* m, const uint16_t* base, int par_h, int par_w, int s, int bw, int bh, int bd) -> bool {
+  // ---- tensor maps (one k-chunk = 8 channels per TMA box; zero padding = OOB fill)
+  // merged (n, chunk) extent ends at the LAST chunk of this view: chunks past it (odd C8in, or the
+  // neighbouring slice of a concat buffer) are out of bounds -> zero filled, never read.
+  const cuuint64_t nc_extent = (cuuint64_t)((long long)(N - 1) * c8_pitch + C8in);
+  const cuuint32_t es5[5] = {1, 1, 1, 1, 1};
+  // stride-2 convs: 5-D map over one (h, w) parity class, 16 B inner box (8 channels of one voxel)
+  auto encode_par = [&](CUtensorMap* m, const uint16_t* base, int par_h, int par_w, int bw, int bh) -> bool {
     const uint16_t* ptr = base + ((long long)par_h * Wi + par_w) * 8;
-    // merged (n, chunk) extent ends at the LAST chunk of this view: chunks past it (odd C8in, or
-    // the neighbouring slice of a concat buffer's tail) are out of bounds -> zero filled, never read
-    cuuint64_t gdim[5] = {8, (cuuint64_t)((Wi - par_w + s - 1) / s), (cuuint64_t)((Hi - par_h + s - 1) / s),
-                          (cuuint64_t)Di, (cuuint64_t)((long long)(N - 1) * c8_pitch + C8in)};
-    cuuint64_t gstr[4] = {(cuuint64_t)16 * s, (cuuint64_t)16 * Wi * s, (cuuint64_t)16 * Wi * Hi,
-                          (cuuint64_t)16 * Vi};
-    cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 2};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, (void*)ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t gdim[5] = {8, (cuuint64_t)((Wi - par_w + 1) / 2), (cuuint64_t)((Hi - par_h + 1) / 2), (cuuint64_t)Di,
+                          nc_extent};
+    cuuint64_t gstr[4] = {32, (cuuint64_t)32 * Wi, (cuuint64_t)16 * Wi * Hi, (cuuint64_t)16 * Vi};
+    cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, (void*)ptr, gdim, gstr, box, es5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  // everything else: 4-D map whose inner dimension is a whole w-row (W*8 contiguous 16-bit values),
+  // so a halo row of wx voxels is ONE wx*16-byte TMA row instead of wx 16-byte rows
+  auto encode_row = [&](CUtensorMap* m, const uint16_t* base, int bw, int bh, int bd) -> bool {
+    cuuint64_t gdim[4] = {(cuuint64_t)Wi * 8, (cuuint64_t)Hi, (cuuint64_t)Di, nc_extent};
+    cuuint64_t gstr[3] = {(cuuint64_t)16 * Wi, (cuuint64_t)16 * Wi * Hi, (cuuint64_t)16 * Vi};
+    cuuint32_t box[4] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, (void*)base, gdim, gstr, box, es5, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
@@ -533,45 +681,40 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
         const int m = ph * 2 + pw;
-        ok = ok && encode(&P.amap[m * 2 + 0], in_hi, ph, pw, 2, pw ? 9 : 8, ph ? 17 : 16, 1);
-        ok = ok && encode(&P.amap[m * 2 + 1], in_lo, ph, pw, 2, pw ? 9 : 8, ph ? 17 : 16, 1);
+        ok = ok && encode_par(&P.amap[m * 2 + 0], in_hi, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
+        if (split) ok = ok && encode_par(&P.amap[m * 2 + 1], in_lo, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
       }
   } else {
-    ok = ok && encode(&P.amap[0], in_hi, 0, 0, 1, wx, hx, geom == GEOM_T2 ? 1 : td);
-    ok = ok && encode(&P.amap[1], in_lo, 0, 0, 1, wx, hx, geom == GEOM_T2 ? 1 : td);
+    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? 1 : td);
+    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, geom == GEOM_T2 ? 1 : td);
   }
   TTA_REQUIRE(ok, "tta_conv_tc: cuTensorMapEncodeTiled failed (dims %d,%d,%d C8 pitch %d)", Di, Hi, Wi, c8_pitch);
 
-  // ---- group tables
-  const int b_entry_tx = 2 * P.ntile * 16;
+  // ---- group tables (A loads; the MMA schedule is compile-time in issue_group<GEOM>)
   if (geom == GEOM_S1 || geom == GEOM_S1T) {
-    P.plane_stride16 = 18 * 10;
     for (int kd = 0; kd < 3; ++kd) {
       TcGroup& G = P.grp[kd];
       G.nloads = 1; G.nmma = 9;
-      G.ld[0] = {0, -1, -1, geom == GEOM_S1 ? kd - 1 : 1 - kd, 0, 18 * 10 * td * 32};
-      for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) {
-          const int rh = geom == GEOM_S1 ? kh : 2 - kh, rw = geom == GEOM_S1 ? kw : 2 - kw;
-          G.mma[kh * 3 + kw] = {(short)(rh * 10 + rw), 10, (short)(td * 18 * 10), (short)(kh * 3 + kw), 0, 0};
-        }
-      G.tx_bytes = 2 * G.ld[0].bytes + 2 * G.nmma * b_entry_tx;
+      G.ld[0] = {0, -1, -1, geom == GEOM_S1 ? kd - 1 : 1 - kd, 0, 18 * 10 * td * 16, P.lbo16[0] * 16, 0};
+      G.tx_bytes = 2 * G.ld[0].bytes;
     }
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
   } else if (geom == GEOM_K1) {
-    P.plane_stride16 = 16 * 8;
     TcGroup& G = P.grp[0];
     G.nloads = 1; G.nmma = 1;
-    G.ld[0] = {0, 0, 0, 0, 0, 16 * 8 * td * 32};
-    G.mma[0] = {0, 8, (short)(td * 16 * 8), 0, 0, 0};
-    G.tx_bytes = 2 * G.ld[0].bytes + 2 * b_entry_tx;
+    G.ld[0] = {0, 0, 0, 0, 0, 16 * 8 * td * 16, P.lbo16[0] * 16, 0};
+    G.tx_bytes = 2 * G.ld[0].bytes;
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
   } else if (geom == GEOM_S2) {
-    P.plane_stride16 = 0;
     int off[4], o = 0;
     const int hxs[2] = {16, 17}, wxs[2] = {8, 9};
     for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw) { off[ph * 2 + pw] = o; o += round128(hxs[ph] * wxs[pw] * 32); }
+      for (int pw = 0; pw < 2; ++pw) {
+        const int m = ph * 2 + pw;
+        P.lbo16[m] = round128(hxs[ph] * wxs[pw] * 16) / 16;
+        off[m] = o;
+        o += 2 * P.lbo16[m] * 16;
+      }
     for (int kd = 0; kd < 3; ++kd) {
       TcGroup& G = P.grp[kd];
       G.nloads = 4; G.nmma = 9;
@@ -579,39 +722,19 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
           const int m = ph * 2 + pw;
-          G.ld[m] = {m, pw ? -1 : 0, ph ? -1 : 0, kd - 1, off[m], hxs[ph] * wxs[pw] * 32};
+          G.ld[m] = {m, pw ? -1 : 0, ph ? -1 : 0, kd - 1, off[m], hxs[ph] * wxs[pw] * 16, P.lbo16[m] * 16, 0};
           abytes += G.ld[m].bytes;
         }
-      for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ph = kh != 1, pw = kw != 1, rh = kh == 2, rw = kw == 2, m = ph * 2 + pw;
-          G.mma[kh * 3 + kw] = {(short)(off[m] / 16 + rh * wxs[pw] + rw), (short)wxs[pw],
-                                (short)(hxs[ph] * wxs[pw]), (short)(kh * 3 + kw), 0, 0};
-        }
-      G.tx_bytes = 2 * abytes + 2 * G.nmma * b_entry_tx;
+      G.tx_bytes = 2 * abytes;
     }
     P.acc_pd[0] = 0;
   } else {  // GEOM_T2
-    P.plane_stride16 = 0;
     for (int jd = 0; jd < 2; ++jd) {
       TcGroup& G = P.grp[jd];
       G.nloads = 1;
-      G.ld[0] = {0, 0, 0, jd, 0, 17 * 9 * 32};
-      int e = 0;
-      const int kds0[2] = {1, 2}, kds1[1] = {0};
-      const int nk = jd == 0 ? 2 : 1;
-      for (int ki = 0; ki < nk; ++ki) {
-        const int kd = jd == 0 ? kds0[ki] : kds1[ki];
-        const int qd = kd != 1;
-        for (int kh = 0; kh < 3; ++kh)
-          for (int kw = 0; kw < 3; ++kw) {
-            const int qh = kh != 1, jh = kh == 0, qw = kw != 1, jw = kw == 0;
-            G.mma[e] = {(short)(jh * 9 + jw), 9, (short)(17 * 9), (short)e, (short)(qd * 4 + qh * 2 + qw), 0};
-            ++e;
-          }
-      }
-      G.nmma = e;
-      G.tx_bytes = 2 * G.ld[0].bytes + 2 * G.nmma * b_entry_tx;
+      G.nmma = jd == 0 ? 18 : 9;
+      G.ld[0] = {0, 0, 0, jd, 0, 17 * 9 * 16, P.lbo16[0] * 16, 0};
+      G.tx_bytes = 2 * G.ld[0].bytes;
     }
     for (int a = 0; a < 8; ++a) {
       P.acc_pd[a] = 0; P.acc_qd[a] = (signed char)(a >> 2); P.acc_qh[a] = (signed char)((a >> 1) & 1);
@@ -627,28 +750,44 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
       if (cudaMemsetAsync(out + nn * out_ns, 0, (size_t)C8out * Vo * 8 * sizeof(float), stream) != cudaSuccess)
         return tta_check_launch("tta_conv_tc(memset)");
   }
-  const dim3 grid(P.tiles_w * P.tiles_h * P.tiles_d, P.n_ntiles * P.ksplit, N);
-#define TTA_TC_LAUNCH(G)                                                                                   \
+  int grid_x = P.work_items < num_sms() ? P.work_items : num_sms();
+  if (flags & 4) grid_x = P.work_items;
+  const dim3 grid(grid_x, 1, 1);
+#define TTA_TC_LAUNCH_S(G, T, S)                                                                              \
   do {                                                                                                     \
     static bool configured = false;                                                                        \
     if (!configured) {                                                                                     \
       cudaFuncAttributes fa;                                                                               \
-      if (cudaFuncGetAttributes(&fa, conv_tc_kernel<G>) != cudaSuccess) return tta_check_launch("tta_conv_tc(attrs)"); \
+      if (cudaFuncGetAttributes(&fa, conv_tc_kernel<G, T, S>) != cudaSuccess)                                 \
+        return tta_check_launch("tta_conv_tc(attrs)");                                                     \
       const int max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;                                            \
-      if (cudaFuncSetAttribute(conv_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != \
-          cudaSuccess)                                                                                     \
+      if (cudaFuncSetAttribute(conv_tc_kernel<G, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                               max_dyn) != cudaSuccess)                                                    \
         return tta_check_launch("tta_conv_tc(cudaFuncSetAttribute)");                                      \
       configured = true;                                                                                   \
     }                                                                                                      \
-    conv_tc_kernel<G><<<grid, kTcThreads, smem, stream>>>(P);                                              \
+    conv_tc_kernel<G, T, S><<<grid, kTcThreads, smem, stream>>>(P);                                           \
   } while (0)
-  switch (geom) {
-    case GEOM_S1: TTA_TC_LAUNCH(GEOM_S1); break;
-    case GEOM_S1T: TTA_TC_LAUNCH(GEOM_S1T); break;
-    case GEOM_K1: TTA_TC_LAUNCH(GEOM_K1); break;
-    case GEOM_S2: TTA_TC_LAUNCH(GEOM_S2); break;
-    default: TTA_TC_LAUNCH(GEOM_T2); break;
+#define TTA_TC_LAUNCH(G, T)                                                                                \
+  do {                                                                                                     \
+    if (split) TTA_TC_LAUNCH_S(G, T, 1); else TTA_TC_LAUNCH_S(G, T, 0);                                    \
+  } while (0)
+#define TTA_TC_LAUNCH_TD(G)                                                                                \
+  switch (td) {                                                                                            \
+    case 1: TTA_TC_LAUNCH(G, 1); break;                                                                    \
+    case 2: TTA_TC_LAUNCH(G, 2); break;                                                                    \
+    case 3: TTA_TC_LAUNCH(G, 3); break;                                                                    \
+    default: TTA_TC_LAUNCH(G, 4); break;                                                                   \
   }
+  switch (geom) {
+    case GEOM_S1: TTA_TC_LAUNCH_TD(GEOM_S1); break;
+    case GEOM_S1T: TTA_TC_LAUNCH_TD(GEOM_S1T); break;
+    case GEOM_K1: TTA_TC_LAUNCH_TD(GEOM_K1); break;
+    case GEOM_S2: TTA_TC_LAUNCH(GEOM_S2, 1); break;
+    default: TTA_TC_LAUNCH(GEOM_T2, 1); break;
+  }
+#undef TTA_TC_LAUNCH_TD
+#undef TTA_TC_LAUNCH_S
 #undef TTA_TC_LAUNCH
   return tta_check_launch("tta_conv_tc");
 }
@@ -656,10 +795,11 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout) {
   const int geom = geom_of(mode, K, stride);
   if (geom == GEOM_NONE) return 0;
-  const int nt = ntile_of(geom, (cout + 7) / 8 * 8);
+  const int nt = ntile_of(geom, (cout + 7) / 8 * 8, 1);
   const int nnt = ((cout + 7) / 8 * 8 + nt - 1) / nt;
   const int ncb = (cin + 15) / 16;
-  return (long long)nnt * ncb * tta_conv_tc_ngroups(mode, K, stride) * 2 * tta_conv_tc_gmax(mode, K, stride) * 2 * nt * 16;
+  return (long long)nnt * ncb * tta_conv_tc_ngroups(mode, K, stride) * tta_conv_tc_gmax(mode, K, stride) * 2 * 2 *
+         nt * 16;
 }
 
 }  // extern "C"

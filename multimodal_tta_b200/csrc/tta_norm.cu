@@ -384,12 +384,17 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
                        int relu, int batch_mode, const float* sums, uint16_t* dy_hi,
                        uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi, uint16_t* aux_lo,
                        long long aux_ns, int out_dtype, cudaStream_t stream) {
-  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dy_hi && dy_lo,
+  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dy_hi && (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_apply: null pointer");
   const float inv_m = (float)(1.0 / ((double)V * (batch_mode ? N : 1)));
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
+  TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_norm_bwd_apply: bad dtype");
   if (out_dtype == TTA_F16)
     norm_bwd_apply_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(
+        g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
+  else if (out_dtype == TTA_F16_HI)
+    norm_bwd_apply_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
   else
@@ -402,10 +407,12 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
 int tta_split_f32(const float* g0, long long g0_ns, const float* g1, long long g1_ns, int N, int C8,
                   long long V, uint16_t* hi, uint16_t* lo, long long o_ns, int out_dtype,
                   cudaStream_t stream) {
-  TTA_REQUIRE(g0 && hi && lo, "tta_split_f32: null pointer");
+  TTA_REQUIRE(g0 && hi && (lo || out_dtype == TTA_F16_HI), "tta_split_f32: null pointer");
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
   if (out_dtype == TTA_F16)
     split_f32_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
+  else if (out_dtype == TTA_F16_HI)
+    split_f32_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
   else
     split_f32_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
   return tta_check_launch("tta_split_f32");

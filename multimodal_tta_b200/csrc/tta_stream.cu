@@ -55,14 +55,15 @@ gather_pack_kernel(const float* __restrict__ vol, int C, int Ds, int Hs, int Ws,
 // dlogits = sample_w[n] * inv_count * dH/dz as split bf16 planes for the first dgrad conv.
 //   mode 0: softmax entropy   H = lse(z) - sum_c p_c z_c ;  dH/dz_k = -p_k (z_k - sum_c p_c z_c)
 //   mode 1: Bernoulli entropy H = sum_c softplus(z_c) - p_c z_c ; dH/dz_c = -z_c p_c (1 - p_c)
+template <int ODT>
 __global__ void __launch_bounds__(kThreads)
 head_entropy_kernel(const float* __restrict__ y, long long y_ns, int R, long long V, int mode,
-                    float inv_count, const float* __restrict__ sample_w,
+                    float inv_count, float grad_scale, const float* __restrict__ sample_w,
                     float* __restrict__ logits, uint16_t* __restrict__ dz_hi,
                     uint16_t* __restrict__ dz_lo, long long dz_ns, float* __restrict__ partial) {
   const int n = blockIdx.y;
   const float sw = sample_w ? sample_w[n] : 1.f;
-  const float gs = sw * inv_count;
+  const float gs = sw * inv_count * grad_scale;  // grad_scale: power-of-two loss scale (fp16 backward)
   float hsum = 0.f;
   for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
        v += (long long)gridDim.x * kThreads) {
@@ -109,7 +110,7 @@ head_entropy_kernel(const float* __restrict__ y, long long y_ns, int R, long lon
         if (i < R) g[i] = -(e[i] * invS) * (z[i] - pz) * gs;
     }
     hsum += Hv * sw;
-    if (dz_hi) store_split8<TTA_BF16>(dz_hi, dz_lo, (long long)n * dz_ns + v * 8, g);
+    if (dz_hi) store_split8<ODT>(dz_hi, dz_lo, (long long)n * dz_ns + v * 8, g);
   }
   __shared__ float red[kThreads / 32];
   hsum = warp_sum(hsum);
@@ -272,17 +273,21 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
 int tta_head_entropy_blocks(int N, long long V) { return xblocks(V, N); }
 
 int tta_head_entropy(const float* y, long long y_ns, int N, int R, long long V, int mode,
-                     float inv_count, const float* sample_w, float* logits, uint16_t* dz_hi,
-                     uint16_t* dz_lo, long long dz_ns, float* partial, float* loss,
+                     float inv_count, float grad_scale, int dz_dtype, const float* sample_w, float* logits,
+                     uint16_t* dz_hi, uint16_t* dz_lo, long long dz_ns, float* partial, float* loss,
                      cudaStream_t stream) {
   TTA_REQUIRE(y && partial && loss, "tta_head_entropy: null pointer");
   TTA_REQUIRE(R >= 1 && R <= 8, "tta_head_entropy: R=%d unsupported (1..8 region channels)", R);
   TTA_REQUIRE(mode == 0 || mode == 1, "tta_head_entropy: mode %d", mode);
   TTA_REQUIRE(!(mode == 0 && R < 2), "tta_head_entropy: softmax entropy is degenerate for R=1");
   const int xb = xblocks(V, N);
-  head_entropy_kernel<<<dim3(xb, N), kThreads, 0, stream>>>(y, y_ns, R, V, mode, inv_count,
-                                                           sample_w, logits, dz_hi, dz_lo, dz_ns,
-                                                           partial);
+  TTA_REQUIRE(dz_dtype == TTA_BF16 || dz_dtype == TTA_F16_HI, "tta_head_entropy: dz dtype %d", dz_dtype);
+  if (dz_dtype == TTA_BF16)
+    head_entropy_kernel<TTA_BF16><<<dim3(xb, N), kThreads, 0, stream>>>(
+        y, y_ns, R, V, mode, inv_count, grad_scale, sample_w, logits, dz_hi, dz_lo, dz_ns, partial);
+  else
+    head_entropy_kernel<TTA_F16_HI><<<dim3(xb, N), kThreads, 0, stream>>>(
+        y, y_ns, R, V, mode, inv_count, grad_scale, sample_w, logits, dz_hi, dz_lo, dz_ns, partial);
   loss_finalize_kernel<<<1, 32, 0, stream>>>(partial, xb * N, inv_count, loss);
   return tta_check_launch("tta_head_entropy");
 }

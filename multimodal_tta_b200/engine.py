@@ -14,6 +14,7 @@ producers write into channel slices of one buffer.
 from __future__ import annotations
 
 import ctypes
+import math
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -21,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import TTA_BF16, TTA_F16, check
+from ._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
 from .layout import pack_bias, pack_weights_simt, pack_weights_tc, wg_dgrad, wg_forward
 from .unet_b200 import (ConvHolder, ConvolutionH, NormHolder, ResidualUnitH, SkipConnectionH, UNetB200)
 
@@ -88,10 +89,12 @@ class Res:
         self.dy: Optional[torch.Tensor] = None
         self.device = device
 
-    def alloc_dy(self):
+    def alloc_dy(self, planes: int = 2):
         if self.dy is None:
             self.dy = torch.zeros((2, self.N, self.C8, self.D, self.H, self.W, 8), dtype=torch.int16,
-                                  device=self.device)
+                                  device=self.device) if planes == 2 else \
+                torch.zeros((1, self.N, self.C8, self.D, self.H, self.W, 8), dtype=torch.int16,
+                            device=self.device).expand(2, -1, -1, -1, -1, -1, -1)
 
     @property
     def ptr(self) -> int:
@@ -107,7 +110,7 @@ class ConvLayer:
         self.cin, self.cout = holder.cin, holder.cout
         self.packed = {}
 
-    def pack(self, device, want_tc: bool):
+    def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16):
         """(Re)pack weights: fp32 for the CUDA-core kernel, split fp16/bf16 for tcgen05."""
         w = self.h.weight.detach().to(device=device, dtype=torch.float32)
         wf = wg_forward(w, self.h.transposed)
@@ -128,7 +131,7 @@ class ConvLayer:
                 self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16)
             bmode = 1 - self.mode
             if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.cin):
-                self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, TTA_BF16)
+                self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype)
 
 
 class NormLayer:
@@ -177,6 +180,8 @@ class TTAEngine:
         self.gb = self.dgb = self.m = self.v = self.step_dev = None
         self.entropy_mode = 1
         self.adam = dict(lr=1e-3, b1=0.9, b2=0.999, eps=1e-8)
+        self.bwd_dtype = TTA_F16_HI if model.bwd_precision == "fp16" else TTA_BF16
+        self.last_inv_scale = 1.0
         self._collect()
 
     # ---------------------------------------------------------------- structure
@@ -228,7 +233,7 @@ class TTAEngine:
             self._bind_params()
             want_tc = self.model.conv_backend in ("auto", "tc")
             for cl in self.conv_layers.values():
-                cl.pack(device, want_tc)
+                cl.pack(device, want_tc, self.bwd_dtype)
             self.model._params_dirty = False
 
     def _bind_params(self):
@@ -259,7 +264,7 @@ class TTAEngine:
         P = self.P
         gs = [self.dgb[nl.off: nl.off + nl.C] for nl in self.norm_layers]
         bs = [self.dgb[P + nl.off: P + nl.off + nl.C] for nl in self.norm_layers]
-        return torch.cat(gs + bs)
+        return torch.cat(gs + bs) * self.last_inv_scale
 
     def reset_optimizer(self):
         self.m.zero_(); self.v.zero_(); self.step_dev.zero_()
@@ -432,7 +437,11 @@ class TTAEngine:
         if not isinstance(final, Res):
             raise ValueError("unet_b200: the top-level up layer must end in a conv (MONAI UNet does)")
         plan.ws = torch.zeros(max_ws[0], dtype=torch.float32, device=dev)
-        final.alloc_dy()
+        bdt = self.bwd_dtype
+        nplanes = 1 if bdt == TTA_F16_HI else 2
+        final.alloc_dy(nplanes)
+        # power-of-two loss scale keeps the fp16 gradient planes in range; Adam divides it out
+        plan.loss_scale = float(2 ** math.ceil(math.log2(4.0 * N * final.V))) if bdt == TTA_F16_HI else 1.0
         nblk = lib.tta_head_entropy_blocks(N, final.V)
         plan.partial = torch.zeros(nblk * N, dtype=torch.float32, device=dev)
         plan.sample_w = torch.ones(N, dtype=torch.float32, device=dev)
@@ -442,7 +451,7 @@ class TTAEngine:
             def run():
                 check(lib.tta_head_entropy(
                     final.ptr, final.ns, N, R, final.V, self.entropy_mode, float(plan.inv_count),
-                    plan.sample_w.data_ptr(), plan.logits.data_ptr(),
+                    float(plan.loss_scale), bdt, plan.sample_w.data_ptr(), plan.logits.data_ptr(),
                     final.dy[0].data_ptr() if train else 0, final.dy[1].data_ptr() if train else 0, final.ns,
                     plan.partial.data_ptr(), plan.loss.data_ptr(), _stream()), "head_entropy")
             return run
@@ -462,9 +471,9 @@ class TTAEngine:
                     raise RuntimeError("partial gradient accumulation state")
                 acc = bool(done)
                 par.written |= chunks
-                y.alloc_dy()
+                y.alloc_dy(nplanes)
                 plan.bwd.append(self._conv_call(
-                    plan, cl, True, (y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns), TTA_BF16, N, y.C8,
+                    plan, cl, True, (y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns), bdt, N, y.C8,
                     (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc))
             else:
                 rec = op[1]
@@ -485,7 +494,7 @@ class TTAEngine:
                 res = rec["residual"]
                 aux = None
                 if isinstance(res, Res) and self._producer_input_needs_grad(ops, res):
-                    res.alloc_dy()
+                    res.alloc_dy(nplanes)
                     aux = res
                 elif isinstance(res, ActView):
                     # identity shortcut: this op's incoming gradient also flows into `res`
@@ -500,12 +509,12 @@ class TTAEngine:
                 do_apply = conv_in_needs or aux is not None
                 bwd_apply_flags.append(do_apply)
                 if do_apply:
-                    y.alloc_dy()
+                    y.alloc_dy(nplanes)
                     ap_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, y.V, rec["mean"].data_ptr(),
                                rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
                                rec["sums"].data_ptr(), y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns,
                                aux.dy[0].data_ptr() if aux else 0, aux.dy[1].data_ptr() if aux else 0,
-                               aux.ns if aux else 0, TTA_BF16)
+                               aux.ns if aux else 0, bdt)
 
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None):
                     check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), _stream()), "norm_bwd_reduce")
@@ -606,6 +615,7 @@ class TTAEngine:
 
     def run_step(self, plan: Plan, adam: bool = True, gscale: float = 1.0):
         """forward + fused head + backward (+ Adam) on whatever is in plan.x."""
+        self.last_inv_scale = 1.0 / plan.loss_scale
         for op in plan.fwd:
             op()
         plan.head_train()
@@ -615,7 +625,10 @@ class TTAEngine:
             self.adam_step(gscale)
 
     def adam_step(self, gscale: float = 1.0):
+        """``gscale`` multiplies the gradient (1/world for the all-reduced sum); the loss scale of
+        the last backward is divided out here as well."""
         a = self.adam
+        gscale = gscale * self.last_inv_scale
         check(self.lib.tta_adam_step(self.gb.data_ptr(), self.dgb.data_ptr(), self.m.data_ptr(),
                                      self.v.data_ptr(), 2 * self.P, a["lr"], a["b1"], a["b2"], a["eps"],
                                      float(gscale), self.step_dev.data_ptr(), _stream()), "adam")

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import TTA_BF16, TTA_F16
+from ._lib import TTA_BF16, TTA_F16, TTA_F16_HI
 
 
 def wg_forward(w: torch.Tensor, transposed: bool) -> torch.Tensor:
@@ -52,8 +52,8 @@ def pack_bias(b: torch.Tensor) -> torch.Tensor:
 
 def split_planes(x: torch.Tensor, dtype_tag: int) -> tuple[torch.Tensor, torch.Tensor]:
     """fp32 -> (hi, lo) 16-bit planes stored as int16, hi = rn16(x), lo = rn16(x - hi)."""
-    dt = torch.float16 if dtype_tag == TTA_F16 else torch.bfloat16
-    if dtype_tag == TTA_F16:
+    dt = torch.bfloat16 if dtype_tag == TTA_BF16 else torch.float16
+    if dtype_tag != TTA_BF16:
         x = x.clamp(-65504.0, 65504.0)
     hi = x.to(dt)
     lo = (x - hi.float()).to(dt)
@@ -61,7 +61,9 @@ def split_planes(x: torch.Tensor, dtype_tag: int) -> tuple[torch.Tensor, torch.T
 
 
 def join_planes(hi: torch.Tensor, lo: torch.Tensor, dtype_tag: int) -> torch.Tensor:
-    dt = torch.float16 if dtype_tag == TTA_F16 else torch.bfloat16
+    dt = torch.bfloat16 if dtype_tag == TTA_BF16 else torch.float16
+    if dtype_tag == TTA_F16_HI:
+        return hi.view(dt).float()
     return hi.view(dt).float() + lo.view(dt).float()
 
 
@@ -98,26 +100,29 @@ def tc_groups(mode: int, K: int, stride: int) -> list[list[int]]:
 
 def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int) -> torch.Tensor:
     """Wg[T][ci][co] -> per-(n_tile, cblk, group) contiguous blobs
-    [ntile][cblk][group][hi|lo][entry][kchunk 2][n_tile rows][8 ci] of 16-bit values.
+    [ntile][cblk][group][entry][kchunk 2][hi NT rows | lo NT rows][8 ci] of 16-bit values.
     A blob is what one pipeline stage of the tcgen05 kernel bulk-copies into shared memory as
-    its B operand (K-major, no swizzle: 8 rows x 16 B core matrices, LBO = n_tile*16 B)."""
+    its B operand (K-major, no swizzle: 8 rows x 16 B core matrices, k-chunk pitch = 2*NT*16 B).
+    Stacking the hi and lo rows lets ONE MMA with N = 2*NT compute A_hi*B_hi and A_hi*B_lo."""
     from . import _lib
     T, ci, co = wg.shape
     lib = _lib.lib()
-    ntile = lib.tta_conv_tc_ntile(mode, K, stride, co)
+    split = dtype_tag != TTA_F16_HI      # TTA_F16_HI: single fp16 plane, B rows are not stacked
+    ntile = lib.tta_conv_tc_ntile(mode, K, stride, co, int(split))
     cip = (ci + 15) // 16 * 16
     cop = (co + ntile - 1) // ntile * ntile
     w = torch.zeros((T, cip, cop), dtype=torch.float32, device=wg.device)
     w[:, :ci, :co] = wg
     hi, lo = split_planes(w, dtype_tag)
+    planes = (hi, lo) if split else (hi,)
     groups = tc_groups(mode, K, stride)
     gmax = max(len(g) for g in groups)
     ncb, nnt = cip // 16, cop // ntile
-    out = torch.zeros((nnt, ncb, len(groups), 2, gmax, 2, ntile, 8), dtype=torch.int16, device=wg.device)
+    out = torch.zeros((nnt, ncb, len(groups), gmax, 2, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
     for gi, taps in enumerate(groups):
         idx = torch.tensor(taps, device=wg.device)
-        for pi, plane in enumerate((hi, lo)):
+        for pi, plane in enumerate(planes):
             sel = plane[idx]                                       # [E][cip][cop]
             sel = sel.reshape(len(taps), ncb, 2, 8, nnt, ntile)    # [E][cb][kc][8][nt][n]
-            out[:, :, gi, pi, : len(taps)] = sel.permute(4, 1, 0, 2, 5, 3)
+            out[:, :, gi, : len(taps), :, pi] = sel.permute(4, 1, 0, 2, 5, 3)   # [nt][cb][E][kc][n][8]
     return out.contiguous()

@@ -148,6 +148,11 @@ class UNetB200(nn.Module):
         self.use_cuda_graph = bool(get_config(cfg, "cuda_graph", True))
         # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
         self.deterministic = bool(get_config(cfg, "deterministic", False))
+        # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
+        # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
+        self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))
+        if self.bwd_precision not in ("fp16", "bf16x2"):
+            raise ValueError("unet_b200: bwd_precision must be 'fp16' or 'bf16x2'")
         k, nru, norm, act, dr = 3, self.num_res_units, self.norm, self.act, self.dropout
 
         def down(cin, cout, stride):

@@ -11,7 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, check
+from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
 from multimodal_tta_b200.layout import (from_chunked, join_planes, pack_bias, pack_weights_tc, split_planes,
                                         to_chunked, wg_dgrad, wg_forward)
 from tests.util import planes_from, rel_l2, stream
@@ -96,6 +96,22 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
                           stream()), "conv_tc dgrad acc")
     torch.cuda.synchronize()
     assert rel_l2(from_chunked(gbuf[:, extra:], cin).cpu(), 2 * g2) < 1e-4
+    # ---- dgrad with ONE fp16 plane (loss-scaled gradients): a single MMA per k-step
+    hhi, _ = split_planes(to_chunked(dy.to(cuda)), TTA_F16_HI)
+    dy16 = from_chunked(hhi.view(torch.float16).float(), cout).cpu()
+    w16 = w.half().float()
+    xr3 = xv.cpu().requires_grad_(True)
+    ref3 = F.conv_transpose3d(xr3, w16, None, stride=s, padding=pad, output_padding=s - 1) if tr else \
+        F.conv3d(xr3, w16, None, stride=s, padding=pad)
+    (g3,) = torch.autograd.grad(ref3, xr3, dy16)
+    wph = pack_weights_tc(wg_dgrad(w.to(cuda), tr), 1 - mode, K, s, TTA_F16_HI)
+    gx3 = torch.zeros((N, c8i, *dims, 8), device=cuda)
+    hhi = hhi.contiguous()
+    check(lib.tta_conv_tc(hhi.data_ptr(), 0, c8o * ref[0, 0].numel() * 8, TTA_F16_HI, N, c8o, *odims,
+                          wph.data_ptr(), 0, gx3.data_ptr(), c8i * Vi * 8, c8i, *dims, 1 - mode, K, s, 0, 0,
+                          stream()), "conv_tc dgrad fp16")
+    torch.cuda.synchronize()
+    assert rel_l2(from_chunked(gx3, cin).cpu(), g3) < 2e-5, rel_l2(from_chunked(gx3, cin).cpu(), g3)
 
 
 def test_conv_tc_reads_concat_slice_view(lib, cuda):

@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, check
+from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
 from multimodal_tta_b200.layout import (from_chunked, join_planes, pack_bias, pack_weights_simt, to_chunked,
                                         wg_dgrad, wg_forward)
 from tests.util import planes_from, rel_l2, stream
@@ -149,13 +149,21 @@ def test_head_entropy(lib, cuda, mode, R):
     dhi = torch.zeros((N, 1, *dims, 8), dtype=torch.int16, device=cuda); dlo = torch.zeros_like(dhi)
     nb = lib.tta_head_entropy_blocks(N, V)
     part = torch.zeros(nb * N, device=cuda); lossd = torch.zeros(1, device=cuda)
-    check(lib.tta_head_entropy(ych.data_ptr(), V * 8, N, R, V, mode, 1.0 / (N * V), 0, logits.data_ptr(),
-                               dhi.data_ptr(), dlo.data_ptr(), V * 8, part.data_ptr(), lossd.data_ptr(), stream()))
+    check(lib.tta_head_entropy(ych.data_ptr(), V * 8, N, R, V, mode, 1.0 / (N * V), 1.0, TTA_BF16, 0,
+                               logits.data_ptr(), dhi.data_ptr(), dlo.data_ptr(), V * 8, part.data_ptr(),
+                               lossd.data_ptr(), stream()))
     assert torch.equal(logits.cpu(), z)               # pure layout change: bit exact
     assert abs(float(lossd) - float(loss.detach())) < 1e-6 * max(1.0, abs(float(loss.detach())))
     dz = from_chunked(join_planes(dhi, dlo, TTA_BF16), R).cpu()
     assert rel_l2(dz, zr.grad) < 2e-5                 # bf16x2 storage
     assert float(join_planes(dhi, dlo, TTA_BF16)[..., R:].abs().max()) == 0.0 if R < 8 else True
+    # loss-scaled single-plane fp16 gradient (the default backward operand format)
+    S = 2.0 ** 12
+    check(lib.tta_head_entropy(ych.data_ptr(), V * 8, N, R, V, mode, 1.0 / (N * V), S, TTA_F16_HI, 0,
+                               logits.data_ptr(), dhi.data_ptr(), 0, V * 8, part.data_ptr(), lossd.data_ptr(),
+                               stream()))
+    dz16 = from_chunked(join_planes(dhi, dlo, TTA_F16_HI), R).cpu() / S
+    assert rel_l2(dz16, zr.grad) < 6e-4              # 11-bit mantissa
 
 
 def test_adam_matches_torch(lib, cuda):
