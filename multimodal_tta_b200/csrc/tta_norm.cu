@@ -35,6 +35,30 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* __re
   }
 }
 
+// ---------------------------------------------------------------- fused finalize (consumer prologue)
+// Sums the 16 per-block partial values of chunk `chunk` over splits (and over samples n0..n1)
+// in fp64 with all 256 threads; result in tot[16] (shared).  Deterministic order.
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int C8, int chunk,
+                                                int splits, int n0, int n1, double (&tot)[16]) {
+  __shared__ double red[16][17];
+  const int v = threadIdx.x & 15, j = threadIdx.x >> 4;  // 16 values x 16 split lanes
+  double a = 0.0;
+  for (int nn = n0; nn < n1; ++nn) {
+    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
+    for (int sp = j; sp < splits; sp += 16) a += (double)p[sp * 16 + v];
+  }
+  red[v][j] = a;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) t += red[i][jj];
+    tot[i] = t;
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------- forward statistics
 // partial[((n*C8 + chunk)*splits + split)*16 + {0..7: sum, 8..15: sumsq}]
 __global__ void __launch_bounds__(kThreads)
@@ -96,14 +120,41 @@ norm_apply_kernel(const float* __restrict__ y, long long y_ns, int C8, long long
                   const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                   const float* __restrict__ res_f32, const uint16_t* __restrict__ res_hi,
                   const uint16_t* __restrict__ res_lo, long long res_ns,
-                  uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, long long out_ns) {
+                  uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, long long out_ns,
+                  const float* __restrict__ partial, int splits, int N, int batch_mode, float eps,
+                  float* __restrict__ mean_w, float* __restrict__ rstd_w) {
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
+  if (partial != nullptr) {
+    // statistics finalize fused here: every block reduces the per-block partial sums itself
+    double tot[16];
+    reduce_partials(partial, C8, chunk, splits, batch_mode ? 0 : n, batch_mode ? N : n + 1, tot);
+    const double M = (double)V * (batch_mode ? N : 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double m = tot[i] / M;
+      double var = tot[8 + i] / M - m * m;
+      if (var < 0.0) var = 0.0;
+      mu[i] = (float)m;
+      rs[i] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // keep them for the backward pass
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        mean_w[n * C + chunk * 8 + i] = mu[i];
+        rstd_w[n * C + chunk * 8 + i] = rs[i];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = mean[n * C + chunk * 8 + i];
+      rs[i] = rstd[n * C + chunk * 8 + i];
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    mu[i] = mean[n * C + chunk * 8 + i];
-    rs[i] = rstd[n * C + chunk * 8 + i];
     ga[i] = gamma[chunk * 8 + i];
     be[i] = beta[chunk * 8 + i];
   }
@@ -233,7 +284,9 @@ norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float
                       const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                       const float* __restrict__ sums, float inv_m, uint16_t* __restrict__ dy_hi,
                       uint16_t* __restrict__ dy_lo, long long dy_ns, uint16_t* __restrict__ aux_hi,
-                      uint16_t* __restrict__ aux_lo, long long aux_ns) {
+                      uint16_t* __restrict__ aux_lo, long long aux_ns, const float* __restrict__ partial,
+                      int splits, int N, int batch_mode, int Creal, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta) {
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
@@ -244,8 +297,36 @@ norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float
     rs[i] = rstd[n * C + c];
     ga[i] = gamma[c];
     be[i] = beta[c];
-    m1[i] = sums[(n * C + c) * 2 + 0] * inv_m;
-    m2[i] = sums[(n * C + c) * 2 + 1] * inv_m;
+  }
+  if (partial != nullptr) {
+    // reduction finalize fused here (no separate kernel): S1 = sum dz, S2 = sum dz*xhat
+    double tot[16];
+    reduce_partials(partial, C8, chunk, splits, batch_mode ? 0 : n, batch_mode ? N : n + 1, tot);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      m1[i] = (float)tot[i] * inv_m;
+      m2[i] = (float)tot[8 + i] * inv_m;
+    }
+    if (blockIdx.x == 0 && n == 0) {  // affine gradients: sums over ALL samples
+      if (!batch_mode && N > 1) reduce_partials(partial, C8, chunk, splits, 0, N, tot);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = chunk * 8 + i;
+          if (c < Creal) {
+            dbeta[c] = (float)tot[i];
+            dgamma[c] = (float)tot[8 + i];
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = chunk * 8 + i;
+      m1[i] = sums[(n * C + c) * 2 + 0] * inv_m;
+      m2[i] = sums[(n * C + c) * 2 + 1] * inv_m;
+    }
   }
   const long long slab = (long long)chunk * V * 8;
   const float* yb = y + (long long)n * y_ns + slab;
@@ -327,16 +408,21 @@ long long tta_norm_workspace_floats(int N, int C8, long long V) {
   return (long long)N * C8 * pick_splits(N, C8, V) * 16;
 }
 
+// finalize = 0: only the per-block partial sums are produced; tta_norm_apply(partial = workspace)
+// then finalizes them in its prologue (one launch less per layer).
 int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, int batch_mode,
-                   float eps, float* mean, float* rstd, float* workspace, cudaStream_t stream) {
-  TTA_REQUIRE(y && mean && rstd && workspace, "tta_norm_stats: null pointer");
+                   float eps, float* mean, float* rstd, float* workspace, int finalize,
+                   cudaStream_t stream) {
+  TTA_REQUIRE(y && workspace && (!finalize || (mean && rstd)), "tta_norm_stats: null pointer");
   TTA_REQUIRE(N > 0 && C8 > 0 && V > 0, "tta_norm_stats: empty shape N=%d C8=%d V=%lld", N, C8, V);
   const int splits = pick_splits(N, C8, V);
   norm_stats_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(y, y_ns, C8, V, splits,
                                                                          workspace);
-  const int tot = N * C8 * 8;
-  norm_stats_finalize_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(workspace, N, C8, splits, V,
-                                                                    batch_mode, eps, mean, rstd);
+  if (finalize) {
+    const int tot = N * C8 * 8;
+    norm_stats_finalize_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(workspace, N, C8, splits, V,
+                                                                      batch_mode, eps, mean, rstd);
+  }
   return tta_check_launch("tta_norm_stats");
 }
 
@@ -344,15 +430,17 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
                    const float* rstd, const float* gamma, const float* beta, int relu,
                    int res_kind, const void* res_a, const void* res_b, long long res_ns,
                    uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int out_dtype,
-                   cudaStream_t stream) {
+                   const float* partial, int batch_mode, float eps, cudaStream_t stream) {
   TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_apply: null pointer");
+  const int splits = pick_splits(N, C8, V);
   TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_apply: res_kind %d", res_kind);
   TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_apply: bad dtype");
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
 #define LAUNCH(RES, DT)                                                                        \
   norm_apply_kernel<RES, DT><<<grid, kThreads, 0, stream>>>(                                   \
       y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
-      (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns)
+      (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns, partial, splits, N,   \
+      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd))
   if (out_dtype == TTA_F16) {
     if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
   } else {
@@ -366,15 +454,18 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
                         const float* y, long long y_ns, int N, int C8, int Creal, long long V,
                         const float* mean, const float* rstd, const float* gamma,
                         const float* beta, int relu, int batch_mode, float* sums, float* dgamma,
-                        float* dbeta, float* workspace, cudaStream_t stream) {
-  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dgamma && dbeta && workspace,
+                        float* dbeta, float* workspace, int finalize, cudaStream_t stream) {
+  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && workspace &&
+                  (!finalize || (sums && dgamma && dbeta)),
               "tta_norm_bwd_reduce: null pointer");
   const int splits = pick_splits(N, C8, V);
   norm_bwd_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(
       g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace);
-  const int C = C8 * 8;
-  norm_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(workspace, N, C8, Creal, splits,
-                                                             batch_mode, sums, dgamma, dbeta);
+  if (finalize) {
+    const int C = C8 * 8;
+    norm_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(workspace, N, C8, Creal, splits,
+                                                               batch_mode, sums, dgamma, dbeta);
+  }
   return tta_check_launch("tta_norm_bwd_reduce");
 }
 
@@ -383,24 +474,27 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
                        const float* mean, const float* rstd, const float* gamma, const float* beta,
                        int relu, int batch_mode, const float* sums, uint16_t* dy_hi,
                        uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi, uint16_t* aux_lo,
-                       long long aux_ns, int out_dtype, cudaStream_t stream) {
-  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dy_hi && (dy_lo || out_dtype == TTA_F16_HI),
+                       long long aux_ns, int out_dtype, const float* partial, int Creal, float* dgamma,
+                       float* dbeta, cudaStream_t stream) {
+  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && (sums || (partial && dgamma && dbeta)) && dy_hi &&
+                  (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_apply: null pointer");
+  const int splits = pick_splits(N, C8, V);
   const float inv_m = (float)(1.0 / ((double)V * (batch_mode ? N : 1)));
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
   TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_norm_bwd_apply: bad dtype");
   if (out_dtype == TTA_F16)
     norm_bwd_apply_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
-        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial, splits, N, batch_mode, Creal, dgamma, dbeta);
   else if (out_dtype == TTA_F16_HI)
     norm_bwd_apply_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
-        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial, splits, N, batch_mode, Creal, dgamma, dbeta);
   else
     norm_bwd_apply_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
-        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns);
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial, splits, N, batch_mode, Creal, dgamma, dbeta);
   return tta_check_launch("tta_norm_bwd_apply");
 }
 

@@ -106,28 +106,51 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     bp = torch.zeros(C8 * 8, device=cuda); bp[:C] = beta.to(cuda)
     ns = C8 * V * 8
     check(lib.tta_norm_stats(ych.data_ptr(), ns, N, C8, V, batch_mode, 1e-5, mean.data_ptr(), rstd.data_ptr(),
-                             ws.data_ptr(), stream()))
+                             ws.data_ptr(), 1, stream()))
     rch = to_chunked(resid.to(cuda))
     ohi = torch.zeros((N, C8, *dims, 8), dtype=torch.int16, device=cuda); olo = torch.zeros_like(ohi)
     check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
                              bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi.data_ptr(), olo.data_ptr(), ns,
-                             TTA_F16, stream()))
+                             TTA_F16, 0, batch_mode, 1e-5, stream()))
     got = from_chunked(join_planes(ohi, olo, TTA_F16), C).cpu()
     assert (got - a.detach()).abs().max() < 2e-5      # fp16x2 storage (22 bits) + fp32 stats
+    # fused path: partial sums only, finalize inside the apply prologue -> identical planes
+    mean2 = torch.zeros_like(mean); rstd2 = torch.zeros_like(rstd)
+    check(lib.tta_norm_stats(ych.data_ptr(), ns, N, C8, V, batch_mode, 1e-5, 0, 0, ws.data_ptr(), 0, stream()))
+    ohi2 = torch.zeros_like(ohi); olo2 = torch.zeros_like(ohi)
+    check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean2.data_ptr(), rstd2.data_ptr(), gp.data_ptr(),
+                             bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi2.data_ptr(), olo2.data_ptr(), ns,
+                             TTA_F16, ws.data_ptr(), batch_mode, 1e-5, stream()))
+    got2 = from_chunked(join_planes(ohi2, olo2, TTA_F16), C).cpu()
+    assert (got2 - got).abs().max() < 2e-6            # same math, fp64 partial sums in another order
+    assert torch.allclose(mean, mean2, rtol=1e-6, atol=1e-7) and torch.allclose(rstd, rstd2, rtol=1e-6)
     # backward
     gch = to_chunked(g_in.to(cuda))
     sums = torch.zeros(N * C8 * 8 * 2, device=cuda)
     dg = torch.zeros(C8 * 8, device=cuda); db = torch.zeros(C8 * 8, device=cuda)
     check(lib.tta_norm_bwd_reduce(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, C, V, mean.data_ptr(),
                                   rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
-                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), stream()))
+                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), 1, stream()))
     assert rel_l2(dg[:C].cpu(), gr.grad) < 1e-5
     assert rel_l2(db[:C].cpu(), br.grad) < 1e-5
     dhi = torch.zeros_like(ohi); dlo = torch.zeros_like(ohi); ahi = torch.zeros_like(ohi); alo = torch.zeros_like(ohi)
     check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
                                  rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
                                  dhi.data_ptr(), dlo.data_ptr(), ns, ahi.data_ptr(), alo.data_ptr(), ns, TTA_BF16,
-                                 stream()))
+                                 0, C, 0, 0, stream()))
+    # fused path: finalize of the reductions inside the bwd-apply prologue
+    dg2 = torch.zeros_like(dg); db2 = torch.zeros_like(db)
+    dhi2 = torch.zeros_like(ohi); dlo2 = torch.zeros_like(ohi)
+    check(lib.tta_norm_bwd_reduce(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, C, V, mean.data_ptr(),
+                                  rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, 0, 0, 0,
+                                  ws.data_ptr(), 0, stream()))
+    check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
+                                 rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, 0,
+                                 dhi2.data_ptr(), dlo2.data_ptr(), ns, 0, 0, 0, TTA_BF16, ws.data_ptr(), C,
+                                 dg2.data_ptr(), db2.data_ptr(), stream()))
+    assert torch.allclose(dg, dg2, rtol=1e-6, atol=1e-7) and torch.allclose(db, db2, rtol=1e-6, atol=1e-7)
+    dy2 = from_chunked(join_planes(dhi2, dlo2, TTA_BF16), C).cpu()
+    assert rel_l2(dy2, yr.grad) < 3e-5
     dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu()
     assert rel_l2(dy, yr.grad) < 3e-5                 # bf16x2 storage (~16 bits)
     aux = from_chunked(join_planes(ahi, alo, TTA_BF16), C).cpu()
