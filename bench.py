@@ -222,7 +222,7 @@ def run_product(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16x3/bf16x3 split operands, f32 accumulate" if "tc" in backends else "f32",
+            "dtype": "fp16 hi/lo split operands fwd (3 products), scaled fp16 bwd, f32 accumulate" if "tc" in backends else "f32",
             "data": "synthetic",
             "config": {"workload": "BraTS-shaped 4x128^3 res-unit 3D UNet (in 4, out 3, INSTANCE norm), TENT "
                                    "norm-affine-only adaptation (Bernoulli entropy, Adam lr 1e-3), batch 2 per GPU",

@@ -1,0 +1,150 @@
+/* tta_b200.h -- C ABI of libtta_b200.so: the sm_100a kernels of the test-time-adaptation step.
+ *
+ * This is the drop-in boundary underneath the reference's (pure Python) plugin surface.  The
+ * reference has no FFI of its own; the Python classes that mirror its registry interface
+ * (multimodal_tta_b200/{unet_b200,tent,evaluation,sliding_window}.py) bind these entry points with
+ * ctypes (multimodal_tta_b200/_lib.py) -- INTEGRATION.md shows the binding.  Each declaration
+ * cites the reference code (or the third-party op the reference reaches) it replaces; paths are
+ * relative to the reference repository (zhm1205/Multimodal_TTA).
+ *
+ * Conventions
+ *   - plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless
+ *     the parameter is documented as HOST; the caller owns all buffers; nothing is allocated.
+ *   - every call is asynchronous on `stream` and may be captured into a CUDA graph.
+ *   - return value: 0 = OK, 1 = bad argument, 2 = CUDA error, 3 = unsupported; the message of the
+ *     last failure on the calling thread is returned by tta_last_error().
+ *   - layouts: channel-blocked [N][C8][D][H][W][8], C8 = ceil(C/8), pad
+ *     channels zero.  "f32 view": fp32 tensor in that layout.  "planes view": two 16-bit planes
+ *     hi/lo with x ~= hi + lo.  A view is (pointer, n_stride in ELEMENTS between samples, C8, dims):
+ *     a channel slice of a wider buffer is the same n_stride with an offset pointer.
+ *   - dtype tags of planes: 0 = fp16 hi/lo, 1 = bf16 hi/lo, 2 = one fp16 plane (lo unused, may be
+ *     NULL): loss-scaled gradients in the backward pass.
+ */
+#ifndef TTA_B200_H
+#define TTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tta_stream_t; /* cudaStream_t */
+
+#define TTA_F16 0
+#define TTA_BF16 1
+#define TTA_F16_HI 2
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* tta_last_error(void);
+int tta_abi_version(void);
+int tta_device_sm(void); /* compute capability major*10+minor of the current device, <0 on error */
+
+/* ---- input staging: replaces the H2D'd NCDHW batch of src/core/trainers/seg_trainer.py:107 and
+ * MONAI sliding_window_inference's window slicing + constant pad (not in tree).
+ * vol: fp32 NCDHW [n_vol][C][Ds][Hs][Ws]; win: int32 [NB][4] = (volume, d0, h0, w0), origins may
+ * lie outside the volume (zero fill); chan_scale: optional fp32 [NB][C] (missing-modality dropout).
+ * Output: fp16 hi/lo planes [NB][C8][D][H][W][8]. */
+int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                    const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi, uint16_t* lo,
+                    long long out_n_stride, int C8, tta_stream_t stream);
+
+/* ---- convolution (forward and input gradient): replaces nn.Conv3d / nn.ConvTranspose3d inside
+ * monai.networks.blocks.Convolution reached from src/models/unet.py:56-66, and autograd's
+ * conv backward-data in loss.backward() (src/core/trainers/seg_trainer.py:142).  No weight
+ * gradient exists: TENT freezes conv weights.
+ * mode 0: out[o] = sum_k in[s*o - p + k] * Wg[k]      (conv; also the dgrad of a transposed conv)
+ * mode 1: out[o] = sum_{k,i: s*i - p + k = o} in[i] * Wg[k]   (transposed conv; dgrad of a conv)
+ * K in {1,3}, stride in {1,2}, p = (K-1)/2. */
+
+/* tcgen05/TMEM/TMA implicit GEMM.  wpacked: layout.pack_weights_tc blob for (mode,K,stride,dtype).
+ * flags: bit0 force one d-plane per work item, bit1 no split-K (deterministic), bit2 non-persistent. */
+int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout);
+int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split);
+int tta_conv_tc_gmax(int mode, int K, int stride);
+int tta_conv_tc_ngroups(int mode, int K, int stride);
+long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout);
+int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
+                int C8in, int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out,
+                long long out_n_stride, int C8out, int Do, int Ho, int Wo, int mode, int K, int stride,
+                int accumulate, int flags, tta_stream_t stream);
+
+/* fp32 CUDA-core conv for any (mode, K, stride); Wp: fp32 [tap][C8in][C8out][8][8]. */
+int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
+                  int C8in, int Di, int Hi, int Wi, const float* Wp, const float* bias, float* out,
+                  long long out_n_stride, int C8out, int Do, int Ho, int Wo, int mode, int K, int stride,
+                  int accumulate, tta_stream_t stream);
+
+/* direct 3x3x3 stride-1 conv for cin, cout <= 4 (the UNet head); W_host: HOST fp32 [27][8][8]. */
+int tta_conv_small_supported(int K, int stride, int cin, int cout);
+int tta_conv_small(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
+                   int cin, int D, int H, int W, const float* W_host, const float* bias, float* out,
+                   long long out_n_stride, int cout, int accumulate, tta_stream_t stream);
+
+/* ---- normalisation: replaces nn.InstanceNorm3d / nn.BatchNorm3d (+ nn.ReLU, the ResidualUnit add
+ * `cx + res`, and torch.cat of SkipConnection via channel-slice views) of MONAI's ADN block,
+ * selected by configs/_global_patches/brats.yaml:17 / src/models/unet.py:44, and their autograd
+ * backward.  batch_mode 0: per-(n,c) statistics (InstanceNorm); 1: per-c over the batch
+ * (BatchNorm in TENT mode, no running statistics). */
+long long tta_norm_workspace_floats(int N, int C8, long long V);
+/* per-block partial sums of y, y^2 into workspace; finalize != 0 also writes mean/rstd [N][C8*8] */
+int tta_norm_stats(const float* y, long long y_n_stride, int N, int C8, long long V, int batch_mode, float eps,
+                   float* mean, float* rstd, float* workspace, int finalize, tta_stream_t stream);
+/* out = relu?(gamma*(y-mean)*rstd+beta) (+ residual) as planes.  res_kind 0 none, 1 f32 view
+ * (res_a), 2 planes view (res_a = hi, res_b = lo).  partial != NULL: statistics are finalized from
+ * the workspace inside this kernel and mean/rstd are written for the backward pass. */
+int tta_norm_apply(const float* y, long long y_n_stride, int N, int C8, long long V, const float* mean,
+                   const float* rstd, const float* gamma, const float* beta, int relu, int res_kind,
+                   const void* res_a, const void* res_b, long long res_n_stride, uint16_t* out_hi,
+                   uint16_t* out_lo, long long out_n_stride, int out_dtype, const float* partial, int batch_mode,
+                   float eps, tta_stream_t stream);
+/* partial sums of dz and dz*xhat (dz = (g0+g1)*[z>0]); finalize != 0 also writes sums[N][C][2] and
+ * dgamma/dbeta[C] */
+int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
+                        const float* y, long long y_n_stride, int N, int C8, int Creal, long long V,
+                        const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                        int batch_mode, float* sums, float* dgamma, float* dbeta, float* workspace, int finalize,
+                        tta_stream_t stream);
+/* dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) as planes; optional aux planes = g0+g1
+ * (feeds the shortcut conv's dgrad).  partial != NULL: reductions finalized here, dgamma/dbeta written. */
+int tta_norm_bwd_apply(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
+                       const float* y, long long y_n_stride, int N, int C8, long long V, const float* mean,
+                       const float* rstd, const float* gamma, const float* beta, int relu, int batch_mode,
+                       const float* sums, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_n_stride,
+                       uint16_t* aux_hi, uint16_t* aux_lo, long long aux_n_stride, int out_dtype,
+                       const float* partial, int Creal, float* dgamma, float* dbeta, tta_stream_t stream);
+int tta_split_f32(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride, int N, int C8,
+                  long long V, uint16_t* hi, uint16_t* lo, long long out_n_stride, int out_dtype,
+                  tta_stream_t stream);
+
+/* ---- fused head: logits + entropy loss + dlogits in one pass.  Replaces the loss + backward
+ * entry of src/core/trainers/seg_trainer.py:141-142 with the TENT entropy (mode 0 softmax,
+ * mode 1 Bernoulli/sigmoid -- the reference's heads are sigmoid, configs/_global_patches/
+ * brats.yaml:12,59) and writes logits in the reference's NCDHW fp32 layout
+ * (src/evaluation/seg_eval.py:300-302).  dz = sample_w[n]*inv_count*grad_scale*dH/dz. */
+int tta_head_entropy_blocks(int N, long long V);
+int tta_head_entropy(const float* y, long long y_n_stride, int N, int R, long long V, int mode, float inv_count,
+                     float grad_scale, int dz_dtype, const float* sample_w, float* logits, uint16_t* dz_hi,
+                     uint16_t* dz_lo, long long dz_n_stride, float* partial, float* loss, tta_stream_t stream);
+
+/* ---- optimizer: torch.optim.Adam built by src/core/experiment_manager.py:199-237 on the flat
+ * [gamma || beta] buffer; *step_dev is incremented on the device (graph replay safe). */
+int tta_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps,
+                  float gscale, int* step_dev, tta_stream_t stream);
+
+/* ---- sliding-window Gaussian blending (MONAI sliding_window_inference(mode="gaussian")) */
+int tta_sw_blend(const float* logits, int NB, int R, int D, int H, int W, const int* win, const float* sample_w,
+                 const float* gd, const float* gh, const float* gw, float wmin, float* acc, float* wsum, int n_vol,
+                 int Ds, int Hs, int Ws, tta_stream_t stream);
+int tta_sw_normalise(const float* acc, const float* wsum, int n_vol, int R, long long Vs, float* out,
+                     tta_stream_t stream);
+
+/* ---- evaluation: sigmoid >= thr, label > 0.5, per-(b,r) {intersection, pred sum, gt sum}:
+ * replaces src/evaluation/seg_eval.py:304-308 + the sums of _binary_dice_iou (:41-68). */
+int tta_dice_counts(const float* logits, const float* label, int BR, long long V, float thr,
+                    unsigned long long* counts, tta_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTA_B200_H */

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),
     "tta_dice_counts": (I, [P, P, I, L, F, P, P]),
     "tta_conv_simt": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, P]),
+    "tta_conv_small_supported": (I, [I, I, I, I]),
+    "tta_conv_small": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, P]),
     "tta_conv_tc_supported": (I, [I, I, I, I, I]),
     "tta_conv_tc_ntile": (I, [I, I, I, I, I]),
     "tta_conv_tc_gmax": (I, [I, I, I]),

@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
-from .layout import pack_bias, pack_weights_simt, pack_weights_tc, wg_dgrad, wg_forward
+from .layout import pack_bias, pack_weights_simt, pack_weights_small, pack_weights_tc, wg_dgrad, wg_forward
 from .unet_b200 import (ConvHolder, ConvolutionH, NormHolder, ResidualUnitH, SkipConnectionH, UNetB200)
 
 
@@ -125,8 +125,12 @@ class ConvLayer:
             "simt_fwd": pack_weights_simt(wf), "simt_bwd": pack_weights_simt(wd),
             "bias": pack_bias(self.h.bias.detach().to(device=device, dtype=torch.float32)),
         }
+        lib = _lib.lib()
+        if lib.tta_conv_small_supported(self.K, self.stride, self.cin, self.cout):
+            # tiny-channel stride-1 convs (UNet head): direct CUDA-core kernel, HBM-bound
+            self.packed["small_fwd"] = pack_weights_small(wf, self.mode)
+            self.packed["small_bwd"] = pack_weights_small(wd, 1 - self.mode)
         if want_tc:
-            lib = _lib.lib()
             if lib.tta_conv_tc_supported(self.mode, self.K, self.stride, self.cin, self.cout):
                 self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16)
             bmode = 1 - self.mode
@@ -279,6 +283,18 @@ class TTAEngine:
         key = "bwd" if backward else "fwd"
         bias = 0 if backward else cl.packed["bias"].data_ptr()
         hi, lo, ns = src
+        if ("small_" + key) in cl.packed and self.model.conv_backend != "simt":
+            wp = cl.packed["small_" + key]
+            plan.keep.append(wp)
+            plan.conv_backends[f"{cl.name}:{key}"] = "small"
+            cin = cl.cout if backward else cl.cin
+            cout = cl.cin if backward else cl.cout
+            sargs = (hi, lo, ns, src_dtype, N, cin, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout,
+                     int(accumulate))
+
+            def run_small():
+                check(lib.tta_conv_small(*sargs, _stream()), f"conv_small {cl.name}")
+            return run_small
         use_tc = ("tc_" + key) in cl.packed and self.model.conv_backend in ("auto", "tc")
         if self.model.conv_backend == "tc" and not use_tc:
             raise RuntimeError(f"conv_backend=tc but {cl.name} ({key}) is not supported by the tcgen05 kernel")
@@ -338,6 +354,8 @@ class TTAEngine:
                 out = a.view()
             if (out.C8, *out.dims) != (y.C8, y.D, y.H, y.W):
                 raise ValueError(f"{nl.name}: output view shape mismatch")
+            if y.V * (N if nl.batch else 1) == 1:
+                plan.single_element_norm = nl.name
             mean = torch.zeros(N * y.C8 * 8, dtype=torch.float32, device=dev)
             rstd = torch.zeros_like(mean)
             sums = torch.zeros(N * y.C8 * 8 * 2, dtype=torch.float32, device=dev)
@@ -554,7 +572,12 @@ class TTAEngine:
         key = (N, D, H, W)
         if key not in self.plans:
             self.plans[key] = self.build_plan(N, D, H, W)
-        return self.plans[key]
+        plan = self.plans[key]
+        bad = getattr(plan, "single_element_norm", None)
+        if bad is not None and self.model.training:
+            # same refusal as torch's instance/batch norm in training mode
+            raise ValueError(f"Expected more than 1 spatial element when training, got a single element at {bad}")
+        return plan
 
     def _load_running_stats(self, plan: Plan):
         """eval()-mode BatchNorm: statistics come from the running buffers, not the batch."""

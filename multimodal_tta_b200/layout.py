@@ -44,6 +44,17 @@ def pack_weights_simt(wg: torch.Tensor) -> torch.Tensor:
     return p.reshape(T, cip // 8, 8, cop // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
 
 
+def pack_weights_small(wg: torch.Tensor, mode: int) -> torch.Tensor:
+    """Wg[27][ci][co] (ci, co <= 4) -> HOST fp32 [27][8][8] for tta_conv_small.  mode 1 (the transposed /
+    input-gradient form, out[o] = sum_k in[o + 1 - k] Wg[k]) is turned into a plain correlation by
+    flipping the tap order."""
+    T, ci, co = wg.shape
+    assert T == 27 and ci <= 8 and co <= 8
+    p = torch.zeros((27, 8, 8), dtype=torch.float32)
+    p[:, :ci, :co] = (wg.flip(0) if mode == 1 else wg).detach().cpu()
+    return p.contiguous()   # HOST tensor: tta_conv_small passes the weights as kernel parameters
+
+
 def pack_bias(b: torch.Tensor) -> torch.Tensor:
     p = torch.zeros(_pad8(b.numel()), dtype=torch.float32, device=b.device)
     p[: b.numel()] = b

@@ -75,6 +75,20 @@ def plan_windows(vol_dims: Sequence[int], roi: Sequence[int], overlap: float):
     return padded, pad_lo, window_starts(padded, roi, iv)
 
 
+def shard_schedule(total: int, sw_batch: int, world: int, rank: int):
+    """Window indices this rank adapts on at every global step: step t covers the ``sw_batch*world``
+    consecutive windows [t*G, (t+1)*G), rank r takes the r-th block of ``sw_batch``; indices past
+    ``total`` are None (zero-weight padding so that every rank joins every all-reduce).
+    Yields (list of index-or-None of length sw_batch, number of valid windows in the global step)."""
+    G = sw_batch * world
+    for g0 in range(0, total, G):
+        idxs = []
+        for j in range(sw_batch):
+            i = g0 + rank * sw_batch + j
+            idxs.append(i if i < total else None)
+        yield idxs, min(G, total - g0)
+
+
 class SlidingWindowTTA:
     def __init__(self, tent: TentB200, roi: Sequence[int], sw_batch: int = 1, overlap: float = 0.5,
                  sigma_scale: float = 0.125):
@@ -115,18 +129,15 @@ class SlidingWindowTTA:
         rank = dist.get_rank(tent.pg) if ws > 1 else 0
         NB, R = self.sw_batch, tent.model.out_channels
         st = self._state(vol.device, (vol.device, NB))
-        G = NB * ws
         acc = torch.zeros((B, R, *padded), dtype=torch.float32, device=vol.device)
         wsum = torch.zeros((B, *padded), dtype=torch.float32, device=vol.device)
         cs_dev = None
         if chan_scale_per_volume is not None:
             cs_dev = torch.ones((NB, C), dtype=torch.float32, device=vol.device)
         steps = 0
-        for g0 in range(0, total, G):
-            n_valid = min(G, total - g0)
-            for j in range(NB):
-                idx = g0 + rank * NB + j
-                valid = idx < total
+        for idxs, n_valid in shard_schedule(total, NB, ws, rank):
+            for j, idx in enumerate(idxs):
+                valid = idx is not None
                 b, s = (idx // nwin, starts[idx % nwin]) if valid else (0, starts[0])
                 # origins in UNPADDED volume coordinates (gather zero-fills outside the volume)
                 st["win_host"][j] = torch.tensor([b, s[0] - pad_lo[0], s[1] - pad_lo[1], s[2] - pad_lo[2]],

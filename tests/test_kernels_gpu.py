@@ -77,6 +77,35 @@ def test_conv_simt_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
     assert rel_l2(from_chunked(gx2, cin).cpu(), 2 * g2) < 2e-6
 
 
+@pytest.mark.parametrize("cin,cout,dims", [(3, 3, (9, 10, 13)), (1, 1, (8, 8, 8)), (4, 2, (5, 6, 7)), (2, 2, (4, 4, 40))])
+def test_conv_small_forward_and_dgrad(lib, cuda, cin, cout, dims):
+    from multimodal_tta_b200.layout import pack_weights_small
+    torch.manual_seed(9)
+    N = 2
+    x = torch.randn(N, cin, *dims)
+    w = torch.randn(cout, cin, 3, 3, 3) * 0.2
+    b = torch.randn(cout)
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    xr = xv.cpu().requires_grad_(True)
+    ref = F.conv3d(xr, w, b, padding=1)
+    V = dims[0] * dims[1] * dims[2]
+    out = torch.zeros((N, 1, *dims, 8), device=cuda)
+    wp = pack_weights_small(wg_forward(w.to(cuda), False), 0)
+    bp = pack_bias(b.to(cuda))
+    check(lib.tta_conv_small(hi.data_ptr(), lo.data_ptr(), V * 8, TTA_F16, N, cin, *dims, wp.data_ptr(), bp.data_ptr(),
+                             out.data_ptr(), V * 8, cout, 0, stream()))
+    assert rel_l2(from_chunked(out, cout).cpu(), ref.detach()) < 2e-6
+    assert float(out[..., cout:].abs().max()) == 0.0 if cout < 8 else True
+    dy = torch.randn_like(ref)
+    dhi, _, dyv = planes_from(dy.to(cuda), TTA_F16_HI)
+    (g,) = torch.autograd.grad(ref, xr, dyv.cpu())
+    wpd = pack_weights_small(wg_dgrad(w.to(cuda), False), 1)
+    gx = torch.zeros((N, 1, *dims, 8), device=cuda)
+    check(lib.tta_conv_small(dhi.data_ptr(), 0, V * 8, TTA_F16_HI, N, cout, *dims, wpd.data_ptr(), 0, gx.data_ptr(),
+                             V * 8, cin, 0, stream()))
+    assert rel_l2(from_chunked(gx, cin).cpu(), g) < 2e-6
+
+
 @pytest.mark.parametrize("batch_mode", [0, 1])
 @pytest.mark.parametrize("C,dims", [(32, (8, 9, 10)), (3, (16, 16, 16)), (20, (5, 7, 3))])
 def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
