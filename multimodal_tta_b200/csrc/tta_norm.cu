@@ -45,7 +45,7 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   double a = 0.0;
   for (int nn = n0; nn < n1; ++nn) {
     const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
-    for (int sp = j; sp < splits; sp += 16) a += (double)p[sp * 16 + v];
+    for (int sp = j; sp < splits; sp += 16) a += (double)__ldcg(p + sp * 16 + v);
   }
   red[v][j] = a;
   __syncthreads();
@@ -58,12 +58,49 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   }
   __syncthreads();
 }
+// same, but every thread only needs value `which` (0..15): avoids dynamic register indexing
+__device__ __forceinline__ double reduce_partials_one(const float* __restrict__ partial, int C8, int chunk,
+                                                      int splits, int n0, int n1, int which) {
+  __shared__ double red1[16][17];
+  const int v = threadIdx.x & 15, j = threadIdx.x >> 4;
+  double a = 0.0;
+  for (int nn = n0; nn < n1; ++nn) {
+    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
+    for (int sp = j; sp < splits; sp += 16) a += (double)__ldcg(p + sp * 16 + v);
+  }
+  red1[v][j] = a;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) t += red1[which][jj];
+  __syncthreads();
+  return t;
+}
+
+// Single-pass reduction: after publishing its partial sums a block bumps the per-chunk counter;
+// the block that observes the final count (all N*splits blocks of this chunk have published)
+// finalizes in a fixed order -> deterministic, no second launch, counter self-resets.
+__device__ __forceinline__ bool last_block_of_chunk(unsigned int* counters, int chunk, unsigned int total) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(&counters[chunk], 1u);
+    s_last = (old == total - 1u) ? 1u : 0u;
+    if (s_last) counters[chunk] = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0u;
+}
 
 // ---------------------------------------------------------------- forward statistics
 // partial[((n*C8 + chunk)*splits + split)*16 + {0..7: sum, 8..15: sumsq}]
 __global__ void __launch_bounds__(kThreads)
 norm_stats_partial_kernel(const float* __restrict__ y, long long n_stride, int C8, long long V,
-                          int splits, float* __restrict__ partial) {
+                          int splits, float* __restrict__ partial, unsigned int* __restrict__ counters,
+                          int N, int batch_mode, float eps, float* __restrict__ mean,
+                          float* __restrict__ rstd) {
   const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
   const float* base = y + (long long)n * n_stride + (long long)chunk * V * 8;
   const long long per = (V + splits - 1) / splits;
@@ -82,6 +119,26 @@ norm_stats_partial_kernel(const float* __restrict__ y, long long n_stride, int C
     }
   }
   block_reduce_store<16>(acc, partial + ((long long)(n * C8 + chunk) * splits + split) * 16);
+  if (counters == nullptr) return;
+  if (!last_block_of_chunk(counters, chunk, (unsigned int)(N * splits))) return;
+  // ---- finalize this chunk (all samples) in fp64
+  const int C = C8 * 8;
+  const double M = (double)V * (batch_mode ? N : 1);
+  for (int nn = 0; nn < (batch_mode ? 1 : N); ++nn) {
+    const int n0 = batch_mode ? 0 : nn, n1 = batch_mode ? N : nn + 1;
+    const double s1 = reduce_partials_one(partial, C8, chunk, splits, n0, n1, threadIdx.x & 7);
+    const double s2 = reduce_partials_one(partial, C8, chunk, splits, n0, n1, 8 + (threadIdx.x & 7));
+    if (threadIdx.x < 8) {
+      const double m = s1 / M;
+      double var = s2 / M - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mu = (float)m, rs = (float)(1.0 / sqrt(var + (double)eps));
+      for (int n2 = batch_mode ? 0 : nn; n2 < (batch_mode ? N : nn + 1); ++n2) {
+        mean[n2 * C + chunk * 8 + threadIdx.x] = mu;
+        rstd[n2 * C + chunk * 8 + threadIdx.x] = rs;
+      }
+    }
+  }
 }
 
 // one thread per (n, channel): combine splits (and n for batch mode) in fp64.
@@ -195,7 +252,9 @@ norm_bwd_partial_kernel(const float* __restrict__ g0, long long g0_ns,
                         const float* __restrict__ y, long long y_ns, int C8, long long V,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                        int splits, float* __restrict__ partial) {
+                        int splits, float* __restrict__ partial, unsigned int* __restrict__ counters, int N,
+                        int batch_mode, int Creal, float* __restrict__ sums, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta) {
   const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
@@ -236,6 +295,25 @@ norm_bwd_partial_kernel(const float* __restrict__ g0, long long g0_ns,
     }
   }
   block_reduce_store<16>(acc, partial + ((long long)(n * C8 + chunk) * splits + split) * 16);
+  if (counters == nullptr) return;
+  if (!last_block_of_chunk(counters, chunk, (unsigned int)(N * splits))) return;
+  // ---- finalize: sums[(n*C + c)*2 + {0,1}] per normalisation group, dgamma/dbeta over all samples
+  const int which = threadIdx.x & 15;
+  const int cc = chunk * 8 + (which & 7);
+  const double tall = reduce_partials_one(partial, C8, chunk, splits, 0, N, which);
+  if (threadIdx.x < 16) {
+    if (cc < Creal) {
+      if (which < 8) dbeta[cc] = (float)tall; else dgamma[cc] = (float)tall;
+    }
+    if (batch_mode)
+      for (int nn = 0; nn < N; ++nn) sums[(nn * C + cc) * 2 + (which >> 3)] = (float)tall;
+  }
+  if (!batch_mode) {
+    for (int nn = 0; nn < N; ++nn) {
+      const double tn = N == 1 ? tall : reduce_partials_one(partial, C8, chunk, splits, nn, nn + 1, which);
+      if (threadIdx.x < 16) sums[(nn * C + cc) * 2 + (which >> 3)] = (float)tn;
+    }
+  }
 }
 
 // sums[(n*C + c)*2 + {0,1}] = {sum dz, sum dz*xhat} over the normalisation group (per n for IN,
@@ -404,8 +482,9 @@ using namespace tta;
 extern "C" {
 
 // Workspace (floats) needed by tta_norm_stats / tta_norm_bwd_reduce for a given shape.
+// workspace = [1024 block counters (zero-initialised once, self-resetting)][per-block partials]
 long long tta_norm_workspace_floats(int N, int C8, long long V) {
-  return (long long)N * C8 * pick_splits(N, C8, V) * 16;
+  return 1024 + (long long)N * C8 * pick_splits(N, C8, V) * 16;
 }
 
 // finalize = 0: only the per-block partial sums are produced; tta_norm_apply(partial = workspace)
@@ -415,14 +494,12 @@ int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, i
                    cudaStream_t stream) {
   TTA_REQUIRE(y && workspace && (!finalize || (mean && rstd)), "tta_norm_stats: null pointer");
   TTA_REQUIRE(N > 0 && C8 > 0 && V > 0, "tta_norm_stats: empty shape N=%d C8=%d V=%lld", N, C8, V);
+  TTA_REQUIRE(C8 <= 1024, "tta_norm_stats: more than 8192 channels unsupported");
   const int splits = pick_splits(N, C8, V);
-  norm_stats_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(y, y_ns, C8, V, splits,
-                                                                         workspace);
-  if (finalize) {
-    const int tot = N * C8 * 8;
-    norm_stats_finalize_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(workspace, N, C8, splits, V,
-                                                                      batch_mode, eps, mean, rstd);
-  }
+  // finalize = 1: the last block of every chunk turns the partial sums into mean/rstd (single pass)
+  norm_stats_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(
+      y, y_ns, C8, V, splits, workspace + 1024, finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N,
+      batch_mode, eps, mean, rstd);
   return tta_check_launch("tta_norm_stats");
 }
 
@@ -439,7 +516,8 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
 #define LAUNCH(RES, DT)                                                                        \
   norm_apply_kernel<RES, DT><<<grid, kThreads, 0, stream>>>(                                   \
       y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
-      (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns, partial, splits, N,   \
+      (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns,                       \
+      partial ? partial + 1024 : nullptr, splits, N,                                                        \
       batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd))
   if (out_dtype == TTA_F16) {
     if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
@@ -458,14 +536,11 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && workspace &&
                   (!finalize || (sums && dgamma && dbeta)),
               "tta_norm_bwd_reduce: null pointer");
+  TTA_REQUIRE(C8 <= 1024, "tta_norm_bwd_reduce: more than 8192 channels unsupported");
   const int splits = pick_splits(N, C8, V);
   norm_bwd_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(
-      g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace);
-  if (finalize) {
-    const int C = C8 * 8;
-    norm_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(workspace, N, C8, Creal, splits,
-                                                               batch_mode, sums, dgamma, dbeta);
-  }
+      g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace + 1024,
+      finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N, batch_mode, Creal, sums, dgamma, dbeta);
   return tta_check_launch("tta_norm_bwd_reduce");
 }
 
@@ -486,15 +561,18 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
   if (out_dtype == TTA_F16)
     norm_bwd_apply_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
-        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial, splits, N, batch_mode, Creal, dgamma, dbeta);
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
+        dbeta);
   else if (out_dtype == TTA_F16_HI)
     norm_bwd_apply_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
-        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial, splits, N, batch_mode, Creal, dgamma, dbeta);
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
+        dbeta);
   else
     norm_bwd_apply_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
-        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial, splits, N, batch_mode, Creal, dgamma, dbeta);
+        dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
+        dbeta);
   return tta_check_launch("tta_norm_bwd_apply");
 }
 

@@ -381,10 +381,9 @@ class TTAEngine:
                     # eval-mode BatchNorm: mean/rstd were filled from the running buffers
                     check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), _stream()), "norm_apply")
                 else:
-                    # per-block partial sums, finalized inside the apply kernel's prologue
-                    check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 0, _stream()), "norm_stats")
-                    check(lib.tta_norm_apply(*ap_args, plan.ws.data_ptr(), nl.batch, float(nl.h.eps), _stream()),
-                          "norm_apply")
+                    # single-pass statistics: the last block of every chunk finalizes mean/rstd
+                    check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 1, _stream()), "norm_stats")
+                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), _stream()), "norm_apply")
             plan.fwd.append(run)
             ops.append(("norm", rec))
             return out
@@ -540,18 +539,16 @@ class TTAEngine:
                                aux.ns if aux else 0, bdt)
 
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db):
-                    if ap_args is None:   # no dgrad below this norm (stem): reduce + finalize only
-                        check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, _stream()), "norm_bwd_reduce")
-                    else:                 # finalize fused into the bwd-apply prologue
-                        check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 0, _stream()), "norm_bwd_reduce")
-                        check(lib.tta_norm_bwd_apply(*ap_args, plan.ws.data_ptr(), nl.C, dg, db, _stream()),
-                              "norm_bwd_apply")
+                    # single-pass reduction: the last block finalizes sums + dgamma/dbeta
+                    check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, _stream()), "norm_bwd_reduce")
+                    if ap_args is not None:
+                        check(lib.tta_norm_bwd_apply(*ap_args, 0, nl.C, dg, db, _stream()), "norm_bwd_apply")
                 plan.bwd.append(run)
         n_conv = sum(1 for o in ops if o[0] == "conv")
         n_norm = sum(1 for o in ops if o[0] == "norm")
         plan.launches_fwd = 1 + n_conv + 2 * n_norm + 2          # gather + convs + (partial stats + apply) + head
         plan.launches_bwd = sum(1 for o in ops if o[0] == "conv" and o[2].parent.needs_grad) + \
-            2 * len(bwd_apply_flags) + 1                          # dgrads + norm bwd (2 each) + adam
+            sum(2 if a else 1 for a in bwd_apply_flags) + 1       # dgrads + norm bwd (reduce [+ apply]) + adam
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:
