@@ -140,6 +140,19 @@ def test_episodic_reset_and_state_dict_view(cuda):
     assert torch.equal(l1, l2)                                 # episodic: same start every batch
 
 
+def test_adapt_stream_equals_step_by_step(cuda):
+    """The prefetching host-batch API yields exactly what step() yields batch by batch."""
+    _, prod_a = make_pair(dict(BRATS_MODEL_CFG, deterministic=True), seed=7)
+    _, prod_b = make_pair(dict(BRATS_MODEL_CFG, deterministic=True), seed=7)
+    ta, tb = TentB200(prod_a, {"cuda_graph": True}), TentB200(prod_b, {"cuda_graph": True})
+    hosts = [brats_volume(1, (32, 32, 32), seed=s).pin_memory() for s in (1, 2, 3, 4)]
+    ref = [ta.step(h.cuda()).clone() for h in hosts]
+    got = [o.clone() for o in tb.adapt_stream(hosts)]
+    assert len(got) == 4 and all(torch.equal(a, b) for a, b in zip(ref, got))
+    assert torch.equal(prod_a.engine.flat_params(), prod_b.engine.flat_params())
+    assert list(tb.adapt_stream([])) == []
+
+
 def test_rejects_bad_inputs(cuda):
     _, prod = make_pair(BRATS_MODEL_CFG, seed=5)
     tp = TentB200(prod, {})
