@@ -78,7 +78,7 @@ class ActView:
 
 
 class Res:
-    """fp32 conv result [N][C8][D][H][W][8] (+ its bf16 split gradient planes dY)."""
+    """fp32 conv result [N][C8][D][H][W][8] (+ the 16-bit gradient planes dY that feed its dgrad)."""
 
     def __init__(self, N, C, D, H, W, device, name: str = ""):
         self.N, self.C, self.C8, self.D, self.H, self.W = N, C, (C + 7) // 8, D, H, W
@@ -88,33 +88,68 @@ class Res:
         self.ns = self.C8 * self.V * 8
         self.dy: Optional[torch.Tensor] = None
         self.device = device
+        self.root, self.c8_off = self, 0
 
     def alloc_dy(self, planes: int = 2):
         if self.dy is None:
-            self.dy = torch.zeros((2, self.N, self.C8, self.D, self.H, self.W, 8), dtype=torch.int16,
-                                  device=self.device) if planes == 2 else \
-                torch.zeros((1, self.N, self.C8, self.D, self.H, self.W, 8), dtype=torch.int16,
-                            device=self.device).expand(2, -1, -1, -1, -1, -1, -1)
+            shape = (self.N, self.C8, self.D, self.H, self.W, 8)
+            self.dy = torch.zeros((2, *shape), dtype=torch.int16, device=self.device) if planes == 2 else \
+                torch.zeros((1, *shape), dtype=torch.int16, device=self.device).expand(2, -1, -1, -1, -1, -1, -1)
 
     @property
     def ptr(self) -> int:
         return self.data.data_ptr()
 
+    def dy_ptr(self, plane: int) -> int:
+        return self.dy[plane].data_ptr()
+
+    def view(self, c8_off: int, c8_len: int, C: int) -> "ResView":
+        return ResView(self, c8_off, c8_len, C)
+
+
+class ResView:
+    """Channel slice of a Res (the two halves of a fused unit0 || shortcut convolution)."""
+
+    def __init__(self, parent: Res, c8_off: int, C8: int, C: int):
+        self.root, self.c8_off, self.C8, self.C = parent, c8_off, C8, C
+        self.N, self.D, self.H, self.W, self.V, self.ns, self.name = (parent.N, parent.D, parent.H, parent.W,
+                                                                      parent.V, parent.ns, parent.name)
+
+    def alloc_dy(self, planes: int = 2):
+        self.root.alloc_dy(planes)
+
+    @property
+    def ptr(self) -> int:
+        return self.root.data.data_ptr() + self.c8_off * self.V * 8 * 4
+
+    def dy_ptr(self, plane: int) -> int:
+        return self.root.dy[plane].data_ptr() + self.c8_off * self.V * 8 * 2
+
 
 # ------------------------------------------------------------------------------ layers
 class ConvLayer:
-    def __init__(self, holder: ConvHolder, name: str, fold_identity: bool = False):
-        self.h, self.name, self.fold_identity = holder, name, fold_identity
+    """One convolution launch.  ``extra`` fuses a second conv with the same input and geometry
+    (ResidualUnit unit0 || strided shortcut) along the output channels: the forward reads the input
+    once with N doubled, the dgrad is one conv over the concatenated gradients (K doubled)."""
+
+    def __init__(self, holder: ConvHolder, name: str, fold_identity: bool = False, extra: Optional[ConvHolder] = None):
+        self.h, self.name, self.fold_identity, self.extra = holder, name, fold_identity, extra
         self.K, self.stride = holder.k, holder.stride
         self.mode = 1 if holder.transposed else 0
-        self.cin, self.cout = holder.cin, holder.cout
+        self.cin, self.cout = holder.cin, holder.cout + (extra.cout if extra is not None else 0)
         self.packed = {}
 
     def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16):
-        """(Re)pack weights: fp32 for the CUDA-core kernel, split fp16/bf16 for tcgen05."""
+        """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05."""
         w = self.h.weight.detach().to(device=device, dtype=torch.float32)
         wf = wg_forward(w, self.h.transposed)
         wd = wg_dgrad(w, self.h.transposed)
+        b = self.h.bias.detach().to(device=device, dtype=torch.float32)
+        if self.extra is not None:
+            w2 = self.extra.weight.detach().to(device=device, dtype=torch.float32)
+            wf = torch.cat([wf, wg_forward(w2, False)], dim=2)      # [T][ci][co0 + co1]
+            wd = torch.cat([wd, wg_dgrad(w2, False)], dim=1)        # [T][ci = dy0 || dy1][co = cin]
+            b = torch.cat([b, self.extra.bias.detach().to(device=device, dtype=torch.float32)])
         if self.fold_identity:
             c = self.K ** 3 // 2
             eye = torch.eye(self.cin, device=device)
@@ -123,7 +158,7 @@ class ConvLayer:
             wd[c] += eye
         self.packed = {
             "simt_fwd": pack_weights_simt(wf), "simt_bwd": pack_weights_simt(wd),
-            "bias": pack_bias(self.h.bias.detach().to(device=device, dtype=torch.float32)),
+            "bias": pack_bias(b),
         }
         lib = _lib.lib()
         if lib.tta_conv_small_supported(self.K, self.stride, self.cin, self.cout):
@@ -201,6 +236,17 @@ class TTAEngine:
         for name, m in self.model.named_modules():
             if isinstance(m, ConvHolder):
                 self.conv_layers[id(m)] = ConvLayer(m, name, fold_identity=id(m) in fold)
+        # unit0 || shortcut fusion candidates: 3x3x3 strided shortcut with unit0's geometry, and at
+        # least two sub-units (the shortcut is added after the LAST unit's norm)
+        self.fused_layers = {}
+        if self.model.fuse_shortcut:
+            for name, m in self.model.named_modules():
+                if isinstance(m, ResidualUnitH) and isinstance(m.residual, ConvHolder):
+                    units = list(m.conv.children())
+                    u0, r = units[0].conv, m.residual
+                    if (len(units) >= 2 and not units[0].conv_only and r.k == u0.k == 3 and r.stride == u0.stride
+                            and r.cin == u0.cin and r.cout == u0.cout and u0.cout % 8 == 0 and not u0.transposed):
+                        self.fused_layers[id(u0)] = ConvLayer(u0, name + ".conv.unit0.conv||residual", extra=r)
         off = 0
         for name, m in self.model.named_modules():
             if isinstance(m, NormHolder):
@@ -236,8 +282,14 @@ class TTAEngine:
         if self.model._params_dirty:
             self._bind_params()
             want_tc = self.model.conv_backend in ("auto", "tc")
-            for cl in self.conv_layers.values():
-                cl.pack(device, want_tc, self.bwd_dtype)
+            fused_members = set()
+            for fl in self.fused_layers.values():
+                fused_members |= {id(fl.h), id(fl.extra)}
+            for key, cl in self.conv_layers.items():
+                if key not in fused_members:
+                    cl.pack(device, want_tc, self.bwd_dtype)
+            for fl in self.fused_layers.values():
+                fl.pack(device, want_tc, self.bwd_dtype)
             self.model._params_dirty = False
 
     def _bind_params(self):
@@ -367,7 +419,7 @@ class TTAEngine:
                        gptr=gptr, bptr=bptr)
             if residual is None:
                 rk, ra, rb, rns = 0, 0, 0, 0
-            elif isinstance(residual, Res):
+            elif isinstance(residual, (Res, ResView)):
                 rk, ra, rb, rns = 1, residual.ptr, 0, residual.ns
             else:
                 rk, ra, rb, rns = 2, residual.hi, residual.lo, residual.ns
@@ -395,15 +447,24 @@ class TTAEngine:
             return normact(self._nl(cv.adn.N), y, True, None, out)
 
         def residual_unit(ru: ResidualUnitH, inp: ActView, out: Optional[ActView]):
-            if isinstance(ru.residual, ConvHolder):
+            units = list(ru.conv.children())
+            u0 = units[0].conv
+            fused = self.fused_layers.get(id(u0))
+            y_first = None
+            if fused is not None:
+                # unit0 || strided shortcut share input and geometry: ONE conv with concatenated couts
+                yf = conv(fused, inp)
+                c = u0.cout
+                y_first = yf.view(0, c // 8, c)
+                res = yf.view(c // 8, c // 8, c)
+            elif isinstance(ru.residual, ConvHolder):
                 res = conv(self.conv_layers[id(ru.residual)], inp)
             else:
                 res = inp
             cur = inp
-            units = list(ru.conv.children())
             for i, u in enumerate(units):
                 last = i == len(units) - 1
-                y = conv(self.conv_layers[id(u.conv)], cur)
+                y = y_first if (i == 0 and y_first is not None) else conv(self.conv_layers[id(u.conv)], cur)
                 if u.conv_only:
                     return y  # identity shortcut folded into the centre tap (ConvLayer.fold_identity)
                 cur = normact(self._nl(u.adn.N), y, True, res if last else None, out if last else None)
@@ -474,7 +535,7 @@ class TTAEngine:
                 check(lib.tta_head_entropy(
                     final.ptr, final.ns, N, R, final.V, self.entropy_mode, float(plan.inv_count),
                     float(plan.loss_scale), bdt, plan.sample_w.data_ptr(), plan.logits.data_ptr(),
-                    final.dy[0].data_ptr() if train else 0, final.dy[1].data_ptr() if train else 0, final.ns,
+                    final.dy_ptr(0) if train else 0, final.dy_ptr(1) if train else 0, final.ns,
                     plan.partial.data_ptr(), plan.loss.data_ptr(), _stream()), "head_entropy")
             return run
         plan.head_infer, plan.head_train = head(False), head(True)
@@ -495,7 +556,7 @@ class TTAEngine:
                 par.written |= chunks
                 y.alloc_dy(nplanes)
                 plan.bwd.append(self._conv_call(
-                    plan, cl, True, (y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns), bdt, N, y.C8,
+                    plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.ns), bdt, N, y.C8,
                     (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc))
             else:
                 rec = op[1]
@@ -515,7 +576,7 @@ class TTAEngine:
                 conv_in_needs = self._producer_input_needs_grad(ops, y)
                 res = rec["residual"]
                 aux = None
-                if isinstance(res, Res) and self._producer_input_needs_grad(ops, res):
+                if isinstance(res, (Res, ResView)) and self._producer_input_needs_grad(ops, res):
                     res.alloc_dy(nplanes)
                     aux = res
                 elif isinstance(res, ActView):
@@ -534,8 +595,8 @@ class TTAEngine:
                     y.alloc_dy(nplanes)
                     ap_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, y.V, rec["mean"].data_ptr(),
                                rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
-                               rec["sums"].data_ptr(), y.dy[0].data_ptr(), y.dy[1].data_ptr(), y.ns,
-                               aux.dy[0].data_ptr() if aux else 0, aux.dy[1].data_ptr() if aux else 0,
+                               rec["sums"].data_ptr(), y.dy_ptr(0), y.dy_ptr(1), y.ns,
+                               aux.dy_ptr(0) if aux else 0, aux.dy_ptr(1) if aux else 0,
                                aux.ns if aux else 0, bdt)
 
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db):
@@ -560,7 +621,7 @@ class TTAEngine:
     @staticmethod
     def _producer_input_needs_grad(ops, y: Res) -> bool:
         for op in ops:
-            if op[0] == "conv" and op[3] is y:
+            if op[0] == "conv" and op[3] is y.root:
                 return op[2].parent.needs_grad
         raise KeyError("no producer conv for result tensor")
 

@@ -148,6 +148,8 @@ class UNetB200(nn.Module):
         self.use_cuda_graph = bool(get_config(cfg, "cuda_graph", True))
         # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
         self.deterministic = bool(get_config(cfg, "deterministic", False))
+        # run a ResidualUnit's unit0 conv and its strided 3x3x3 shortcut conv as ONE launch
+        self.fuse_shortcut = bool(get_config(cfg, "fuse_shortcut", True))
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))

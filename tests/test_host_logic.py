@@ -116,7 +116,8 @@ def test_tent_configure_selects_only_norm_affine():
     assert m.training and "model.0.conv.unit0.adn.N.weight" in m.state_dict()
 
 
-@pytest.mark.parametrize("cfg,nconv,nnorm,ndgrad", [(BRATS_MODEL_CFG, 23, 17, 21),
+@pytest.mark.parametrize("cfg,nconv,nnorm,ndgrad", [(dict(BRATS_MODEL_CFG, fuse_shortcut=False), 23, 17, 21),
+                                                    (BRATS_MODEL_CFG, 19, 17, 18),   # 4 unit0||shortcut pairs fused
                                                     (dict(BARE_DEFAULT_MODEL_CFG, in_channels=4), 9, 8, 8)])
 def test_op_graph_layer_counts(cfg, nconv, nnorm, ndgrad):
     m = UNetB200(dict(cfg))
@@ -129,6 +130,7 @@ def test_op_graph_layer_counts(cfg, nconv, nnorm, ndgrad):
     assert set(plan.conv_backends.values()) <= {"tc", "small", "simt"}
     if cfg is BRATS_MODEL_CFG:
         assert plan.conv_backends["model.2.1.conv.unit0.conv:fwd"] == "small"
+        assert plan.conv_backends["model.0.conv.unit0.conv||residual:fwd"] == "tc"
     with pytest.raises(ValueError):
         eng.build_plan(1, 24, 32, 32)        # not divisible by 16
 

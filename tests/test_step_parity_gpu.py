@@ -98,6 +98,11 @@ def test_simt_backend_alone(cuda):
     _check_step(BRATS_MODEL_CFG, x, "sigmoid", steps=1, use_graph=False, backend="simt")
 
 
+def test_unfused_shortcut_convs(cuda):
+    x = brats_volume(1, (32, 32, 32), seed=46)
+    _check_step(dict(BRATS_MODEL_CFG, fuse_shortcut=False), x, "sigmoid", steps=2, use_graph=True)
+
+
 def test_inference_forward_matches_oracle_eval_and_train(cuda):
     for cfg in (BRATS_MODEL_CFG, dict(BARE_DEFAULT_MODEL_CFG, in_channels=4)):
         oracle, prod = make_pair(cfg, seed=3)
