@@ -44,10 +44,11 @@ int tta_device_sm(void); /* compute capability major*10+minor of the current dev
  * MONAI sliding_window_inference's window slicing + constant pad (not in tree).
  * vol: fp32 NCDHW [n_vol][C][Ds][Hs][Ws]; win: int32 [NB][4] = (volume, d0, h0, w0), origins may
  * lie outside the volume (zero fill); chan_scale: optional fp32 [NB][C] (missing-modality dropout).
- * Output: fp16 hi/lo planes [NB][C8][D][H][W][8]. */
+ * Output: fp16 hi/lo planes [NB][C8][D][H][W][8]; wsplit != 0 stores every w-row parity-split
+ * ([H][2][W/2][8]: even-w voxels first), the operand layout of a stride-2 tcgen05 conv (flags bit3). */
 int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                     const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi, uint16_t* lo,
-                    long long out_n_stride, int C8, tta_stream_t stream);
+                    long long out_n_stride, int C8, int wsplit, tta_stream_t stream);
 
 /* ---- convolution (forward and input gradient): replaces nn.Conv3d / nn.ConvTranspose3d inside
  * monai.networks.blocks.Convolution reached from src/models/unet.py:56-66, and autograd's
@@ -58,7 +59,8 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
  * K in {1,3}, stride in {1,2}, p = (K-1)/2. */
 
 /* tcgen05/TMEM/TMA implicit GEMM.  wpacked: layout.pack_weights_tc blob for (mode,K,stride,dtype).
- * flags: bit0 force one d-plane per work item, bit1 no split-K (deterministic), bit2 non-persistent. */
+ * flags: bit0 force one d-plane per work item, bit1 no split-K (deterministic), bit2 non-persistent,
+ * bit3 stride-2 conv input planes are w-parity-split ([N][C8][D][H][2][W/2][8]). */
 int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout);
 int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split);
 int tta_conv_tc_gmax(int mode, int K, int stride);
@@ -92,12 +94,14 @@ int tta_norm_stats(const float* y, long long y_n_stride, int N, int C8, long lon
                    float* mean, float* rstd, float* workspace, int finalize, tta_stream_t stream);
 /* out = relu?(gamma*(y-mean)*rstd+beta) (+ residual) as planes.  res_kind 0 none, 1 f32 view
  * (res_a), 2 planes view (res_a = hi, res_b = lo).  partial != NULL: statistics are finalized from
- * the workspace inside this kernel and mean/rstd are written for the backward pass. */
+ * the workspace inside this kernel and mean/rstd are written for the backward pass.
+ * ws_hi/ws_lo != NULL: a second copy of the planes in the w-parity-split layout (row length W) for a
+ * stride-2 tcgen05 consumer (skip tensors feed both the next level's strided conv and the concat). */
 int tta_norm_apply(const float* y, long long y_n_stride, int N, int C8, long long V, const float* mean,
                    const float* rstd, const float* gamma, const float* beta, int relu, int res_kind,
                    const void* res_a, const void* res_b, long long res_n_stride, uint16_t* out_hi,
                    uint16_t* out_lo, long long out_n_stride, int out_dtype, const float* partial, int batch_mode,
-                   float eps, tta_stream_t stream);
+                   float eps, uint16_t* ws_hi, uint16_t* ws_lo, long long ws_n_stride, int W, tta_stream_t stream);
 /* partial sums of dz and dz*xhat (dz = (g0+g1)*[z>0]); finalize != 0 also writes sums[N][C][2] and
  * dgamma/dbeta[C] */
 int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
@@ -106,16 +110,39 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1,
                         int batch_mode, float* sums, float* dgamma, float* dbeta, float* workspace, int finalize,
                         tta_stream_t stream);
 /* dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) as planes; optional aux planes = g0+g1
- * (feeds the shortcut conv's dgrad).  partial != NULL: reductions finalized here, dgamma/dbeta written. */
+ * (feeds the shortcut conv's dgrad).  partial != NULL: reductions finalized here, dgamma/dbeta written.
+ * dy_wsplit_w > 0: dy is stored w-parity-split with row length W = dy_wsplit_w (its dgrad is a
+ * stride-2 tcgen05 conv). */
 int tta_norm_bwd_apply(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
                        const float* y, long long y_n_stride, int N, int C8, long long V, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, int relu, int batch_mode,
                        const float* sums, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_n_stride,
                        uint16_t* aux_hi, uint16_t* aux_lo, long long aux_n_stride, int out_dtype,
-                       const float* partial, int Creal, float* dgamma, float* dbeta, tta_stream_t stream);
+                       const float* partial, int Creal, float* dgamma, float* dbeta, int dy_wsplit_w,
+                       tta_stream_t stream);
 int tta_split_f32(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride, int N, int C8,
                   long long V, uint16_t* hi, uint16_t* lo, long long out_n_stride, int out_dtype,
                   tta_stream_t stream);
+
+/* ---- fused full-resolution tail (csrc/tta_head.cu): the last ADN(norm, ReLU) -> 3x3x3 conv(C->C,
+ * identity shortcut folded) -> entropy of MONAI's top ResidualUnit(last_conv_only) as ONE kernel, and
+ * its backward (conv dgrad + ReLU mask + norm-backward reduction) as ONE kernel.  Replaces, for
+ * C <= 4 heads, tta_norm_apply + tta_conv_small + tta_head_entropy and tta_conv_small(dgrad) +
+ * tta_norm_bwd_reduce; semantics as those (src/core/trainers/seg_trainer.py:105-145).
+ * y: f32 view [N][1][D][H][W][8]; mean/rstd [N][8]; W_host: HOST fp32 [27][8][8] = Wg[tap][ci][co];
+ * logits/dlogits: NCDHW fp32 (dlogits NULL = inference); dz: f32 view of the masked gradient that
+ * tta_norm_bwd_apply then consumes as g0; sums/dgamma/dbeta as tta_norm_bwd_reduce(finalize=1). */
+int tta_head_fused_supported(int K, int stride, int cin, int cout);
+int tta_head_fused_tiles(int D, int H, int W);
+long long tta_head_fused_workspace_floats(int N, int D, int H, int W);
+int tta_head_fused_fwd(const float* y, long long y_n_stride, int N, int C, int D, int H, int W, const float* mean,
+                       const float* rstd, const float* gamma, const float* beta, int relu, const float* W_host,
+                       const float* bias, int mode, float inv_count, float grad_scale, const float* sample_w,
+                       float* logits, float* dlogits, float* workspace, float* loss, tta_stream_t stream);
+int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, const float* W_host, const float* y,
+                       long long y_n_stride, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int relu, int batch_mode, float* dz, long long dz_n_stride, float* sums,
+                       float* dgamma, float* dbeta, float* workspace, tta_stream_t stream);
 
 /* ---- fused head: logits + entropy loss + dlogits in one pass.  Replaces the loss + backward
  * entry of src/core/trainers/seg_trainer.py:141-142 with the TENT entropy (mode 0 softmax,

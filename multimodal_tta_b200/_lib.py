@@ -56,13 +56,18 @@ _SIGNATURES = {
     "tta_device_sm": (I, []),
     "tta_norm_workspace_floats": (L, [I, I, L]),
     "tta_norm_stats": (I, [P, L, I, I, L, I, F, P, P, P, I, P]),
-    "tta_norm_apply": (I, [P, L, I, I, L, P, P, P, P, I, I, P, P, L, P, P, L, I, P, I, F, P]),
+    "tta_norm_apply": (I, [P, L, I, I, L, P, P, P, P, I, I, P, P, L, P, P, L, I, P, I, F, P, P, L, I, P]),
     "tta_norm_bwd_reduce": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, I, P, P, P, P, I, P]),
-    "tta_norm_bwd_apply": (I, [P, L, P, L, P, L, I, I, L, P, P, P, P, I, I, P, P, P, L, P, P, L, I, P, I, P, P, P]),
+    "tta_norm_bwd_apply": (I, [P, L, P, L, P, L, I, I, L, P, P, P, P, I, I, P, P, P, L, P, P, L, I, P, I, P, P, I, P]),
     "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
-    "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, P]),
+    "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, I, P]),
     "tta_head_entropy_blocks": (I, [I, L]),
     "tta_head_entropy": (I, [P, L, I, I, L, I, F, F, I, P, P, P, P, L, P, P, P]),
+    "tta_head_fused_supported": (I, [I, I, I, I]),
+    "tta_head_fused_tiles": (I, [I, I, I]),
+    "tta_head_fused_workspace_floats": (L, [I, I, I, I]),
+    "tta_head_fused_fwd": (I, [P, L, I, I, I, I, I, P, P, P, P, I, P, P, I, F, F, P, P, P, P, P, P]),
+    "tta_head_fused_bwd": (I, [P, I, I, I, I, I, P, P, L, P, P, P, P, I, I, P, L, P, P, P, P, P]),
     "tta_adam_step": (I, [P, P, P, P, I, F, F, F, F, F, P, P]),
     "tta_sw_blend": (I, [P, I, I, I, I, I, P, P, P, P, P, F, P, P, I, I, I, I, P]),
     "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),

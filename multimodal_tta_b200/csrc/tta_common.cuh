@@ -109,6 +109,56 @@ __device__ __forceinline__ void load_split8(const uint16_t* __restrict__ hi,
   for (int i = 0; i < 8; ++i) x[i] = u16_to_f32<DT>(h.v[i]) + u16_to_f32<DT>(l.v[i]);
 }
 
+// w-parity-split ("wsplit") position of voxel v = (d*H + h)*W + w inside its [D][H][2][W/2] slab:
+// the even-w voxels of a row come first, then the odd ones.  Operand planes that feed a stride-2
+// tcgen05 conv are stored this way so that every parity class is a dense TMA row (W must be even).
+__device__ __forceinline__ long long wsplit_index(long long v, int W) {
+  const int w = (int)(v % W);
+  return v - w + (w & 1) * (W >> 1) + (w >> 1);
+}
+
+// Per-voxel entropy of R logits and its gradient, returns H:
+//   mode 0: softmax entropy   H = lse(z) - sum_c p_c z_c ;  dH/dz_k = -p_k (z_k - sum_c p_c z_c)
+//   mode 1: Bernoulli entropy H = sum_c softplus(z_c) - p_c z_c ; dH/dz_c = -z_c p_c (1 - p_c)
+// g[c] = gs * dH/dz_c for c < R (entries >= R are left untouched).
+template <int RMAX>
+__device__ __forceinline__ float entropy_point(const float (&z)[RMAX], int R, int mode, float gs, float (&g)[RMAX]) {
+  float Hv = 0.f;
+  if (mode == 1) {
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      if (i < R) {
+        const float zi = z[i];
+        const float p = 1.f / (1.f + expf(-zi));
+        const float sp = fmaxf(zi, 0.f) + log1pf(expf(-fabsf(zi)));
+        Hv += sp - p * zi;
+        g[i] = -zi * p * (1.f - p) * gs;
+      }
+    }
+  } else {
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+      if (i < R) m = fmaxf(m, z[i]);
+    float e[RMAX], S = 0.f;
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      e[i] = (i < R) ? expf(z[i] - m) : 0.f;
+      S += e[i];
+    }
+    const float invS = 1.f / S;
+    float pz = 0.f;
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+      if (i < R) pz = fmaf(e[i] * invS, z[i], pz);
+    Hv = (m + logf(S)) - pz;
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+      if (i < R) g[i] = -(e[i] * invS) * (z[i] - pz) * gs;
+  }
+  return Hv;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -54,6 +54,7 @@ struct TcParams {
   int c8_view, c8in, single_chunk, tmem_cols;
   int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n;
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
+  int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
   int lbo16[4];  // k-chunk pitch (16 B units, 128 B aligned) per A sub-tile
   signed char acc_pd[kMaxAcc], acc_qd[kMaxAcc], acc_qh[kMaxAcc], acc_qw[kMaxAcc];
   long long out_ns;
@@ -346,9 +347,15 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
             for (int kc = 0; kc < nkc; ++kc) {
               const uint32_t dst = stage + L.smem_off + kc * L.chunk_pitch;
               if (GEOM == GEOM_S2) {
-                tma_load_5d(dst, &P.amap[L.map * 2 + 0], full, 0, cw, chh, cd, c4 + kc);
-                if (SPLIT)
-                  tma_load_5d(dst + P.a_plane_bytes, &P.amap[L.map * 2 + 1], full, 0, cw, chh, cd, c4 + kc);
+                if (P.s2_rows) {
+                  tma_load_4d(dst, &P.amap[L.map * 2 + 0], full, cw * 8, chh, cd, c4 + kc);
+                  if (SPLIT)
+                    tma_load_4d(dst + P.a_plane_bytes, &P.amap[L.map * 2 + 1], full, cw * 8, chh, cd, c4 + kc);
+                } else {
+                  tma_load_5d(dst, &P.amap[L.map * 2 + 0], full, 0, cw, chh, cd, c4 + kc);
+                  if (SPLIT)
+                    tma_load_5d(dst + P.a_plane_bytes, &P.amap[L.map * 2 + 1], full, 0, cw, chh, cd, c4 + kc);
+                }
               } else {
                 tma_load_4d(dst, &P.amap[0], full, cw * 8, chh, cd, c4 + kc);
                 if (SPLIT) tma_load_4d(dst + P.a_plane_bytes, &P.amap[1], full, cw * 8, chh, cd, c4 + kc);
@@ -412,45 +419,70 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
         const long long vox = ((long long)od * P.Ho + oh) * P.Wo + ow;
         float* obase = P.out + (long long)wi.n * P.out_ns + vox * 8;
         const uint32_t tacc = tbase + acc * acc_cols;
-        for (int c16 = 0; c16 < (P.ntile >> 4); ++c16) {
-          uint32_t ra[16], rb[16];
-          tmem_ld16_nowait(tacc + c16 * 16, ra);            // hi*hi + lo*hi columns
-          if (SPLIT) {
-            tmem_ld16_nowait(tacc + P.ntile + c16 * 16, rb);  // hi*lo columns
-          } else {
+        // 64 accumulator columns per round.  The accumulate epilogue (gradient fan-in) is a
+        // read-modify-write: all old values of the round are requested BEFORE the TMEM loads, so
+        // the round pays one memory latency instead of one per 8-channel chunk.
+        const bool rmw = P.accumulate && P.ksplit == 1;
+        const int n16 = P.ntile >> 4;
+        for (int cb = 0; cb < n16; cb += 4) {
+          float4 old[4][2][2];
+          if (rmw) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rb[i] = 0u;
-          }
-          tmem_ld_wait();
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const int co_chunk = wi.nt * nchunks + c16 * 2 + hlf;
-            if (valid && co_chunk < P.C8out) {
-              float* dst = obase + (long long)co_chunk * Vo * 8;
-              const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
-              const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
-              const int o = hlf * 8;
-              float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
-                                      __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
-                                      __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
-                                      __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
-              float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
-                                      __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
-                                      __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
-                                      __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
-              if (P.ksplit > 1) {
-                // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
-                atomicAdd(reinterpret_cast<float4*>(dst), r0);
-                atomicAdd(reinterpret_cast<float4*>(dst + 4), r1);
-              } else {
-                if (P.accumulate) {
-                  const float4 o0 = *reinterpret_cast<const float4*>(dst);
-                  const float4 o1 = *reinterpret_cast<const float4*>(dst + 4);
-                  r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w;
-                  r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                const int co_chunk = wi.nt * nchunks + (cb + j) * 2 + hlf;
+                if (cb + j < n16 && valid && co_chunk < P.C8out) {
+                  const float* src = obase + (long long)co_chunk * Vo * 8;
+                  old[j][hlf][0] = __ldcg(reinterpret_cast<const float4*>(src));
+                  old[j][hlf][1] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                } else {
+                  old[j][hlf][0] = old[j][hlf][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                *reinterpret_cast<float4*>(dst) = r0;
-                *reinterpret_cast<float4*>(dst + 4) = r1;
+              }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c16 = cb + j;
+            if (c16 >= n16) break;
+            uint32_t ra[16], rb[16];
+            tmem_ld16_nowait(tacc + c16 * 16, ra);            // hi*hi + lo*hi columns
+            if (SPLIT) {
+              tmem_ld16_nowait(tacc + P.ntile + c16 * 16, rb);  // hi*lo columns
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) rb[i] = 0u;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const int co_chunk = wi.nt * nchunks + c16 * 2 + hlf;
+              if (valid && co_chunk < P.C8out) {
+                float* dst = obase + (long long)co_chunk * Vo * 8;
+                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
+                const int o = hlf * 8;
+                float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
+                                        __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
+                                        __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
+                                        __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
+                float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
+                                        __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
+                                        __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
+                                        __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
+                if (P.ksplit > 1) {
+                  // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
+                  atomicAdd(reinterpret_cast<float4*>(dst), r0);
+                  atomicAdd(reinterpret_cast<float4*>(dst + 4), r1);
+                } else {
+                  if (rmw) {
+                    const float4 o0 = old[j][hlf][0], o1 = old[j][hlf][1];
+                    r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w;
+                    r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+                  }
+                  *reinterpret_cast<float4*>(dst) = r0;
+                  *reinterpret_cast<float4*>(dst + 4) = r1;
+                }
               }
             }
           }
@@ -543,7 +575,8 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
 
 // in: split planes view [N][C8in (pitch from in_ns)][Di][Hi][Wi][8];  out: fp32 view; wpacked from
 // layout.pack_weights_tc.  flags bit0: force TD=1, bit1: no split-K (deterministic), bit2: one
-// work item per CTA (non-persistent; testing).
+// work item per CTA (non-persistent; testing), bit3: the input planes of a stride-2 conv are stored
+// w-parity-split ([N][C8][D][H][2][W/2][8]: even-w voxels of a row first, then the odd ones).
 int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
                 int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
                 int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
@@ -676,13 +709,31 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
+  // stride-2 convs over a w-parity-split input ([..][H][2][W/2][8], flags bit3): every (h, w) parity
+  // class is a dense run of W/2 voxels per row -> one bw*16-byte TMA row per halo row instead of bw
+  // 16-byte requests (the 5-D path is TMA-issue bound: ~2 cycles per 16 B)
+  auto encode_par_rows = [&](CUtensorMap* m, const uint16_t* base, int par_h, int par_w, int bw, int bh) -> bool {
+    const uint16_t* ptr = base + ((long long)par_h * Wi + (long long)par_w * (Wi / 2)) * 8;
+    cuuint64_t gdim[4] = {(cuuint64_t)(Wi / 2) * 8, (cuuint64_t)((Hi - par_h + 1) / 2), (cuuint64_t)Di, nc_extent};
+    cuuint64_t gstr[3] = {(cuuint64_t)32 * Wi, (cuuint64_t)16 * Wi * Hi, (cuuint64_t)16 * Vi};
+    cuuint32_t box[4] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, (void*)ptr, gdim, gstr, box, es5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
   bool ok = true;
+  P.s2_rows = (geom == GEOM_S2 && (flags & 8)) ? 1 : 0;
   if (geom == GEOM_S2) {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
         const int m = ph * 2 + pw;
-        ok = ok && encode_par(&P.amap[m * 2 + 0], in_hi, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
-        if (split) ok = ok && encode_par(&P.amap[m * 2 + 1], in_lo, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
+        if (P.s2_rows) {
+          ok = ok && encode_par_rows(&P.amap[m * 2 + 0], in_hi, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
+          if (split) ok = ok && encode_par_rows(&P.amap[m * 2 + 1], in_lo, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
+        } else {
+          ok = ok && encode_par(&P.amap[m * 2 + 0], in_hi, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
+          if (split) ok = ok && encode_par(&P.amap[m * 2 + 1], in_lo, ph, pw, pw ? 9 : 8, ph ? 17 : 16);
+        }
       }
   } else {
     ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? 1 : td);

@@ -10,89 +10,9 @@
 //   backward: dbeta = sum dz, dgamma = sum dz*xhat,
 //             dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dz = g * [z > 0]
 #include "tta_common.cuh"
+#include "tta_reduce.cuh"
 
 namespace tta {
-
-constexpr int kThreads = 256;
-
-// ---------------------------------------------------------------- block reduction of 16 values
-template <int NV>
-__device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* __restrict__ dst) {
-  __shared__ float red[kThreads / 32][NV];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) red[warp][i] = acc[i];
-  }
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
-    dst[threadIdx.x] = s;
-  }
-}
-
-// ---------------------------------------------------------------- fused finalize (consumer prologue)
-// Sums the 16 per-block partial values of chunk `chunk` over splits (and over samples n0..n1)
-// in fp64 with all 256 threads; result in tot[16] (shared).  Deterministic order.
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int C8, int chunk,
-                                                int splits, int n0, int n1, double (&tot)[16]) {
-  __shared__ double red[16][17];
-  const int v = threadIdx.x & 15, j = threadIdx.x >> 4;  // 16 values x 16 split lanes
-  double a = 0.0;
-  for (int nn = n0; nn < n1; ++nn) {
-    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
-    for (int sp = j; sp < splits; sp += 16) a += (double)__ldcg(p + sp * 16 + v);
-  }
-  red[v][j] = a;
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    double t = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < 16; ++jj) t += red[i][jj];
-    tot[i] = t;
-  }
-  __syncthreads();
-}
-// same, but every thread only needs value `which` (0..15): avoids dynamic register indexing
-__device__ __forceinline__ double reduce_partials_one(const float* __restrict__ partial, int C8, int chunk,
-                                                      int splits, int n0, int n1, int which) {
-  __shared__ double red1[16][17];
-  const int v = threadIdx.x & 15, j = threadIdx.x >> 4;
-  double a = 0.0;
-  for (int nn = n0; nn < n1; ++nn) {
-    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
-    for (int sp = j; sp < splits; sp += 16) a += (double)__ldcg(p + sp * 16 + v);
-  }
-  red1[v][j] = a;
-  __syncthreads();
-  double t = 0.0;
-#pragma unroll
-  for (int jj = 0; jj < 16; ++jj) t += red1[which][jj];
-  __syncthreads();
-  return t;
-}
-
-// Single-pass reduction: after publishing its partial sums a block bumps the per-chunk counter;
-// the block that observes the final count (all N*splits blocks of this chunk have published)
-// finalizes in a fixed order -> deterministic, no second launch, counter self-resets.
-__device__ __forceinline__ bool last_block_of_chunk(unsigned int* counters, int chunk, unsigned int total) {
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int old = atomicAdd(&counters[chunk], 1u);
-    s_last = (old == total - 1u) ? 1u : 0u;
-    if (s_last) counters[chunk] = 0u;
-  }
-  __syncthreads();
-  if (s_last) __threadfence();
-  return s_last != 0u;
-}
 
 // ---------------------------------------------------------------- forward statistics
 // partial[((n*C8 + chunk)*splits + split)*16 + {0..7: sum, 8..15: sumsq}]
@@ -179,7 +99,8 @@ norm_apply_kernel(const float* __restrict__ y, long long y_ns, int C8, long long
                   const uint16_t* __restrict__ res_lo, long long res_ns,
                   uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, long long out_ns,
                   const float* __restrict__ partial, int splits, int N, int batch_mode, float eps,
-                  float* __restrict__ mean_w, float* __restrict__ rstd_w) {
+                  float* __restrict__ mean_w, float* __restrict__ rstd_w, uint16_t* __restrict__ ws_hi,
+                  uint16_t* __restrict__ ws_lo, long long ws_ns, int Wd) {
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
@@ -241,6 +162,8 @@ norm_apply_kernel(const float* __restrict__ y, long long y_ns, int C8, long long
       for (int i = 0; i < 8; ++i) x[i] += r[i];
     }
     store_split8<ODT>(out_hi, out_lo, ob + v * 8, x);
+    // second copy in the w-parity-split layout for a stride-2 tcgen05 consumer
+    if (ws_hi) store_split8<ODT>(ws_hi, ws_lo, (long long)n * ws_ns + slab + wsplit_index(v, Wd) * 8, x);
   }
 }
 
@@ -297,23 +220,7 @@ norm_bwd_partial_kernel(const float* __restrict__ g0, long long g0_ns,
   block_reduce_store<16>(acc, partial + ((long long)(n * C8 + chunk) * splits + split) * 16);
   if (counters == nullptr) return;
   if (!last_block_of_chunk(counters, chunk, (unsigned int)(N * splits))) return;
-  // ---- finalize: sums[(n*C + c)*2 + {0,1}] per normalisation group, dgamma/dbeta over all samples
-  const int which = threadIdx.x & 15;
-  const int cc = chunk * 8 + (which & 7);
-  const double tall = reduce_partials_one(partial, C8, chunk, splits, 0, N, which);
-  if (threadIdx.x < 16) {
-    if (cc < Creal) {
-      if (which < 8) dbeta[cc] = (float)tall; else dgamma[cc] = (float)tall;
-    }
-    if (batch_mode)
-      for (int nn = 0; nn < N; ++nn) sums[(nn * C + cc) * 2 + (which >> 3)] = (float)tall;
-  }
-  if (!batch_mode) {
-    for (int nn = 0; nn < N; ++nn) {
-      const double tn = N == 1 ? tall : reduce_partials_one(partial, C8, chunk, splits, nn, nn + 1, which);
-      if (threadIdx.x < 16) sums[(nn * C + cc) * 2 + (which >> 3)] = (float)tn;
-    }
-  }
+  norm_bwd_finalize_tail(partial, C8, chunk, splits, N, batch_mode, Creal, sums, dgamma, dbeta);
 }
 
 // sums[(n*C + c)*2 + {0,1}] = {sum dz, sum dz*xhat} over the normalisation group (per n for IN,
@@ -364,7 +271,7 @@ norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float
                       uint16_t* __restrict__ dy_lo, long long dy_ns, uint16_t* __restrict__ aux_hi,
                       uint16_t* __restrict__ aux_lo, long long aux_ns, const float* __restrict__ partial,
                       int splits, int N, int batch_mode, int Creal, float* __restrict__ dgamma,
-                      float* __restrict__ dbeta) {
+                      float* __restrict__ dbeta, int dy_wsplit_w) {
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
@@ -431,7 +338,8 @@ norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float
       const float dz = (relu && !(z > 0.f)) ? 0.f : g[i];
       x[i] = ga[i] * rs[i] * (dz - m1[i] - xh * m2[i]);
     }
-    store_split8<ODT>(dy_hi, dy_lo, ob + v * 8, x);
+    // dy_wsplit_w = W > 0: the dgrad that consumes dy is a stride-2 tcgen05 conv (w-parity-split)
+    store_split8<ODT>(dy_hi, dy_lo, ob + (dy_wsplit_w > 0 ? wsplit_index(v, dy_wsplit_w) : v) * 8, x);
   }
 }
 
@@ -459,9 +367,10 @@ split_f32_kernel(const float* __restrict__ g0, long long g0_ns, const float* __r
 }
 
 static inline int pick_splits(int N, int C8, long long V) {
-  // enough CTAs for ~4 waves of 148 SMs, at least 2048 voxels per CTA
+  // enough CTAs for ~4 waves of 148 SMs, at least 512 voxel-chunks (two per thread) per CTA: the
+  // small 8^3..32^3 layers are latency bound and want every SM streaming
   long long want = (4LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
-  long long maxs = (V + 2047) / 2048;
+  long long maxs = (V + 511) / 512;
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
@@ -507,8 +416,11 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
                    const float* rstd, const float* gamma, const float* beta, int relu,
                    int res_kind, const void* res_a, const void* res_b, long long res_ns,
                    uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int out_dtype,
-                   const float* partial, int batch_mode, float eps, cudaStream_t stream) {
+                   const float* partial, int batch_mode, float eps, uint16_t* ws_hi, uint16_t* ws_lo,
+                   long long ws_ns, int W, cudaStream_t stream) {
   TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_apply: null pointer");
+  TTA_REQUIRE(!ws_hi || (ws_lo && W > 0 && W % 2 == 0 && V % W == 0),
+              "tta_norm_apply: w-parity-split copy needs an even row length W=%d dividing V", W);
   const int splits = pick_splits(N, C8, V);
   TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_apply: res_kind %d", res_kind);
   TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_apply: bad dtype");
@@ -518,7 +430,7 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
       y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
       (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns,                       \
       partial ? partial + 1024 : nullptr, splits, N,                                                        \
-      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd))
+      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd), ws_hi, ws_lo, ws_ns, W)
   if (out_dtype == TTA_F16) {
     if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
   } else {
@@ -550,7 +462,9 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
                        int relu, int batch_mode, const float* sums, uint16_t* dy_hi,
                        uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi, uint16_t* aux_lo,
                        long long aux_ns, int out_dtype, const float* partial, int Creal, float* dgamma,
-                       float* dbeta, cudaStream_t stream) {
+                       float* dbeta, int dy_wsplit_w, cudaStream_t stream) {
+  TTA_REQUIRE(dy_wsplit_w == 0 || (dy_wsplit_w > 0 && dy_wsplit_w % 2 == 0 && V % dy_wsplit_w == 0),
+              "tta_norm_bwd_apply: w-parity-split dy needs an even row length dividing V (got %d)", dy_wsplit_w);
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && (sums || (partial && dgamma && dbeta)) && dy_hi &&
                   (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_apply: null pointer");
@@ -562,17 +476,17 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
     norm_bwd_apply_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta);
+        dbeta, dy_wsplit_w);
   else if (out_dtype == TTA_F16_HI)
     norm_bwd_apply_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta);
+        dbeta, dy_wsplit_w);
   else
     norm_bwd_apply_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta);
+        dbeta, dy_wsplit_w);
   return tta_check_launch("tta_norm_bwd_apply");
 }
 

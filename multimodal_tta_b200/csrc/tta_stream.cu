@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(kThreads)
 gather_pack_kernel(const float* __restrict__ vol, int C, int Ds, int Hs, int Ws,
                    const int* __restrict__ win, const float* __restrict__ chan_scale, int D, int H,
                    int W, int C8, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                   long long o_ns) {
+                   long long o_ns, int wsplit) {
   const int chunk = blockIdx.y, b = blockIdx.z;
   const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
   const long long V = (long long)D * H * W;
@@ -45,7 +45,9 @@ gather_pack_kernel(const float* __restrict__ vol, int C, int Ds, int Hs, int Ws,
       const int c = chunk * 8 + i;
       x[i] = (inside && c < C) ? src[(long long)c * Vs + so] * sc[i] : 0.f;
     }
-    store_split8<TTA_F16>(hi, lo, (long long)b * o_ns + ((long long)chunk * V + v) * 8, x);
+    // wsplit: the first conv is a stride-2 tcgen05 conv -> w-parity-split rows (tta_common.cuh)
+    const long long vo = wsplit ? v - w + (w & 1) * (W >> 1) + (w >> 1) : v;
+    store_split8<TTA_F16>(hi, lo, (long long)b * o_ns + ((long long)chunk * V + vo) * 8, x);
   }
 }
 
@@ -74,41 +76,9 @@ head_entropy_kernel(const float* __restrict__ y, long long y_ns, int R, long lon
       for (int c = 0; c < 8; ++c)
         if (c < R) logits[((long long)n * R + c) * V + v] = z[c];
     }
-    float Hv = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = 0.f;
-    if (mode == 1) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i < R) {
-          const float zi = z[i];
-          const float p = 1.f / (1.f + expf(-zi));
-          const float sp = fmaxf(zi, 0.f) + log1pf(expf(-fabsf(zi)));
-          Hv += sp - p * zi;
-          g[i] = -zi * p * (1.f - p) * gs;
-        }
-      }
-    } else {
-      float m = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < R) m = fmaxf(m, z[i]);
-      float e[8], S = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        e[i] = (i < R) ? expf(z[i] - m) : 0.f;
-        S += e[i];
-      }
-      const float invS = 1.f / S;
-      float pz = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < R) pz = fmaf(e[i] * invS, z[i], pz);
-      Hv = (m + logf(S)) - pz;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < R) g[i] = -(e[i] * invS) * (z[i] - pz) * gs;
-    }
+    const float Hv = entropy_point<8>(z, R, mode, gs, g);
     hsum += Hv * sw;
     if (dz_hi) store_split8<ODT>(dz_hi, dz_lo, (long long)n * dz_ns + v * 8, g);
   }
@@ -261,12 +231,13 @@ extern "C" {
 
 int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                     const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi,
-                    uint16_t* lo, long long o_ns, int C8, cudaStream_t stream) {
+                    uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
   TTA_REQUIRE(vol && win && hi && lo, "tta_gather_pack: null pointer");
+  TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
   const long long V = (long long)D * H * W;
   gather_pack_kernel<<<dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream>>>(
-      vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns);
+      vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
   return tta_check_launch("tta_gather_pack");
 }
 

@@ -45,6 +45,16 @@ class Act:
         self.ns = self.C8 * self.V * 8  # elements between samples
         self.written: set = set()       # chunks of .grad written so far in this backward
         self.extra: List["ActView"] = []  # identity-residual gradient contributions
+        # operands of a stride-2 tcgen05 conv are stored w-parity-split: either the
+        # planes themselves (`wsplit`, single consumer: the network input) or a second copy written by
+        # the producing norm (`ws_planes`, skip tensors that also feed the concat)
+        self.wsplit = False
+        self.ws_planes: Optional[torch.Tensor] = None
+        self.device = device
+
+    def need_ws_copy(self):
+        if self.ws_planes is None:
+            self.ws_planes = torch.zeros_like(self.planes)
 
     def view(self, c8_off: int = 0, c8_len: Optional[int] = None) -> "ActView":
         return ActView(self, c8_off, self.C8 - c8_off if c8_len is None else c8_len)
@@ -69,6 +79,14 @@ class ActView:
         return self.parent.planes[1].data_ptr() + self.c8_off * self.parent.V * 8 * 2
 
     @property
+    def ws_hi(self) -> int:
+        return self.parent.ws_planes[0].data_ptr() + self.c8_off * self.parent.V * 8 * 2
+
+    @property
+    def ws_lo(self) -> int:
+        return self.parent.ws_planes[1].data_ptr() + self.c8_off * self.parent.V * 8 * 2
+
+    @property
     def g(self) -> int:
         return self.parent.grad.data_ptr() + self.c8_off * self.parent.V * 8 * 4
 
@@ -87,6 +105,7 @@ class Res:
         self.data = torch.zeros((N, self.C8, D, H, W, 8), dtype=torch.float32, device=device)
         self.ns = self.C8 * self.V * 8
         self.dy: Optional[torch.Tensor] = None
+        self.dy_wsplit = False  # dY feeds a stride-2 tcgen05 dgrad: stored w-parity-split
         self.device = device
         self.root, self.c8_off = self, 0
 
@@ -326,8 +345,18 @@ class TTAEngine:
         self.m.zero_(); self.v.zero_(); self.step_dev.zero_()
 
     # ---------------------------------------------------------------- op emitters
+    def _uses_tc_s2(self, cl: ConvLayer, backward: bool) -> bool:
+        """True when this launch is a stride-2 (non-transposed) conv on the tcgen05 kernel, whose
+        input planes must be w-parity-split."""
+        mode = (1 - cl.mode) if backward else cl.mode
+        key = "bwd" if backward else "fwd"
+        if ("small_" + key) in cl.packed and self.model.conv_backend != "simt":
+            return False
+        return (mode == 0 and cl.stride == 2 and cl.K == 3 and ("tc_" + key) in cl.packed
+                and self.model.conv_backend in ("auto", "tc"))
+
     def _conv_call(self, plan: Plan, cl: ConvLayer, backward: bool, src, src_dtype, N, cin8, idims,
-                   dst_ptr, dst_ns, cout8, odims, accumulate: bool):
+                   dst_ptr, dst_ns, cout8, odims, accumulate: bool, wsplit_in: bool = False):
         """Returns a closure launching one conv (tcgen05 kernel when the geometry is supported,
         otherwise the fp32 CUDA-core kernel)."""
         lib = self.lib
@@ -355,7 +384,8 @@ class TTAEngine:
             wp = cl.packed["tc_" + key]
             plan.keep.append(wp)
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
-                    *odims, mode, cl.K, cl.stride, int(accumulate), 2 if self.model.deterministic else 0)
+                    *odims, mode, cl.K, cl.stride, int(accumulate),
+                    (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0))
 
             def run():
                 check(lib.tta_conv_tc(*args, _stream()), f"conv_tc {cl.name}")
@@ -393,8 +423,23 @@ class TTAEngine:
                 raise ValueError(f"{cl.name}: input has {inp.C8} channel chunks, layer expects {cl.cin} channels")
             y = Res(N, cl.cout, od, oh, ow, dev, name=cl.name)
             plan.keep.append(y)
-            run = self._conv_call(plan, cl, False, (inp.hi, inp.lo, inp.ns), TTA_F16, N, inp.C8, inp.dims,
-                                  y.ptr, y.ns, y.C8, (od, oh, ow), False)
+            src = (inp.hi, inp.lo, inp.ns)
+            ws_in = self._uses_tc_s2(cl, False) and w % 2 == 0
+            if inp.parent is plan.x:
+                # the packed network input has ONE copy: every consumer must agree on its layout
+                prev = getattr(plan, "x_layout", None)
+                if prev is not None and prev != ws_in:
+                    raise ValueError("unet_b200: the network input feeds both a strided and an unstrided conv")
+                plan.x_layout = ws_in
+            if ws_in:
+                par = inp.parent
+                if par is plan.x:
+                    par.wsplit = True          # gather_pack writes the only copy parity-split
+                else:
+                    par.need_ws_copy()         # the producing norm writes a second, parity-split copy
+                    src = (inp.ws_hi, inp.ws_lo, inp.ns)
+            run = self._conv_call(plan, cl, False, src, TTA_F16, N, inp.C8, inp.dims,
+                                  y.ptr, y.ns, y.C8, (od, oh, ow), False, wsplit_in=ws_in)
             plan.fwd.append(run)
             ops.append(("conv", cl, inp, y))
             return y
@@ -427,15 +472,24 @@ class TTAEngine:
             ap_args = (y.ptr, y.ns, N, y.C8, y.V, mean.data_ptr(), rstd.data_ptr(), gptr, bptr, int(relu),
                        rk, ra, rb, rns, out.hi, out.lo, out.ns, TTA_F16)
             plan.stats_ops.append((nl, mean, rstd, y))
+            rec["st_args"] = st_args
+
+            def ws_args():
+                # resolved at launch time: a later strided conv may have asked for the parity-split copy
+                if out.parent.ws_planes is None:
+                    return (0, 0, 0, 0)
+                return (out.ws_hi, out.ws_lo, out.ns, y.W)
 
             def run():
                 if nl.batch and not model.training and nl.h.track_running_stats:
                     # eval-mode BatchNorm: mean/rstd were filled from the running buffers
-                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), _stream()), "norm_apply")
+                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
+                          "norm_apply")
                 else:
                     # single-pass statistics: the last block of every chunk finalizes mean/rstd
                     check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 1, _stream()), "norm_stats")
-                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), _stream()), "norm_apply")
+                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
+                          "norm_apply")
             plan.fwd.append(run)
             ops.append(("norm", rec))
             return out
@@ -516,13 +570,29 @@ class TTAEngine:
                 layer(sub, dv, sv)
             return layer(up, cat.view(), out)
 
+        def final_dims(r):
+            return r.D, r.H, r.W
+
         final = block(model.model, x.view(), None)
         if not isinstance(final, Res):
             raise ValueError("unet_b200: the top-level up layer must end in a conv (MONAI UNet does)")
-        plan.ws = torch.zeros(max_ws[0], dtype=torch.float32, device=dev)
         bdt = self.bwd_dtype
         nplanes = 1 if bdt == TTA_F16_HI else 2
-        final.alloc_dy(nplanes)
+        # ---- fused full-resolution tail: [norm apply -> small 3x3x3 conv -> entropy] as one kernel
+        fused_head = None
+        if (model.fuse_head and model.conv_backend != "simt" and len(ops) >= 2 and ops[-1][0] == "conv"
+                and ops[-2][0] == "norm"):
+            _, hcl, hinp, hy = ops[-1]
+            hrec = ops[-2][1]
+            if (hy is final and hrec["out"] is hinp and hrec["residual"] is None and hcl.mode == 0
+                    and "small_fwd" in hcl.packed and hrec["y"].C8 == 1 and hcl.cout == R
+                    and lib.tta_head_fused_supported(hcl.K, hcl.stride, hcl.cin, hcl.cout)):
+                fused_head = (hcl, hrec, hinp)
+                max_ws[0] = max(max_ws[0], lib.tta_head_fused_workspace_floats(N, *final_dims(final)))
+        plan.fused_head = fused_head is not None
+        plan.ws = torch.zeros(max_ws[0], dtype=torch.float32, device=dev)
+        if fused_head is None:
+            final.alloc_dy(nplanes)
         # power-of-two loss scale keeps the fp16 gradient planes in range; Adam divides it out
         plan.loss_scale = float(2 ** math.ceil(math.log2(4.0 * N * final.V))) if bdt == TTA_F16_HI else 1.0
         nblk = lib.tta_head_entropy_blocks(N, final.V)
@@ -538,6 +608,33 @@ class TTAEngine:
                     final.dy_ptr(0) if train else 0, final.dy_ptr(1) if train else 0, final.ns,
                     plan.partial.data_ptr(), plan.loss.data_ptr(), _stream()), "head_entropy")
             return run
+
+        if fused_head is not None:
+            hcl, hrec, hinp = fused_head
+            hy, hnl = hrec["y"], hrec["nl"]
+            wp = hcl.packed["small_fwd"]          # HOST [27][8][8], identity shortcut folded in
+            plan.keep.append(wp)
+            plan.dlogits = torch.zeros((N, R, D, H, W), dtype=torch.float32, device=dev)
+            plan.conv_backends[f"{hcl.name}:fwd"] = "head"
+            plan.conv_backends[f"{hcl.name}:bwd"] = "head"
+            # the norm's apply and the conv disappear from the forward list: statistics only
+            del plan.fwd[-2:]
+
+            def stats_only(st_args=hrec["st_args"], nl=hnl):
+                if not (nl.batch and not model.training and nl.h.track_running_stats):
+                    check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 1, _stream()), "norm_stats")
+            plan.fwd.append(stats_only)
+
+            def head(train: bool):  # noqa: F811  (fused variant replaces the streaming head)
+                def run():
+                    check(lib.tta_head_fused_fwd(
+                        hy.ptr, hy.ns, N, R, hy.D, hy.H, hy.W, hrec["mean"].data_ptr(), hrec["rstd"].data_ptr(),
+                        hrec["gptr"], hrec["bptr"], int(hrec["relu"]), wp.data_ptr(),
+                        hcl.packed["bias"].data_ptr(), self.entropy_mode, float(plan.inv_count),
+                        float(plan.loss_scale), plan.sample_w.data_ptr(), plan.logits.data_ptr(),
+                        plan.dlogits.data_ptr() if train else 0, plan.ws.data_ptr(), plan.loss.data_ptr(),
+                        _stream()), "head_fused_fwd")
+                return run
         plan.head_infer, plan.head_train = head(False), head(True)
 
         # ------------------------------------------------------------ backward emission
@@ -554,10 +651,24 @@ class TTAEngine:
                     raise RuntimeError("partial gradient accumulation state")
                 acc = bool(done)
                 par.written |= chunks
+                if fused_head is not None and cl is fused_head[0]:
+                    # fused tail: dgrad of the small conv + ReLU mask + norm-backward reduction in ONE
+                    # kernel; the masked gradient lands in inp.g, sums/dgamma/dbeta are finalized
+                    hrec, hnl = fused_head[1], fused_head[1]["nl"]
+                    hb_args = (plan.dlogits.data_ptr(), N, R, y.D, y.H, y.W, cl.packed["small_fwd"].data_ptr(),
+                               hrec["y"].ptr, hrec["y"].ns, hrec["mean"].data_ptr(), hrec["rstd"].data_ptr(),
+                               hrec["gptr"], hrec["bptr"], int(hrec["relu"]), hnl.batch, inp.g, inp.ns,
+                               hrec["sums"].data_ptr(), self.dgb.data_ptr() + hnl.off * 4,
+                               self.dgb.data_ptr() + (P + hnl.off) * 4)
+
+                    def run_head_bwd(hb_args=hb_args):
+                        check(lib.tta_head_fused_bwd(*hb_args, plan.ws.data_ptr(), _stream()), "head_fused_bwd")
+                    plan.bwd.append(run_head_bwd)
+                    continue
                 y.alloc_dy(nplanes)
                 plan.bwd.append(self._conv_call(
                     plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.ns), bdt, N, y.C8,
-                    (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc))
+                    (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc, wsplit_in=y.root.dy_wsplit))
             else:
                 rec = op[1]
                 nl, y, out = rec["nl"], rec["y"], rec["out"]
@@ -591,25 +702,38 @@ class TTAEngine:
                            rec["sums"].data_ptr(), dg, db)
                 do_apply = conv_in_needs or aux is not None
                 bwd_apply_flags.append(do_apply)
+                dy_ws = 0
                 if do_apply:
                     y.alloc_dy(nplanes)
+                    pcl = self._producer_conv(ops, y)
+                    if self._uses_tc_s2(pcl, True) and y.W % 2 == 0 and y.root is y:
+                        y.dy_wsplit = True
+                        dy_ws = y.W
                     ap_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, y.V, rec["mean"].data_ptr(),
                                rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
                                rec["sums"].data_ptr(), y.dy_ptr(0), y.dy_ptr(1), y.ns,
                                aux.dy_ptr(0) if aux else 0, aux.dy_ptr(1) if aux else 0,
                                aux.ns if aux else 0, bdt)
 
-                def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db):
+                skip_reduce = fused_head is not None and rec is fused_head[1]   # done by tta_head_fused_bwd
+
+                def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db, dy_ws=dy_ws,
+                        skip_reduce=skip_reduce):
                     # single-pass reduction: the last block finalizes sums + dgamma/dbeta
-                    check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, _stream()), "norm_bwd_reduce")
+                    if not skip_reduce:
+                        check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, _stream()),
+                              "norm_bwd_reduce")
                     if ap_args is not None:
-                        check(lib.tta_norm_bwd_apply(*ap_args, 0, nl.C, dg, db, _stream()), "norm_bwd_apply")
+                        check(lib.tta_norm_bwd_apply(*ap_args, 0, nl.C, dg, db, dy_ws, _stream()), "norm_bwd_apply")
                 plan.bwd.append(run)
         n_conv = sum(1 for o in ops if o[0] == "conv")
         n_norm = sum(1 for o in ops if o[0] == "norm")
         plan.launches_fwd = 1 + n_conv + 2 * n_norm + 2          # gather + convs + (partial stats + apply) + head
         plan.launches_bwd = sum(1 for o in ops if o[0] == "conv" and o[2].parent.needs_grad) + \
             sum(2 if a else 1 for a in bwd_apply_flags) + 1       # dgrads + norm bwd (reduce [+ apply]) + adam
+        if fused_head is not None:
+            plan.launches_fwd -= 3   # norm apply + small conv + loss finalize folded into the fused head
+            plan.launches_bwd -= 1   # small-conv dgrad + norm reduce are one kernel
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:
@@ -617,6 +741,13 @@ class TTAEngine:
             if nl.h is holder:
                 return nl
         raise KeyError("norm holder not registered")
+
+    @staticmethod
+    def _producer_conv(ops, y) -> "ConvLayer":
+        for op in ops:
+            if op[0] == "conv" and op[3] is y.root:
+                return op[1]
+        raise KeyError("no producer conv for result tensor")
 
     @staticmethod
     def _producer_input_needs_grad(ops, y: Res) -> bool:
@@ -676,7 +807,8 @@ class TTAEngine:
         a = plan.x
         check(self.lib.tta_gather_pack(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
                                        chan_scale.data_ptr() if chan_scale is not None else 0, N, D, H, W,
-                                       a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8, _stream()),
+                                       a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8,
+                                       int(a.wsplit), _stream()),
               "gather_pack")
 
     def _check_input(self, x: torch.Tensor):

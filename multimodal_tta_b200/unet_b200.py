@@ -150,6 +150,9 @@ class UNetB200(nn.Module):
         self.deterministic = bool(get_config(cfg, "deterministic", False))
         # run a ResidualUnit's unit0 conv and its strided 3x3x3 shortcut conv as ONE launch
         self.fuse_shortcut = bool(get_config(cfg, "fuse_shortcut", True))
+        # run the full-resolution tail (norm apply + 3x3x3 conv + entropy, and its backward) as two
+        # fused CUDA-core kernels instead of five streaming passes (csrc/tta_head.cu)
+        self.fuse_head = bool(get_config(cfg, "fuse_head", True))
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))

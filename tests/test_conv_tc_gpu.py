@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
 from multimodal_tta_b200.layout import (from_chunked, join_planes, pack_bias, pack_weights_tc, split_planes,
                                         to_chunked, wg_dgrad, wg_forward)
-from tests.util import planes_from, rel_l2, stream
+from tests.util import planes_from, rel_l2, stream, wsplit
 
 pytestmark = pytest.mark.gpu
 
@@ -64,6 +64,13 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
         c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s)
     got = from_chunked(out, cout).cpu()
     assert rel_l2(got, ref.detach()) < 2e-5, rel_l2(got, ref.detach())
+    if not tr and s == 2:
+        # w-parity-split operand layout (flags bit3): same MMAs on the same bits -> identical result
+        o_std = torch.zeros_like(out); o_ws = torch.zeros_like(out)
+        args = (c8i * xv[0, 0].numel() * 8, TTA_F16, N, c8i, dims, wp, pack_bias(b.to(cuda)))
+        _tc(lib, hi, lo, *args, o_std, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2)
+        _tc(lib, wsplit(hi), wsplit(lo), *args, o_ws, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 8)
+        assert torch.equal(o_ws, o_std)
     # pad channels of the last chunk stay exactly zero (+ bias pad 0)
     if cout % 8:
         assert float(out[:, -1, ..., cout % 8:].abs().max()) == 0.0
@@ -112,6 +119,16 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
                           stream()), "conv_tc dgrad fp16")
     torch.cuda.synchronize()
     assert rel_l2(from_chunked(gx3, cin).cpu(), g3) < 2e-5, rel_l2(from_chunked(gx3, cin).cpu(), g3)
+    if tr and s == 2:
+        # the dgrad of a transposed conv is a stride-2 conv: w-parity-split dY (flags bit3)
+        g_std = torch.zeros_like(gx3); g_ws = torch.zeros_like(gx3)
+        hws = wsplit(hhi)
+        for buf, src, fl in ((g_std, hhi, 2), (g_ws, hws, 2 | 8)):
+            check(lib.tta_conv_tc(src.data_ptr(), 0, c8o * ref[0, 0].numel() * 8, TTA_F16_HI, N, c8o, *odims,
+                                  wph.data_ptr(), 0, buf.data_ptr(), c8i * Vi * 8, c8i, *dims, 1 - mode, K, s, 0, fl,
+                                  stream()), "conv_tc dgrad wsplit")
+        torch.cuda.synchronize()
+        assert torch.equal(g_ws, g_std)
 
 
 def test_conv_tc_reads_concat_slice_view(lib, cuda):

@@ -125,11 +125,15 @@ def test_op_graph_layer_counts(cfg, nconv, nnorm, ndgrad):
     eng = m.engine
     eng._ensure_device(torch.device("cpu"), dry=True)
     plan = eng.build_plan(1, 32, 32, 32)
-    assert len(plan.fwd) == nconv + nnorm and len(plan.bwd) == ndgrad + nnorm
-    assert plan.launches_fwd == 1 + nconv + 2 * nnorm + 2
-    assert set(plan.conv_backends.values()) <= {"tc", "small", "simt"}
+    # res-unit UNets end in norm -> 3x3x3 conv(R->R) -> entropy: that tail runs as the fused head
+    # (norm apply + conv + loss finalize leave the forward list, dgrad + norm reduce merge)
+    fh = int(plan.fused_head)
+    assert fh == (cfg is not BARE_DEFAULT_MODEL_CFG and "num_res_units" in cfg and cfg["num_res_units"] > 0)
+    assert len(plan.fwd) == nconv + nnorm - fh and len(plan.bwd) == ndgrad + nnorm
+    assert plan.launches_fwd == 1 + nconv + 2 * nnorm + 2 - 3 * fh
+    assert set(plan.conv_backends.values()) <= {"tc", "small", "simt", "head"}
     if cfg is BRATS_MODEL_CFG:
-        assert plan.conv_backends["model.2.1.conv.unit0.conv:fwd"] == "small"
+        assert plan.conv_backends["model.2.1.conv.unit0.conv:fwd"] == "head"
         assert plan.conv_backends["model.0.conv.unit0.conv||residual:fwd"] == "tc"
     with pytest.raises(ValueError):
         eng.build_plan(1, 24, 32, 32)        # not divisible by 16

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
 from multimodal_tta_b200.layout import (from_chunked, join_planes, pack_bias, pack_weights_simt, to_chunked,
                                         wg_dgrad, wg_forward)
-from tests.util import planes_from, rel_l2, stream
+from tests.util import planes_from, rel_l2, stream, wsplit
 
 pytestmark = pytest.mark.gpu
 
@@ -140,7 +140,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     ohi = torch.zeros((N, C8, *dims, 8), dtype=torch.int16, device=cuda); olo = torch.zeros_like(ohi)
     check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
                              bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi.data_ptr(), olo.data_ptr(), ns,
-                             TTA_F16, 0, batch_mode, 1e-5, stream()))
+                             TTA_F16, 0, batch_mode, 1e-5, 0, 0, 0, 0, stream()))
     got = from_chunked(join_planes(ohi, olo, TTA_F16), C).cpu()
     assert (got - a.detach()).abs().max() < 2e-5      # fp16x2 storage (22 bits) + fp32 stats
     # fused path: partial sums only, finalize inside the apply prologue -> identical planes
@@ -149,9 +149,20 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     ohi2 = torch.zeros_like(ohi); olo2 = torch.zeros_like(ohi)
     check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean2.data_ptr(), rstd2.data_ptr(), gp.data_ptr(),
                              bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi2.data_ptr(), olo2.data_ptr(), ns,
-                             TTA_F16, ws.data_ptr(), batch_mode, 1e-5, stream()))
+                             TTA_F16, ws.data_ptr(), batch_mode, 1e-5, 0, 0, 0, 0, stream()))
     got2 = from_chunked(join_planes(ohi2, olo2, TTA_F16), C).cpu()
     assert (got2 - got).abs().max() < 2e-6            # same math, fp64 partial sums in another order
+    if dims[2] % 2 == 0:
+        # second copy in the w-parity-split layout (operand of a stride-2 tcgen05 conv): same bits,
+        # rows permuted to [even w | odd w]
+        whi = torch.zeros_like(ohi); wlo = torch.zeros_like(ohi)
+        ohi3 = torch.zeros_like(ohi); olo3 = torch.zeros_like(ohi)
+        check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
+                                 bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi3.data_ptr(), olo3.data_ptr(), ns,
+                                 TTA_F16, 0, batch_mode, 1e-5, whi.data_ptr(), wlo.data_ptr(), ns, dims[2],
+                                 stream()))
+        assert torch.equal(ohi3, ohi) and torch.equal(olo3, olo)
+        assert torch.equal(whi, wsplit(ohi)) and torch.equal(wlo, wsplit(olo))
     assert torch.allclose(mean, mean2, rtol=1e-6, atol=1e-7) and torch.allclose(rstd, rstd2, rtol=1e-6)
     # backward
     gch = to_chunked(g_in.to(cuda))
@@ -166,7 +177,14 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
                                  rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
                                  dhi.data_ptr(), dlo.data_ptr(), ns, ahi.data_ptr(), alo.data_ptr(), ns, TTA_BF16,
-                                 0, C, 0, 0, stream()))
+                                 0, C, 0, 0, 0, stream()))
+    if dims[2] % 2 == 0:
+        dhw = torch.zeros_like(ohi); dlw = torch.zeros_like(ohi)
+        check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
+                                     rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
+                                     dhw.data_ptr(), dlw.data_ptr(), ns, 0, 0, 0, TTA_BF16,
+                                     0, C, 0, 0, dims[2], stream()))
+        assert torch.equal(dhw, wsplit(dhi)) and torch.equal(dlw, wsplit(dlo))
     # fused path: finalize of the reductions inside the bwd-apply prologue
     dg2 = torch.zeros_like(dg); db2 = torch.zeros_like(db)
     dhi2 = torch.zeros_like(ohi); dlo2 = torch.zeros_like(ohi)
@@ -176,7 +194,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
                                  rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, 0,
                                  dhi2.data_ptr(), dlo2.data_ptr(), ns, 0, 0, 0, TTA_BF16, ws.data_ptr(), C,
-                                 dg2.data_ptr(), db2.data_ptr(), stream()))
+                                 dg2.data_ptr(), db2.data_ptr(), 0, stream()))
     assert torch.allclose(dg, dg2, rtol=1e-6, atol=1e-7) and torch.allclose(db, db2, rtol=1e-6, atol=1e-7)
     dy2 = from_chunked(join_planes(dhi2, dlo2, TTA_BF16), C).cpu()
     assert rel_l2(dy2, yr.grad) < 3e-5
@@ -247,7 +265,12 @@ def test_gather_pack_windows_and_padding(lib, cuda):
     vd, wd, sd = vol.to(cuda), wins.to(cuda), scale.to(cuda)   # keep alive across the async launch
     check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, 11, wd.data_ptr(),
                               sd.data_ptr(), 3, *roi, hi.data_ptr(), lo.data_ptr(),
-                              roi[0] * roi[1] * roi[2] * 8, 1, stream()))
+                              roi[0] * roi[1] * roi[2] * 8, 1, 0, stream()))
+    hw = torch.zeros_like(hi); lw = torch.zeros_like(hi)
+    check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, 11, wd.data_ptr(),
+                              sd.data_ptr(), 3, *roi, hw.data_ptr(), lw.data_ptr(),
+                              roi[0] * roi[1] * roi[2] * 8, 1, 1, stream()))
+    assert torch.equal(hw, wsplit(hi)) and torch.equal(lw, wsplit(lo))   # w-parity-split variant
     got = from_chunked(join_planes(hi, lo, TTA_F16), 3).cpu()
     pv = F.pad(vol, (8, 8, 8, 8, 8, 8))
     for b, (vi, d0, h0, w0) in enumerate(wins.tolist()):
@@ -267,3 +290,79 @@ def test_dice_counts_match_reference_golden(lib, cuda):
         assert torch.equal(dice, torch.from_numpy(gold[f"dice{i}"]))     # bit exact
         assert torch.equal(iou, torch.from_numpy(gold[f"iou{i}"]))
         assert torch.equal(valid, torch.from_numpy(gold[f"valid{i}"]))
+
+
+@pytest.mark.parametrize("mode,C,dims,batch_mode", [(1, 3, (9, 10, 37), 0), (0, 3, (8, 8, 32), 0), (1, 1, (5, 17, 6), 0),
+                                                     (1, 2, (16, 8, 40), 1), (0, 4, (3, 9, 33), 0)])
+def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode):
+    """tta_head_fused_{fwd,bwd} (norm apply + 3x3x3 conv + entropy, and its backward up to the
+    norm-backward reduction) against torch fp32 autograd on the CPU; ragged tiles (dims are not
+    multiples of the 8x8x32 tile).  fp32 FMA chains in a different order: 3e-6 relative."""
+    from multimodal_tta_b200.layout import pack_weights_small
+    from oracle.tent_oracle import entropy_loss
+    torch.manual_seed(11)
+    N = 2
+    V = dims[0] * dims[1] * dims[2]
+    y = torch.randn(N, C, *dims) * 2 + 0.5
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.3
+    w = torch.randn(C, C, 3, 3, 3) * 0.2
+    b = torch.randn(C) * 0.1
+    S = 2.0 ** 10                                   # loss scale carried by dlogits / dz / dgamma
+    # ---- oracle
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    zn = F.batch_norm(yr, None, None, gr, br, training=True, eps=1e-5) if batch_mode else \
+        F.instance_norm(yr, weight=gr, bias=br, eps=1e-5)
+    a = torch.relu(zn)
+    a.retain_grad()
+    z = F.conv3d(a, w, b, padding=1)
+    z.retain_grad()
+    loss = entropy_loss(z, "sigmoid" if mode == 1 else "softmax")
+    loss.backward()
+    # ---- device
+    ych = to_chunked(y.to(cuda))
+    ns = V * 8
+    mean = torch.zeros(N * 8, device=cuda); rstd = torch.zeros_like(mean)
+    nws = max(lib.tta_norm_workspace_floats(N, 1, V), lib.tta_head_fused_workspace_floats(N, *dims))
+    ws = torch.zeros(nws, device=cuda)
+    gp = torch.zeros(8, device=cuda); gp[:C] = gamma.to(cuda)
+    bp = torch.zeros(8, device=cuda); bp[:C] = beta.to(cuda)
+    check(lib.tta_norm_stats(ych.data_ptr(), ns, N, 1, V, batch_mode, 1e-5, mean.data_ptr(), rstd.data_ptr(),
+                             ws.data_ptr(), 1, stream()))
+    wh = pack_weights_small(wg_forward(w, False), 0)            # HOST [27][8][8]
+    bias = pack_bias(b.to(cuda))
+    logits = torch.zeros(N, C, *dims, device=cuda); dlog = torch.zeros_like(logits)
+    lossd = torch.zeros(1, device=cuda)
+    check(lib.tta_head_fused_fwd(ych.data_ptr(), ns, N, C, *dims, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
+                                 bp.data_ptr(), 1, wh.data_ptr(), bias.data_ptr(), mode, 1.0 / (N * V), S, 0,
+                                 logits.data_ptr(), dlog.data_ptr(), ws.data_ptr(), lossd.data_ptr(), stream()))
+    assert rel_l2(logits.cpu(), z.detach()) < 3e-6
+    assert abs(float(lossd) - float(loss.detach())) < 2e-6 * max(1.0, abs(float(loss.detach())))
+    assert rel_l2(dlog.cpu() / S, z.grad) < 1e-5
+    # inference variant: no dlogits, same logits; a second call also proves the block counter reset
+    logits2 = torch.zeros_like(logits); loss2 = torch.zeros(1, device=cuda)
+    check(lib.tta_head_fused_fwd(ych.data_ptr(), ns, N, C, *dims, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
+                                 bp.data_ptr(), 1, wh.data_ptr(), bias.data_ptr(), mode, 1.0 / (N * V), S, 0,
+                                 logits2.data_ptr(), 0, ws.data_ptr(), loss2.data_ptr(), stream()))
+    assert torch.equal(logits2, logits) and torch.equal(loss2, lossd)
+    # ---- backward: masked gradient w.r.t. the norm output + reductions
+    dz = torch.full((N, 1, *dims, 8), 7.0, device=cuda)
+    sums = torch.zeros(N * 8 * 2, device=cuda)
+    dg = torch.zeros(8, device=cuda); db = torch.zeros(8, device=cuda)
+    for _ in range(2):                               # twice: self-resetting counters
+        check(lib.tta_head_fused_bwd(dlog.data_ptr(), N, C, *dims, wh.data_ptr(), ych.data_ptr(), ns,
+                                     mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode,
+                                     dz.data_ptr(), ns, sums.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                     ws.data_ptr(), stream()))
+    dz_ref = a.grad * (zn.detach() > 0)
+    assert rel_l2(from_chunked(dz, C).cpu() / S, dz_ref) < 1e-5
+    assert float(dz[..., C:].abs().max()) == 0.0     # pad channels exactly zero
+    assert rel_l2(dg[:C].cpu() / S, gr.grad) < 2e-5
+    assert rel_l2(db[:C].cpu() / S, br.grad) < 2e-5
+    # the existing norm-backward apply consumes dz as its gradient source: dy = autograd's dL/dy
+    dhi = torch.zeros((N, 1, *dims, 8), dtype=torch.int16, device=cuda); dlo = torch.zeros_like(dhi)
+    check(lib.tta_norm_bwd_apply(dz.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, 1, V, mean.data_ptr(),
+                                 rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
+                                 dhi.data_ptr(), dlo.data_ptr(), ns, 0, 0, 0, TTA_BF16, 0, C, 0, 0, 0, stream()))
+    dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu() / S
+    assert rel_l2(dy, yr.grad) < 5e-5                # bf16x2 storage (~16 bits)

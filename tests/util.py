@@ -34,3 +34,8 @@ def planes_from(x_ncdhw: torch.Tensor, dtype_tag: int):
     hi, lo = split_planes(ch, dtype_tag)
     val = from_chunked(join_planes(hi, lo, dtype_tag), x_ncdhw.shape[1])
     return hi.contiguous(), lo.contiguous(), val
+
+
+def wsplit(planes: torch.Tensor) -> torch.Tensor:
+    """[..., W, 8] chunked planes -> the w-parity-split layout [..., (even w | odd w), 8]."""
+    return torch.cat([planes[..., 0::2, :], planes[..., 1::2, :]], dim=-2).contiguous()
