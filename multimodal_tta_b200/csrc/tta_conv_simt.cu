@@ -30,9 +30,11 @@ struct ConvGeom {
 
 template <int DT>
 __global__ void __launch_bounds__(kConvThreads)
-conv_simt_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo,
-                 const float* __restrict__ Wp, const float* __restrict__ bias,
-                 float* __restrict__ out, ConvGeom g, int accumulate) {
+conv_simt_kernel(const uint16_t* in_hi, const uint16_t* in_lo,
+                 const float* Wp, const float* bias,
+                 float* out, ConvGeom g, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float wsm[];  // [taps][8 ci][8 co]
   const int co_chunk = blockIdx.y, n = blockIdx.z;
   const int K = g.K, taps = K * K * K, pad = (K - 1) / 2, s = g.stride;
@@ -173,10 +175,10 @@ extern "C" int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long 
   const dim3 grid((unsigned)((groups + kConvThreads - 1) / kConvThreads), C8out, N);
   const size_t smem = (size_t)K * K * K * 64 * sizeof(float);
   if (in_dtype == TTA_F16)
-    conv_simt_kernel<TTA_F16><<<grid, kConvThreads, smem, stream>>>(in_hi, in_lo, Wp, bias, out, g, accumulate);
+    tta_launch(conv_simt_kernel<TTA_F16>, grid, kConvThreads, smem, stream, tta_pdl_family(1), in_hi, in_lo, Wp, bias, out, g, accumulate);
   else if (in_dtype == TTA_F16_HI)
-    conv_simt_kernel<TTA_F16_HI><<<grid, kConvThreads, smem, stream>>>(in_hi, in_lo, Wp, bias, out, g, accumulate);
+    tta_launch(conv_simt_kernel<TTA_F16_HI>, grid, kConvThreads, smem, stream, tta_pdl_family(1), in_hi, in_lo, Wp, bias, out, g, accumulate);
   else
-    conv_simt_kernel<TTA_BF16><<<grid, kConvThreads, smem, stream>>>(in_hi, in_lo, Wp, bias, out, g, accumulate);
+    tta_launch(conv_simt_kernel<TTA_BF16>, grid, kConvThreads, smem, stream, tta_pdl_family(1), in_hi, in_lo, Wp, bias, out, g, accumulate);
   return tta_check_launch("tta_conv_simt");
 }

@@ -25,9 +25,11 @@ struct SmallW {
 
 template <int DT, int CIN, int COUT>
 __global__ void __launch_bounds__(kSmallThreads)
-conv_small_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo, long long in_ns,
-                  const __grid_constant__ SmallW<27 * CIN * COUT> Wc, const float* __restrict__ bias,
-                  float* __restrict__ out, long long out_ns, int D, int H, int Wd, int accumulate) {
+conv_small_kernel(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns,
+                  const __grid_constant__ SmallW<27 * CIN * COUT> Wc, const float* bias,
+                  float* out, long long out_ns, int D, int H, int Wd, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const long long V = (long long)D * H * Wd;
   const long long gi0 = (long long)blockIdx.x * kSmallThreads + threadIdx.x;
@@ -129,11 +131,11 @@ static int launch_small(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     for (int ci = 0; ci < CIN; ++ci)
       for (int co = 0; co < COUT; ++co) Wc.w[(tap * CIN + ci) * COUT + co] = W[(tap * 8 + ci) * 8 + co];
   if (in_dtype == TTA_F16)
-    conv_small_kernel<TTA_F16, CIN, COUT><<<grid, kSmallThreads, 0, stream>>>(in_hi, in_lo, in_ns, Wc, bias, out, out_ns, D, H, Wd, accumulate);
+    tta_launch(conv_small_kernel<TTA_F16, CIN, COUT>, grid, kSmallThreads, 0, stream, tta_pdl_family(32), in_hi, in_lo, in_ns, Wc, bias, out, out_ns, D, H, Wd, accumulate);
   else if (in_dtype == TTA_BF16)
-    conv_small_kernel<TTA_BF16, CIN, COUT><<<grid, kSmallThreads, 0, stream>>>(in_hi, in_lo, in_ns, Wc, bias, out, out_ns, D, H, Wd, accumulate);
+    tta_launch(conv_small_kernel<TTA_BF16, CIN, COUT>, grid, kSmallThreads, 0, stream, tta_pdl_family(32), in_hi, in_lo, in_ns, Wc, bias, out, out_ns, D, H, Wd, accumulate);
   else
-    conv_small_kernel<TTA_F16_HI, CIN, COUT><<<grid, kSmallThreads, 0, stream>>>(in_hi, in_lo, in_ns, Wc, bias, out, out_ns, D, H, Wd, accumulate);
+    tta_launch(conv_small_kernel<TTA_F16_HI, CIN, COUT>, grid, kSmallThreads, 0, stream, tta_pdl_family(32), in_hi, in_lo, in_ns, Wc, bias, out, out_ns, D, H, Wd, accumulate);
   return tta_check_launch("tta_conv_small");
 }
 

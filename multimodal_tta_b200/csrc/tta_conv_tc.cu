@@ -291,6 +291,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   __shared__ __align__(16) float bias_s[128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();  // the next kernel's CTAs may be scheduled (they block in their own pdl_wait)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) {
@@ -319,6 +320,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // everything above (barriers, TMEM allocation, smem clear) overlapped the previous kernel's tail;
+  // activations / gradients written by it are only touched from here on
+  pdl_wait();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t acc_cols = SPLIT ? 2u * P.ntile : (uint32_t)P.ntile;
@@ -794,6 +798,7 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   }
 
   const size_t smem = (size_t)P.nstages * P.stage_bytes + 1024;
+  const bool pdl_ok = !(P.ksplit > 1 && !accumulate);  // a memset precedes the split-K launch
   if (P.ksplit > 1 && !accumulate) {
     // partial sums are combined with float4 atomics: start from zero
     const long long Vo = (long long)Do * Ho * Wo;
@@ -817,7 +822,7 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
         return tta_check_launch("tta_conv_tc(cudaFuncSetAttribute)");                                      \
       configured = true;                                                                                   \
     }                                                                                                      \
-    conv_tc_kernel<G, T, S><<<grid, kTcThreads, smem, stream>>>(P);                                           \
+    tta_launch(conv_tc_kernel<G, T, S>, grid, kTcThreads, smem, stream, pdl_ok && tta_pdl_family(8), P);                                           \
   } while (0)
 #define TTA_TC_LAUNCH(G, T)                                                                                \
   do {                                                                                                     \

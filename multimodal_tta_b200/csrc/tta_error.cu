@@ -2,6 +2,8 @@
 // failure on the calling thread is read back with tta_last_error().
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "tta_common.cuh"
 
@@ -12,6 +14,24 @@ void tta_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool tta_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("TTA_PDL");
+    on = (v != nullptr && strcmp(v, "1") == 0) ? 1 : 0;  // opt-in: measured slower inside the CUDA graph
+  }
+  return on != 0;
+}
+
+bool tta_pdl_family(int family_bit) {
+  static int off = -1;
+  if (off < 0) {
+    const char* v = getenv("TTA_PDL_OFF");
+    off = v ? atoi(v) : 0;
+  }
+  return (off & family_bit) == 0;
 }
 
 int tta_check_launch(const char* what) {

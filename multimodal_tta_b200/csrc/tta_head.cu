@@ -50,12 +50,14 @@ __device__ __forceinline__ void tile_origin(const HeadGeom& G, int& d0, int& h0,
 // ---------------------------------------------------------------- forward
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 3)
-head_fwd_kernel(const float* __restrict__ y, long long y_ns, const HeadGeom G, const float* __restrict__ mean,
-                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                int relu, const __grid_constant__ HeadW<27 * CIN * COUT> Wc, const float* __restrict__ bias, int mode,
-                float inv_count, float grad_scale, const float* __restrict__ sample_w, float* __restrict__ logits,
-                float* __restrict__ dlogits, float* __restrict__ partial, unsigned int* __restrict__ counter,
-                float* __restrict__ loss) {
+head_fwd_kernel(const float* y, long long y_ns, const HeadGeom G, const float* mean,
+                const float* rstd, const float* gamma, const float* beta,
+                int relu, const __grid_constant__ HeadW<27 * CIN * COUT> Wc, const float* bias, int mode,
+                float inv_count, float grad_scale, const float* sample_w, float* logits,
+                float* dlogits, float* partial, unsigned int* counter,
+                float* loss) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float tile[];  // [CIN][kHD][kHH][kPitch]
   const int n = blockIdx.y;
   int d0, h0, w0;
@@ -71,33 +73,41 @@ head_fwd_kernel(const float* __restrict__ y, long long y_ns, const HeadGeom G, c
     be[c] = beta[c];
   }
   // ---- stage the normalised halo tile (zero padding applies to the ACTIVATION, so OOB -> 0).
-  // All of a thread's global loads are issued before the first use: one memory latency per CTA.
+  // A thread owns up to two fixed (h, w) positions of the 10 x 34 halo plane and walks the ten
+  // d-planes: no index divisions in the loop, five independent 16-byte loads in flight per position.
   {
-    constexpr int kIters = (kHD * kHH * kHW + kThreads - 1) / kThreads;
-    float4 x[kIters];
+    const long long HW = (long long)G.H * G.W;
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int idx = threadIdx.x + it * kThreads;
-      const int ww = idx % kHW, hh = (idx / kHW) % kHH, dd = idx / (kHW * kHH);
-      const int gd = d0 + dd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
-      const bool in = idx < kHD * kHH * kHW && gd >= 0 && gd < G.D && gh >= 0 && gh < G.H && gw >= 0 && gw < G.W;
-      x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (in) x[it] = __ldg(reinterpret_cast<const float4*>(yb + (((long long)gd * G.H + gh) * G.W + gw) * 8));
-    }
+    for (int k = 0; k < 2; ++k) {
+      const int p = threadIdx.x + k * kThreads;
+      if (p < kHH * kHW) {  // warp-uniform for all but one warp
+        const int hh = p / kHW, ww = p - hh * kHW;
+        const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+        const bool hw_in = gh >= 0 && gh < G.H && gw >= 0 && gw < G.W;
+        const float* src = yb + ((long long)gh * G.W + gw) * 8;
+        float* dst = tile + hh * kPitch + ww;
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int idx = threadIdx.x + it * kThreads;
-      const int ww = idx % kHW, hh = (idx / kHW) % kHH, dd = idx / (kHW * kHH);
-      const int gd = d0 + dd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
-      const bool in = gd >= 0 && gd < G.D && gh >= 0 && gh < G.H && gw >= 0 && gw < G.W;
-      if (idx < kHD * kHH * kHW) {
-        const float xv[4] = {x[it].x, x[it].y, x[it].z, x[it].w};
+        for (int half = 0; half < 2; ++half) {
+          float4 x[kHD / 2];
+          bool in[kHD / 2];
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) {
-          float z = (xv[c] - mu[c]) * rs[c];
-          z = fmaf(z, ga[c], be[c]);
-          if (relu) z = fmaxf(z, 0.f);
-          tile[c * kVol + dd * kPlane + hh * kPitch + ww] = in ? z : 0.f;
+          for (int j = 0; j < kHD / 2; ++j) {
+            const int gd = d0 + half * (kHD / 2) + j - 1;
+            in[j] = hw_in && gd >= 0 && gd < G.D;
+            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[j]) x[j] = __ldcg(reinterpret_cast<const float4*>(src + gd * HW * 8));
+          }
+#pragma unroll
+          for (int j = 0; j < kHD / 2; ++j) {
+            const float xv[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+              float z = (xv[c] - mu[c]) * rs[c];
+              z = fmaf(z, ga[c], be[c]);
+              if (relu) z = fmaxf(z, 0.f);
+              dst[c * kVol + (half * (kHD / 2) + j) * kPlane] = in[j] ? z : 0.f;
+            }
+          }
         }
       }
     }
@@ -111,6 +121,10 @@ head_fwd_kernel(const float* __restrict__ y, long long y_ns, const HeadGeom G, c
   const float gs = sw * inv_count * grad_scale;
   const int h = h0 + hl, w = w0 + wl;
   const bool hw_ok = h < G.H && w < G.W;
+  const long long HWo = (long long)G.H * G.W;
+  const long long vbase = (long long)n * COUT * V + ((long long)d0 * G.H + h) * G.W + w;  // plane o: + o*HWo
+  float* lg = logits + vbase;
+  float* dl = dlogits + vbase;
   float hsum = 0.f;
   float bi[COUT];
 #pragma unroll
@@ -142,18 +156,17 @@ head_fwd_kernel(const float* __restrict__ y, long long y_ns, const HeadGeom G, c
     if (dd >= 2) {
       const int o = dd - 2, d = d0 + o;
       if (d < G.D && hw_ok) {
-        const long long v = ((long long)d * G.H + h) * G.W + w;
         float z[COUT], g[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
           z[c] = acc[o][c] + bi[c];
           g[c] = 0.f;
-          if (logits) logits[((long long)n * COUT + c) * V + v] = z[c];
+          if (logits) lg[c * V + o * HWo] = z[c];
         }
         hsum += entropy_point<COUT>(z, COUT, mode, gs, g) * sw;
         if (dlogits) {
 #pragma unroll
-          for (int c = 0; c < COUT; ++c) dlogits[((long long)n * COUT + c) * V + v] = g[c];
+          for (int c = 0; c < COUT; ++c) dl[c * V + o * HWo] = g[c];
         }
       }
     }
@@ -196,37 +209,45 @@ head_fwd_kernel(const float* __restrict__ y, long long y_ns, const HeadGeom G, c
 // ---------------------------------------------------------------- backward
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 3)
-head_bwd_kernel(const float* __restrict__ dlogits, const HeadGeom G, const __grid_constant__ HeadW<27 * CIN * COUT> Wc,
-                const float* __restrict__ y, long long y_ns, const float* __restrict__ mean,
-                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                int relu, float* __restrict__ dz, long long dz_ns, float* __restrict__ partial,
-                unsigned int* __restrict__ counters, int N, int batch_mode, float* __restrict__ sums,
-                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+head_bwd_kernel(const float* dlogits, const HeadGeom G, const __grid_constant__ HeadW<27 * CIN * COUT> Wc,
+                const float* y, long long y_ns, const float* mean,
+                const float* rstd, const float* gamma, const float* beta,
+                int relu, float* dz, long long dz_ns, float* partial,
+                unsigned int* counters, int N, int batch_mode, float* sums,
+                float* dgamma, float* dbeta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float tile[];  // [COUT][kHD][kHH][kPitch]
   const int n = blockIdx.y;
   int d0, h0, w0;
   tile_origin(G, d0, h0, w0);
   const long long V = (long long)G.D * G.H * G.W;
   {
-    constexpr int kIters = (kHD * kHH * kHW + kThreads - 1) / kThreads;
-    float x[kIters][COUT];
+    const long long HW = (long long)G.H * G.W;
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int idx = threadIdx.x + it * kThreads;
-      const int ww = idx % kHW, hh = (idx / kHW) % kHH, dd = idx / (kHW * kHH);
-      const int gd = d0 + dd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
-      const bool in = idx < kHD * kHH * kHW && gd >= 0 && gd < G.D && gh >= 0 && gh < G.H && gw >= 0 && gw < G.W;
-      const long long v = ((long long)gd * G.H + gh) * G.W + gw;
+    for (int k = 0; k < 2; ++k) {
+      const int p = threadIdx.x + k * kThreads;
+      if (p < kHH * kHW) {
+        const int hh = p / kHW, ww = p - hh * kHW;
+        const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+        const bool hw_in = gh >= 0 && gh < G.H && gw >= 0 && gw < G.W;
+        const float* src = dlogits + (long long)n * COUT * V + (long long)gh * G.W + gw;
+        float* dst = tile + hh * kPitch + ww;
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) x[it][c] = in ? __ldg(dlogits + ((long long)n * COUT + c) * V + v) : 0.f;
-    }
+        for (int half = 0; half < 2; ++half) {
+          float x[kHD / 2][COUT];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int idx = threadIdx.x + it * kThreads;
-      const int ww = idx % kHW, hh = (idx / kHW) % kHH, dd = idx / (kHW * kHH);
-      if (idx < kHD * kHH * kHW) {
+          for (int j = 0; j < kHD / 2; ++j) {
+            const int gd = d0 + half * (kHD / 2) + j - 1;
+            const bool in = hw_in && gd >= 0 && gd < G.D;
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) tile[c * kVol + dd * kPlane + hh * kPitch + ww] = x[it][c];
+            for (int c = 0; c < COUT; ++c) x[j][c] = in ? __ldcg(src + c * V + gd * HW) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < kHD / 2; ++j)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) dst[c * kVol + (half * (kHD / 2) + j) * kPlane] = x[j][c];
+        }
       }
     }
   }
@@ -247,6 +268,8 @@ head_bwd_kernel(const float* __restrict__ dlogits, const HeadGeom G, const __gri
   const bool hw_ok = h < G.H && w < G.W;
   const float* yb = y + (long long)n * y_ns;
   float* ob = dz + (long long)n * dz_ns;
+  const long long HWo = (long long)G.H * G.W;
+  const long long vbase = ((long long)d0 * G.H + h) * G.W + w;  // voxel of output plane o: + o*HWo
   float acc[kTD][CIN];
 #pragma unroll
   for (int o = 0; o < kTD; ++o)
@@ -258,7 +281,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const HeadGeom G, const __gri
     if (dd >= 1 && dd <= kTD) {
       const int o = dd - 1, d = d0 + o;
       yv[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (d < G.D && hw_ok) yv[o] = __ldg(reinterpret_cast<const float4*>(yb + (((long long)d * G.H + h) * G.W + w) * 8));
+      if (d < G.D && hw_ok) yv[o] = __ldcg(reinterpret_cast<const float4*>(yb + (vbase + o * HWo) * 8));
     }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
@@ -281,7 +304,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const HeadGeom G, const __gri
       // output plane o = dd - 2 is complete: ReLU mask, norm-backward partial sums, masked gradient out
       const int o = dd - 2, d = d0 + o;
       if (d < G.D && hw_ok) {
-        const long long v = ((long long)d * G.H + h) * G.W + w;
+        const long long v = vbase + o * HWo;
         const float xv[4] = {yv[o].x, yv[o].y, yv[o].z, yv[o].w};
         float r[8];
 #pragma unroll
@@ -373,7 +396,7 @@ int tta_head_fused_fwd(const float* y, long long y_ns, int N, int C, int D, int 
       TTA_REQUIRE(set_smem(head_fwd_kernel<CC, CC>, smem), "tta_head_fused_fwd: cudaFuncSetAttribute failed"); \
       configured = true;                                                                                      \
     }                                                                                                         \
-    head_fwd_kernel<CC, CC><<<grid, kThreads, smem, stream>>>(y, y_ns, G, mean, rstd, gamma, beta, relu, Wc, bias, \
+    tta_launch(head_fwd_kernel<CC, CC>, grid, kThreads, smem, stream, tta_pdl_family(16), y, y_ns, G, mean, rstd, gamma, beta, relu, Wc, bias, \
                                                               mode, inv_count, grad_scale, sample_w, logits,   \
                                                               dlogits, workspace + 1024, counter, loss);       \
   } while (0)
@@ -405,7 +428,7 @@ int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, 
       TTA_REQUIRE(set_smem(head_bwd_kernel<CC, CC>, smem), "tta_head_fused_bwd: cudaFuncSetAttribute failed"); \
       configured = true;                                                                                      \
     }                                                                                                         \
-    head_bwd_kernel<CC, CC><<<grid, kThreads, smem, stream>>>(dlogits, G, Wc, y, y_ns, mean, rstd, gamma, beta, \
+    tta_launch(head_bwd_kernel<CC, CC>, grid, kThreads, smem, stream, tta_pdl_family(16), dlogits, G, Wc, y, y_ns, mean, rstd, gamma, beta, \
                                                               relu, dz, dz_ns, workspace + 1024, counters, N,  \
                                                               batch_mode, sums, dgamma, dbeta);                \
   } while (0)

@@ -17,10 +17,12 @@ namespace tta {
 // ---------------------------------------------------------------- forward statistics
 // partial[((n*C8 + chunk)*splits + split)*16 + {0..7: sum, 8..15: sumsq}]
 __global__ void __launch_bounds__(kThreads)
-norm_stats_partial_kernel(const float* __restrict__ y, long long n_stride, int C8, long long V,
-                          int splits, float* __restrict__ partial, unsigned int* __restrict__ counters,
-                          int N, int batch_mode, float eps, float* __restrict__ mean,
-                          float* __restrict__ rstd) {
+norm_stats_partial_kernel(const float* y, long long n_stride, int C8, long long V,
+                          int splits, float* partial, unsigned int* counters,
+                          int N, int batch_mode, float eps, float* mean,
+                          float* rstd) {
+  pdl_trigger();
+  pdl_wait();
   const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
   const float* base = y + (long long)n * n_stride + (long long)chunk * V * 8;
   const long long per = (V + splits - 1) / splits;
@@ -63,9 +65,11 @@ norm_stats_partial_kernel(const float* __restrict__ y, long long n_stride, int C
 
 // one thread per (n, channel): combine splits (and n for batch mode) in fp64.
 // mean/rstd are written per (n, c) in both modes so consumers are mode-agnostic.
-__global__ void norm_stats_finalize_kernel(const float* __restrict__ partial, int N, int C8,
+__global__ void norm_stats_finalize_kernel(const float* partial, int N, int C8,
                                            int splits, long long V, int batch_mode, float eps,
-                                           float* __restrict__ mean, float* __restrict__ rstd) {
+                                           float* mean, float* rstd) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int C = C8 * 8;
   if (idx >= N * C) return;
@@ -92,15 +96,17 @@ __global__ void norm_stats_finalize_kernel(const float* __restrict__ partial, in
 // RES: 0 none, 1 fp32 view, 2 split-plane view (dtype ODT)
 template <int RES, int ODT>
 __global__ void __launch_bounds__(kThreads)
-norm_apply_kernel(const float* __restrict__ y, long long y_ns, int C8, long long V,
-                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                  const float* __restrict__ res_f32, const uint16_t* __restrict__ res_hi,
-                  const uint16_t* __restrict__ res_lo, long long res_ns,
-                  uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, long long out_ns,
-                  const float* __restrict__ partial, int splits, int N, int batch_mode, float eps,
-                  float* __restrict__ mean_w, float* __restrict__ rstd_w, uint16_t* __restrict__ ws_hi,
-                  uint16_t* __restrict__ ws_lo, long long ws_ns, int Wd) {
+norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
+                  const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, int relu,
+                  const float* res_f32, const uint16_t* res_hi,
+                  const uint16_t* res_lo, long long res_ns,
+                  uint16_t* out_hi, uint16_t* out_lo, long long out_ns,
+                  const float* partial, int splits, int N, int batch_mode, float eps,
+                  float* mean_w, float* rstd_w, uint16_t* ws_hi,
+                  uint16_t* ws_lo, long long ws_ns, int Wd) {
+  pdl_trigger();
+  pdl_wait();
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
@@ -170,14 +176,16 @@ norm_apply_kernel(const float* __restrict__ y, long long y_ns, int C8, long long
 // ---------------------------------------------------------------- backward reductions
 // partial[..][0..7] = sum dz, [8..15] = sum dz*xhat     (dz = (g0+g1) * [z>0])
 __global__ void __launch_bounds__(kThreads)
-norm_bwd_partial_kernel(const float* __restrict__ g0, long long g0_ns,
-                        const float* __restrict__ g1, long long g1_ns,
-                        const float* __restrict__ y, long long y_ns, int C8, long long V,
-                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                        const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                        int splits, float* __restrict__ partial, unsigned int* __restrict__ counters, int N,
-                        int batch_mode, int Creal, float* __restrict__ sums, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta) {
+norm_bwd_partial_kernel(const float* g0, long long g0_ns,
+                        const float* g1, long long g1_ns,
+                        const float* y, long long y_ns, int C8, long long V,
+                        const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, int relu,
+                        int splits, float* partial, unsigned int* counters, int N,
+                        int batch_mode, int Creal, float* sums, float* dgamma,
+                        float* dbeta) {
+  pdl_trigger();
+  pdl_wait();
   const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
@@ -225,9 +233,11 @@ norm_bwd_partial_kernel(const float* __restrict__ g0, long long g0_ns,
 
 // sums[(n*C + c)*2 + {0,1}] = {sum dz, sum dz*xhat} over the normalisation group (per n for IN,
 // over all n for BN, broadcast to every n);  dgamma[c], dbeta[c] = sums over n (IN) / the group (BN).
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int N, int C8, int Creal,
-                                         int splits, int batch_mode, float* __restrict__ sums,
-                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void norm_bwd_finalize_kernel(const float* partial, int N, int C8, int Creal,
+                                         int splits, int batch_mode, float* sums,
+                                         float* dgamma, float* dbeta) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int C = C8 * 8;
   if (c >= C) return;
@@ -263,15 +273,17 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int 
 // incoming gradient itself as split planes (aux), which feeds the shortcut conv's dgrad.
 template <int ODT>
 __global__ void __launch_bounds__(kThreads)
-norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float* __restrict__ g1,
-                      long long g1_ns, const float* __restrict__ y, long long y_ns, int C8,
-                      long long V, const float* __restrict__ mean, const float* __restrict__ rstd,
-                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                      const float* __restrict__ sums, float inv_m, uint16_t* __restrict__ dy_hi,
-                      uint16_t* __restrict__ dy_lo, long long dy_ns, uint16_t* __restrict__ aux_hi,
-                      uint16_t* __restrict__ aux_lo, long long aux_ns, const float* __restrict__ partial,
-                      int splits, int N, int batch_mode, int Creal, float* __restrict__ dgamma,
-                      float* __restrict__ dbeta, int dy_wsplit_w) {
+norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
+                      long long g1_ns, const float* y, long long y_ns, int C8,
+                      long long V, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, int relu,
+                      const float* sums, float inv_m, uint16_t* dy_hi,
+                      uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi,
+                      uint16_t* aux_lo, long long aux_ns, const float* partial,
+                      int splits, int N, int batch_mode, int Creal, float* dgamma,
+                      float* dbeta, int dy_wsplit_w) {
+  pdl_trigger();
+  pdl_wait();
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
@@ -347,9 +359,11 @@ norm_bwd_apply_kernel(const float* __restrict__ g0, long long g0_ns, const float
 // directly without a norm in between.
 template <int ODT>
 __global__ void __launch_bounds__(kThreads)
-split_f32_kernel(const float* __restrict__ g0, long long g0_ns, const float* __restrict__ g1,
-                 long long g1_ns, int C8, long long V, uint16_t* __restrict__ hi,
-                 uint16_t* __restrict__ lo, long long o_ns) {
+split_f32_kernel(const float* g0, long long g0_ns, const float* g1,
+                 long long g1_ns, int C8, long long V, uint16_t* hi,
+                 uint16_t* lo, long long o_ns) {
+  pdl_trigger();
+  pdl_wait();
   const int chunk = blockIdx.y, n = blockIdx.z;
   const long long slab = (long long)chunk * V * 8;
   for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
@@ -406,7 +420,7 @@ int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, i
   TTA_REQUIRE(C8 <= 1024, "tta_norm_stats: more than 8192 channels unsupported");
   const int splits = pick_splits(N, C8, V);
   // finalize = 1: the last block of every chunk turns the partial sums into mean/rstd (single pass)
-  norm_stats_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(
+  tta_launch(norm_stats_partial_kernel, dim3(splits, C8, N), kThreads, 0, stream, tta_pdl_family(2), 
       y, y_ns, C8, V, splits, workspace + 1024, finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N,
       batch_mode, eps, mean, rstd);
   return tta_check_launch("tta_norm_stats");
@@ -426,7 +440,7 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
   TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_apply: bad dtype");
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
 #define LAUNCH(RES, DT)                                                                        \
-  norm_apply_kernel<RES, DT><<<grid, kThreads, 0, stream>>>(                                   \
+  tta_launch(norm_apply_kernel<RES, DT>, grid, kThreads, 0, stream, tta_pdl_family(2),                                    \
       y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
       (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns,                       \
       partial ? partial + 1024 : nullptr, splits, N,                                                        \
@@ -450,7 +464,7 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
               "tta_norm_bwd_reduce: null pointer");
   TTA_REQUIRE(C8 <= 1024, "tta_norm_bwd_reduce: more than 8192 channels unsupported");
   const int splits = pick_splits(N, C8, V);
-  norm_bwd_partial_kernel<<<dim3(splits, C8, N), kThreads, 0, stream>>>(
+  tta_launch(norm_bwd_partial_kernel, dim3(splits, C8, N), kThreads, 0, stream, tta_pdl_family(2), 
       g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace + 1024,
       finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N, batch_mode, Creal, sums, dgamma, dbeta);
   return tta_check_launch("tta_norm_bwd_reduce");
@@ -473,17 +487,17 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
   TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_norm_bwd_apply: bad dtype");
   if (out_dtype == TTA_F16)
-    norm_bwd_apply_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(
+    tta_launch(norm_bwd_apply_kernel<TTA_F16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
         dbeta, dy_wsplit_w);
   else if (out_dtype == TTA_F16_HI)
-    norm_bwd_apply_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(
+    tta_launch(norm_bwd_apply_kernel<TTA_F16_HI>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
         dbeta, dy_wsplit_w);
   else
-    norm_bwd_apply_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(
+    tta_launch(norm_bwd_apply_kernel<TTA_BF16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
         dbeta, dy_wsplit_w);
@@ -496,11 +510,11 @@ int tta_split_f32(const float* g0, long long g0_ns, const float* g1, long long g
   TTA_REQUIRE(g0 && hi && (lo || out_dtype == TTA_F16_HI), "tta_split_f32: null pointer");
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
   if (out_dtype == TTA_F16)
-    split_f32_kernel<TTA_F16><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
+    tta_launch(split_f32_kernel<TTA_F16>, grid, kThreads, 0, stream, tta_pdl_family(2), g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
   else if (out_dtype == TTA_F16_HI)
-    split_f32_kernel<TTA_F16_HI><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
+    tta_launch(split_f32_kernel<TTA_F16_HI>, grid, kThreads, 0, stream, tta_pdl_family(2), g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
   else
-    split_f32_kernel<TTA_BF16><<<grid, kThreads, 0, stream>>>(g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
+    tta_launch(split_f32_kernel<TTA_BF16>, grid, kThreads, 0, stream, tta_pdl_family(2), g0, g0_ns, g1, g1_ns, C8, V, hi, lo, o_ns);
   return tta_check_launch("tta_split_f32");
 }
 

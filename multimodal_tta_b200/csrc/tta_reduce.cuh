@@ -11,7 +11,7 @@ constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------- block reduction of 16 values
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* __restrict__ dst) {
+__device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* dst) {
   __shared__ float red[kThreads / 32][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -32,7 +32,7 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* __re
 // ---------------------------------------------------------------- fused finalize (consumer prologue)
 // Sums the 16 per-block partial values of chunk `chunk` over splits (and over samples n0..n1)
 // in fp64 with all 256 threads; result in tot[16] (shared).  Deterministic order.
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int C8, int chunk,
+__device__ __forceinline__ void reduce_partials(const float* partial, int C8, int chunk,
                                                 int splits, int n0, int n1, double (&tot)[16]) {
   __shared__ double red[16][17];
   const int v = threadIdx.x & 15, j = threadIdx.x >> 4;  // 16 values x 16 split lanes
@@ -53,7 +53,7 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   __syncthreads();
 }
 // same, but every thread only needs value `which` (0..15): avoids dynamic register indexing
-__device__ __forceinline__ double reduce_partials_one(const float* __restrict__ partial, int C8, int chunk,
+__device__ __forceinline__ double reduce_partials_one(const float* partial, int C8, int chunk,
                                                       int splits, int n0, int n1, int which) {
   __shared__ double red1[16][17];
   const int v = threadIdx.x & 15, j = threadIdx.x >> 4;
@@ -92,10 +92,10 @@ __device__ __forceinline__ bool last_block_of_chunk(unsigned int* counters, int 
 // Tail of the norm-backward reduction, executed by the LAST block of a chunk: sums[(n*C + c)*2 +
 // {0,1}] = {sum dz, sum dz*xhat} per normalisation group (per n for InstanceNorm, over all n for
 // BatchNorm, broadcast to every n); dgamma/dbeta[c] = the sums over all samples.
-__device__ __forceinline__ void norm_bwd_finalize_tail(const float* __restrict__ partial, int C8, int chunk,
+__device__ __forceinline__ void norm_bwd_finalize_tail(const float* partial, int C8, int chunk,
                                                        int splits, int N, int batch_mode, int Creal,
-                                                       float* __restrict__ sums, float* __restrict__ dgamma,
-                                                       float* __restrict__ dbeta) {
+                                                       float* sums, float* dgamma,
+                                                       float* dbeta) {
   const int C = C8 * 8;
   const int which = threadIdx.x & 15;
   const int cc = chunk * 8 + (which & 7);

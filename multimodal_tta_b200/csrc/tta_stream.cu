@@ -16,10 +16,12 @@ constexpr int kThreads = 256;
 // win[b*4 + {0,1,2,3}] = {volume index, d0, h0, w0} of window b (origins may be negative or
 // run past the volume: those voxels read 0 = MONAI's constant pad).
 __global__ void __launch_bounds__(kThreads)
-gather_pack_kernel(const float* __restrict__ vol, int C, int Ds, int Hs, int Ws,
-                   const int* __restrict__ win, const float* __restrict__ chan_scale, int D, int H,
-                   int W, int C8, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
+                   const int* win, const float* chan_scale, int D, int H,
+                   int W, int C8, uint16_t* hi, uint16_t* lo,
                    long long o_ns, int wsplit) {
+  pdl_trigger();
+  pdl_wait();
   const int chunk = blockIdx.y, b = blockIdx.z;
   const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
   const long long V = (long long)D * H * W;
@@ -59,10 +61,12 @@ gather_pack_kernel(const float* __restrict__ vol, int C, int Ds, int Hs, int Ws,
 //   mode 1: Bernoulli entropy H = sum_c softplus(z_c) - p_c z_c ; dH/dz_c = -z_c p_c (1 - p_c)
 template <int ODT>
 __global__ void __launch_bounds__(kThreads)
-head_entropy_kernel(const float* __restrict__ y, long long y_ns, int R, long long V, int mode,
-                    float inv_count, float grad_scale, const float* __restrict__ sample_w,
-                    float* __restrict__ logits, uint16_t* __restrict__ dz_hi,
-                    uint16_t* __restrict__ dz_lo, long long dz_ns, float* __restrict__ partial) {
+head_entropy_kernel(const float* y, long long y_ns, int R, long long V, int mode,
+                    float inv_count, float grad_scale, const float* sample_w,
+                    float* logits, uint16_t* dz_hi,
+                    uint16_t* dz_lo, long long dz_ns, float* partial) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const float sw = sample_w ? sample_w[n] : 1.f;
   const float gs = sw * inv_count * grad_scale;  // grad_scale: power-of-two loss scale (fp16 backward)
@@ -94,8 +98,10 @@ head_entropy_kernel(const float* __restrict__ y, long long y_ns, int R, long lon
   }
 }
 
-__global__ void loss_finalize_kernel(const float* __restrict__ partial, int count, float inv_count,
-                                     float* __restrict__ loss) {
+__global__ void loss_finalize_kernel(const float* partial, int count, float inv_count,
+                                     float* loss) {
+  pdl_trigger();
+  pdl_wait();
   double s = 0.0;
   for (int i = threadIdx.x; i < count; i += 32) s += (double)partial[i];
   s = warp_sum_d(s);
@@ -104,9 +110,11 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int coun
 
 // ---------------------------------------------------------------- Adam (torch.optim.Adam math)
 __global__ void __launch_bounds__(1024)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-            float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float gscale,
-            int* __restrict__ step_dev) {
+adam_kernel(float* p, const float* g, float* m,
+            float* v, int n, float lr, float b1, float b2, float eps, float gscale,
+            int* step_dev) {
+  pdl_trigger();
+  pdl_wait();
   const int t = *step_dev + 1;
   __syncthreads();
   const double bc1 = 1.0 - pow((double)b1, (double)t);
@@ -130,11 +138,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // in order and accumulates  acc += w * logit,  wsum += w  with
 // w = max(gd[d]*gh[h]*gw[w], wmin)  (MONAI gaussian importance map, clamped).
 __global__ void __launch_bounds__(kThreads)
-sw_blend_kernel(const float* __restrict__ logits, int NB, int R, int D, int H, int W,
-                const int* __restrict__ win, const float* __restrict__ sample_w,
-                const float* __restrict__ gd, const float* __restrict__ gh,
-                const float* __restrict__ gw, float wmin, float* __restrict__ acc,
-                float* __restrict__ wsum, int Ds, int Hs, int Ws) {
+sw_blend_kernel(const float* logits, int NB, int R, int D, int H, int W,
+                const int* win, const float* sample_w,
+                const float* gd, const float* gh,
+                const float* gw, float wmin, float* acc,
+                float* wsum, int Ds, int Hs, int Ws) {
+  pdl_trigger();
+  pdl_wait();
   const long long Vs = (long long)Ds * Hs * Ws;
   const long long V = (long long)D * H * W;
   const int vi = blockIdx.y;
@@ -171,8 +181,10 @@ sw_blend_kernel(const float* __restrict__ logits, int NB, int R, int D, int H, i
 }
 
 __global__ void __launch_bounds__(kThreads)
-sw_normalise_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, int R,
-                    long long Vs, float* __restrict__ out) {
+sw_normalise_kernel(const float* acc, const float* wsum, int R,
+                    long long Vs, float* out) {
+  pdl_trigger();
+  pdl_wait();
   const int vi = blockIdx.y;
   for (long long s = (long long)blockIdx.x * kThreads + threadIdx.x; s < Vs;
        s += (long long)gridDim.x * kThreads) {
@@ -188,8 +200,10 @@ sw_normalise_kernel(const float* __restrict__ acc, const float* __restrict__ wsu
 // counts[(b*R + r)*3 + {0,1,2}] += {sum pred*gt, sum pred, sum gt} with
 // pred = sigmoid(z) >= thr, gt = label > 0.5 (integer atomics: order-independent, exact).
 __global__ void __launch_bounds__(kThreads)
-dice_counts_kernel(const float* __restrict__ logits, const float* __restrict__ label, long long V,
-                   float thr, unsigned long long* __restrict__ counts) {
+dice_counts_kernel(const float* logits, const float* label, long long V,
+                   float thr, unsigned long long* counts) {
+  pdl_trigger();
+  pdl_wait();
   const int br = blockIdx.y;
   const float* z = logits + (long long)br * V;
   const float* y = label + (long long)br * V;
@@ -236,7 +250,7 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
   TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
   const long long V = (long long)D * H * W;
-  gather_pack_kernel<<<dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream>>>(
+  tta_launch(gather_pack_kernel, dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream, tta_pdl_family(4), 
       vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
   return tta_check_launch("tta_gather_pack");
 }
@@ -254,12 +268,12 @@ int tta_head_entropy(const float* y, long long y_ns, int N, int R, long long V, 
   const int xb = xblocks(V, N);
   TTA_REQUIRE(dz_dtype == TTA_BF16 || dz_dtype == TTA_F16_HI, "tta_head_entropy: dz dtype %d", dz_dtype);
   if (dz_dtype == TTA_BF16)
-    head_entropy_kernel<TTA_BF16><<<dim3(xb, N), kThreads, 0, stream>>>(
+    tta_launch(head_entropy_kernel<TTA_BF16>, dim3(xb, N), kThreads, 0, stream, tta_pdl_family(4), 
         y, y_ns, R, V, mode, inv_count, grad_scale, sample_w, logits, dz_hi, dz_lo, dz_ns, partial);
   else
-    head_entropy_kernel<TTA_F16_HI><<<dim3(xb, N), kThreads, 0, stream>>>(
+    tta_launch(head_entropy_kernel<TTA_F16_HI>, dim3(xb, N), kThreads, 0, stream, tta_pdl_family(4), 
         y, y_ns, R, V, mode, inv_count, grad_scale, sample_w, logits, dz_hi, dz_lo, dz_ns, partial);
-  loss_finalize_kernel<<<1, 32, 0, stream>>>(partial, xb * N, inv_count, loss);
+  tta_launch(loss_finalize_kernel, 1, 32, 0, stream, tta_pdl_family(4), partial, xb * N, inv_count, loss);
   return tta_check_launch("tta_head_entropy");
 }
 
@@ -268,7 +282,7 @@ int tta_adam_step(float* p, const float* g, float* m, float* v, int n, float lr,
   TTA_REQUIRE(p && g && m && v && step_dev, "tta_adam_step: null pointer");
   TTA_REQUIRE(n >= 0, "tta_adam_step: n=%d", n);
   if (n == 0) return TTA_OK;
-  adam_kernel<<<1, 1024, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, gscale, step_dev);
+  tta_launch(adam_kernel, 1, 1024, 0, stream, tta_pdl_family(4), p, g, m, v, n, lr, b1, b2, eps, gscale, step_dev);
   return tta_check_launch("tta_adam_step");
 }
 
@@ -279,7 +293,7 @@ int tta_sw_blend(const float* logits, int NB, int R, int D, int H, int W, const 
   TTA_REQUIRE(logits && win && gd && gh && gw && acc && wsum, "tta_sw_blend: null pointer");
   TTA_REQUIRE(R >= 1 && R <= 8, "tta_sw_blend: R=%d unsupported", R);
   const long long Vs = (long long)Ds * Hs * Ws;
-  sw_blend_kernel<<<dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream>>>(
+  tta_launch(sw_blend_kernel, dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream, tta_pdl_family(4), 
       logits, NB, R, D, H, W, win, sample_w, gd, gh, gw, wmin, acc, wsum, Ds, Hs, Ws);
   return tta_check_launch("tta_sw_blend");
 }
@@ -287,14 +301,14 @@ int tta_sw_blend(const float* logits, int NB, int R, int D, int H, int W, const 
 int tta_sw_normalise(const float* acc, const float* wsum, int n_vol, int R, long long Vs, float* out,
                      cudaStream_t stream) {
   TTA_REQUIRE(acc && wsum && out, "tta_sw_normalise: null pointer");
-  sw_normalise_kernel<<<dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream>>>(acc, wsum, R, Vs, out);
+  tta_launch(sw_normalise_kernel, dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream, tta_pdl_family(4), acc, wsum, R, Vs, out);
   return tta_check_launch("tta_sw_normalise");
 }
 
 int tta_dice_counts(const float* logits, const float* label, int BR, long long V, float thr,
                     unsigned long long* counts, cudaStream_t stream) {
   TTA_REQUIRE(logits && label && counts, "tta_dice_counts: null pointer");
-  dice_counts_kernel<<<dim3(xblocks(V, BR), BR), kThreads, 0, stream>>>(logits, label, V, thr, counts);
+  tta_launch(dice_counts_kernel, dim3(xblocks(V, BR), BR), kThreads, 0, stream, tta_pdl_family(4), logits, label, V, thr, counts);
   return tta_check_launch("tta_dice_counts");
 }
 
