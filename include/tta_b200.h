@@ -69,7 +69,15 @@ long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cou
 int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
                 int C8in, int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out,
                 long long out_n_stride, int C8out, int Do, int Ho, int Wo, int mode, int K, int stride,
-                int accumulate, int flags, tta_stream_t stream);
+                int accumulate, int flags, float* stats_workspace, int stats_c8, tta_stream_t stream);
+/* launch shape for the same arguments: *ksplit = split-K factor, *grid = CTAs, *nbuf = TMEM
+ * accumulator buffers (2 = the epilogue overlaps the next work item's MMAs; may be NULL).  With
+ * stats_workspace != NULL (requires ksplit == 1, accumulate == 0) the epilogue also leaves per-CTA
+ * partial sums of y and y^2 over the leading stats_c8 output chunks in the workspace, which
+ * tta_norm_stats_finalize(splits = grid) / tta_norm_apply(partial, partial_splits = grid) consume:
+ * the separate statistics pass over y (tta_norm_stats) disappears. */
+int tta_conv_tc_query(int in_dtype, int N, int C8in, int Di, int Hi, int Wi, int C8out, int Do, int Ho, int Wo,
+                      int mode, int K, int stride, int accumulate, int flags, int* ksplit, int* grid, int* nbuf);
 
 /* fp32 CUDA-core conv for any (mode, K, stride); Wp: fp32 [tap][C8in][C8out][8][8]. */
 int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
@@ -100,8 +108,12 @@ int tta_norm_stats(const float* y, long long y_n_stride, int N, int C8, long lon
 int tta_norm_apply(const float* y, long long y_n_stride, int N, int C8, long long V, const float* mean,
                    const float* rstd, const float* gamma, const float* beta, int relu, int res_kind,
                    const void* res_a, const void* res_b, long long res_n_stride, uint16_t* out_hi,
-                   uint16_t* out_lo, long long out_n_stride, int out_dtype, const float* partial, int batch_mode,
-                   float eps, uint16_t* ws_hi, uint16_t* ws_lo, long long ws_n_stride, int W, tta_stream_t stream);
+                   uint16_t* out_lo, long long out_n_stride, int out_dtype, const float* partial,
+                   int partial_splits, int batch_mode, float eps, uint16_t* ws_hi, uint16_t* ws_lo,
+                   long long ws_n_stride, int W, tta_stream_t stream);
+/* mean/rstd from the partial sums in a workspace with `splits` slots per (n, chunk) */
+int tta_norm_stats_finalize(const float* workspace, int N, int C8, int splits, long long V, int batch_mode,
+                            float eps, float* mean, float* rstd, tta_stream_t stream);
 /* partial sums of dz and dz*xhat (dz = (g0+g1)*[z>0]); finalize != 0 also writes sums[N][C][2] and
  * dgamma/dbeta[C] */
 int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,

@@ -56,7 +56,8 @@ _SIGNATURES = {
     "tta_device_sm": (I, []),
     "tta_norm_workspace_floats": (L, [I, I, L]),
     "tta_norm_stats": (I, [P, L, I, I, L, I, F, P, P, P, I, P]),
-    "tta_norm_apply": (I, [P, L, I, I, L, P, P, P, P, I, I, P, P, L, P, P, L, I, P, I, F, P, P, L, I, P]),
+    "tta_norm_apply": (I, [P, L, I, I, L, P, P, P, P, I, I, P, P, L, P, P, L, I, P, I, I, F, P, P, L, I, P]),
+    "tta_norm_stats_finalize": (I, [P, I, I, I, L, I, F, P, P, P]),
     "tta_norm_bwd_reduce": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, I, P, P, P, P, I, P]),
     "tta_norm_bwd_apply": (I, [P, L, P, L, P, L, I, I, L, P, P, P, P, I, I, P, P, P, L, P, P, L, I, P, I, P, P, I, P]),
     "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
@@ -80,7 +81,8 @@ _SIGNATURES = {
     "tta_conv_tc_gmax": (I, [I, I, I]),
     "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),
-    "tta_conv_tc": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, I, P]),
+    "tta_conv_tc": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, I, P, I, P]),
+    "tta_conv_tc_query": (I, [I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P, P, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -55,6 +55,11 @@ struct TcParams {
   int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n;
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
+  // fused norm statistics: per-CTA partial sums of y and y^2 over the leading stats_c8 chunks of the
+  // output, layout [n][chunk][cta][16] (0..7 sum, 8..15 sum of squares) = what tta_norm_apply
+  // finalizes with splits = gridDim.x
+  int stats_c8, n_batch;
+  float* stats;
   int lbo16[4];  // k-chunk pitch (16 B units, 128 B aligned) per A sub-tile
   signed char acc_pd[kMaxAcc], acc_qd[kMaxAcc], acc_qh[kMaxAcc], acc_qw[kMaxAcc];
   long long out_ns;
@@ -255,6 +260,32 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
   }
 }
 
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (halving butterfly): on
+// return lane l holds the warp total of value (l >> 1); both lanes of a pair hold the same number.
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+  float a8[8], a4[4], a2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? a8[i] : a8[i + 4], keep = b3 ? a8[i + 4] : a8[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? a4[i] : a4[i + 2], keep = b2 ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? a2[0] : a2[1], keep = b1 ? a2[1] : a2[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 struct WorkItem {
   int n, nt, ks, w0, h0, d0, cb0, nit;
 };
@@ -279,7 +310,7 @@ __device__ __forceinline__ WorkItem decode_item(const TcParams& P, int item) {
   return w;
 }
 
-template <int GEOM, int TD, int SPLIT>
+template <int GEOM, int TD, int SPLIT, int STATS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -289,6 +320,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[128];
+  __shared__ float stat_s[STATS ? 4 : 1][STATS ? 16 * 16 : 1];  // [epilogue warp][chunk of the n-tile][16]: fused norm statistics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();  // the next kernel's CTAs may be scheduled (they block in their own pdl_wait)
@@ -402,9 +434,38 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     const long long Vo = (long long)P.Do * P.Ho * P.Wo;
     const int nchunks = P.ntile >> 3;
     uint32_t local = 0;
+    // ---- fused norm statistics (forward convs that feed a norm, no split-K): every warp adds its
+    // 32 rows into a private smem slot; when the CTA moves on to another (n, n-tile) the four slots
+    // are summed in a fixed order into this CTA's own global slot -> deterministic, no atomics
+    constexpr bool do_stats = STATS != 0;
+    int st_n = -1, st_nt = -1;
+    auto stats_flush = [&]() {
+      if (!STATS) return;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int t = et; t < nchunks * 16; t += 128) {
+        const int gchunk = st_nt * nchunks + (t >> 4);
+        if (gchunk < P.stats_c8) {
+          float* slot = P.stats + (((long long)st_n * P.stats_c8 + gchunk) * gridDim.x + blockIdx.x) * 16 + (t & 15);
+          *slot += (stat_s[0][t] + stat_s[STATS ? 1 : 0][t]) + (stat_s[STATS ? 2 : 0][t] + stat_s[STATS ? 3 : 0][t]);
+        }
+        stat_s[0][t] = stat_s[STATS ? 1 : 0][t] = stat_s[STATS ? 2 : 0][t] = stat_s[STATS ? 3 : 0][t] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    if (do_stats) {
+      for (int t = et; t < (STATS ? 4 * 256 : 0); t += 128) (&stat_s[0][0])[t] = 0.f;
+      for (int t = et; t < P.n_batch * P.stats_c8 * 16; t += 128)
+        P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
       const WorkItem wi = decode_item(P, item);
       const uint32_t buf = local % P.nbuf, use = local / P.nbuf;
+      if (do_stats && (wi.n != st_n || wi.nt != st_nt)) {
+        if (st_n >= 0) stats_flush();
+        st_n = wi.n;
+        st_nt = wi.nt;
+      }
       // bias of this n-tile -> smem (only split 0 adds it)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers are done with bias_s
       if (et < P.ntile) {
@@ -461,19 +522,20 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
               const int co_chunk = wi.nt * nchunks + c16 * 2 + hlf;
-              if (valid && co_chunk < P.C8out) {
+              const bool live = valid && co_chunk < P.C8out;
+              const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
+              const int o = hlf * 8;
+              float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
+                                      __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
+                                      __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
+                                      __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
+              float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
+                                      __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
+                                      __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
+                                      __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
+              if (live) {
                 float* dst = obase + (long long)co_chunk * Vo * 8;
-                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
-                const int o = hlf * 8;
-                float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
-                                        __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
-                                        __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
-                                        __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
-                float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
-                                        __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
-                                        __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
-                                        __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
                 if (P.ksplit > 1) {
                   // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
                   atomicAdd(reinterpret_cast<float4*>(dst), r0);
@@ -488,6 +550,15 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                   *reinterpret_cast<float4*>(dst + 4) = r1;
                 }
               }
+              if (do_stats && co_chunk < P.stats_c8) {  // warp-uniform: the whole warp reduces
+                float sv[16];
+                sv[0] = live ? r0.x : 0.f; sv[1] = live ? r0.y : 0.f; sv[2] = live ? r0.z : 0.f; sv[3] = live ? r0.w : 0.f;
+                sv[4] = live ? r1.x : 0.f; sv[5] = live ? r1.y : 0.f; sv[6] = live ? r1.z : 0.f; sv[7] = live ? r1.w : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sv[8 + i] = sv[i] * sv[i];
+                const float tot = warp_reduce16(sv, lane);
+                if (!(lane & 1)) stat_s[q][(c16 * 2 + hlf) * 16 + (lane >> 1)] += tot;
+              }
             }
           }
         }
@@ -497,6 +568,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
     }
+    if (do_stats && st_n >= 0) stats_flush();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -581,12 +653,15 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
 // layout.pack_weights_tc.  flags bit0: force TD=1, bit1: no split-K (deterministic), bit2: one
 // work item per CTA (non-persistent; testing), bit3: the input planes of a stride-2 conv are stored
 // w-parity-split ([N][C8][D][H][2][W/2][8]: even-w voxels of a row first, then the odd ones).
-int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
-                int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
-                int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
-                cudaStream_t stream) {
+}  // extern "C"
+
+static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
+                        int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
+                        int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
+                        float* stats_ws, int stats_c8, int* q_ksplit, int* q_grid, int* q_nbuf, cudaStream_t stream) {
   const int split = in_dtype == TTA_F16_HI ? 0 : 1;
-  TTA_REQUIRE(in_hi && (in_lo || !split) && wpacked && out, "tta_conv_tc: null pointer");
+  const bool query = q_ksplit != nullptr;  // shape the launch only: report split-K factor and grid
+  TTA_REQUIRE(query || (in_hi && (in_lo || !split) && wpacked && out), "tta_conv_tc: null pointer");
   const int geom = geom_of(mode, K, stride);
   TTA_REQUIRE(geom != GEOM_NONE, "tta_conv_tc: unsupported geometry mode=%d K=%d stride=%d", mode, K, stride);
   TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_tc: bad dtype");
@@ -601,8 +676,8 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   } else {
     TTA_REQUIRE(Do == Di && Ho == Hi && Wo == Wi, "tta_conv_tc: stride-1 dims must match");
   }
-  EncodeTiledFn enc = get_encode();
-  TTA_REQUIRE(enc != nullptr, "tta_conv_tc: cuTensorMapEncodeTiled entry point not found");
+  EncodeTiledFn enc = query ? nullptr : get_encode();
+  TTA_REQUIRE(query || enc != nullptr, "tta_conv_tc: cuTensorMapEncodeTiled entry point not found");
 
   TcParams P;
   memset(&P, 0, sizeof(P));
@@ -646,7 +721,7 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   auto a_plane_of = [&](int td_) { return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * 16); };
   const int a_planes = split ? 2 : 1;
   auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + P.b_blob_bytes); };
-  const int smem_budget = 227 * 1024 - 4096;
+  const int smem_budget = 227 * 1024 - 8192;  // static smem: barriers, bias, 4 KB statistics slots
   int td = td_max;
   while (td > 1 && smem_budget / stage_bytes_of(td) < 2) --td;
   int nacc = geom == GEOM_T2 ? 8 : td;
@@ -685,6 +760,22 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
     P.cb_per_split = (P.ncblk + ks - 1) / ks;
     P.ksplit = (P.ncblk + P.cb_per_split - 1) / P.cb_per_split;
     P.work_items = (int)(items * P.ksplit);
+  }
+  if (query) {
+    *q_ksplit = P.ksplit;
+    if (q_nbuf) *q_nbuf = P.nbuf;
+    *q_grid = (flags & 4) ? P.work_items : (P.work_items < num_sms() ? P.work_items : num_sms());
+    return TTA_OK;
+  }
+  // ---- fused norm statistics (see the epilogue): needs the whole K sum in one CTA and plain stores
+  P.stats_c8 = 0;
+  if (stats_ws != nullptr && stats_c8 > 0) {
+    TTA_REQUIRE(P.ksplit == 1 && !accumulate && split,
+                "tta_conv_tc: fused statistics need split-plane operands, ksplit == 1 and no accumulate");
+    TTA_REQUIRE(stats_c8 <= C8out, "tta_conv_tc: stats_c8 %d > C8out %d", stats_c8, C8out);
+    P.stats_c8 = stats_c8;
+    P.n_batch = N;
+    P.stats = stats_ws + 1024;  // same workspace convention as tta_norm_stats: [1024 counters][partials]
   }
 
   // ---- tensor maps (one k-chunk = 8 channels per TMA box; zero padding = OOB fill)
@@ -809,24 +900,30 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
   int grid_x = P.work_items < num_sms() ? P.work_items : num_sms();
   if (flags & 4) grid_x = P.work_items;
   const dim3 grid(grid_x, 1, 1);
-#define TTA_TC_LAUNCH_S(G, T, S)                                                                              \
+#define TTA_TC_LAUNCH_ST(G, T, S, ST)                                                                         \
   do {                                                                                                     \
     static bool configured = false;                                                                        \
     if (!configured) {                                                                                     \
       cudaFuncAttributes fa;                                                                               \
-      if (cudaFuncGetAttributes(&fa, conv_tc_kernel<G, T, S>) != cudaSuccess)                                 \
+      if (cudaFuncGetAttributes(&fa, conv_tc_kernel<G, T, S, ST>) != cudaSuccess)                             \
         return tta_check_launch("tta_conv_tc(attrs)");                                                     \
       const int max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;                                            \
-      if (cudaFuncSetAttribute(conv_tc_kernel<G, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+      if (cudaFuncSetAttribute(conv_tc_kernel<G, T, S, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                max_dyn) != cudaSuccess)                                                    \
         return tta_check_launch("tta_conv_tc(cudaFuncSetAttribute)");                                      \
       configured = true;                                                                                   \
     }                                                                                                      \
-    tta_launch(conv_tc_kernel<G, T, S>, grid, kTcThreads, smem, stream, pdl_ok && tta_pdl_family(8), P);                                           \
+    tta_launch(conv_tc_kernel<G, T, S, ST>, grid, kTcThreads, smem, stream, pdl_ok && tta_pdl_family(8), P);                                           \
   } while (0)
 #define TTA_TC_LAUNCH(G, T)                                                                                \
   do {                                                                                                     \
-    if (split) TTA_TC_LAUNCH_S(G, T, 1); else TTA_TC_LAUNCH_S(G, T, 0);                                    \
+    if (P.stats_c8 > 0) { /* fused statistics: forward (split-plane) convs only */                        \
+      TTA_TC_LAUNCH_ST(G, T, 1, 1);                                                                        \
+    } else if (split) {                                                                                    \
+      TTA_TC_LAUNCH_ST(G, T, 1, 0);                                                                        \
+    } else {                                                                                               \
+      TTA_TC_LAUNCH_ST(G, T, 0, 0);                                                                        \
+    }                                                                                                      \
   } while (0)
 #define TTA_TC_LAUNCH_TD(G)                                                                                \
   switch (td) {                                                                                            \
@@ -843,9 +940,31 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
     default: TTA_TC_LAUNCH(GEOM_T2, 1); break;
   }
 #undef TTA_TC_LAUNCH_TD
-#undef TTA_TC_LAUNCH_S
+#undef TTA_TC_LAUNCH_ST
 #undef TTA_TC_LAUNCH
   return tta_check_launch("tta_conv_tc");
+}
+
+extern "C" {
+
+int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
+                int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
+                int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
+                float* stats_ws, int stats_c8, cudaStream_t stream) {
+  return conv_tc_impl(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, C8out, Do, Ho,
+                      Wo, mode, K, stride, accumulate, flags, stats_ws, stats_c8, nullptr, nullptr, nullptr, stream);
+}
+
+// Launch shape of tta_conv_tc for these arguments: *ksplit = split-K factor (fused statistics need
+// 1), *grid = CTAs (= the `splits` of the statistics partials), *nbuf = TMEM accumulator buffers
+// (2: the epilogue, and with it the statistics reduction, overlaps the next item's MMAs).
+int tta_conv_tc_query(int in_dtype, int N, int C8in, int Di, int Hi, int Wi, int C8out, int Do, int Ho, int Wo,
+                      int mode, int K, int stride, int accumulate, int flags, int* ksplit, int* grid, int* nbuf) {
+  TTA_REQUIRE(ksplit && grid, "tta_conv_tc_query: null pointer");
+  const long long Vi = (long long)Di * Hi * Wi;
+  return conv_tc_impl(nullptr, nullptr, (long long)C8in * Vi * 8, in_dtype, N, C8in, Di, Hi, Wi, nullptr, nullptr,
+                      nullptr, 0, C8out, Do, Ho, Wo, mode, K, stride, accumulate, flags, nullptr, 0, ksplit, grid,
+                      nbuf, nullptr);
 }
 
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout) {

@@ -91,6 +91,33 @@ __global__ void norm_stats_finalize_kernel(const float* partial, int N, int C8,
   rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// one CTA per channel chunk: fp64 reduction of the `splits` partial slots with all 256 threads
+// (the partials may come from norm_stats_partial_kernel or from the tcgen05 conv epilogue)
+__global__ void __launch_bounds__(kThreads)
+norm_stats_finalize_chunk_kernel(const float* partial, int N, int C8, int splits, long long V, int batch_mode,
+                                 float eps, float* mean, float* rstd) {
+  pdl_trigger();
+  pdl_wait();
+  const int chunk = blockIdx.x;
+  const int C = C8 * 8;
+  const double M = (double)V * (batch_mode ? N : 1);
+  for (int nn = 0; nn < (batch_mode ? 1 : N); ++nn) {
+    const int n0 = batch_mode ? 0 : nn, n1 = batch_mode ? N : nn + 1;
+    const double s1 = reduce_partials_one(partial, C8, chunk, splits, n0, n1, threadIdx.x & 7);
+    const double s2 = reduce_partials_one(partial, C8, chunk, splits, n0, n1, 8 + (threadIdx.x & 7));
+    if (threadIdx.x < 8) {
+      const double m = s1 / M;
+      double var = s2 / M - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mu = (float)m, rs = (float)(1.0 / sqrt(var + (double)eps));
+      for (int n2 = n0; n2 < n1; ++n2) {
+        mean[n2 * C + chunk * 8 + threadIdx.x] = mu;
+        rstd[n2 * C + chunk * 8 + threadIdx.x] = rs;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- forward apply
 // out = relu?(gamma*(y-mean)*rstd + beta) (+ residual), written as split 16-bit planes.
 // RES: 0 none, 1 fp32 view, 2 split-plane view (dtype ODT)
@@ -426,16 +453,27 @@ int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, i
   return tta_check_launch("tta_norm_stats");
 }
 
+// mean/rstd [N][C8*8] from partial sums in `workspace` laid out for `splits` slots per (n, chunk)
+// (tta_norm_stats with finalize = 0, or the fused statistics of tta_conv_tc with splits = its grid)
+int tta_norm_stats_finalize(const float* workspace, int N, int C8, int splits, long long V, int batch_mode,
+                            float eps, float* mean, float* rstd, cudaStream_t stream) {
+  TTA_REQUIRE(workspace && mean && rstd && splits > 0, "tta_norm_stats_finalize: bad argument");
+  tta_launch(norm_stats_finalize_chunk_kernel, C8, kThreads, 0, stream, tta_pdl_family(2), workspace + 1024, N, C8,
+             splits, V, batch_mode, eps, mean, rstd);
+  return tta_check_launch("tta_norm_stats_finalize");
+}
+
 int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, const float* mean,
                    const float* rstd, const float* gamma, const float* beta, int relu,
                    int res_kind, const void* res_a, const void* res_b, long long res_ns,
                    uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int out_dtype,
-                   const float* partial, int batch_mode, float eps, uint16_t* ws_hi, uint16_t* ws_lo,
-                   long long ws_ns, int W, cudaStream_t stream) {
+                   const float* partial, int partial_splits, int batch_mode, float eps, uint16_t* ws_hi,
+                   uint16_t* ws_lo, long long ws_ns, int W, cudaStream_t stream) {
   TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_apply: null pointer");
   TTA_REQUIRE(!ws_hi || (ws_lo && W > 0 && W % 2 == 0 && V % W == 0),
               "tta_norm_apply: w-parity-split copy needs an even row length W=%d dividing V", W);
-  const int splits = pick_splits(N, C8, V);
+  // partial_splits > 0: the partial sums were produced by the conv epilogue (one slot per conv CTA)
+  const int splits = partial_splits > 0 ? partial_splits : pick_splits(N, C8, V);
   TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_apply: res_kind %d", res_kind);
   TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_apply: bad dtype");
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);

@@ -106,6 +106,9 @@ class Res:
         self.ns = self.C8 * self.V * 8
         self.dy: Optional[torch.Tensor] = None
         self.dy_wsplit = False  # dY feeds a stride-2 tcgen05 dgrad: stored w-parity-split
+        self.stats_c8 = 0       # > 0: the producing tcgen05 conv also emits norm statistics partials
+        self.stats_grid = 0     #      ... with this many slots (= its CTA count) per (n, chunk)
+        self.tc_query = None    # (ksplit, grid) of the producing tcgen05 launch, None for other backends
         self.device = device
         self.root, self.c8_off = self, 0
 
@@ -356,7 +359,8 @@ class TTAEngine:
                 and self.model.conv_backend in ("auto", "tc"))
 
     def _conv_call(self, plan: Plan, cl: ConvLayer, backward: bool, src, src_dtype, N, cin8, idims,
-                   dst_ptr, dst_ns, cout8, odims, accumulate: bool, wsplit_in: bool = False):
+                   dst_ptr, dst_ns, cout8, odims, accumulate: bool, wsplit_in: bool = False,
+                   stats_res: Optional["Res"] = None):
         """Returns a closure launching one conv (tcgen05 kernel when the geometry is supported,
         otherwise the fp32 CUDA-core kernel)."""
         lib = self.lib
@@ -383,12 +387,21 @@ class TTAEngine:
         if use_tc:
             wp = cl.packed["tc_" + key]
             plan.keep.append(wp)
+            flags = (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0)
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
-                    *odims, mode, cl.K, cl.stride, int(accumulate),
-                    (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0))
+                    *odims, mode, cl.K, cl.stride, int(accumulate), flags)
+            if stats_res is not None:
+                ks, grid, nbuf = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+                check(lib.tta_conv_tc_query(src_dtype, N, cin8, *idims, cout8, *odims, mode, cl.K, cl.stride,
+                                            int(accumulate), flags, ctypes.byref(ks), ctypes.byref(grid),
+                                            ctypes.byref(nbuf)), "conv_tc_query")
+                stats_res.tc_query = (ks.value, grid.value, nbuf.value)
 
             def run():
-                check(lib.tta_conv_tc(*args, _stream()), f"conv_tc {cl.name}")
+                # fused statistics are requested (later, by the norm that consumes this result) via the Res
+                st = (plan.ws.data_ptr(), stats_res.stats_c8) if (stats_res is not None and stats_res.stats_c8) \
+                    else (0, 0)
+                check(lib.tta_conv_tc(*args, *st, _stream()), f"conv_tc {cl.name}")
         else:
             wp = cl.packed["simt_" + key]
             plan.keep.append(wp)
@@ -439,7 +452,7 @@ class TTAEngine:
                     par.need_ws_copy()         # the producing norm writes a second, parity-split copy
                     src = (inp.ws_hi, inp.ws_lo, inp.ns)
             run = self._conv_call(plan, cl, False, src, TTA_F16, N, inp.C8, inp.dims,
-                                  y.ptr, y.ns, y.C8, (od, oh, ow), False, wsplit_in=ws_in)
+                                  y.ptr, y.ns, y.C8, (od, oh, ow), False, wsplit_in=ws_in, stats_res=y)
             plan.fwd.append(run)
             ops.append(("conv", cl, inp, y))
             return y
@@ -468,6 +481,17 @@ class TTAEngine:
                 rk, ra, rb, rns = 1, residual.ptr, 0, residual.ns
             else:
                 rk, ra, rb, rns = 2, residual.hi, residual.lo, residual.ns
+            # statistics from the producing conv's epilogue: tcgen05 launch without split-K, and this
+            # norm reads the LEADING channel chunks of the conv result (whole result, or the unit0 half
+            # of a fused unit0 || shortcut conv)
+            q = y.root.tc_query
+            # ... and double-buffered TMEM accumulators, so the reduction hides behind the next item's MMAs
+            fuse_st = (model.fuse_stats and q is not None and q[0] == 1 and q[2] == 2 and y.c8_off == 0
+                       and y.root.stats_c8 == 0)
+            if fuse_st:
+                y.root.stats_c8, y.root.stats_grid = y.C8, q[1]
+                max_ws[0] = max(max_ws[0], 1024 + N * y.C8 * q[1] * 16)
+            rec["fused_stats"] = fuse_st
             st_args = (y.ptr, y.ns, N, y.C8, y.V, nl.batch, float(nl.h.eps), mean.data_ptr(), rstd.data_ptr())
             ap_args = (y.ptr, y.ns, N, y.C8, y.V, mean.data_ptr(), rstd.data_ptr(), gptr, bptr, int(relu),
                        rk, ra, rb, rns, out.hi, out.lo, out.ns, TTA_F16)
@@ -483,12 +507,19 @@ class TTAEngine:
             def run():
                 if nl.batch and not model.training and nl.h.track_running_stats:
                     # eval-mode BatchNorm: mean/rstd were filled from the running buffers
-                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
+                    check(lib.tta_norm_apply(*ap_args, 0, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
+                          "norm_apply")
+                elif fuse_st:
+                    # partial sums were left in the workspace by the conv epilogue: tiny parallel finalize
+                    check(lib.tta_norm_stats_finalize(plan.ws.data_ptr(), N, y.C8, y.root.stats_grid, y.V, nl.batch,
+                                                      float(nl.h.eps), mean.data_ptr(), rstd.data_ptr(), _stream()),
+                          "norm_stats_finalize")
+                    check(lib.tta_norm_apply(*ap_args, 0, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
                           "norm_apply")
                 else:
                     # single-pass statistics: the last block of every chunk finalizes mean/rstd
                     check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 1, _stream()), "norm_stats")
-                    check(lib.tta_norm_apply(*ap_args, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
+                    check(lib.tta_norm_apply(*ap_args, 0, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
                           "norm_apply")
             plan.fwd.append(run)
             ops.append(("norm", rec))
@@ -621,7 +652,13 @@ class TTAEngine:
             del plan.fwd[-2:]
 
             def stats_only(st_args=hrec["st_args"], nl=hnl):
-                if not (nl.batch and not model.training and nl.h.track_running_stats):
+                if nl.batch and not model.training and nl.h.track_running_stats:
+                    return
+                if hrec["fused_stats"]:   # partials came out of the transposed conv's epilogue
+                    check(lib.tta_norm_stats_finalize(plan.ws.data_ptr(), N, hy.C8, hy.root.stats_grid, hy.V,
+                                                      nl.batch, float(nl.h.eps), hrec["mean"].data_ptr(),
+                                                      hrec["rstd"].data_ptr(), _stream()), "norm_stats_finalize")
+                else:
                     check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 1, _stream()), "norm_stats")
             plan.fwd.append(stats_only)
 
@@ -734,6 +771,10 @@ class TTAEngine:
         if fused_head is not None:
             plan.launches_fwd -= 3   # norm apply + small conv + loss finalize folded into the fused head
             plan.launches_bwd -= 1   # small-conv dgrad + norm reduce are one kernel
+        # statistics produced by the conv epilogue: no tta_norm_stats launch (the fused head still
+        # needs mean/rstd up front: one tiny finalize launch takes its place)
+        # (launch count unchanged: a tiny finalize launch takes the place of the statistics pass)
+        plan.n_fused_stats = sum(1 for o in ops if o[0] == "norm" and o[1]["fused_stats"])
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:

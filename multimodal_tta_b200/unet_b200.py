@@ -153,6 +153,9 @@ class UNetB200(nn.Module):
         # run the full-resolution tail (norm apply + 3x3x3 conv + entropy, and its backward) as two
         # fused CUDA-core kernels instead of five streaming passes (csrc/tta_head.cu)
         self.fuse_head = bool(get_config(cfg, "fuse_head", True))
+        # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
+        # a separate pass over y (only where the conv runs without split-K)
+        self.fuse_stats = bool(get_config(cfg, "fuse_stats", True))
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))

@@ -49,12 +49,12 @@ for name, cin, cout, K, s, mode, S in LAYERS:
             c8o * So ** 3 * 8, c8o, So, So, So, mode, K, s, 0, flags)
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
-        check(lib.tta_conv_tc(*args, st))
+        check(lib.tta_conv_tc(*args, 0, 0, st))
     ts = []
     for _ in range(5):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); check(lib.tta_conv_tc(*args, st)); b.record(); torch.cuda.synchronize()
+        a.record(); check(lib.tta_conv_tc(*args, 0, 0, st)); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     us = sorted(ts)[2]
     Vout = So ** 3 if mode == 0 else S ** 3 * 8

@@ -36,7 +36,7 @@ GEOMS = [  # cin, cout, K, stride, transposed, dims
 def _tc(lib, hi, lo, ns, dt, N, c8i, idims, wp, bias, out, ons, c8o, odims, mode, K, s, acc=0, flags=0):
     check(lib.tta_conv_tc(hi.data_ptr(), lo.data_ptr(), ns, dt, N, c8i, *idims, wp.data_ptr(),
                           bias.data_ptr() if bias is not None else 0, out.data_ptr(), ons, c8o, *odims, mode, K, s,
-                          acc, flags, stream()), "conv_tc")
+                          acc, flags, 0, 0, stream()), "conv_tc")
     torch.cuda.synchronize()
 
 
@@ -92,7 +92,7 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
     sub = gflat[gview_ptr_off:]
     check(lib.tta_conv_tc(dhi.data_ptr(), dlo.data_ptr(), c8o * ref[0, 0].numel() * 8, TTA_BF16, N, c8o, *odims,
                           wpd.data_ptr(), 0, sub.data_ptr(), (c8i + extra) * Vi * 8, c8i, *dims, 1 - mode, K, s, 0, 0,
-                          stream()), "conv_tc dgrad")
+                          0, 0, stream()), "conv_tc dgrad")
     torch.cuda.synchronize()
     gx = from_chunked(gbuf[:, extra:], cin).cpu()
     assert rel_l2(gx, g2) < 1e-4, rel_l2(gx, g2)
@@ -100,7 +100,7 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
     # accumulate epilogue
     check(lib.tta_conv_tc(dhi.data_ptr(), dlo.data_ptr(), c8o * ref[0, 0].numel() * 8, TTA_BF16, N, c8o, *odims,
                           wpd.data_ptr(), 0, sub.data_ptr(), (c8i + extra) * Vi * 8, c8i, *dims, 1 - mode, K, s, 1, 0,
-                          stream()), "conv_tc dgrad acc")
+                          0, 0, stream()), "conv_tc dgrad acc")
     torch.cuda.synchronize()
     assert rel_l2(from_chunked(gbuf[:, extra:], cin).cpu(), 2 * g2) < 1e-4
     # ---- dgrad with ONE fp16 plane (loss-scaled gradients): a single MMA per k-step
@@ -116,7 +116,7 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
     hhi = hhi.contiguous()
     check(lib.tta_conv_tc(hhi.data_ptr(), 0, c8o * ref[0, 0].numel() * 8, TTA_F16_HI, N, c8o, *odims,
                           wph.data_ptr(), 0, gx3.data_ptr(), c8i * Vi * 8, c8i, *dims, 1 - mode, K, s, 0, 0,
-                          stream()), "conv_tc dgrad fp16")
+                          0, 0, stream()), "conv_tc dgrad fp16")
     torch.cuda.synchronize()
     assert rel_l2(from_chunked(gx3, cin).cpu(), g3) < 2e-5, rel_l2(from_chunked(gx3, cin).cpu(), g3)
     if tr and s == 2:
@@ -126,7 +126,7 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
         for buf, src, fl in ((g_std, hhi, 2), (g_ws, hws, 2 | 8)):
             check(lib.tta_conv_tc(src.data_ptr(), 0, c8o * ref[0, 0].numel() * 8, TTA_F16_HI, N, c8o, *odims,
                                   wph.data_ptr(), 0, buf.data_ptr(), c8i * Vi * 8, c8i, *dims, 1 - mode, K, s, 0, fl,
-                                  stream()), "conv_tc dgrad wsplit")
+                                  0, 0, stream()), "conv_tc dgrad wsplit")
         torch.cuda.synchronize()
         assert torch.equal(g_ws, g_std)
 
@@ -146,6 +146,53 @@ def test_conv_tc_reads_concat_slice_view(lib, cuda):
     off = (c0 // 8) * V * 8
     check(lib.tta_conv_tc(hi.view(-1)[off:].data_ptr(), lo.view(-1)[off:].data_ptr(), (ctot // 8) * V * 8, TTA_F16,
                           N, cin // 8, *dims, wp.data_ptr(), 0, out.data_ptr(), (cout // 8) * V * 8, cout // 8, *dims,
-                          0, 3, 1, 0, 0, stream()), "conv_tc view")
+                          0, 3, 1, 0, 0, 0, 0, stream()), "conv_tc view")
     torch.cuda.synchronize()
     assert rel_l2(from_chunked(out, cout).cpu(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,s,tr,dims,stats_c", [(32, 32, 1, False, (5, 20, 12), 32), (32, 64, 2, False, (8, 16, 16), 32),
+                                                         (48, 16, 2, True, (3, 10, 6), 16), (64, 3, 2, True, (4, 16, 8), 3),
+                                                         (128, 256, 1, False, (2, 6, 6), 256)])
+def test_conv_tc_fused_norm_statistics(lib, cuda, cin, cout, s, tr, dims, stats_c):
+    """The conv epilogue leaves per-CTA partial sums of y and y^2 over the leading chunks
+    (tta_conv_tc stats_workspace); tta_norm_stats_finalize turns them into mean/rstd.  Checked against
+    torch statistics of the kernel's own fp32 output: 1e-5 relative (fp32 partial sums, fp64 finalize),
+    instance and batch mode, twice (the CTA slots are re-zeroed by every launch)."""
+    import ctypes
+    torch.manual_seed(9)
+    N = 2
+    x = torch.randn(N, cin, *dims) + 0.3
+    w = torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3)) * 0.1
+    b = torch.randn(cout)
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    mode = 1 if tr else 0
+    odims = tuple(d * s for d in dims) if tr else tuple((d - 1) // s + 1 for d in dims)
+    c8i, c8o, sc8 = (cin + 7) // 8, (cout + 7) // 8, (stats_c + 7) // 8
+    Vi, Vo = dims[0] * dims[1] * dims[2], odims[0] * odims[1] * odims[2]
+    wp = pack_weights_tc(wg_forward(w.to(cuda), tr), mode, 3, s, TTA_F16)
+    ks, grid = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.tta_conv_tc_query(TTA_F16, N, c8i, *dims, c8o, *odims, mode, 3, s, 0, 2, ctypes.byref(ks),
+                                ctypes.byref(grid), 0), "query")
+    assert ks.value == 1 and 1 <= grid.value <= 148
+    ws = torch.full((1024 + N * sc8 * grid.value * 16,), 123.0, device=cuda)   # garbage: the conv must zero its slots
+    out = torch.zeros((N, c8o, *odims, 8), device=cuda)
+    bias = pack_bias(b.to(cuda))
+    for _ in range(2):
+        check(lib.tta_conv_tc(hi.data_ptr(), lo.data_ptr(), c8i * Vi * 8, TTA_F16, N, c8i, *dims, wp.data_ptr(),
+                              bias.data_ptr(), out.data_ptr(), c8o * Vo * 8, c8o, *odims, mode, 3, s, 0, 2,
+                              ws.data_ptr(), sc8, stream()), "conv_tc stats")
+    y = from_chunked(out, cout)[:, :stats_c]
+    for batch_mode in (0, 1):
+        mean = torch.zeros(N * sc8 * 8, device=cuda); rstd = torch.zeros_like(mean)
+        check(lib.tta_norm_stats_finalize(ws.data_ptr(), N, sc8, grid.value, Vo, batch_mode, 1e-5, mean.data_ptr(),
+                                          rstd.data_ptr(), stream()), "finalize")
+        dimsr = (0, 2, 3, 4) if batch_mode else (2, 3, 4)
+        mu = y.double().mean(dimsr, keepdim=True)
+        var = ((y.double() - mu) ** 2).mean(dimsr, keepdim=True)
+        mu_ref = mu.expand(N, stats_c, 1, 1, 1).reshape(N, stats_c)
+        rs_ref = (1.0 / torch.sqrt(var + 1e-5)).expand(N, stats_c, 1, 1, 1).reshape(N, stats_c)
+        got_mu = mean.view(N, sc8 * 8)[:, :stats_c].double()
+        got_rs = rstd.view(N, sc8 * 8)[:, :stats_c].double()
+        assert float((got_mu - mu_ref).abs().max()) < 1e-5 * float(y.abs().max())
+        assert float(((got_rs - rs_ref) / rs_ref).abs().max()) < 1e-5

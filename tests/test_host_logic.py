@@ -130,6 +130,8 @@ def test_op_graph_layer_counts(cfg, nconv, nnorm, ndgrad):
     fh = int(plan.fused_head)
     assert fh == (cfg is not BARE_DEFAULT_MODEL_CFG and "num_res_units" in cfg and cfg["num_res_units"] > 0)
     assert len(plan.fwd) == nconv + nnorm - fh and len(plan.bwd) == ndgrad + nnorm
+    # norms fed by a tcgen05 conv without split-K take their statistics from the conv epilogue
+    assert 0 < plan.n_fused_stats <= nnorm
     assert plan.launches_fwd == 1 + nconv + 2 * nnorm + 2 - 3 * fh
     assert set(plan.conv_backends.values()) <= {"tc", "small", "simt", "head"}
     if cfg is BRATS_MODEL_CFG:

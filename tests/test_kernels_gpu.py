@@ -36,7 +36,7 @@ def _run_conv(lib, which, hi, lo, dt, N, cin, idims, wp, bias, cout, odims, mode
     if which == "simt":
         check(lib.tta_conv_simt(*args, stream()), "conv_simt")
     else:
-        check(lib.tta_conv_tc(*args, 0, stream()), "conv_tc")
+        check(lib.tta_conv_tc(*args, 0, 0, 0, stream()), "conv_tc")
     return out
 
 
@@ -140,7 +140,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     ohi = torch.zeros((N, C8, *dims, 8), dtype=torch.int16, device=cuda); olo = torch.zeros_like(ohi)
     check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
                              bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi.data_ptr(), olo.data_ptr(), ns,
-                             TTA_F16, 0, batch_mode, 1e-5, 0, 0, 0, 0, stream()))
+                             TTA_F16, 0, 0, batch_mode, 1e-5, 0, 0, 0, 0, stream()))
     got = from_chunked(join_planes(ohi, olo, TTA_F16), C).cpu()
     assert (got - a.detach()).abs().max() < 2e-5      # fp16x2 storage (22 bits) + fp32 stats
     # fused path: partial sums only, finalize inside the apply prologue -> identical planes
@@ -149,7 +149,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     ohi2 = torch.zeros_like(ohi); olo2 = torch.zeros_like(ohi)
     check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean2.data_ptr(), rstd2.data_ptr(), gp.data_ptr(),
                              bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi2.data_ptr(), olo2.data_ptr(), ns,
-                             TTA_F16, ws.data_ptr(), batch_mode, 1e-5, 0, 0, 0, 0, stream()))
+                             TTA_F16, ws.data_ptr(), 0, batch_mode, 1e-5, 0, 0, 0, 0, stream()))
     got2 = from_chunked(join_planes(ohi2, olo2, TTA_F16), C).cpu()
     assert (got2 - got).abs().max() < 2e-6            # same math, fp64 partial sums in another order
     if dims[2] % 2 == 0:
@@ -159,7 +159,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
         ohi3 = torch.zeros_like(ohi); olo3 = torch.zeros_like(ohi)
         check(lib.tta_norm_apply(ych.data_ptr(), ns, N, C8, V, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
                                  bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi3.data_ptr(), olo3.data_ptr(), ns,
-                                 TTA_F16, 0, batch_mode, 1e-5, whi.data_ptr(), wlo.data_ptr(), ns, dims[2],
+                                 TTA_F16, 0, 0, batch_mode, 1e-5, whi.data_ptr(), wlo.data_ptr(), ns, dims[2],
                                  stream()))
         assert torch.equal(ohi3, ohi) and torch.equal(olo3, olo)
         assert torch.equal(whi, wsplit(ohi)) and torch.equal(wlo, wsplit(olo))
