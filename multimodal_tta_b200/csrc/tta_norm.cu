@@ -16,7 +16,7 @@ namespace tta {
 
 // ---------------------------------------------------------------- forward statistics
 // partial[((n*C8 + chunk)*splits + split)*16 + {0..7: sum, 8..15: sumsq}]
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 norm_stats_partial_kernel(const float* y, long long n_stride, int C8, long long V,
                           int splits, float* partial, unsigned int* counters,
                           int N, int batch_mode, float eps, float* mean,
@@ -31,6 +31,7 @@ norm_stats_partial_kernel(const float* y, long long n_stride, int C8, long long 
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 2
   for (long long v = v0 + threadIdx.x; v < v1; v += kThreads) {
     float x[8];
     load_f32x8(base + v * 8, x);
@@ -122,7 +123,7 @@ norm_stats_finalize_chunk_kernel(const float* partial, int N, int C8, int splits
 // out = relu?(gamma*(y-mean)*rstd + beta) (+ residual), written as split 16-bit planes.
 // RES: 0 none, 1 fp32 view, 2 split-plane view (dtype ODT)
 template <int RES, int ODT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
                   const float* mean, const float* rstd,
                   const float* gamma, const float* beta, int relu,
@@ -173,6 +174,7 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
   const float* yb = y + (long long)n * y_ns + slab;
   const long long ob = (long long)n * out_ns + slab;
   const long long rb = (long long)n * res_ns + slab;
+#pragma unroll 2
   for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
        v += (long long)gridDim.x * kThreads) {
     float x[8];
@@ -202,7 +204,7 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
 
 // ---------------------------------------------------------------- backward reductions
 // partial[..][0..7] = sum dz, [8..15] = sum dz*xhat     (dz = (g0+g1) * [z>0])
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 norm_bwd_partial_kernel(const float* g0, long long g0_ns,
                         const float* g1, long long g1_ns,
                         const float* y, long long y_ns, int C8, long long V,
@@ -233,6 +235,7 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 2
   for (long long v = v0 + threadIdx.x; v < v1; v += kThreads) {
     float x[8], g[8];
     load_f32x8(yb + v * 8, x);
@@ -299,7 +302,7 @@ __global__ void norm_bwd_finalize_kernel(const float* partial, int N, int C8, in
 // dy = gamma*rstd*(dz - S1/M - xhat*S2/M) -> split planes (ODT);  optionally also the summed
 // incoming gradient itself as split planes (aux), which feeds the shortcut conv's dgrad.
 template <int ODT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
                       long long g1_ns, const float* y, long long y_ns, int C8,
                       long long V, const float* mean, const float* rstd,
@@ -358,6 +361,7 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
   const float* g1b = g1 ? g1 + (long long)n * g1_ns + slab : nullptr;
   const long long ob = (long long)n * dy_ns + slab;
   const long long ab = (long long)n * aux_ns + slab;
+#pragma unroll 2
   for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
        v += (long long)gridDim.x * kThreads) {
     float x[8], g[8];
@@ -408,9 +412,9 @@ split_f32_kernel(const float* g0, long long g0_ns, const float* g1,
 }
 
 static inline int pick_splits(int N, int C8, long long V) {
-  // enough CTAs for ~4 waves of 148 SMs, at least 512 voxel-chunks (two per thread) per CTA: the
+  // enough CTAs for two waves of 4 resident CTAs on 148 SMs, at least 512 voxel-chunks (two per thread) per CTA: the
   // small 8^3..32^3 layers are latency bound and want every SM streaming
-  long long want = (4LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
+  long long want = (8LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
   long long maxs = (V + 511) / 512;
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
