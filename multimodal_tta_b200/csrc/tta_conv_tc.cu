@@ -34,7 +34,7 @@ constexpr int kTcThreads = 192;
 constexpr int kMaxGroups = 3;
 constexpr int kMaxLoads = 4;
 constexpr int kMaxAcc = 8;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 
 enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2 };
 
@@ -60,6 +60,9 @@ struct TcParams {
   // finalizes with splits = gridDim.x
   int stats_c8, n_batch;
   float* stats;
+  // resident weights: all (channel block, group) blobs of the single n-tile are copied into shared
+  // memory ONCE per CTA (persistent), stages then carry only the A operand
+  int b_res, b_res_off, pad_res;
   int lbo16[4];  // k-chunk pitch (16 B units, 128 B aligned) per A sub-tile
   signed char acc_pd[kMaxAcc], acc_qd[kMaxAcc], acc_qh[kMaxAcc], acc_qw[kMaxAcc];
   long long out_ns;
@@ -187,11 +190,11 @@ __device__ __forceinline__ void mma_pair(uint32_t leader, uint32_t d, uint32_t a
 // (the first MMA into each accumulator overwrites instead of accumulating).
 template <int GEOM, int TD, int SPLIT>
 __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, int g, uint32_t stage,
-                                            uint32_t tmem_acc0, bool first) {
+                                            uint32_t bsrc, uint32_t tmem_acc0, bool first) {
   const uint32_t nt = P.ntile;
   const uint32_t acc_cols = SPLIT ? 2u * nt : nt;
   const uint32_t a_hi0 = stage >> 4, a_lo0 = (stage + P.a_plane_bytes) >> 4;
-  const uint32_t b_w0 = ((stage + P.b_off) >> 4) | (acc_cols << 16);  // lbo16 = B rows per k-chunk
+  const uint32_t b_w0 = (bsrc >> 4) | (acc_cols << 16);  // bsrc: this (cblk, group) blob; lbo16 = B rows per k-chunk
   const uint32_t b_ent = (uint32_t)P.b_entry_bytes >> 4;                          // entry pitch, 16 B units
   const uint32_t b_w1 = 8u | (1u << 14);                                          // sbo16 = 8 (128 B)
   const uint32_t i2n = P.idesc_2n, in_ = P.idesc_n;
@@ -318,6 +321,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_bres;
+  __shared__ TcGroup grp_s[kMaxGroups];  // per-lane indexed by the producer (constant bank would serialise)
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[128];
   __shared__ float stat_s[STATS ? 4 : 1][STATS ? 16 * 16 : 1];  // [epilogue warp][chunk of the n-tile][16]: fused norm statistics
@@ -325,6 +330,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();  // the next kernel's CTAs may be scheduled (they block in their own pdl_wait)
 
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(TcGroup) * kMaxGroups / 4))
+    reinterpret_cast<int*>(grp_s)[threadIdx.x - 64] = reinterpret_cast<const int*>(P.grp)[threadIdx.x - 64];
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
@@ -334,6 +341,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
       mbar_init(smem_u32(&bar_acc_empty[b]), 4);  // one arrival per epilogue warp
     }
+    mbar_init(smem_u32(&bar_bres), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -362,45 +370,57 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t ring = 0;  // stage-ring position, continues across work items
-      for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
-        const WorkItem wi = decode_item(P, item);
-        for (int it = 0; it < wi.nit; ++it, ++ring) {
-          const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
-          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-          const int g = it % P.ngroups, cb = wi.cb0 + it / P.ngroups;
-          const TcGroup& G = P.grp[g];
-          const uint32_t full = smem_u32(&bar_full[s]);
-          const uint32_t stage = smem_base + s * P.stage_bytes;
-          const int c4 = wi.n * P.c8_view + cb * 2;
-          const int nkc = (cb * 2 + 1 < P.c8in || !P.single_chunk) ? 2 : 1;
-          const uint32_t bbytes = (uint32_t)G.nmma * P.b_entry_bytes;
+    // The whole warp walks the stage ring; every lane owns ONE tensor copy of a stage
+    // (load x k-chunk x plane, <= 16 per stage) and issues it itself, so a stage costs one pass of
+    // uniform control flow instead of a serial per-copy loop in a single thread (measured on the
+    // stride-2 stem: the MMA warp sat 59 % of the time on the full barrier while lane 0 spent
+    // ~300 cycles per copy on index arithmetic and constant-bank lookups).
+    if (P.b_res && lane == 0) {
+      // weights never change: one copy per CTA lifetime instead of one per stage
+      const int nblob = P.ncblk * P.ngroups;
+      mbar_expect_tx(smem_u32(&bar_bres), (uint32_t)(nblob * P.b_blob_bytes));
+      for (int b = 0; b < nblob; ++b)
+        bulk_load(smem_base + P.b_res_off + b * P.b_blob_bytes, P.wpacked + (long long)b * P.b_blob_bytes,
+                  (uint32_t)P.b_blob_bytes, smem_u32(&bar_bres));
+    }
+    constexpr int kPlanes = SPLIT ? 2 : 1;
+    const int my_plane = lane % kPlanes;
+    const int my_kc = (lane / kPlanes) & 1;
+    const int my_l = lane / (kPlanes * 2);
+    uint32_t ring = 0;  // stage-ring position, continues across work items
+    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
+      const WorkItem wi = decode_item(P, item);
+      for (int it = 0; it < wi.nit; ++it, ++ring) {
+        const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
+        if (lane == 0) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+        __syncwarp();
+        const int g = it % P.ngroups, cb = wi.cb0 + it / P.ngroups;
+        const TcGroup& G = grp_s[g];
+        const uint32_t full = smem_u32(&bar_full[s]);
+        const uint32_t stage = smem_base + s * P.stage_bytes;
+        const int c4 = wi.n * P.c8_view + cb * 2;
+        const int nkc = (cb * 2 + 1 < P.c8in || !P.single_chunk) ? 2 : 1;
+        const uint32_t bbytes = P.b_res ? 0u : (uint32_t)G.nmma * P.b_entry_bytes;
+        if (lane == 0) {
           mbar_expect_tx(full, (uint32_t)((SPLIT ? G.tx_bytes : G.tx_bytes / 2) * nkc) + bbytes);
-          for (int l = 0; l < G.nloads; ++l) {
-            const TcLoad& L = G.ld[l];
-            const int cw = wi.w0 + L.dw, chh = wi.h0 + L.dh, cd = wi.d0 * P.d_mul + L.dd;
-            for (int kc = 0; kc < nkc; ++kc) {
-              const uint32_t dst = stage + L.smem_off + kc * L.chunk_pitch;
-              if (GEOM == GEOM_S2) {
-                if (P.s2_rows) {
-                  tma_load_4d(dst, &P.amap[L.map * 2 + 0], full, cw * 8, chh, cd, c4 + kc);
-                  if (SPLIT)
-                    tma_load_4d(dst + P.a_plane_bytes, &P.amap[L.map * 2 + 1], full, cw * 8, chh, cd, c4 + kc);
-                } else {
-                  tma_load_5d(dst, &P.amap[L.map * 2 + 0], full, 0, cw, chh, cd, c4 + kc);
-                  if (SPLIT)
-                    tma_load_5d(dst + P.a_plane_bytes, &P.amap[L.map * 2 + 1], full, 0, cw, chh, cd, c4 + kc);
-                }
-              } else {
-                tma_load_4d(dst, &P.amap[0], full, cw * 8, chh, cd, c4 + kc);
-                if (SPLIT) tma_load_4d(dst + P.a_plane_bytes, &P.amap[1], full, cw * 8, chh, cd, c4 + kc);
-              }
-            }
+          if (!P.b_res) {
+            // every (nt, cb, g) blob reserves gmax entries; only this group's nmma entries are copied
+            const long long blob = ((long long)wi.nt * P.ncblk + cb) * P.ngroups + g;
+            bulk_load(stage + P.b_off, P.wpacked + blob * P.b_blob_bytes, bbytes, full);
           }
-          // every (nt, cb, g) blob reserves gmax entries; only this group's nmma entries are copied
-          const long long blob = ((long long)wi.nt * P.ncblk + cb) * P.ngroups + g;
-          bulk_load(stage + P.b_off, P.wpacked + blob * P.b_blob_bytes, bbytes, full);
+        }
+        __syncwarp();
+        if (my_l < G.nloads && my_kc < nkc) {
+          const TcLoad& L = G.ld[my_l];
+          const int cw = wi.w0 + L.dw, chh = wi.h0 + L.dh, cd = wi.d0 * P.d_mul + L.dd;
+          const uint32_t dst = stage + L.smem_off + my_kc * L.chunk_pitch + my_plane * P.a_plane_bytes;
+          if (GEOM == GEOM_S2) {
+            const CUtensorMap* m = &P.amap[L.map * 2 + my_plane];
+            if (P.s2_rows) tma_load_4d(dst, m, full, cw * 8, chh, cd, c4 + my_kc);
+            else tma_load_5d(dst, m, full, 0, cw, chh, cd, c4 + my_kc);
+          } else {
+            tma_load_4d(dst, &P.amap[my_plane], full, cw * 8, chh, cd, c4 + my_kc);
+          }
         }
       }
     }
@@ -408,6 +428,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // ===================== MMA issuer (whole warp runs uniform code, one elected lane issues) =====
     const uint32_t leader = elect_one();
     uint32_t ring = 0, local = 0;
+    if (P.b_res) mbar_wait(smem_u32(&bar_bres), 0);  // resident weights have landed
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
       const WorkItem wi = decode_item(P, item);
       const uint32_t buf = local % P.nbuf, use = local / P.nbuf;
@@ -418,7 +439,11 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
         const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
         mbar_wait(smem_u32(&bar_full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_group<GEOM, TD, SPLIT>(P, leader, it % P.ngroups, smem_base + s * P.stage_bytes, acc0, it == 0);
+        const uint32_t stage = smem_base + s * P.stage_bytes;
+        const int g = it % P.ngroups;
+        const uint32_t bsrc = P.b_res ? smem_base + P.b_res_off + ((wi.cb0 + it / P.ngroups) * P.ngroups + g) * P.b_blob_bytes
+                                      : stage + P.b_off;
+        issue_group<GEOM, TD, SPLIT>(P, leader, g, stage, bsrc, acc0, it == 0);
         __syncwarp();
         if (leader) umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
       }
@@ -651,7 +676,7 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
 
 // in: split planes view [N][C8in (pitch from in_ns)][Di][Hi][Wi][8];  out: fp32 view; wpacked from
 // layout.pack_weights_tc.  flags bit0: force TD=1, bit1: no split-K (deterministic), bit2: one
-// work item per CTA (non-persistent; testing), bit3: the input planes of a stride-2 conv are stored
+// work item per CTA (non-persistent; testing), bit4: no resident weights (testing), bit3: the input planes of a stride-2 conv are stored
 // w-parity-split ([N][C8][D][H][2][W/2][8]: even-w voxels of a row first, then the odd ones).
 }  // extern "C"
 
@@ -720,8 +745,14 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   }
   auto a_plane_of = [&](int td_) { return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * 16); };
   const int a_planes = split ? 2 : 1;
-  auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + P.b_blob_bytes); };
-  const int smem_budget = 227 * 1024 - 8192;  // static smem: barriers, bias, 4 KB statistics slots
+  // small-channel layers (C <= 32: the full-resolution levels, where items are many): keep ALL
+  // weights of the single n-tile resident -> the per-stage B re-fetch (up to 2/3 of the L2->SM fill
+  // traffic of the stride-2 stem) disappears
+  const int b_total = P.ncblk * P.ngroups * P.b_blob_bytes;
+  const bool b_res = P.n_ntiles == 1 && geom != GEOM_T2 && b_total <= 112 * 1024 && !(flags & 16);
+  P.b_res = b_res ? 1 : 0;
+  auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + (b_res ? 0 : P.b_blob_bytes)); };
+  const int smem_budget = 227 * 1024 - 8192 - (b_res ? b_total : 0);  // static smem: barriers, bias, statistics slots
   int td = td_max;
   while (td > 1 && smem_budget / stage_bytes_of(td) < 2) --td;
   int nacc = geom == GEOM_T2 ? 8 : td;
@@ -742,6 +773,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.nstages = smem_budget / P.stage_bytes;
   TTA_REQUIRE(P.nstages >= 1, "tta_conv_tc: stage of %d bytes does not fit shared memory", P.stage_bytes);
   if (P.nstages > kMaxStages) P.nstages = kMaxStages;
+  P.b_res_off = P.nstages * P.stage_bytes;
   int cols = 32;
   while (cols < nbuf * nacc * acc_cols) cols *= 2;
   TTA_REQUIRE(cols <= 512, "tta_conv_tc: %d accumulator columns exceed TMEM", nbuf * nacc * acc_cols);
@@ -888,7 +920,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     }
   }
 
-  const size_t smem = (size_t)P.nstages * P.stage_bytes + 1024;
+  const size_t smem = (size_t)P.nstages * P.stage_bytes + (P.b_res ? b_total : 0) + 1024;
   const bool pdl_ok = !(P.ksplit > 1 && !accumulate);  // a memset precedes the split-K launch
   if (P.ksplit > 1 && !accumulate) {
     // partial sums are combined with float4 atomics: start from zero

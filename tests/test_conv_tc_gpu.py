@@ -64,6 +64,14 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
         c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s)
     got = from_chunked(out, cout).cpu()
     assert rel_l2(got, ref.detach()) < 2e-5, rel_l2(got, ref.detach())
+    if K == 3:
+        # resident weights (small-channel layers keep every weight blob in smem for the CTA's lifetime)
+        # vs. per-stage weight copies (flags bit4): same MMAs in the same order -> identical result
+        o_res = torch.zeros_like(out); o_str = torch.zeros_like(out)
+        args = (c8i * xv[0, 0].numel() * 8, TTA_F16, N, c8i, dims, wp, pack_bias(b.to(cuda)))
+        _tc(lib, hi, lo, *args, o_res, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2)
+        _tc(lib, hi, lo, *args, o_str, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 16)
+        assert torch.equal(o_res, o_str)
     if not tr and s == 2:
         # w-parity-split operand layout (flags bit3): same MMAs on the same bits -> identical result
         o_std = torch.zeros_like(out); o_ws = torch.zeros_like(out)
