@@ -79,15 +79,18 @@ struct alignas(16) F32x4 {
   float v[4];
 };
 
+// One voxel-chunk of fp32 = 32 B = exactly one DRAM/L2 sector: moved with ONE 256-bit access
+// (sm_100 LDG/STG.256).  Two 128-bit accesses would each touch half of every sector of the warp's
+// 1 KB run, i.e. twice the L1/L2 transactions for the same bytes.
 __device__ __forceinline__ void load_f32x8(const float* p, float (&o)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+               : "l"(p));
 }
 __device__ __forceinline__ void store_f32x8(float* p, const float (&o)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+               "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+               : "memory");
 }
 
 template <int DT>

@@ -524,8 +524,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                 const int co_chunk = wi.nt * nchunks + (cb + j) * 2 + hlf;
                 if (cb + j < n16 && valid && co_chunk < P.C8out) {
                   const float* src = obase + (long long)co_chunk * Vo * 8;
-                  old[j][hlf][0] = __ldcg(reinterpret_cast<const float4*>(src));
-                  old[j][hlf][1] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                  float ov[8];
+                  load_f32x8(src, ov);  // one 256-bit load per 32-byte voxel-chunk
+                  old[j][hlf][0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                  old[j][hlf][1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
                 } else {
                   old[j][hlf][0] = old[j][hlf][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -571,8 +573,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                     r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w;
                     r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
                   }
-                  *reinterpret_cast<float4*>(dst) = r0;
-                  *reinterpret_cast<float4*>(dst + 4) = r1;
+                  const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                  store_f32x8(dst, rv);  // whole 32-byte sector in one store
                 }
               }
               if (do_stats && co_chunk < P.stats_c8) {  // warp-uniform: the whole warp reduces
