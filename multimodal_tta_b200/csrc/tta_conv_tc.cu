@@ -387,14 +387,16 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     const int my_plane = lane % kPlanes;
     const int my_kc = (lane / kPlanes) & 1;
     const int my_l = lane / (kPlanes * 2);
-    uint32_t ring = 0;  // stage-ring position, continues across work items
+    // stage-ring position (s, phase) continues across work items; (g, cb) walk the groups of an
+    // item -- all advanced by compare-and-wrap: an integer division costs ~100 dependent cycles and
+    // this loop is the critical path of every layer with few MMAs per stage
+    int s = 0, ph = 0;
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
       const WorkItem wi = decode_item(P, item);
-      for (int it = 0; it < wi.nit; ++it, ++ring) {
-        const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
+      int g = 0, cb = wi.cb0;
+      for (int it = 0; it < wi.nit; ++it) {
         if (lane == 0) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
         __syncwarp();
-        const int g = it % P.ngroups, cb = wi.cb0 + it / P.ngroups;
         const TcGroup& G = grp_s[g];
         const uint32_t full = smem_u32(&bar_full[s]);
         const uint32_t stage = smem_base + s * P.stage_bytes;
@@ -422,30 +424,35 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
             tma_load_4d(dst, &P.amap[my_plane], full, cw * 8, chh, cd, c4 + my_kc);
           }
         }
+        if (++g == P.ngroups) { g = 0; ++cb; }
+        if (++s == P.nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs uniform code, one elected lane issues) =====
     const uint32_t leader = elect_one();
-    uint32_t ring = 0, local = 0;
+    uint32_t local = 0;
+    int s = 0, ph = 0;
     if (P.b_res) mbar_wait(smem_u32(&bar_bres), 0);  // resident weights have landed
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
       const WorkItem wi = decode_item(P, item);
-      const uint32_t buf = local % P.nbuf, use = local / P.nbuf;
+      const uint32_t buf = P.nbuf == 2 ? (local & 1u) : 0u, use = P.nbuf == 2 ? (local >> 1) : local;
       mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);  // epilogue drained this buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc0 = tmem_base + buf * buf_cols;
-      for (int it = 0; it < wi.nit; ++it, ++ring) {
-        const int s = ring % P.nstages, ph = (ring / P.nstages) & 1;
+      int g = 0;
+      uint32_t bres = smem_base + P.b_res_off + (uint32_t)(wi.cb0 * P.ngroups) * P.b_blob_bytes;
+      for (int it = 0; it < wi.nit; ++it) {
         mbar_wait(smem_u32(&bar_full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t stage = smem_base + s * P.stage_bytes;
-        const int g = it % P.ngroups;
-        const uint32_t bsrc = P.b_res ? smem_base + P.b_res_off + ((wi.cb0 + it / P.ngroups) * P.ngroups + g) * P.b_blob_bytes
-                                      : stage + P.b_off;
+        const uint32_t bsrc = P.b_res ? bres : stage + P.b_off;
         issue_group<GEOM, TD, SPLIT>(P, leader, g, stage, bsrc, acc0, it == 0);
         __syncwarp();
         if (leader) umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
+        bres += P.b_blob_bytes;
+        if (++g == P.ngroups) g = 0;
+        if (++s == P.nstages) { s = 0; ph ^= 1; }
       }
       if (leader) umma_commit(smem_u32(&bar_acc_full[buf]));  // accumulators of this item complete
       __syncwarp();
@@ -485,7 +492,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     }
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
       const WorkItem wi = decode_item(P, item);
-      const uint32_t buf = local % P.nbuf, use = local / P.nbuf;
+      const uint32_t buf = P.nbuf == 2 ? (local & 1u) : 0u, use = P.nbuf == 2 ? (local >> 1) : local;
       if (do_stats && (wi.n != st_n || wi.nt != st_nt)) {
         if (st_n >= 0) stats_flush();
         st_n = wi.n;
