@@ -26,6 +26,8 @@
 //    of item i overlaps the main loop of item i+1.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "tta_common.cuh"
 
 namespace tta {
@@ -63,6 +65,8 @@ struct TcParams {
   // resident weights: all (channel block, group) blobs of the single n-tile are copied into shared
   // memory ONCE per CTA (persistent), stages then carry only the A operand
   int b_res, b_res_off, pad_res;
+  // x / d == __umulhi(x, magic(d)) for every work-item index (host checks work_items * d < 2^32)
+  unsigned mg_per_tile, mg_tiles, mg_ksplit, mg_tiles_w, mg_tiles_h;
   int lbo16[4];  // k-chunk pitch (16 B units, 128 B aligned) per A sub-tile
   signed char acc_pd[kMaxAcc], acc_qd[kMaxAcc], acc_qh[kMaxAcc], acc_qw[kMaxAcc];
   long long out_ns;
@@ -293,17 +297,26 @@ struct WorkItem {
   int n, nt, ks, w0, h0, d0, cb0, nit;
 };
 // item = ((n * tiles + tile) * n_ntiles + nt) * ksplit + ks : neighbouring CTAs share the A tile in L2
+// x / d through the host-made reciprocal (0 encodes d == 1)
+__device__ __forceinline__ int fast_div(int x, unsigned mg) { return mg ? (int)__umulhi((unsigned)x, mg) : x; }
+
 __device__ __forceinline__ WorkItem decode_item(const TcParams& P, int item) {
+  // divisions by launch constants as multiply-high with host-made reciprocals: every role decodes
+  // every item, and seven hardware-emulated integer divisions (~100 dependent cycles each) were a
+  // measurable part of the per-item critical path of the MMA-light layers
   WorkItem w;
   const int per_tile = P.n_ntiles * P.ksplit;
-  const int ntks = item % per_tile;
-  int t = item / per_tile;
+  int t = fast_div(item, P.mg_per_tile);
+  const int ntks = item - t * per_tile;
   const int tiles = P.tiles_w * P.tiles_h * P.tiles_d;
-  w.n = t / tiles;
+  w.n = fast_div(t, P.mg_tiles);
   t -= w.n * tiles;
-  w.nt = ntks / P.ksplit;
+  w.nt = fast_div(ntks, P.mg_ksplit);
   w.ks = ntks - w.nt * P.ksplit;
-  const int tw = t % P.tiles_w, th = (t / P.tiles_w) % P.tiles_h, tdi = t / (P.tiles_w * P.tiles_h);
+  const int row = fast_div(t, P.mg_tiles_w);      // t / tiles_w
+  const int tw = t - row * P.tiles_w;
+  const int tdi = fast_div(row, P.mg_tiles_h);    // t / (tiles_w * tiles_h)
+  const int th = row - tdi * P.tiles_h;
   w.w0 = tw * 8;
   w.h0 = th * 16;
   w.d0 = tdi * P.td;
@@ -801,6 +814,19 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     P.cb_per_split = (P.ncblk + ks - 1) / ks;
     P.ksplit = (P.ncblk + P.cb_per_split - 1) / P.cb_per_split;
     P.work_items = (int)(items * P.ksplit);
+  }
+  {
+    // magic(d) = floor(2^32 / d) + 1: __umulhi(x, magic) == x / d whenever x * d < 2^32; d == 1 -> 0 (identity)
+    auto magic = [](unsigned d) -> unsigned { return d <= 1 ? 0u : (unsigned)((0x100000000ull / d) + 1ull); };
+    const unsigned dmax = (unsigned)std::max(std::max(P.n_ntiles * P.ksplit, P.tiles_w * P.tiles_h * P.tiles_d),
+                                             std::max(P.tiles_w, P.tiles_h));
+    TTA_REQUIRE((unsigned long long)(P.work_items + 1) * dmax < 0x100000000ull,
+                "tta_conv_tc: %d work items exceed the index arithmetic range", P.work_items);
+    P.mg_per_tile = magic((unsigned)(P.n_ntiles * P.ksplit));
+    P.mg_tiles = magic((unsigned)(P.tiles_w * P.tiles_h * P.tiles_d));
+    P.mg_ksplit = magic((unsigned)P.ksplit);
+    P.mg_tiles_w = magic((unsigned)P.tiles_w);
+    P.mg_tiles_h = magic((unsigned)P.tiles_h);
   }
   if (query) {
     *q_ksplit = P.ksplit;
