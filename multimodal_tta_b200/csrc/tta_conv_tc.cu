@@ -32,7 +32,7 @@
 
 namespace tta {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 224;  // TMA producer, MMA issuer, 4 epilogue warps, second TMA producer
 constexpr int kMaxGroups = 3;
 constexpr int kMaxLoads = 4;
 constexpr int kMaxAcc = 8;
@@ -381,14 +381,18 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   const uint32_t acc_cols = SPLIT ? 2u * P.ntile : (uint32_t)P.ntile;
   const uint32_t buf_cols = (uint32_t)P.nacc * acc_cols;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == 6) {
+    // ===================== TMA producers (warp 0: even ring positions, warp 6: odd) =====================
+    // Two warps alternate over the stage ring: filling a stage is a serial chain of address
+    // arithmetic + per-copy operand broadcasts, and for layers with few MMAs per stage one warp
+    // could not keep the tensor pipe fed.
+    const int my_par = warp == 0 ? 0 : 1;
     // The whole warp walks the stage ring; every lane owns ONE tensor copy of a stage
     // (load x k-chunk x plane, <= 16 per stage) and issues it itself, so a stage costs one pass of
     // uniform control flow instead of a serial per-copy loop in a single thread (measured on the
     // stride-2 stem: the MMA warp sat 59 % of the time on the full barrier while lane 0 spent
     // ~300 cycles per copy on index arithmetic and constant-bank lookups).
-    if (P.b_res && lane == 0) {
+    if (P.b_res && lane == 0 && warp == 0) {
       // weights never change: one copy per CTA lifetime instead of one per stage
       const int nblob = P.ncblk * P.ngroups;
       mbar_expect_tx(smem_u32(&bar_bres), (uint32_t)(nblob * P.b_blob_bytes));
@@ -403,11 +407,16 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // stage-ring position (s, phase) continues across work items; (g, cb) walk the groups of an
     // item -- all advanced by compare-and-wrap: an integer division costs ~100 dependent cycles and
     // this loop is the critical path of every layer with few MMAs per stage
-    int s = 0, ph = 0;
+    int s = 0, ph = 0, par = 0;
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
       const WorkItem wi = decode_item(P, item);
       int g = 0, cb = wi.cb0;
-      for (int it = 0; it < wi.nit; ++it) {
+      for (int it = 0; it < wi.nit; ++it, par ^= 1) {
+        if (par != my_par) {  // the other producer's stage: only advance the counters
+          if (++g == P.ngroups) { g = 0; ++cb; }
+          if (++s == P.nstages) { s = 0; ph ^= 1; }
+          continue;
+        }
         if (lane == 0) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
         __syncwarp();
         const TcGroup& G = grp_s[g];
@@ -470,7 +479,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       if (leader) umma_commit(smem_u32(&bar_acc_full[buf]));  // accumulators of this item complete
       __syncwarp();
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
