@@ -32,7 +32,7 @@
 
 namespace tta {
 
-constexpr int kTcThreads = 224;  // TMA producer, MMA issuer, 4 epilogue warps, second TMA producer
+constexpr int kTcThreads = 352;  // TMA producer, MMA issuer, 8 epilogue warps, second TMA producer
 constexpr int kMaxGroups = 3;
 constexpr int kMaxLoads = 4;
 constexpr int kMaxAcc = 8;
@@ -338,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   __shared__ TcGroup grp_s[kMaxGroups];  // per-lane indexed by the producer (constant bank would serialise)
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[128];
-  __shared__ float stat_s[STATS ? 4 : 1][STATS ? 16 * 16 : 1];  // [epilogue warp][chunk of the n-tile][16]: fused norm statistics
+  __shared__ float stat_s[STATS ? 8 : 1][STATS ? 16 * 16 : 1];  // [epilogue warp][chunk of the n-tile][16]: fused norm statistics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();  // the next kernel's CTAs may be scheduled (they block in their own pdl_wait)
@@ -352,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[b]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&bar_acc_empty[b]), 8);  // one arrival per epilogue warp
     }
     mbar_init(smem_u32(&bar_bres), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -381,8 +381,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   const uint32_t acc_cols = SPLIT ? 2u * P.ntile : (uint32_t)P.ntile;
   const uint32_t buf_cols = (uint32_t)P.nacc * acc_cols;
 
-  if (warp == 0 || warp == 6) {
-    // ===================== TMA producers (warp 0: even ring positions, warp 6: odd) =====================
+  if (warp == 0 || warp == 10) {
+    // ===================== TMA producers (warp 0: even ring positions, warp 10: odd) =====================
     // Two warps alternate over the stage ring: filling a stage is a serial chain of address
     // arithmetic + per-copy operand broadcasts, and for layers with few MMAs per stage one warp
     // could not keep the tensor pipe fed.
@@ -479,38 +479,52 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       if (leader) umma_commit(smem_u32(&bar_acc_full[buf]));  // accumulators of this item complete
       __syncwarp();
     }
-  } else if (warp < 6) {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    const int q = warp & 3;
+  } else if (warp < 10) {
+    // ===================== epilogue (8 warps: two per TMEM lane quarter) =====================
+    // Small-K layers (stem, every single-product dgrad) do little MMA work per 128 x NT tile, so the
+    // TMEM -> registers -> HBM drain is their critical path: measured on the stride-2 stem, four
+    // epilogue warps (one per scheduler, nothing to hide latency with) were busy 80 % of the time
+    // while the MMA warp idled.  Two warps per lane quarter split the (accumulator, 16-column)
+    // units of an item between them.
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // which of the quarter's two warps
     const int row = q * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int et = threadIdx.x - 64;        // 0..255
+    const int ew = warp - 2;                // 0..7: statistics slot
     const long long Vo = (long long)P.Do * P.Ho * P.Wo;
     const int nchunks = P.ntile >> 3;
+    const int n16 = P.ntile >> 4;
+    const int nunits = P.nacc * n16;
+    const bool rmw = P.accumulate && P.ksplit == 1;
     uint32_t local = 0;
     // ---- fused norm statistics (forward convs that feed a norm, no split-K): every warp adds its
-    // 32 rows into a private smem slot; when the CTA moves on to another (n, n-tile) the four slots
+    // 32 rows into a private smem slot; when the CTA moves on to another (n, n-tile) the eight slots
     // are summed in a fixed order into this CTA's own global slot -> deterministic, no atomics
     constexpr bool do_stats = STATS != 0;
+    constexpr int kSlots = STATS ? 8 : 1;
     int st_n = -1, st_nt = -1;
     auto stats_flush = [&]() {
       if (!STATS) return;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int t = et; t < nchunks * 16; t += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int t = et; t < nchunks * 16; t += 256) {
         const int gchunk = st_nt * nchunks + (t >> 4);
-        if (gchunk < P.stats_c8) {
-          float* slot = P.stats + (((long long)st_n * P.stats_c8 + gchunk) * gridDim.x + blockIdx.x) * 16 + (t & 15);
-          *slot += (stat_s[0][t] + stat_s[STATS ? 1 : 0][t]) + (stat_s[STATS ? 2 : 0][t] + stat_s[STATS ? 3 : 0][t]);
+        float tot = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < kSlots; ++w8) {
+          tot += stat_s[w8][t];
+          stat_s[w8][t] = 0.f;
         }
-        stat_s[0][t] = stat_s[STATS ? 1 : 0][t] = stat_s[STATS ? 2 : 0][t] = stat_s[STATS ? 3 : 0][t] = 0.f;
+        if (gchunk < P.stats_c8)
+          P.stats[(((long long)st_n * P.stats_c8 + gchunk) * gridDim.x + blockIdx.x) * 16 + (t & 15)] += tot;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     if (do_stats) {
-      for (int t = et; t < (STATS ? 4 * 256 : 0); t += 128) (&stat_s[0][0])[t] = 0.f;
-      for (int t = et; t < P.n_batch * P.stats_c8 * 16; t += 128)
+      for (int t = et; t < kSlots * 256; t += 256) (&stat_s[0][0])[t] = 0.f;
+      for (int t = et; t < P.n_batch * P.stats_c8 * 16; t += 256)
         P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
       const WorkItem wi = decode_item(P, item);
@@ -521,100 +535,104 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
         st_nt = wi.nt;
       }
       // bias of this n-tile -> smem (only split 0 adds it)
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers are done with bias_s
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous item's readers are done with bias_s
       if (et < P.ntile) {
         const int c = wi.nt * P.ntile + et;
         bias_s[et] = (P.bias != nullptr && wi.ks == 0 && c < P.C8out * 8) ? P.bias[c] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16);
-      for (int acc = 0; acc < P.nacc; ++acc) {
-        const int od = P.out_mul * (wi.d0 + P.acc_pd[acc]) + P.acc_qd[acc];
-        const int oh = P.out_mul * (wi.h0 + hh) + P.acc_qh[acc];
-        const int ow = P.out_mul * (wi.w0 + ww) + P.acc_qw[acc];
-        const bool valid = od < P.Do && oh < P.Ho && ow < P.Wo;
-        const long long vox = ((long long)od * P.Ho + oh) * P.Wo + ow;
-        float* obase = P.out + (long long)wi.n * P.out_ns + vox * 8;
-        const uint32_t tacc = tbase + acc * acc_cols;
-        // 64 accumulator columns per round.  The accumulate epilogue (gradient fan-in) is a
-        // read-modify-write: all old values of the round are requested BEFORE the TMEM loads, so
-        // the round pays one memory latency instead of one per 8-channel chunk.
-        const bool rmw = P.accumulate && P.ksplit == 1;
-        const int n16 = P.ntile >> 4;
-        for (int cb = 0; cb < n16; cb += 4) {
-          float4 old[4][2][2];
+      // units = (accumulator, 16-column block); this warp takes every second one, two per round so
+      // that the read-modify-write variant (gradient fan-in) has four 32-byte loads in flight before
+      // it touches TMEM
+      for (int u0 = half; u0 < nunits; u0 += 4) {
+        float4 old[2][2][2];
+        float* obase[2];
+        bool valid[2];
+        int c16s[2];
+        uint32_t tacc[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int u = u0 + 2 * k;
+          const int acc = u < nunits ? u / n16 : 0;
+          c16s[k] = u < nunits ? u - acc * n16 : 0;
+          const int od = P.out_mul * (wi.d0 + P.acc_pd[acc]) + P.acc_qd[acc];
+          const int oh = P.out_mul * (wi.h0 + hh) + P.acc_qh[acc];
+          const int ow = P.out_mul * (wi.w0 + ww) + P.acc_qw[acc];
+          valid[k] = u < nunits && od < P.Do && oh < P.Ho && ow < P.Wo;
+          const long long vox = ((long long)od * P.Ho + oh) * P.Wo + ow;
+          obase[k] = P.out + (long long)wi.n * P.out_ns + vox * 8;
+          tacc[k] = tbase + acc * acc_cols;
           if (rmw) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                const int co_chunk = wi.nt * nchunks + (cb + j) * 2 + hlf;
-                if (cb + j < n16 && valid && co_chunk < P.C8out) {
-                  const float* src = obase + (long long)co_chunk * Vo * 8;
-                  float ov[8];
-                  load_f32x8(src, ov);  // one 256-bit load per 32-byte voxel-chunk
-                  old[j][hlf][0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
-                  old[j][hlf][1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
-                } else {
-                  old[j][hlf][0] = old[j][hlf][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-              }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c16 = cb + j;
-            if (c16 >= n16) break;
-            uint32_t ra[16], rb[16];
-            tmem_ld16_nowait(tacc + c16 * 16, ra);            // hi*hi + lo*hi columns
-            if (SPLIT) {
-              tmem_ld16_nowait(tacc + P.ntile + c16 * 16, rb);  // hi*lo columns
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) rb[i] = 0u;
-            }
-            tmem_ld_wait();
-#pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
-              const int co_chunk = wi.nt * nchunks + c16 * 2 + hlf;
-              const bool live = valid && co_chunk < P.C8out;
-              const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
-              const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
-              const int o = hlf * 8;
-              float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
-                                      __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
-                                      __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
-                                      __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
-              float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
-                                      __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
-                                      __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
-                                      __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
-              if (live) {
-                float* dst = obase + (long long)co_chunk * Vo * 8;
-                if (P.ksplit > 1) {
-                  // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
-                  atomicAdd(reinterpret_cast<float4*>(dst), r0);
-                  atomicAdd(reinterpret_cast<float4*>(dst + 4), r1);
-                } else {
-                  if (rmw) {
-                    const float4 o0 = old[j][hlf][0], o1 = old[j][hlf][1];
-                    r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w;
-                    r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
-                  }
-                  const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                  store_f32x8(dst, rv);  // whole 32-byte sector in one store
-                }
+              const int co_chunk = wi.nt * nchunks + c16s[k] * 2 + hlf;
+              if (valid[k] && co_chunk < P.C8out) {
+                const float* src = obase[k] + (long long)co_chunk * Vo * 8;
+                float ov[8];
+                load_f32x8(src, ov);  // one 256-bit load per 32-byte voxel-chunk
+                old[k][hlf][0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                old[k][hlf][1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
+              } else {
+                old[k][hlf][0] = old[k][hlf][1] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              if (do_stats && co_chunk < P.stats_c8) {  // warp-uniform: the whole warp reduces
-                float sv[16];
-                sv[0] = live ? r0.x : 0.f; sv[1] = live ? r0.y : 0.f; sv[2] = live ? r0.z : 0.f; sv[3] = live ? r0.w : 0.f;
-                sv[4] = live ? r1.x : 0.f; sv[5] = live ? r1.y : 0.f; sv[6] = live ? r1.z : 0.f; sv[7] = live ? r1.w : 0.f;
+            }
+          }
+        }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sv[8 + i] = sv[i] * sv[i];
-                const float tot = warp_reduce16(sv, lane);
-                if (!(lane & 1)) stat_s[q][(c16 * 2 + hlf) * 16 + (lane >> 1)] += tot;
+        for (int k = 0; k < 2; ++k) {
+          if (u0 + 2 * k >= nunits) break;  // warp-uniform
+          const int c16 = c16s[k];
+          uint32_t ra[16], rb[16];
+          tmem_ld16_nowait(tacc[k] + c16 * 16, ra);            // hi*hi + lo*hi columns
+          if (SPLIT) {
+            tmem_ld16_nowait(tacc[k] + P.ntile + c16 * 16, rb);  // hi*lo columns
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rb[i] = 0u;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int co_chunk = wi.nt * nchunks + c16 * 2 + hlf;
+            const bool live = valid[k] && co_chunk < P.C8out;
+            const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c16 * 16 + hlf * 8 + 4]);
+            const int o = hlf * 8;
+            float4 r0 = make_float4(__uint_as_float(ra[o + 0]) + __uint_as_float(rb[o + 0]) + b0.x,
+                                    __uint_as_float(ra[o + 1]) + __uint_as_float(rb[o + 1]) + b0.y,
+                                    __uint_as_float(ra[o + 2]) + __uint_as_float(rb[o + 2]) + b0.z,
+                                    __uint_as_float(ra[o + 3]) + __uint_as_float(rb[o + 3]) + b0.w);
+            float4 r1 = make_float4(__uint_as_float(ra[o + 4]) + __uint_as_float(rb[o + 4]) + b1.x,
+                                    __uint_as_float(ra[o + 5]) + __uint_as_float(rb[o + 5]) + b1.y,
+                                    __uint_as_float(ra[o + 6]) + __uint_as_float(rb[o + 6]) + b1.z,
+                                    __uint_as_float(ra[o + 7]) + __uint_as_float(rb[o + 7]) + b1.w);
+            if (live) {
+              float* dst = obase[k] + (long long)co_chunk * Vo * 8;
+              if (P.ksplit > 1) {
+                // split-K partial sums meet in HBM (destination pre-zeroed unless accumulating)
+                atomicAdd(reinterpret_cast<float4*>(dst), r0);
+                atomicAdd(reinterpret_cast<float4*>(dst + 4), r1);
+              } else {
+                if (rmw) {
+                  const float4 o0 = old[k][hlf][0], o1 = old[k][hlf][1];
+                  r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w;
+                  r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+                }
+                const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                store_f32x8(dst, rv);  // whole 32-byte sector in one store
               }
+            }
+            if (do_stats && co_chunk < P.stats_c8) {  // warp-uniform: the whole warp reduces
+              float sv[16];
+              sv[0] = live ? r0.x : 0.f; sv[1] = live ? r0.y : 0.f; sv[2] = live ? r0.z : 0.f; sv[3] = live ? r0.w : 0.f;
+              sv[4] = live ? r1.x : 0.f; sv[5] = live ? r1.y : 0.f; sv[6] = live ? r1.z : 0.f; sv[7] = live ? r1.w : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sv[8 + i] = sv[i] * sv[i];
+              const float tot = warp_reduce16(sv, lane);
+              if (!(lane & 1)) stat_s[STATS ? ew : 0][(c16 * 2 + hlf) * 16 + (lane >> 1)] += tot;
             }
           }
         }
@@ -783,7 +801,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const bool b_res = P.n_ntiles == 1 && geom != GEOM_T2 && b_total <= 112 * 1024 && !(flags & 16);
   P.b_res = b_res ? 1 : 0;
   auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + (b_res ? 0 : P.b_blob_bytes)); };
-  const int smem_budget = 227 * 1024 - 8192 - (b_res ? b_total : 0);  // static smem: barriers, bias, statistics slots
+  const int smem_budget = 227 * 1024 - 12288 - (b_res ? b_total : 0);  // static smem: barriers, bias, statistics slots
   int td = td_max;
   while (td > 1 && smem_budget / stage_bytes_of(td) < 2) --td;
   int nacc = geom == GEOM_T2 ? 8 : td;
