@@ -154,7 +154,11 @@ def run_product(args):
         torch.cuda.synchronize()
 
     torch.manual_seed(42)
-    model = UNetB200(dict(BRATS_MODEL_CFG, conv_backend=args.conv_backend)).to(dev)
+    overrides = {}
+    for kv in args.set or []:     # experiment switches, e.g. --set fuse_stats=false
+        k, v = kv.split("=", 1)
+        overrides[k] = {"true": True, "false": False}.get(v.lower(), v)
+    model = UNetB200(dict(BRATS_MODEL_CFG, conv_backend=args.conv_backend, **overrides)).to(dev)
     tent = TentB200(model, {"entropy": "sigmoid", "cuda_graph": not args.no_graph})
     eng = model.engine
     NROT = 4  # distinct resident input batches (4 x 67 MB > 126 MB L2)
@@ -278,6 +282,7 @@ def main():
     ap.add_argument("--conv-backend", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--set", action="append", help="model config override key=value (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

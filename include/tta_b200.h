@@ -79,6 +79,28 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_str
 int tta_conv_tc_query(int in_dtype, int N, int C8in, int Di, int Hi, int Wi, int C8out, int Do, int Ho, int Wo,
                       int mode, int K, int stride, int accumulate, int flags, int* ksplit, int* grid, int* nbuf);
 
+/* input-gradient conv whose result is the COMPLETE gradient w.r.t. the outputs of up to two norm
+ * layers (channel segments of the output view, e.g. the two halves of a skip concat): the epilogue
+ * also leaves, per segment, per-CTA partial sums of dz = g*[gamma*xhat+beta > 0] and dz*xhat in
+ * seg.partial ([N][c8_count][grid][16] floats, grid from tta_conv_tc_query), reduced by
+ * tta_norm_bwd_finalize(splits = grid) -- autograd's norm backward reduction (loss.backward(),
+ * src/core/trainers/seg_trainer.py:142) without a separate pass over g and y.  Requires one fp16
+ * plane (in_dtype 2) and ksplit == 1.  segs: HOST pointer. */
+typedef struct tta_norm_bwd_seg {
+  int c8_begin, c8_count, relu, pad;
+  const float* y;          /* f32 view of the norm layer's conv result, same spatial dims as `out` */
+  long long y_n_stride;
+  const float* mean;       /* [N][c8_count*8] */
+  const float* rstd;
+  const float* gamma;      /* [c8_count*8] */
+  const float* beta;
+  float* partial;
+} tta_norm_bwd_seg;
+int tta_conv_tc_bwd_norm(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
+                         int C8in, int Di, int Hi, int Wi, const void* wpacked, float* out, long long out_n_stride,
+                         int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
+                         const tta_norm_bwd_seg* segs, int nsegs, tta_stream_t stream);
+
 /* fp32 CUDA-core conv for any (mode, K, stride); Wp: fp32 [tap][C8in][C8out][8][8]. */
 int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long long in_n_stride, int in_dtype, int N,
                   int C8in, int Di, int Hi, int Wi, const float* Wp, const float* bias, float* out,
@@ -121,6 +143,9 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1,
                         const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
                         int batch_mode, float* sums, float* dgamma, float* dbeta, float* workspace, int finalize,
                         tta_stream_t stream);
+/* sums / dgamma / dbeta from partial sums laid out [N][C8][splits][16] (partial points at the slots) */
+int tta_norm_bwd_finalize(const float* partial, int N, int C8, int Creal, int splits, int batch_mode, float* sums,
+                          float* dgamma, float* dbeta, tta_stream_t stream);
 /* dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) as planes; optional aux planes = g0+g1
  * (feeds the shortcut conv's dgrad).  partial != NULL: reductions finalized here, dgamma/dbeta written.
  * dy_wsplit_w > 0: dy is stored w-parity-split with row length W = dy_wsplit_w (its dgrad is a

@@ -82,6 +82,8 @@ _SIGNATURES = {
     "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),
     "tta_conv_tc": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, I, P, I, P]),
+    "tta_conv_tc_bwd_norm": (I, [P, P, L, I, I, I, I, I, I, P, P, L, I, I, I, I, I, I, I, I, I, P, I, P]),
+    "tta_norm_bwd_finalize": (I, [P, I, I, I, I, I, P, P, P, P]),
     "tta_conv_tc_query": (I, [I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P, P, P]),
 }
 

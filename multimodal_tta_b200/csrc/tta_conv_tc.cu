@@ -62,6 +62,22 @@ struct TcParams {
   // finalizes with splits = gridDim.x
   int stats_c8, n_batch;
   float* stats;
+  // fused norm-BACKWARD reductions (STATS == 2): the gradient this dgrad writes is the complete
+  // dL/d(act) of up to two norm layers (channel segments of a concat buffer); the epilogue turns it
+  // into dz = g * [gamma*xhat + beta > 0] and leaves per-CTA partial sums of dz and dz*xhat, layout
+  // [n][chunk - c8_begin][cta][16], which tta_norm_bwd_finalize reduces (tta_norm_bwd_reduce's pass
+  // over g and y disappears)
+  struct BwdSeg {
+    int c8_begin, c8_end, relu, pad;
+    const float* y;
+    long long y_ns;
+    const float* mean;
+    const float* rstd;
+    const float* gamma;
+    const float* beta;
+    float* partial;
+  } seg[2];
+  int nseg;
   // resident weights: all (channel block, group) blobs of the single n-tile are copied into shared
   // memory ONCE per CTA (persistent), stages then carry only the A operand
   int b_res, b_res_off, pad_res;
@@ -293,6 +309,20 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
   return r;
 }
 
+}  // namespace tta
+// HOST-side description of one fused norm-backward segment (include/tta_b200.h: tta_norm_bwd_seg)
+struct tta_norm_bwd_seg {
+  int c8_begin, c8_count, relu, pad;
+  const float* y;
+  long long y_n_stride;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const float* beta;
+  float* partial;
+};
+namespace tta {
+
 struct WorkItem {
   int n, nt, ks, w0, h0, d0, cb0, nit;
 };
@@ -338,7 +368,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   __shared__ TcGroup grp_s[kMaxGroups];  // per-lane indexed by the producer (constant bank would serialise)
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[128];
-  __shared__ float stat_s[STATS ? 8 : 1][STATS ? 16 * 16 : 1];  // [epilogue warp][chunk of the n-tile][16]: fused norm statistics
+  __shared__ float stat_s[STATS ? 8 : 1][STATS ? 16 * 16 : 1];
+  __shared__ float ncst_s[STATS == 2 ? 4 : 1][STATS == 2 ? 128 : 1];  // mean, rstd, gamma, beta of the n-tile's channels  // [epilogue warp][chunk of the n-tile][16]: fused norm statistics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();  // the next kernel's CTAs may be scheduled (they block in their own pdl_wait)
@@ -386,6 +417,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // Two warps alternate over the stage ring: filling a stage is a serial chain of address
     // arithmetic + per-copy operand broadcasts, and for layers with few MMAs per stage one warp
     // could not keep the tensor pipe fed.
+    // (parity waits only order a waiter that is at most one phase ahead: with a single stage the
+    // idle producer would skip ahead and see a stale "completed" parity, so one stage = one producer)
+    const bool two_prod = P.nstages >= 2;
     const int my_par = warp == 0 ? 0 : 1;
     // The whole warp walks the stage ring; every lane owns ONE tensor copy of a stage
     // (load x k-chunk x plane, <= 16 per stage) and issues it itself, so a stage costs one pass of
@@ -408,11 +442,11 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // item -- all advanced by compare-and-wrap: an integer division costs ~100 dependent cycles and
     // this loop is the critical path of every layer with few MMAs per stage
     int s = 0, ph = 0, par = 0;
-    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
+    for (int item = (two_prod || warp == 0) ? blockIdx.x : P.work_items; item < P.work_items; item += gridDim.x) {
       const WorkItem wi = decode_item(P, item);
       int g = 0, cb = wi.cb0;
       for (int it = 0; it < wi.nit; ++it, par ^= 1) {
-        if (par != my_par) {  // the other producer's stage: only advance the counters
+        if (two_prod && par != my_par) {  // the other producer's stage: only advance the counters
           if (++g == P.ngroups) { g = 0; ++cb; }
           if (++s == P.nstages) { s = 0; ph ^= 1; }
           continue;
@@ -515,15 +549,32 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
           tot += stat_s[w8][t];
           stat_s[w8][t] = 0.f;
         }
-        if (gchunk < P.stats_c8)
-          P.stats[(((long long)st_n * P.stats_c8 + gchunk) * gridDim.x + blockIdx.x) * 16 + (t & 15)] += tot;
+        if (STATS == 1) {
+          if (gchunk < P.stats_c8)
+            P.stats[(((long long)st_n * P.stats_c8 + gchunk) * gridDim.x + blockIdx.x) * 16 + (t & 15)] += tot;
+        } else {
+          for (int sg = 0; sg < P.nseg; ++sg) {
+            const TcParams::BwdSeg& S = P.seg[sg];
+            if (gchunk >= S.c8_begin && gchunk < S.c8_end)
+              S.partial[(((long long)st_n * (S.c8_end - S.c8_begin) + (gchunk - S.c8_begin)) * gridDim.x + blockIdx.x) * 16 +
+                        (t & 15)] += tot;
+          }
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     if (do_stats) {
       for (int t = et; t < kSlots * 256; t += 256) (&stat_s[0][0])[t] = 0.f;
-      for (int t = et; t < P.n_batch * P.stats_c8 * 16; t += 256)
-        P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
+      if (STATS == 1) {
+        for (int t = et; t < P.n_batch * P.stats_c8 * 16; t += 256)
+          P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
+      } else {
+        for (int sg = 0; sg < P.nseg; ++sg) {
+          const TcParams::BwdSeg& S = P.seg[sg];
+          for (int t = et; t < P.n_batch * (S.c8_end - S.c8_begin) * 16; t += 256)
+            S.partial[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
+        }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
@@ -539,6 +590,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       if (et < P.ntile) {
         const int c = wi.nt * P.ntile + et;
         bias_s[et] = (P.bias != nullptr && wi.ks == 0 && c < P.C8out * 8) ? P.bias[c] : 0.f;
+        if (STATS == 2) {
+          float mu = 0.f, rs = 0.f, ga = 0.f, be = 0.f;
+          for (int sg = 0; sg < P.nseg; ++sg) {
+            const TcParams::BwdSeg& S = P.seg[sg];
+            if ((c >> 3) >= S.c8_begin && (c >> 3) < S.c8_end) {
+              const int cl = c - S.c8_begin * 8, Cn = (S.c8_end - S.c8_begin) * 8;
+              mu = S.mean[wi.n * Cn + cl];
+              rs = S.rstd[wi.n * Cn + cl];
+              ga = S.gamma[cl];
+              be = S.beta[cl];
+            }
+          }
+          ncst_s[0][STATS == 2 ? et : 0] = mu;
+          ncst_s[STATS == 2 ? 1 : 0][STATS == 2 ? et : 0] = rs;
+          ncst_s[STATS == 2 ? 2 : 0][STATS == 2 ? et : 0] = ga;
+          ncst_s[STATS == 2 ? 3 : 0][STATS == 2 ? et : 0] = be;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
@@ -549,6 +617,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       // it touches TMEM
       for (int u0 = half; u0 < nunits; u0 += 4) {
         float4 old[2][2][2];
+        float yv[STATS == 2 ? 2 : 1][STATS == 2 ? 2 : 1][8];  // conv results of the norm layer (backward statistics)
+        bool ylive[2][2];
         float* obase[2];
         bool valid[2];
         int c16s[2];
@@ -565,6 +635,25 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
           const long long vox = ((long long)od * P.Ho + oh) * P.Wo + ow;
           obase[k] = P.out + (long long)wi.n * P.out_ns + vox * 8;
           tacc[k] = tbase + acc * acc_cols;
+          if (STATS == 2) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const int co_chunk = wi.nt * nchunks + c16s[k] * 2 + hlf;
+              const float* ysrc = nullptr;
+              for (int sg = 0; sg < P.nseg; ++sg) {
+                const TcParams::BwdSeg& S = P.seg[sg];
+                if (co_chunk >= S.c8_begin && co_chunk < S.c8_end)
+                  ysrc = S.y + (long long)wi.n * S.y_ns + ((long long)(co_chunk - S.c8_begin) * Vo + vox) * 8;
+              }
+              ylive[k][hlf] = valid[k] && ysrc != nullptr;
+              if (ylive[k][hlf]) {
+                load_f32x8(ysrc, yv[k][hlf]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) yv[k][hlf][i] = 0.f;
+              }
+            }
+          }
           if (rmw) {
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
@@ -625,7 +714,34 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                 store_f32x8(dst, rv);  // whole 32-byte sector in one store
               }
             }
-            if (do_stats && co_chunk < P.stats_c8) {  // warp-uniform: the whole warp reduces
+            if (STATS == 2) {
+              // norm backward: dz = g * relu'(gamma*xhat + beta); sums of dz and dz*xhat (warp-uniform branch)
+              bool in_seg = false;
+              int relu = 0;
+              for (int sg = 0; sg < P.nseg; ++sg)
+                if (co_chunk >= P.seg[sg].c8_begin && co_chunk < P.seg[sg].c8_end) {
+                  in_seg = true;
+                  relu = P.seg[sg].relu;
+                }
+              if (in_seg) {
+                const float gv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                const bool yl = ylive[STATS == 2 ? k : 0][STATS == 2 ? hlf : 0];
+                float sv[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int cc = c16 * 16 + hlf * 8 + i;
+                  const float xh = (yv[STATS == 2 ? k : 0][STATS == 2 ? hlf : 0][i] - ncst_s[0][STATS == 2 ? cc : 0]) *
+                                   ncst_s[STATS == 2 ? 1 : 0][STATS == 2 ? cc : 0];
+                  const float z = fmaf(xh, ncst_s[STATS == 2 ? 2 : 0][STATS == 2 ? cc : 0], ncst_s[STATS == 2 ? 3 : 0][STATS == 2 ? cc : 0]);
+                  const float dzv = (!yl || (relu && !(z > 0.f))) ? 0.f : gv[i];
+                  sv[i] = dzv;
+                  sv[8 + i] = dzv * xh;
+                }
+                const float tot = warp_reduce16(sv, lane);
+                if (!(lane & 1)) stat_s[STATS ? ew : 0][(c16 * 2 + hlf) * 16 + (lane >> 1)] += tot;
+              }
+            }
+            if (STATS == 1 && co_chunk < P.stats_c8) {  // warp-uniform: the whole warp reduces
               float sv[16];
               sv[0] = live ? r0.x : 0.f; sv[1] = live ? r0.y : 0.f; sv[2] = live ? r0.z : 0.f; sv[3] = live ? r0.w : 0.f;
               sv[4] = live ? r1.x : 0.f; sv[5] = live ? r1.y : 0.f; sv[6] = live ? r1.z : 0.f; sv[7] = live ? r1.w : 0.f;
@@ -732,7 +848,8 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
 static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
                         int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
                         int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
-                        float* stats_ws, int stats_c8, int* q_ksplit, int* q_grid, int* q_nbuf, cudaStream_t stream) {
+                        float* stats_ws, int stats_c8, const tta_norm_bwd_seg* segs, int nsegs, int* q_ksplit, int* q_grid,
+                        int* q_nbuf, cudaStream_t stream) {
   const int split = in_dtype == TTA_F16_HI ? 0 : 1;
   const bool query = q_ksplit != nullptr;  // shape the launch only: report split-K factor and grid
   TTA_REQUIRE(query || (in_hi && (in_lo || !split) && wpacked && out), "tta_conv_tc: null pointer");
@@ -801,7 +918,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const bool b_res = P.n_ntiles == 1 && geom != GEOM_T2 && b_total <= 112 * 1024 && !(flags & 16);
   P.b_res = b_res ? 1 : 0;
   auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + (b_res ? 0 : P.b_blob_bytes)); };
-  const int smem_budget = 227 * 1024 - 12288 - (b_res ? b_total : 0);  // static smem: barriers, bias, statistics slots
+  const int smem_budget = 227 * 1024 - 14336 - (b_res ? b_total : 0);  // static smem: barriers, bias, statistics slots
   int td = td_max;
   while (td > 1 && smem_budget / stage_bytes_of(td) < 2) --td;
   int nacc = geom == GEOM_T2 ? 8 : td;
@@ -819,7 +936,11 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.stage_bytes = stage_bytes_of(td);
   P.b_off = a_planes * P.a_plane_bytes;
   P.lbo16[0] = round128(hx * wx * td * 16) / 16;
-  P.nstages = smem_budget / P.stage_bytes;
+  // pipeline depth from what THIS instantiation leaves free (the statistics variants carry 8-10 KB of
+  // static slots); td / split-K above were shaped with the most conservative budget so that
+  // tta_conv_tc_query and the launch always agree on the grid
+  const int static_smem = (stats_ws != nullptr && stats_c8 > 0) ? 11264 : ((segs != nullptr && nsegs > 0) ? 13312 : 3072);
+  P.nstages = (227 * 1024 - static_smem - 1024 - (b_res ? b_total : 0)) / P.stage_bytes;
   TTA_REQUIRE(P.nstages >= 1, "tta_conv_tc: stage of %d bytes does not fit shared memory", P.stage_bytes);
   if (P.nstages > kMaxStages) P.nstages = kMaxStages;
   P.b_res_off = P.nstages * P.stage_bytes;
@@ -870,6 +991,24 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     P.stats_c8 = stats_c8;
     P.n_batch = N;
     P.stats = stats_ws + 1024;  // same workspace convention as tta_norm_stats: [1024 counters][partials]
+  }
+  // ---- fused norm-backward reductions (dgrad whose output is the complete gradient of <= 2 norms)
+  P.nseg = 0;
+  if (segs != nullptr && nsegs > 0) {
+    TTA_REQUIRE(nsegs <= 2 && P.ksplit == 1 && !split && P.stats_c8 == 0,
+                "tta_conv_tc: fused norm-backward sums need <= 2 segments, ksplit == 1, one fp16 plane");
+    for (int i = 0; i < nsegs; ++i) {
+      const tta_norm_bwd_seg& h = segs[i];
+      TTA_REQUIRE(h.y && h.mean && h.rstd && h.gamma && h.beta && h.partial && h.c8_begin >= 0 && h.c8_count > 0 &&
+                      h.c8_begin + h.c8_count <= C8out,
+                  "tta_conv_tc: bad norm-backward segment %d", i);
+      TcParams::BwdSeg& d = P.seg[i];
+      d.c8_begin = h.c8_begin; d.c8_end = h.c8_begin + h.c8_count; d.relu = h.relu; d.pad = 0;
+      d.y = h.y; d.y_ns = h.y_n_stride; d.mean = h.mean; d.rstd = h.rstd; d.gamma = h.gamma; d.beta = h.beta;
+      d.partial = h.partial;
+    }
+    P.nseg = nsegs;
+    P.n_batch = N;
   }
 
   // ---- tensor maps (one k-chunk = 8 channels per TMA box; zero padding = OOB fill)
@@ -1013,6 +1152,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   do {                                                                                                     \
     if (P.stats_c8 > 0) { /* fused statistics: forward (split-plane) convs only */                        \
       TTA_TC_LAUNCH_ST(G, T, 1, 1);                                                                        \
+    } else if (P.nseg > 0) { /* fused norm-backward sums: single-plane dgrads only */                      \
+      TTA_TC_LAUNCH_ST(G, T, 0, 2);                                                                        \
     } else if (split) {                                                                                    \
       TTA_TC_LAUNCH_ST(G, T, 1, 0);                                                                        \
     } else {                                                                                               \
@@ -1046,7 +1187,21 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
                 int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
                 float* stats_ws, int stats_c8, cudaStream_t stream) {
   return conv_tc_impl(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, C8out, Do, Ho,
-                      Wo, mode, K, stride, accumulate, flags, stats_ws, stats_c8, nullptr, nullptr, nullptr, stream);
+                      Wo, mode, K, stride, accumulate, flags, stats_ws, stats_c8, nullptr, 0, nullptr, nullptr, nullptr,
+                      stream);
+}
+
+// tta_conv_tc for an input-gradient conv whose result is the COMPLETE gradient w.r.t. the outputs of
+// up to two norm layers (channel segments [c8_begin, c8_begin + c8_count) of the output view): the
+// epilogue additionally leaves per-CTA partial sums of dz = g*[z > 0] and dz*xhat for each segment in
+// seg.partial ([N][c8_count][grid][16] floats, grid from tta_conv_tc_query), which
+// tta_norm_bwd_finalize(splits = grid) reduces.  segs is a HOST pointer.
+int tta_conv_tc_bwd_norm(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
+                         int Di, int Hi, int Wi, const void* wpacked, float* out, long long out_ns, int C8out, int Do,
+                         int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
+                         const tta_norm_bwd_seg* segs, int nsegs, cudaStream_t stream) {
+  return conv_tc_impl(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, nullptr, out, out_ns, C8out, Do, Ho,
+                      Wo, mode, K, stride, accumulate, flags, nullptr, 0, segs, nsegs, nullptr, nullptr, nullptr, stream);
 }
 
 // Launch shape of tta_conv_tc for these arguments: *ksplit = split-K factor (fused statistics need
@@ -1057,8 +1212,8 @@ int tta_conv_tc_query(int in_dtype, int N, int C8in, int Di, int Hi, int Wi, int
   TTA_REQUIRE(ksplit && grid, "tta_conv_tc_query: null pointer");
   const long long Vi = (long long)Di * Hi * Wi;
   return conv_tc_impl(nullptr, nullptr, (long long)C8in * Vi * 8, in_dtype, N, C8in, Di, Hi, Wi, nullptr, nullptr,
-                      nullptr, 0, C8out, Do, Ho, Wo, mode, K, stride, accumulate, flags, nullptr, 0, ksplit, grid,
-                      nbuf, nullptr);
+                      nullptr, 0, C8out, Do, Ho, Wo, mode, K, stride, accumulate, flags, nullptr, 0, nullptr, 0, ksplit,
+                      grid, nbuf, nullptr);
 }
 
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout) {

@@ -119,6 +119,16 @@ norm_stats_finalize_chunk_kernel(const float* partial, int N, int C8, int splits
   }
 }
 
+// one CTA per channel chunk: norm-backward sums / dgamma / dbeta from `splits` partial slots
+// (produced by norm_bwd_partial_kernel or by the tcgen05 dgrad epilogue)
+__global__ void __launch_bounds__(kThreads)
+norm_bwd_finalize_chunk_kernel(const float* partial, int N, int C8, int Creal, int splits, int batch_mode,
+                               float* sums, float* dgamma, float* dbeta) {
+  pdl_trigger();
+  pdl_wait();
+  norm_bwd_finalize_tail(partial, C8, blockIdx.x, splits, N, batch_mode, Creal, sums, dgamma, dbeta);
+}
+
 // ---------------------------------------------------------------- forward apply
 // out = relu?(gamma*(y-mean)*rstd + beta) (+ residual), written as split 16-bit planes.
 // RES: 0 none, 1 fp32 view, 2 split-plane view (dtype ODT)
@@ -494,6 +504,16 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
   }
 #undef LAUNCH
   return tta_check_launch("tta_norm_apply");
+}
+
+// sums [N][C8*8][2], dgamma/dbeta [Creal] from partial sums laid out [N][C8][splits][16] (NO
+// 1024-float counter prefix: `partial` points at the slots themselves)
+int tta_norm_bwd_finalize(const float* partial, int N, int C8, int Creal, int splits, int batch_mode, float* sums,
+                          float* dgamma, float* dbeta, cudaStream_t stream) {
+  TTA_REQUIRE(partial && sums && dgamma && dbeta && splits > 0, "tta_norm_bwd_finalize: bad argument");
+  tta_launch(norm_bwd_finalize_chunk_kernel, C8, kThreads, 0, stream, tta_pdl_family(2), partial, N, C8, Creal, splits,
+             batch_mode, sums, dgamma, dbeta);
+  return tta_check_launch("tta_norm_bwd_finalize");
 }
 
 int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long long g1_ns,

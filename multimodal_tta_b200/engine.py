@@ -31,6 +31,14 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class NormBwdSeg(ctypes.Structure):
+    """include/tta_b200.h: tta_norm_bwd_seg (HOST struct handed to tta_conv_tc_bwd_norm)."""
+    _fields_ = [("c8_begin", ctypes.c_int), ("c8_count", ctypes.c_int), ("relu", ctypes.c_int), ("pad", ctypes.c_int),
+                ("y", ctypes.c_void_p), ("y_ns", ctypes.c_longlong), ("mean", ctypes.c_void_p),
+                ("rstd", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("partial", ctypes.c_void_p)]
+
+
 # ------------------------------------------------------------------------------ tensors
 class Act:
     """Conv-operand activation: split fp16 planes [2][N][C8][D][H][W][8] (+ fp32 grad)."""
@@ -48,6 +56,7 @@ class Act:
         # operands of a stride-2 tcgen05 conv are stored w-parity-split: either the
         # planes themselves (`wsplit`, single consumer: the network input) or a second copy written by
         # the producing norm (`ws_planes`, skip tensors that also feed the concat)
+        self.writers: list = []         # dgrad launches that wrote .grad: (c8_begin, c8_end, record, accumulate)
         self.wsplit = False
         self.ws_planes: Optional[torch.Tensor] = None
         self.device = device
@@ -360,7 +369,7 @@ class TTAEngine:
 
     def _conv_call(self, plan: Plan, cl: ConvLayer, backward: bool, src, src_dtype, N, cin8, idims,
                    dst_ptr, dst_ns, cout8, odims, accumulate: bool, wsplit_in: bool = False,
-                   stats_res: Optional["Res"] = None):
+                   stats_res: Optional["Res"] = None, bwd_rec: Optional[dict] = None):
         """Returns a closure launching one conv (tcgen05 kernel when the geometry is supported,
         otherwise the fp32 CUDA-core kernel)."""
         lib = self.lib
@@ -396,6 +405,29 @@ class TTAEngine:
                                             int(accumulate), flags, ctypes.byref(ks), ctypes.byref(grid),
                                             ctypes.byref(nbuf)), "conv_tc_query")
                 stats_res.tc_query = (ks.value, grid.value, nbuf.value)
+            if bwd_rec is not None:
+                ks, grid, nbuf = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+                check(lib.tta_conv_tc_query(src_dtype, N, cin8, *idims, cout8, *odims, mode, cl.K, cl.stride,
+                                            int(accumulate), flags, ctypes.byref(ks), ctypes.byref(grid),
+                                            ctypes.byref(nbuf)), "conv_tc_query")
+                bwd_rec["info"] = (ks.value, grid.value, nbuf.value)
+                bn_args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), dst_ptr, dst_ns, cout8,
+                           *odims, mode, cl.K, cl.stride, int(accumulate), flags)
+
+                def run_bwd():
+                    # norm layers whose complete gradient this dgrad produces asked (later, at their own
+                    # emission) for the backward reductions to come out of this epilogue
+                    if bwd_rec["segs"]:
+                        if "carr" not in bwd_rec:
+                            arr = (NormBwdSeg * len(bwd_rec["segs"]))()
+                            for i, sg in enumerate(bwd_rec["segs"]):
+                                arr[i] = NormBwdSeg(*sg)
+                            bwd_rec["carr"] = arr
+                        check(lib.tta_conv_tc_bwd_norm(*bn_args, bwd_rec["carr"], len(bwd_rec["segs"]), _stream()),
+                              f"conv_tc_bwd_norm {cl.name}")
+                    else:
+                        check(lib.tta_conv_tc(*args, 0, 0, _stream()), f"conv_tc {cl.name}")
+                return run_bwd
 
             def run():
                 # fused statistics are requested (later, by the norm that consumes this result) via the Res
@@ -703,9 +735,12 @@ class TTAEngine:
                     plan.bwd.append(run_head_bwd)
                     continue
                 y.alloc_dy(nplanes)
+                crec = dict(segs=[], info=None)
                 plan.bwd.append(self._conv_call(
                     plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.ns), bdt, N, y.C8,
-                    (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc, wsplit_in=y.root.dy_wsplit))
+                    (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc, wsplit_in=y.root.dy_wsplit,
+                    bwd_rec=crec))
+                par.writers.append((inp.c8_off, inp.c8_off + inp.C8, crec, acc))
             else:
                 rec = op[1]
                 nl, y, out = rec["nl"], rec["y"], rec["out"]
@@ -721,6 +756,25 @@ class TTAEngine:
                     raise RuntimeError(f"{nl.name}: {len(srcs)} gradient sources (supported: 1 or 2)")
                 g0, g0ns = srcs[0]
                 g1, g1ns = srcs[1] if len(srcs) > 1 else (0, 0)
+                # backward reductions from the epilogue of the dgrad that COMPLETES this gradient: single
+                # source (the parent's grad slice), every writer of the slice covers it, the last one is
+                # a tcgen05 launch without split-K on one fp16 plane
+                fuse_bwd = None
+                cb0, cb1 = out.c8_off, out.c8_off + out.C8
+                if (model.fuse_bwd_stats and bdt == TTA_F16_HI and len(srcs) == 1 and chunks <= par.written
+                        and not (fused_head is not None and rec is fused_head[1])):
+                    touching = [w for w in par.writers if w[0] < cb1 and w[1] > cb0]
+                    if touching and all(w[0] <= cb0 and w[1] >= cb1 for w in touching):
+                        last = touching[-1]
+                        info = last[2]["info"]
+                        if (info is not None and info[0] == 1 and len(last[2]["segs"]) < 2
+                                and last[3] == (len(touching) > 1)):
+                            pbuf = torch.zeros(N * y.C8 * info[1] * 16, dtype=torch.float32, device=dev)
+                            plan.keep.append(pbuf)
+                            last[2]["segs"].append((cb0 - last[0], y.C8, int(rec["relu"]), 0, y.ptr, y.ns,
+                                                    rec["mean"].data_ptr(), rec["rstd"].data_ptr(), rec["gptr"],
+                                                    rec["bptr"], pbuf.data_ptr()))
+                            fuse_bwd = (pbuf, info[1])
                 conv_in_needs = self._producer_input_needs_grad(ops, y)
                 res = rec["residual"]
                 aux = None
@@ -753,11 +807,18 @@ class TTAEngine:
                                aux.ns if aux else 0, bdt)
 
                 skip_reduce = fused_head is not None and rec is fused_head[1]   # done by tta_head_fused_bwd
+                fin_args = None
+                if fuse_bwd is not None:
+                    fin_args = (fuse_bwd[0].data_ptr(), N, y.C8, nl.C, fuse_bwd[1], nl.batch, rec["sums"].data_ptr(),
+                                dg, db)
+                rec["fused_bwd"] = fuse_bwd is not None
 
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db, dy_ws=dy_ws,
-                        skip_reduce=skip_reduce):
+                        skip_reduce=skip_reduce, fin_args=fin_args):
                     # single-pass reduction: the last block finalizes sums + dgamma/dbeta
-                    if not skip_reduce:
+                    if fin_args is not None:
+                        check(lib.tta_norm_bwd_finalize(*fin_args, _stream()), "norm_bwd_finalize")
+                    elif not skip_reduce:
                         check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, _stream()),
                               "norm_bwd_reduce")
                     if ap_args is not None:
@@ -775,6 +836,7 @@ class TTAEngine:
         # needs mean/rstd up front: one tiny finalize launch takes its place)
         # (launch count unchanged: a tiny finalize launch takes the place of the statistics pass)
         plan.n_fused_stats = sum(1 for o in ops if o[0] == "norm" and o[1]["fused_stats"])
+        plan.n_fused_bwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("fused_bwd"))
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:

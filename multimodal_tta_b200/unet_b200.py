@@ -156,6 +156,12 @@ class UNetB200(nn.Module):
         # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
         # a separate pass over y (only where the conv runs without split-K)
         self.fuse_stats = bool(get_config(cfg, "fuse_stats", True))
+        # ... and, OPT-IN, the norm-BACKWARD reductions (sum dz, sum dz*xhat) out of the epilogue of
+        # the dgrad conv that completes the layer's incoming gradient.  Measured on B200 (2x4x128^3):
+        # the four 64^3 / 32^3 layers it applies to lose 162 us in their dgrads (the epilogue has
+        # 8 warps per SM for ~100 instructions per voxel-chunk) and save 144 us of streaming passes
+        # (2048 threads per SM) -> default off; the streaming tta_norm_bwd_reduce stays the product path
+        self.fuse_bwd_stats = bool(get_config(cfg, "fuse_bwd_stats", False))
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))

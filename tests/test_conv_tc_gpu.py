@@ -204,3 +204,79 @@ def test_conv_tc_fused_norm_statistics(lib, cuda, cin, cout, s, tr, dims, stats_
         got_rs = rstd.view(N, sc8 * 8)[:, :stats_c].double()
         assert float((got_mu - mu_ref).abs().max()) < 1e-5 * float(y.abs().max())
         assert float(((got_rs - rs_ref) / rs_ref).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,s,tr,dims,acc", [(32, 32, 1, False, (5, 20, 12), 0), (32, 64, 2, False, (8, 16, 16), 1),
+                                                     (16, 3, 2, True, (3, 10, 6), 0), (32, 32, 1, False, (4, 16, 8), 1)])
+def test_conv_tc_fused_norm_backward_sums(lib, cuda, cin, cout, s, tr, dims, acc):
+    """tta_conv_tc_bwd_norm: the dgrad epilogue also reduces dz = g*[gamma*xhat+beta > 0] and dz*xhat for
+    up to two norm layers (two channel segments of its output, as in a skip concat);
+    tta_norm_bwd_finalize turns the per-CTA partials into sums / dgamma / dbeta.  Reference: torch on
+    the kernel's own g output (fp32 partial sums, fp64 finalize: 2e-5 relative)."""
+    import ctypes
+
+    class Seg(ctypes.Structure):
+        _fields_ = [("c8_begin", ctypes.c_int), ("c8_count", ctypes.c_int), ("relu", ctypes.c_int), ("pad", ctypes.c_int),
+                    ("y", ctypes.c_void_p), ("y_ns", ctypes.c_longlong), ("mean", ctypes.c_void_p),
+                    ("rstd", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                    ("partial", ctypes.c_void_p)]
+    torch.manual_seed(13)
+    N = 2
+    # forward conv cin -> cout; its dgrad maps dy [N, cout, odims] to g [N, cin, dims]
+    w = torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3)) * 0.1
+    odims = tuple(d * s for d in dims) if tr else tuple((d - 1) // s + 1 for d in dims)
+    dy = torch.randn(N, cout, *odims)
+    mode = 1 if tr else 0
+    c8i, c8o = (cin + 7) // 8, (cout + 7) // 8
+    Vi, Vo = dims[0] * dims[1] * dims[2], odims[0] * odims[1] * odims[2]
+    hhi, _ = split_planes(to_chunked(dy.to(cuda)), TTA_F16_HI)
+    hhi = hhi.contiguous()
+    wph = pack_weights_tc(wg_dgrad(w.to(cuda), tr), 1 - mode, 3, s, TTA_F16_HI)
+    ks, grid = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.tta_conv_tc_query(TTA_F16_HI, N, c8o, *odims, c8i, *dims, 1 - mode, 3, s, acc, 2, ctypes.byref(ks),
+                                ctypes.byref(grid), 0), "query")
+    assert ks.value == 1
+    # two norm layers own the two halves of the gradient's channels (one when there is a single chunk)
+    bounds = [(0, c8i)] if c8i == 1 else [(0, c8i // 2), (c8i // 2, c8i)]
+    segs = (Seg * len(bounds))()
+    keep, layers = [], []
+    for i, (b0, b1) in enumerate(bounds):
+        C = min(cin, b1 * 8) - b0 * 8                          # real channels of this segment
+        Cp = (b1 - b0) * 8
+        y = torch.randn(N, C, *dims) * 1.5 + 0.2
+        gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.5
+        mu = y.mean((2, 3, 4)); rs = 1.0 / torch.sqrt(y.var((2, 3, 4), unbiased=False) + 1e-5)
+        ych = to_chunked(y.to(cuda))
+        mean = torch.zeros(N, Cp, device=cuda); mean[:, :C] = mu.to(cuda)
+        rstd = torch.zeros(N, Cp, device=cuda); rstd[:, :C] = rs.to(cuda)
+        gp = torch.zeros(Cp, device=cuda); gp[:C] = gamma.to(cuda)
+        bp = torch.zeros(Cp, device=cuda); bp[:C] = beta.to(cuda)
+        part = torch.full((N * (b1 - b0) * grid.value * 16,), 55.0, device=cuda)   # garbage: kernel zeroes its slots
+        keep += [ych, mean, rstd, gp, bp, part]
+        segs[i] = Seg(b0, b1 - b0, 1, 0, ych.data_ptr(), (b1 - b0) * Vi * 8, mean.data_ptr(), rstd.data_ptr(),
+                      gp.data_ptr(), bp.data_ptr(), part.data_ptr())
+        layers.append((b0, b1, C, y, gamma, beta, mu, rs, part))
+    g = torch.full((N, c8i, *dims, 8), 0.25 if acc else 0.0, device=cuda)
+    g[..., :] = g[..., :] if cin % 8 == 0 else g
+    for _ in range(2 if not acc else 1):
+        check(lib.tta_conv_tc_bwd_norm(hhi.data_ptr(), 0, c8o * Vo * 8, TTA_F16_HI, N, c8o, *odims, wph.data_ptr(),
+                                       g.data_ptr(), c8i * Vi * 8, c8i, *dims, 1 - mode, 3, s, acc, 2, segs, len(bounds),
+                                       stream()), "conv_tc_bwd_norm")
+    torch.cuda.synchronize()
+    gout = from_chunked(g, c8i * 8).cpu()
+    for (b0, b1, C, y, gamma, beta, mu, rs, part) in layers:
+        gs = gout[:, b0 * 8:b0 * 8 + C]
+        xh = (y - mu[:, :, None, None, None]) * rs[:, :, None, None, None]
+        z = xh * gamma[None, :, None, None, None] + beta[None, :, None, None, None]
+        dz = gs * (z > 0)
+        s1, s2 = dz.sum((2, 3, 4)), (dz * xh).sum((2, 3, 4))
+        Cp = (b1 - b0) * 8
+        sums = torch.zeros(N * Cp * 2, device=cuda); dg = torch.zeros(Cp, device=cuda); db = torch.zeros(Cp, device=cuda)
+        check(lib.tta_norm_bwd_finalize(part.data_ptr(), N, b1 - b0, C, grid.value, 0, sums.data_ptr(), dg.data_ptr(),
+                                        db.data_ptr(), stream()), "bwd_finalize")
+        sm = sums.view(N, Cp, 2).cpu()
+        scale = float(s1.abs().max()) + float(s2.abs().max())
+        assert float((sm[:, :C, 0] - s1).abs().max()) < 2e-5 * scale
+        assert float((sm[:, :C, 1] - s2).abs().max()) < 2e-5 * scale
+        assert float((db[:C].cpu() - s1.sum(0)).abs().max()) < 2e-5 * scale * N
+        assert float((dg[:C].cpu() - s2.sum(0)).abs().max()) < 2e-5 * scale * N
