@@ -54,7 +54,7 @@ struct TcParams {
   int tiles_w, tiles_h, tiles_d, d_mul;
   int a_plane_bytes, b_entry_bytes, b_blob_bytes, stage_bytes;
   int c8_view, c8in, single_chunk, tmem_cols;
-  int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n;
+  int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n, idesc0, pad_i;
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
   // fused norm statistics: per-CTA partial sums of y and y^2 over the leading stats_c8 chunks of the
@@ -260,25 +260,53 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
         const uint32_t accum = (first && g == 0 && kh == 0 && kw == 0) ? 0u : 1u;
         mma_pair<SPLIT>(leader, tmem_acc0, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, b_w1, i2n, in_, accum);
       }
-  } else {  // GEOM_T2: group 0 = input plane d0 (kd = 1 -> even, kd = 2 -> odd out planes), group 1 = d0+1 (kd = 0)
+  } else {
+    // GEOM_T2: group 0 = input plane d0 (kd = 1 -> even, kd = 2 -> odd out planes), group 1 = d0+1
+    // (kd = 0).  Output-parity accumulator a = qd*4 + qh*2 + qw.  Taps that read the SAME shifted A
+    // tile feed different parity accumulators, so they are issued as ONE MMA over a stack of their
+    // weights (N = k * acc_cols, accumulators contiguous in TMEM): 14 A-tile reads per 16-channel
+    // block instead of 27.  The 128x16 A tile read (4 KB at 128 B/clk) is what bounds these small-N
+    // MMAs.  With split planes both A_hi and A_lo multiply the whole [B_hi | B_lo] stack (the extra
+    // lo*lo term is below fp32 resolution).  Stack tables mirror layout.t2_stacks().
     const uint32_t a_w1 = 9u | (1u << 14);
     const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
     const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;
-    const int nk = g == 0 ? 2 : 1;
-    for (int ki = 0; ki < nk; ++ki) {
-      const int qd = (g == 0 && ki == 0) ? 0 : 1;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int qh = kh != 1, jh = kh == 0, qw = kw != 1, jw = kw == 0;
-          const uint32_t acc = (uint32_t)(qd * 4 + qh * 2 + qw);
-          const uint32_t ao = (uint32_t)(jh * 9 + jw);
-          const uint32_t bo = b_w0 + (uint32_t)(ki * 9 + kh * 3 + kw) * b_ent;
-          // each parity accumulator is first written in group 0 by its (kh < 2, kw < 2) tap
-          const uint32_t accum = (first && g == 0 && kh < 2 && kw < 2) ? 0u : 1u;
-          mma_pair<SPLIT>(leader, tmem_acc0 + acc * acc_cols, ah + ao, al + ao, a_w1, bo, b_w1, i2n, in_, accum);
+    const uint32_t maxk = 256u / acc_cols;  // accumulators one MMA may span (N <= 256)
+    constexpr int kG0[9][4] = {{0, 8, 0, 0}, {2, 2, 1, 0}, {6, 2, 1, 0}, {1, 1, 0, 1}, {3, 1, 0, 1},
+                               {5, 1, 0, 1}, {7, 1, 0, 1}, {3, 1, 1, 1}, {7, 1, 1, 1}};  // {acc0, k, jh, jw}
+    constexpr int kG1[5][4] = {{4, 4, 0, 0}, {6, 2, 1, 0}, {5, 1, 0, 1}, {7, 1, 0, 1}, {7, 1, 1, 1}};
+    auto stack = [&](int acc0, int k, int jh, int jw, uint32_t tap_off, bool overwrite) {
+      const uint32_t ao = (uint32_t)(jh * 9 + jw);
+      const uint32_t lbo_b = ((uint32_t)k * acc_cols) << 16;          // rows of the whole stack per k-chunk
+      const uint32_t sbase = (bsrc >> 4) + tap_off * b_ent;
+      const uint32_t kk = (uint32_t)k > maxk ? maxk : (uint32_t)k;
+      for (uint32_t part = 0; part * kk < (uint32_t)k; ++part) {
+        const uint32_t n = kk * acc_cols;
+        const uint32_t idesc = P.idesc0 | ((n >> 3) << 17);
+        const uint32_t d = tmem_acc0 + ((uint32_t)acc0 + part * kk) * acc_cols;
+        const uint32_t bw0 = (sbase + part * kk * acc_cols) | lbo_b;   // 16-byte rows: kk accumulators further
+        const uint64_t bd = ((uint64_t)b_w1 << 32) | bw0;
+        const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | (ah + ao), ad_lo = ((uint64_t)a_w1 << 32) | (al + ao);
+        if (leader) {
+          umma_f16(d, ad_hi, bd, idesc, overwrite ? 0u : 1u);
+          if (SPLIT) umma_f16(d, ad_lo, bd, idesc, 1u);
         }
+      }
+    };
+    if (g == 0) {
+      uint32_t off = 0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        stack(kG0[i][0], kG0[i][1], kG0[i][2], kG0[i][3], off, first && i == 0);
+        off += (uint32_t)kG0[i][1];
+      }
+    } else {
+      uint32_t off = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        stack(kG1[i][0], kG1[i][1], kG1[i][2], kG1[i][3], off, false);
+        off += (uint32_t)kG1[i][1];
+      }
     }
   }
 }
@@ -885,6 +913,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.out_ns = out_ns; P.wpacked = (const uint8_t*)wpacked; P.bias = bias; P.out = out;
   const int fmt = in_dtype == TTA_BF16 ? 1 : 0;
   const int idesc0 = (1 << 4) | (fmt << 7) | (fmt << 10) | ((128 >> 4) << 24);
+  P.idesc0 = idesc0;
   P.idesc_n = idesc0 | ((P.ntile >> 3) << 17);
   P.idesc_2n = idesc0 | (((2 * P.ntile) >> 3) << 17);
 

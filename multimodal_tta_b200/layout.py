@@ -109,6 +109,29 @@ def tc_groups(mode: int, K: int, stride: int) -> list[list[int]]:
     return [taps([1, 2]), taps([0])]
 
 
+def t2_stacks() -> list[list[list[tuple[int, int]]]]:
+    """Transposed stride-2 conv: per pipeline group, the weight STACKS the kernel multiplies with one
+    shifted A tile (csrc/tta_conv_tc.cu, GEOM_T2 tables kG0 / kG1).  A stack is a list of
+    (accumulator, tap) in accumulator order; accumulator a = qd*4 + qh*2 + qw is the output parity
+    class, tap = kd*9 + kh*3 + kw.  Parity 0 along an axis uses k = 1 (shift 0), parity 1 uses k = 2
+    (shift 0) and k = 0 (shift 1 = next input voxel)."""
+    def tap(qd, qh, qw, jd, jh, jw):
+        kd = 0 if jd else (2 if qd else 1)
+        kh = 0 if jh else (2 if qh else 1)
+        kw = 0 if jw else (2 if qw else 1)
+        return kd * 9 + kh * 3 + kw
+
+    def stacks(jd, tables):
+        out = []
+        for acc0, k, jh, jw in tables:
+            out.append([(a, tap(a >> 2, (a >> 1) & 1, a & 1, jd, jh, jw)) for a in range(acc0, acc0 + k)])
+        return out
+    g0 = [(0, 8, 0, 0), (2, 2, 1, 0), (6, 2, 1, 0), (1, 1, 0, 1), (3, 1, 0, 1), (5, 1, 0, 1), (7, 1, 0, 1),
+          (3, 1, 1, 1), (7, 1, 1, 1)]
+    g1 = [(4, 4, 0, 0), (6, 2, 1, 0), (5, 1, 0, 1), (7, 1, 0, 1), (7, 1, 1, 1)]
+    return [stacks(0, g0), stacks(1, g1)]
+
+
 def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int) -> torch.Tensor:
     """Wg[T][ci][co] -> per-(n_tile, cblk, group) contiguous blobs
     [ntile][cblk][group][entry][kchunk 2][hi NT rows | lo NT rows][8 ci] of 16-bit values.
@@ -130,6 +153,21 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
     gmax = max(len(g) for g in groups)
     ncb, nnt = cip // 16, cop // ntile
     out = torch.zeros((nnt, ncb, len(groups), gmax, 2, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+    if K == 3 and mode == 1 and stride == 2:
+        # transposed stride-2: per group a sequence of stacks, each [kchunk][accumulators of the stack]
+        # [hi NT | lo NT][8]: ONE MMA covers all accumulators of a stack (N = k * planes * NT)
+        flat = out.view(nnt, ncb, len(groups), -1)
+        pl = torch.stack(planes)                                       # [P][T][cip][cop]
+        for gi, stacks in enumerate(t2_stacks()):
+            pos = 0
+            for st in stacks:
+                idx = torch.tensor([t for _, t in st], device=wg.device)
+                sel = pl[:, idx]                                       # [P][k][cip][cop]
+                sel = sel.reshape(len(planes), len(st), ncb, 2, 8, nnt, ntile)   # [P][k][cb][kc][8][nt][n]
+                blk = sel.permute(5, 2, 3, 1, 0, 6, 4).reshape(nnt, ncb, -1)     # [nt][cb][kc][k][P][n][8]
+                flat[:, :, gi, pos: pos + blk.shape[-1]] = blk
+                pos += blk.shape[-1]
+        return out.contiguous()
     for gi, taps in enumerate(groups):
         idx = torch.tensor(taps, device=wg.device)
         for pi, plane in enumerate(planes):
