@@ -36,6 +36,18 @@ NORM_ELEMS_PER_VOLUME = 51.1e6
 LOGIT_ELEMS_PER_VOLUME = 3 * 128 ** 3
 
 
+def measured_traffic():
+    """Per-step DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, summed over the launches of
+    a kernel family in ONE step) from the committed ncu launch list -- profiles/traffic_r1.json is
+    written by scripts/summarize_step.py; None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("conv_dram_bytes_per_step"), d.get("stream_dram_bytes_per_step")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -214,6 +226,7 @@ def run_product(args):
     hbm_bytes = BATCH * (NORM_ELEMS_PER_VOLUME * (2 * 4 + 3 * 4) + 2 * LOGIT_ELEMS_PER_VOLUME * 4)
     hbm_gbs = hbm_bytes / 1e9 / (roof["stream_ms"] / 1e3)
 
+    conv_traffic, stream_traffic = measured_traffic()
     if rank == 0:
         if args.skip_cpu:
             cpu = None
@@ -238,11 +251,13 @@ def run_product(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": f"conv3d fwd+dgrad ({roof['conv_launches']} launches/step)",
                          "achieved": conv_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": conv_tflops / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
+                         "frac": conv_tflops / pk["tf_sust"], "traffic": conv_traffic, "peak_source": pk["src"],
+                         "traffic_note": "DRAM bytes of all conv launches of one step (ncu, profiles/traffic_r1.json)",
                          "ms_per_step": roof["conv_ms"], "share_of_step": roof["conv_ms"] / roof["total_ms"]},
             "roofline_hbm": {"bound": "hbm", "kernel": "norm stats/apply/bwd + fused entropy head",
                              "achieved": hbm_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_gbs / pk["hbm"],
-                             "traffic": None, "ms_per_step": roof["stream_ms"],
+                             "traffic": stream_traffic, "algorithmic_bytes": hbm_bytes,
+                             "ms_per_step": roof["stream_ms"],
                              "share_of_step": roof["stream_ms"] / roof["total_ms"]},
             "cpu_baseline": cpu,
         }
