@@ -157,6 +157,21 @@ int tta_norm_bwd_apply(const float* g0, long long g0_n_stride, const float* g1, 
                        uint16_t* aux_hi, uint16_t* aux_lo, long long aux_n_stride, int out_dtype,
                        const float* partial, int Creal, float* dgamma, float* dbeta, int dy_wsplit_w,
                        tta_stream_t stream);
+/* small layers (2 <= V <= 4096 voxels per instance, InstanceNorm): statistics + apply, and backward
+ * reduction + apply, as ONE launch each (a CTA owns a whole (n, chunk) slab).  Same math and outputs
+ * as tta_norm_stats + tta_norm_apply / tta_norm_bwd_reduce + tta_norm_bwd_apply. */
+int tta_norm_small_supported(int N, long long V, int batch_mode);
+int tta_norm_fwd_small(const float* y, long long y_n_stride, int N, int C8, long long V, float eps, float* mean,
+                       float* rstd, const float* gamma, const float* beta, int relu, int res_kind,
+                       const void* res_a, const void* res_b, long long res_n_stride, uint16_t* out_hi,
+                       uint16_t* out_lo, long long out_n_stride, int out_dtype, uint16_t* ws_hi, uint16_t* ws_lo,
+                       long long ws_n_stride, int W, tta_stream_t stream);
+int tta_norm_bwd_small(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
+                       const float* y, long long y_n_stride, int N, int C8, int Creal, long long V,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                       float* sums, float* dgamma, float* dbeta, uint16_t* dy_hi, uint16_t* dy_lo,
+                       long long dy_n_stride, uint16_t* aux_hi, uint16_t* aux_lo, long long aux_n_stride,
+                       int out_dtype, int dy_wsplit_w, float* workspace, tta_stream_t stream);
 int tta_split_f32(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride, int N, int C8,
                   long long V, uint16_t* hi, uint16_t* lo, long long out_n_stride, int out_dtype,
                   tta_stream_t stream);

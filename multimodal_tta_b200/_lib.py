@@ -60,6 +60,9 @@ _SIGNATURES = {
     "tta_norm_stats_finalize": (I, [P, I, I, I, L, I, F, P, P, P]),
     "tta_norm_bwd_reduce": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, I, P, P, P, P, I, P]),
     "tta_norm_bwd_apply": (I, [P, L, P, L, P, L, I, I, L, P, P, P, P, I, I, P, P, P, L, P, P, L, I, P, I, P, P, I, P]),
+    "tta_norm_small_supported": (I, [I, L, I]),
+    "tta_norm_fwd_small": (I, [P, L, I, I, L, F, P, P, P, P, I, I, P, P, L, P, P, L, I, P, P, L, I, P]),
+    "tta_norm_bwd_small": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, P, P, P, P, P, L, P, P, L, I, I, P, P]),
     "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
     "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, I, P]),
     "tta_head_entropy_blocks": (I, [I, L]),

@@ -148,7 +148,42 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
   const int chunk = blockIdx.y, n = blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
-  if (partial != nullptr) {
+  if (splits < 0) {
+    // SMALL mode (one CTA owns the whole (n, chunk) slab, V <= 4096, per-instance statistics): the
+    // statistics pass runs right here -- the slab (<= 128 KB) is then re-read from L1/L2 by the
+    // apply loop below, and the separate tta_norm_stats launch disappears
+    float acc[16], tot[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const float* ys = y + (long long)n * y_ns + (long long)chunk * V * 8;
+#pragma unroll 4
+    for (long long v = threadIdx.x; v < V; v += kThreads) {
+      float x[8];
+      load_f32x8(ys + v * 8, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += x[i];
+        acc[8 + i] = fmaf(x[i], x[i], acc[8 + i]);
+      }
+    }
+    block_reduce_bcast<16>(acc, tot);
+    const double M = (double)V;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double m = (double)tot[i] / M;
+      double var = (double)tot[8 + i] / M - m * m;
+      if (var < 0.0) var = 0.0;
+      mu[i] = (float)m;
+      rs[i] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    if (threadIdx.x == 0) {  // keep them for the backward pass
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        mean_w[n * C + chunk * 8 + i] = mu[i];
+        rstd_w[n * C + chunk * 8 + i] = rs[i];
+      }
+    }
+  } else if (partial != nullptr) {
     // statistics finalize fused here: every block reduces the per-block partial sums itself
     double tot[16];
     reduce_partials(partial, C8, chunk, splits, batch_mode ? 0 : n, batch_mode ? N : n + 1, tot);
@@ -321,7 +356,8 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
                       uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi,
                       uint16_t* aux_lo, long long aux_ns, const float* partial,
                       int splits, int N, int batch_mode, int Creal, float* dgamma,
-                      float* dbeta, int dy_wsplit_w) {
+                      float* dbeta, int dy_wsplit_w, float* small_partial, unsigned int* small_counters,
+                      float* sums_w) {
   pdl_trigger();
   pdl_wait();
   const int chunk = blockIdx.y, n = blockIdx.z;
@@ -335,7 +371,45 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
     ga[i] = gamma[c];
     be[i] = beta[c];
   }
-  if (partial != nullptr) {
+  if (splits < 0) {
+    // SMALL mode (one CTA owns the whole (n, chunk) slab): the reduction pass runs here, the slab is
+    // re-read from L1/L2 below; the last CTA of the chunk (over n) finalizes dgamma / dbeta
+    float acc[16], tot[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const long long sl = (long long)chunk * V * 8;
+    const float* ys = y + (long long)n * y_ns + sl;
+    const float* gs0 = g0 + (long long)n * g0_ns + sl;
+    const float* gs1 = g1 ? g1 + (long long)n * g1_ns + sl : nullptr;
+#pragma unroll 2
+    for (long long v = threadIdx.x; v < V; v += kThreads) {
+      float x[8], g[8];
+      load_f32x8(ys + v * 8, x);
+      load_f32x8(gs0 + v * 8, g);
+      if (gs1) {
+        float h[8];
+        load_f32x8(gs1 + v * 8, h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += h[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (x[i] - mu[i]) * rs[i];
+        const float z = fmaf(xh, ga[i], be[i]);
+        const float dz = (relu && !(z > 0.f)) ? 0.f : g[i];
+        acc[i] += dz;
+        acc[8 + i] = fmaf(dz, xh, acc[8 + i]);
+      }
+    }
+    block_reduce_bcast<16>(acc, tot, small_partial + (long long)(n * C8 + chunk) * 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      m1[i] = tot[i] * inv_m;
+      m2[i] = tot[8 + i] * inv_m;
+    }
+    if (last_block_of_chunk(small_counters, chunk, (unsigned int)N))
+      norm_bwd_finalize_tail(small_partial, C8, chunk, 1, N, 0, Creal, sums_w, dgamma, dbeta);
+  } else if (partial != nullptr) {
     // reduction finalize fused here (no separate kernel): S1 = sum dz, S2 = sum dz*xhat
     double tot[16];
     reduce_partials(partial, C8, chunk, splits, batch_mode ? 0 : n, batch_mode ? N : n + 1, tot);
@@ -552,18 +626,76 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
     tta_launch(norm_bwd_apply_kernel<TTA_F16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w);
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr);
   else if (out_dtype == TTA_F16_HI)
     tta_launch(norm_bwd_apply_kernel<TTA_F16_HI>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w);
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr);
   else
     tta_launch(norm_bwd_apply_kernel<TTA_BF16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w);
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr);
   return tta_check_launch("tta_norm_bwd_apply");
+}
+
+// ---- small layers (V <= 4096 voxels per instance, per-instance statistics): statistics + apply,
+// and reduction + apply, as ONE launch each -- a CTA owns a whole (n, chunk) slab, reduces it, and
+// re-reads it from L1/L2.  The 8^3 / 16^3 levels are pure launch latency otherwise.
+int tta_norm_small_supported(int N, long long V, int batch_mode) {
+  return V >= 2 && V <= 4096 && !batch_mode && N >= 1;
+}
+
+int tta_norm_fwd_small(const float* y, long long y_ns, int N, int C8, long long V, float eps, float* mean,
+                       float* rstd, const float* gamma, const float* beta, int relu, int res_kind,
+                       const void* res_a, const void* res_b, long long res_ns, uint16_t* out_hi,
+                       uint16_t* out_lo, long long out_ns, int out_dtype, uint16_t* ws_hi, uint16_t* ws_lo,
+                       long long ws_ns, int W, cudaStream_t stream) {
+  TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_fwd_small: null pointer");
+  TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_fwd_small: V=%lld unsupported (2..4096)", V);
+  TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_fwd_small: res_kind %d", res_kind);
+  TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_fwd_small: bad dtype");
+  TTA_REQUIRE(!ws_hi || (ws_lo && W > 0 && W % 2 == 0 && V % W == 0), "tta_norm_fwd_small: bad parity-split copy");
+  const dim3 grid(1, C8, N);
+#define LAUNCH(RES, DT)                                                                              \
+  tta_launch(norm_apply_kernel<RES, DT>, grid, kThreads, 0, stream, tta_pdl_family(2), y, y_ns, C8, V, mean, \
+             rstd, gamma, beta, relu, (const float*)res_a, (const uint16_t*)res_a, (const uint16_t*)res_b, \
+             res_ns, out_hi, out_lo, out_ns, (const float*)nullptr, -1, N, 0, eps, mean, rstd, ws_hi, ws_lo, \
+             ws_ns, W)
+  if (out_dtype == TTA_F16) {
+    if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
+  } else {
+    if (res_kind == 0) LAUNCH(0, TTA_BF16); else if (res_kind == 1) LAUNCH(1, TTA_BF16); else LAUNCH(2, TTA_BF16);
+  }
+#undef LAUNCH
+  return tta_check_launch("tta_norm_fwd_small");
+}
+
+// workspace: as tta_norm_bwd_reduce ([1024 counters][partials], tta_norm_workspace_floats)
+int tta_norm_bwd_small(const float* g0, long long g0_ns, const float* g1, long long g1_ns, const float* y,
+                       long long y_ns, int N, int C8, int Creal, long long V, const float* mean,
+                       const float* rstd, const float* gamma, const float* beta, int relu, float* sums,
+                       float* dgamma, float* dbeta, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
+                       uint16_t* aux_hi, uint16_t* aux_lo, long long aux_ns, int out_dtype, int dy_wsplit_w,
+                       float* workspace, cudaStream_t stream) {
+  TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dgamma && dbeta && dy_hi && workspace &&
+                  (dy_lo || out_dtype == TTA_F16_HI),
+              "tta_norm_bwd_small: null pointer");
+  TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_bwd_small: V=%lld unsupported (2..4096)", V);
+  TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_norm_bwd_small: bad dtype");
+  TTA_REQUIRE(dy_wsplit_w == 0 || (dy_wsplit_w > 0 && dy_wsplit_w % 2 == 0 && V % dy_wsplit_w == 0),
+              "tta_norm_bwd_small: bad parity-split row length %d", dy_wsplit_w);
+  const float inv_m = (float)(1.0 / (double)V);
+  const dim3 grid(1, C8, N);
+#define LAUNCH(DT)                                                                                          \
+  tta_launch(norm_bwd_apply_kernel<DT>, grid, kThreads, 0, stream, tta_pdl_family(2), g0, g0_ns, g1, g1_ns, y, \
+             y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)nullptr, inv_m, dy_hi, dy_lo, dy_ns, aux_hi, \
+             aux_lo, aux_ns, (const float*)nullptr, -1, N, 0, Creal, dgamma, dbeta, dy_wsplit_w, workspace + 1024,  \
+             reinterpret_cast<unsigned int*>(workspace), sums)
+  if (out_dtype == TTA_F16) LAUNCH(TTA_F16); else if (out_dtype == TTA_F16_HI) LAUNCH(TTA_F16_HI); else LAUNCH(TTA_BF16);
+#undef LAUNCH
+  return tta_check_launch("tta_norm_bwd_small");
 }
 
 int tta_split_f32(const float* g0, long long g0_ns, const float* g1, long long g1_ns, int N, int C8,

@@ -29,6 +29,31 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[NV], float* dst)
   }
 }
 
+// same reduction, totals broadcast to every thread through shared memory (fp32 in, fp32 out)
+template <int NV>
+__device__ __forceinline__ void block_reduce_bcast(float (&acc)[NV], float (&tot)[NV], float* gdst = nullptr) {
+  __shared__ float red[kThreads / 32][NV];
+  __shared__ float tots[NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
+    tots[threadIdx.x] = s;
+    if (gdst) gdst[threadIdx.x] = s;  // also publish the totals (one value per thread)
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) tot[i] = tots[i];
+}
+
 // ---------------------------------------------------------------- fused finalize (consumer prologue)
 // Sums the 16 per-block partial values of chunk `chunk` over splits (and over samples n0..n1)
 // in fp64 with all 256 threads; result in tot[16] (shared).  Deterministic order.

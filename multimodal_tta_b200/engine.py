@@ -536,7 +536,16 @@ class TTAEngine:
                     return (0, 0, 0, 0)
                 return (out.ws_hi, out.ws_lo, out.ns, y.W)
 
+            small = (model.fuse_small_norm and not fuse_st and y.V <= model.small_norm_max_voxels
+                     and bool(lib.tta_norm_small_supported(N, y.V, nl.batch)))
+            rec["small"] = small
+            sm_args = (y.ptr, y.ns, N, y.C8, y.V, float(nl.h.eps), mean.data_ptr(), rstd.data_ptr(), gptr, bptr,
+                       int(relu), rk, ra, rb, rns, out.hi, out.lo, out.ns, TTA_F16)
+
             def run():
+                if small and not (nl.batch and not model.training and nl.h.track_running_stats):
+                    check(lib.tta_norm_fwd_small(*sm_args, *ws_args(), _stream()), "norm_fwd_small")
+                    return
                 if nl.batch and not model.training and nl.h.track_running_stats:
                     # eval-mode BatchNorm: mean/rstd were filled from the running buffers
                     check(lib.tta_norm_apply(*ap_args, 0, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
@@ -813,8 +822,22 @@ class TTAEngine:
                                 dg, db)
                 rec["fused_bwd"] = fuse_bwd is not None
 
+                sm_bwd = None
+                if (model.fuse_small_norm and do_apply and fin_args is None and not skip_reduce
+                        and y.V <= model.small_norm_max_voxels
+                        and lib.tta_norm_small_supported(N, y.V, nl.batch)):
+                    sm_bwd = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, nl.C, y.V, rec["mean"].data_ptr(),
+                              rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]),
+                              rec["sums"].data_ptr(), dg, db, y.dy_ptr(0), y.dy_ptr(1), y.ns,
+                              aux.dy_ptr(0) if aux else 0, aux.dy_ptr(1) if aux else 0, aux.ns if aux else 0, bdt,
+                              dy_ws)
+                rec["small_bwd"] = sm_bwd is not None
+
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db, dy_ws=dy_ws,
-                        skip_reduce=skip_reduce, fin_args=fin_args):
+                        skip_reduce=skip_reduce, fin_args=fin_args, sm_bwd=sm_bwd):
+                    if sm_bwd is not None:
+                        check(lib.tta_norm_bwd_small(*sm_bwd, plan.ws.data_ptr(), _stream()), "norm_bwd_small")
+                        return
                     # single-pass reduction: the last block finalizes sums + dgamma/dbeta
                     if fin_args is not None:
                         check(lib.tta_norm_bwd_finalize(*fin_args, _stream()), "norm_bwd_finalize")
@@ -837,6 +860,11 @@ class TTAEngine:
         # (launch count unchanged: a tiny finalize launch takes the place of the statistics pass)
         plan.n_fused_stats = sum(1 for o in ops if o[0] == "norm" and o[1]["fused_stats"])
         plan.n_fused_bwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("fused_bwd"))
+        plan.n_small_fwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("small")
+                               and not (fused_head is not None and o[1] is fused_head[1]))
+        plan.n_small_bwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("small_bwd"))
+        plan.launches_fwd -= plan.n_small_fwd      # statistics + apply in one launch
+        plan.launches_bwd -= plan.n_small_bwd      # reduction + apply in one launch
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:

@@ -162,6 +162,12 @@ class UNetB200(nn.Module):
         # 8 warps per SM for ~100 instructions per voxel-chunk) and save 144 us of streaming passes
         # (2048 threads per SM) -> default off; the streaming tta_norm_bwd_reduce stays the product path
         self.fuse_bwd_stats = bool(get_config(cfg, "fuse_bwd_stats", False))
+        # layers with <= 4096 voxels per instance (8^3, 16^3): statistics + apply, and backward
+        # reduction + apply, as one launch each
+        self.fuse_small_norm = bool(get_config(cfg, "fuse_small_norm", True))
+        # ... up to this many voxels per instance: one CTA per (n, chunk) slab only pays while the slab
+        # is a few voxel-chunks per thread (measured: 16^3 slabs on 32 CTAs are slower than two launches)
+        self.small_norm_max_voxels = int(get_config(cfg, "small_norm_max_voxels", 512))
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))

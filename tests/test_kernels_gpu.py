@@ -202,6 +202,28 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     assert rel_l2(dy, yr.grad) < 3e-5                 # bf16x2 storage (~16 bits)
     aux = from_chunked(join_planes(ahi, alo, TTA_BF16), C).cpu()
     assert rel_l2(aux, g_in) < 2e-5
+    if lib.tta_norm_small_supported(N, V, batch_mode):
+        # small-layer variants: statistics + apply (and reduction + apply) in ONE launch each; the
+        # sums are reduced in another order (fp32 tree per CTA), everything else is the same code
+        mean3 = torch.zeros_like(mean); rstd3 = torch.zeros_like(rstd)
+        ohi4 = torch.zeros_like(ohi); olo4 = torch.zeros_like(ohi)
+        check(lib.tta_norm_fwd_small(ych.data_ptr(), ns, N, C8, V, 1e-5, mean3.data_ptr(), rstd3.data_ptr(),
+                                     gp.data_ptr(), bp.data_ptr(), 1, 1, rch.data_ptr(), 0, ns, ohi4.data_ptr(),
+                                     olo4.data_ptr(), ns, TTA_F16, 0, 0, 0, 0, stream()))
+        assert torch.allclose(mean3, mean, rtol=1e-5, atol=1e-6) and torch.allclose(rstd3, rstd, rtol=1e-5)
+        got4 = from_chunked(join_planes(ohi4, olo4, TTA_F16), C).cpu()
+        assert (got4 - a.detach()).abs().max() < 2e-5
+        sums3 = torch.zeros_like(sums); dg3 = torch.zeros_like(dg); db3 = torch.zeros_like(db)
+        dhi3 = torch.zeros_like(ohi); dlo3 = torch.zeros_like(ohi); ahi3 = torch.zeros_like(ohi); alo3 = torch.zeros_like(ohi)
+        for _ in range(2):                           # twice: self-resetting block counters
+            check(lib.tta_norm_bwd_small(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, C, V, mean.data_ptr(),
+                                         rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, sums3.data_ptr(),
+                                         dg3.data_ptr(), db3.data_ptr(), dhi3.data_ptr(), dlo3.data_ptr(), ns,
+                                         ahi3.data_ptr(), alo3.data_ptr(), ns, TTA_BF16, 0, ws.data_ptr(), stream()))
+        assert rel_l2(dg3[:C].cpu(), gr.grad) < 1e-5 and rel_l2(db3[:C].cpu(), br.grad) < 1e-5
+        assert torch.allclose(sums3, sums, rtol=1e-4, atol=1e-5)
+        assert rel_l2(from_chunked(join_planes(dhi3, dlo3, TTA_BF16), C).cpu(), yr.grad) < 3e-5
+        assert torch.equal(ahi3, ahi) and torch.equal(alo3, alo)
 
 
 @pytest.mark.parametrize("mode,R", [(1, 3), (1, 1), (0, 3), (0, 2)])
