@@ -277,6 +277,11 @@ def kernel_family_times(torch, eng, tent, xs, reps: int):
     nconv = sum(1 for k, _ in ops if k == "conv")
     for _ in range(reps):
         evs = []
+        # park the stream behind a ~20 ms spin kernel while the host enqueues every op with its event
+        # pair: the GPU then runs them back to back and an event pair brackets the kernel only (in
+        # plain eager order the host is slower than the small kernels and every pair would also time
+        # the launch gap in front of its kernel)
+        torch.cuda._sleep(40_000_000)
         for kind, op in ops:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); op(); b.record()

@@ -960,6 +960,22 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
       if (2 * t2 * acc_cols <= 512) { td = t2; nacc = td; nbuf = 2; }
     }
   }
+  if (conv_like && !(flags & 2)) {
+    // SM-starved layers (16^3 / 8^3 levels): even with the split-K factor capped at ncblk/2 the grid
+    // may fill less than half of the SMs -> fewer d-planes per item (more, shorter items) until it does
+    auto items_of = [&](int td_) {
+      const long long it = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td_ - 1) / td_) * P.n_ntiles * N;
+      long long ks = 1;
+      if (it < num_sms() && P.ncblk >= 4) {
+        ks = (num_sms() + it - 1) / it;
+        if (ks > P.ncblk / 2) ks = P.ncblk / 2;
+      }
+      return it * ks;
+    };
+    while (td > 1 && items_of(td) * 2 <= num_sms()) td = (td + 1) / 2;
+    nacc = td;
+    nbuf = (2 * nacc * acc_cols <= 512) ? 2 : 1;
+  }
   P.td = td; P.nacc = nacc; P.nbuf = nbuf;
   P.a_plane_bytes = a_plane_of(td);
   P.stage_bytes = stage_bytes_of(td);
