@@ -137,12 +137,13 @@ int tta_norm_apply(const float* y, long long y_n_stride, int N, int C8, long lon
 int tta_norm_stats_finalize(const float* workspace, int N, int C8, int splits, long long V, int batch_mode,
                             float eps, float* mean, float* rstd, tta_stream_t stream);
 /* partial sums of dz and dz*xhat (dz = (g0+g1)*[z>0]); finalize != 0 also writes sums[N][C][2] and
- * dgamma/dbeta[C] */
+ * dgamma/dbeta[C] (accumulate_dgb != 0: adds to them -- a layer processed sample by sample, each call
+ * with N = 1 and pointers advanced by one sample, so that the apply pass re-reads g and y from L2) */
 int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
                         const float* y, long long y_n_stride, int N, int C8, int Creal, long long V,
                         const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
                         int batch_mode, float* sums, float* dgamma, float* dbeta, float* workspace, int finalize,
-                        tta_stream_t stream);
+                        int accumulate_dgb, tta_stream_t stream);
 /* sums / dgamma / dbeta from partial sums laid out [N][C8][splits][16] (partial points at the slots) */
 int tta_norm_bwd_finalize(const float* partial, int N, int C8, int Creal, int splits, int batch_mode, float* sums,
                           float* dgamma, float* dbeta, tta_stream_t stream);

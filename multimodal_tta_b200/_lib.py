@@ -58,7 +58,7 @@ _SIGNATURES = {
     "tta_norm_stats": (I, [P, L, I, I, L, I, F, P, P, P, I, P]),
     "tta_norm_apply": (I, [P, L, I, I, L, P, P, P, P, I, I, P, P, L, P, P, L, I, P, I, I, F, P, P, L, I, P]),
     "tta_norm_stats_finalize": (I, [P, I, I, I, L, I, F, P, P, P]),
-    "tta_norm_bwd_reduce": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, I, P, P, P, P, I, P]),
+    "tta_norm_bwd_reduce": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, I, P, P, P, P, I, I, P]),
     "tta_norm_bwd_apply": (I, [P, L, P, L, P, L, I, I, L, P, P, P, P, I, I, P, P, P, L, P, P, L, I, P, I, P, P, I, P]),
     "tta_norm_small_supported": (I, [I, L, I]),
     "tta_norm_fwd_small": (I, [P, L, I, I, L, F, P, P, P, P, I, I, P, P, L, P, P, L, I, P, P, L, I, P]),

@@ -257,7 +257,7 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
                         const float* gamma, const float* beta, int relu,
                         int splits, float* partial, unsigned int* counters, int N,
                         int batch_mode, int Creal, float* sums, float* dgamma,
-                        float* dbeta) {
+                        float* dbeta, int acc_dgb) {
   pdl_trigger();
   pdl_wait();
   const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
@@ -303,7 +303,7 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
   block_reduce_store<16>(acc, partial + ((long long)(n * C8 + chunk) * splits + split) * 16);
   if (counters == nullptr) return;
   if (!last_block_of_chunk(counters, chunk, (unsigned int)(N * splits))) return;
-  norm_bwd_finalize_tail(partial, C8, chunk, splits, N, batch_mode, Creal, sums, dgamma, dbeta);
+  norm_bwd_finalize_tail(partial, C8, chunk, splits, N, batch_mode, Creal, sums, dgamma, dbeta, acc_dgb);
 }
 
 // sums[(n*C + c)*2 + {0,1}] = {sum dz, sum dz*xhat} over the normalisation group (per n for IN,
@@ -594,7 +594,7 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
                         const float* y, long long y_ns, int N, int C8, int Creal, long long V,
                         const float* mean, const float* rstd, const float* gamma,
                         const float* beta, int relu, int batch_mode, float* sums, float* dgamma,
-                        float* dbeta, float* workspace, int finalize, cudaStream_t stream) {
+                        float* dbeta, float* workspace, int finalize, int accumulate_dgb, cudaStream_t stream) {
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && workspace &&
                   (!finalize || (sums && dgamma && dbeta)),
               "tta_norm_bwd_reduce: null pointer");
@@ -602,7 +602,8 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
   const int splits = pick_splits(N, C8, V);
   tta_launch(norm_bwd_partial_kernel, dim3(splits, C8, N), kThreads, 0, stream, tta_pdl_family(2), 
       g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace + 1024,
-      finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N, batch_mode, Creal, sums, dgamma, dbeta);
+      finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N, batch_mode, Creal, sums, dgamma, dbeta,
+      accumulate_dgb);
   return tta_check_launch("tta_norm_bwd_reduce");
 }
 

@@ -120,14 +120,17 @@ __device__ __forceinline__ bool last_block_of_chunk(unsigned int* counters, int 
 __device__ __forceinline__ void norm_bwd_finalize_tail(const float* partial, int C8, int chunk,
                                                        int splits, int N, int batch_mode, int Creal,
                                                        float* sums, float* dgamma,
-                                                       float* dbeta) {
+                                                       float* dbeta, int acc_dgb = 0) {
   const int C = C8 * 8;
   const int which = threadIdx.x & 15;
   const int cc = chunk * 8 + (which & 7);
   const double tall = reduce_partials_one(partial, C8, chunk, splits, 0, N, which);
   if (threadIdx.x < 16) {
     if (cc < Creal) {
-      if (which < 8) dbeta[cc] = (float)tall; else dgamma[cc] = (float)tall;
+      // acc_dgb: this launch covers a subset of the samples (per-sample backward, see engine.py):
+      // the affine gradients of the launches add up in launch order (deterministic)
+      float* dst = which < 8 ? dbeta + cc : dgamma + cc;
+      *dst = acc_dgb ? *dst + (float)tall : (float)tall;
     }
     if (batch_mode)
       for (int nn = 0; nn < N; ++nn) sums[(nn * C + cc) * 2 + (which >> 3)] = (float)tall;

@@ -502,7 +502,8 @@ class TTAEngine:
             rstd = torch.zeros_like(mean)
             sums = torch.zeros(N * y.C8 * 8 * 2, dtype=torch.float32, device=dev)
             plan.keep += [mean, rstd, sums]
-            max_ws[0] = max(max_ws[0], lib.tta_norm_workspace_floats(N, y.C8, y.V))
+            max_ws[0] = max(max_ws[0], lib.tta_norm_workspace_floats(N, y.C8, y.V),
+                            lib.tta_norm_workspace_floats(1, y.C8, y.V))   # (per-sample backward launches)
             gptr = self.gb.data_ptr() + nl.off * 4
             bptr = self.gb.data_ptr() + (P + nl.off) * 4
             rec = dict(nl=nl, y=y, relu=relu, residual=residual, out=out, mean=mean, rstd=rstd, sums=sums,
@@ -833,8 +834,39 @@ class TTAEngine:
                               dy_ws)
                 rec["small_bwd"] = sm_bwd is not None
 
+                # per-sample reduce -> apply: bytes one sample's pass reads (g sources + y) must fit L2 with
+                # room to spare, while the whole batch must not (otherwise the batched form hits L2 anyway)
+                per_n = None
+                nsrc = 1 + (1 if g1 else 0)
+                bytes_n = (nsrc + 1) * y.C8 * y.V * 32
+                if (model.per_sample_norm_bwd and do_apply and fin_args is None and not skip_reduce and sm_bwd is None
+                        and not nl.batch and N > 1 and bytes_n <= 96e6 and N * bytes_n > 100e6):
+                    per_n = []
+                    Cp = y.C8 * 8
+                    for n_ in range(N):
+                        rd_n = (g0 + n_ * g0ns * 4, g0ns, (g1 + n_ * g1ns * 4) if g1 else 0, g1ns, y.ptr + n_ * y.ns * 4,
+                                y.ns, 1, y.C8, nl.C, y.V, rec["mean"].data_ptr() + n_ * Cp * 4,
+                                rec["rstd"].data_ptr() + n_ * Cp * 4, rec["gptr"], rec["bptr"], int(rec["relu"]),
+                                nl.batch, rec["sums"].data_ptr() + n_ * Cp * 8, dg, db)
+                        ap_n = (g0 + n_ * g0ns * 4, g0ns, (g1 + n_ * g1ns * 4) if g1 else 0, g1ns, y.ptr + n_ * y.ns * 4,
+                                y.ns, 1, y.C8, y.V, rec["mean"].data_ptr() + n_ * Cp * 4,
+                                rec["rstd"].data_ptr() + n_ * Cp * 4, rec["gptr"], rec["bptr"], int(rec["relu"]),
+                                nl.batch, rec["sums"].data_ptr() + n_ * Cp * 8, y.dy_ptr(0) + n_ * y.ns * 2,
+                                (y.dy_ptr(1) + n_ * y.ns * 2) if nplanes == 2 else y.dy_ptr(1), y.ns,
+                                (aux.dy_ptr(0) + n_ * aux.ns * 2) if aux else 0,
+                                ((aux.dy_ptr(1) + n_ * aux.ns * 2) if nplanes == 2 else aux.dy_ptr(1)) if aux else 0,
+                                aux.ns if aux else 0, bdt)
+                        per_n.append((rd_n, ap_n, int(n_ > 0)))
+                rec["per_sample_bwd"] = per_n is not None
+
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db, dy_ws=dy_ws,
-                        skip_reduce=skip_reduce, fin_args=fin_args, sm_bwd=sm_bwd):
+                        skip_reduce=skip_reduce, fin_args=fin_args, sm_bwd=sm_bwd, per_n=per_n):
+                    if per_n is not None:
+                        for rd_n, ap_n, accum in per_n:
+                            check(lib.tta_norm_bwd_reduce(*rd_n, plan.ws.data_ptr(), 1, accum, _stream()),
+                                  "norm_bwd_reduce")
+                            check(lib.tta_norm_bwd_apply(*ap_n, 0, nl.C, dg, db, dy_ws, _stream()), "norm_bwd_apply")
+                        return
                     if sm_bwd is not None:
                         check(lib.tta_norm_bwd_small(*sm_bwd, plan.ws.data_ptr(), _stream()), "norm_bwd_small")
                         return
@@ -842,7 +874,7 @@ class TTAEngine:
                     if fin_args is not None:
                         check(lib.tta_norm_bwd_finalize(*fin_args, _stream()), "norm_bwd_finalize")
                     elif not skip_reduce:
-                        check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, _stream()),
+                        check(lib.tta_norm_bwd_reduce(*rd_args, plan.ws.data_ptr(), 1, 0, _stream()),
                               "norm_bwd_reduce")
                     if ap_args is not None:
                         check(lib.tta_norm_bwd_apply(*ap_args, 0, nl.C, dg, db, dy_ws, _stream()), "norm_bwd_apply")
@@ -865,6 +897,7 @@ class TTAEngine:
         plan.n_small_bwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("small_bwd"))
         plan.launches_fwd -= plan.n_small_fwd      # statistics + apply in one launch
         plan.launches_bwd -= plan.n_small_bwd      # reduction + apply in one launch
+        plan.launches_bwd += 2 * (N - 1) * sum(1 for o in ops if o[0] == "norm" and o[1].get("per_sample_bwd"))
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:

@@ -168,6 +168,11 @@ class UNetB200(nn.Module):
         # ... up to this many voxels per instance: one CTA per (n, chunk) slab only pays while the slab
         # is a few voxel-chunks per thread (measured: 16^3 slabs on 32 CTAs are slower than two launches)
         self.small_norm_max_voxels = int(get_config(cfg, "small_norm_max_voxels", 512))
+        # OPT-IN: InstanceNorm backward sample by sample when one sample's gradient + conv result fit
+        # the 126 MB L2 but the batch does not, hoping the apply pass re-reads them from L2.  Measured
+        # on the four 64^3 layers (67 MB per sample): 2.578 ms vs 2.556 ms per step -- the second pass
+        # does not hit, the two extra launches per layer cost more; default off
+        self.per_sample_norm_bwd = bool(get_config(cfg, "per_sample_norm_bwd", False))
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))

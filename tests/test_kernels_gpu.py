@@ -170,7 +170,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     dg = torch.zeros(C8 * 8, device=cuda); db = torch.zeros(C8 * 8, device=cuda)
     check(lib.tta_norm_bwd_reduce(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, C, V, mean.data_ptr(),
                                   rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
-                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), 1, stream()))
+                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), 1, 0, stream()))
     assert rel_l2(dg[:C].cpu(), gr.grad) < 1e-5
     assert rel_l2(db[:C].cpu(), br.grad) < 1e-5
     dhi = torch.zeros_like(ohi); dlo = torch.zeros_like(ohi); ahi = torch.zeros_like(ohi); alo = torch.zeros_like(ohi)
@@ -190,7 +190,7 @@ def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     dhi2 = torch.zeros_like(ohi); dlo2 = torch.zeros_like(ohi)
     check(lib.tta_norm_bwd_reduce(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, C, V, mean.data_ptr(),
                                   rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, 0, 0, 0,
-                                  ws.data_ptr(), 0, stream()))
+                                  ws.data_ptr(), 0, 0, stream()))
     check(lib.tta_norm_bwd_apply(gch.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, C8, V, mean.data_ptr(),
                                  rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, 0,
                                  dhi2.data_ptr(), dlo2.data_ptr(), ns, 0, 0, 0, TTA_BF16, ws.data_ptr(), C,
