@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtta_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--threads", "0", "-split-compile", "0"]
 
 TTA_F16, TTA_BF16, TTA_F16_HI = 0, 1, 2
 

@@ -33,12 +33,12 @@
 namespace tta {
 
 constexpr int kTcThreads = 352;  // TMA producer, MMA issuer, 8 epilogue warps, second TMA producer
-constexpr int kMaxGroups = 3;
+constexpr int kMaxGroups = 9;
 constexpr int kMaxLoads = 4;
 constexpr int kMaxAcc = 8;
 constexpr int kMaxStages = 8;
 
-enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2 };
+enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2, GEOM_S1P, GEOM_S1TP };
 
 struct TcLoad {
   int map, dw, dh, dd, smem_off, bytes, chunk_pitch, pad;  // bytes / pitch are per k-chunk (8 channels)
@@ -57,6 +57,7 @@ struct TcParams {
   int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n, idesc0, pad_i;
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
+  int pl2;      // small-plane tiles (H <= 8): the 128 rows are 2 d-planes x 8 h x 8 w (GEOM_S1P / GEOM_S1TP)
   // fused norm statistics: per-CTA partial sums of y and y^2 over the leading stats_c8 chunks of the
   // output, layout [n][chunk][cta][16] (0..7 sum, 8..15 sum of squares) = what tta_norm_apply
   // finalizes with splits = gridDim.x
@@ -235,6 +236,26 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
           mma_pair<SPLIT>(leader, tmem_acc0 + p * acc_cols, ah + ao, al + ao, a_w1, bo, b_w1, i2n, in_, accum);
         }
       }
+  } else if (GEOM == GEOM_S1P || GEOM == GEOM_S1TP) {
+    // Small planes (H <= 8, the 8^3 level): a 16 x 8 tile of ONE plane would be half empty, so the
+    // 128 rows are 2 d-planes x 8 h x 8 w.  The descriptor needs ONE stride between 8-row groups,
+    // i.e. a plane pitch of exactly 8 halo rows: every (kd, kh) pair is its own pipeline group that
+    // loads an [2*TD planes][8 rows][10 w] box at (d + kd - 1, h + kh - 1); only kw is a start-address
+    // shift.  Accumulator p = planes 2p, 2p + 1; g = kd*3 + kh; weight entries of the group = [kw].
+    const uint32_t a_w1 = 10u | (1u << 14);
+    const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
+    const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int rw = GEOM == GEOM_S1P ? kw : 2 - kw;
+      const uint32_t bo = b_w0 + (uint32_t)kw * b_ent;
+      const uint32_t accum = (first && kw == 0) ? 0u : 1u;
+#pragma unroll
+      for (int p = 0; p < TD; ++p) {
+        const uint32_t ao = (uint32_t)(rw + p * 160);
+        mma_pair<SPLIT>(leader, tmem_acc0 + p * acc_cols, ah + ao, al + ao, a_w1, bo, b_w1, i2n, in_, accum);
+      }
+    }
   } else if (GEOM == GEOM_K1) {
     const uint32_t a_w1 = 8u | (1u << 14);
     const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
@@ -402,8 +423,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();  // the next kernel's CTAs may be scheduled (they block in their own pdl_wait)
 
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(TcGroup) * kMaxGroups / 4))
-    reinterpret_cast<int*>(grp_s)[threadIdx.x - 64] = reinterpret_cast<const int*>(P.grp)[threadIdx.x - 64];
+  for (int i = threadIdx.x; i < (int)(sizeof(TcGroup) * kMaxGroups / 4); i += kTcThreads)
+    reinterpret_cast<int*>(grp_s)[i] = reinterpret_cast<const int*>(P.grp)[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
@@ -551,7 +572,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which of the quarter's two warps
     const int row = q * 32 + lane;
-    const int hh = row >> 3, ww = row & 7;
+    const int hh = P.pl2 ? (row >> 3) & 7 : row >> 3, ww = row & 7;
+    const int dr = P.pl2 ? row >> 6 : 0;    // small-plane tiles: rows 64..127 are the second d-plane
     const int et = threadIdx.x - 64;        // 0..255
     const int ew = warp - 2;                // 0..7: statistics slot
     const long long Vo = (long long)P.Do * P.Ho * P.Wo;
@@ -656,7 +678,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
           const int u = u0 + 2 * k;
           const int acc = u < nunits ? u / n16 : 0;
           c16s[k] = u < nunits ? u - acc * n16 : 0;
-          const int od = P.out_mul * (wi.d0 + P.acc_pd[acc]) + P.acc_qd[acc];
+          const int od = P.out_mul * (wi.d0 + P.acc_pd[acc] + dr) + P.acc_qd[acc];
           const int oh = P.out_mul * (wi.h0 + hh) + P.acc_qh[acc];
           const int ow = P.out_mul * (wi.w0 + ww) + P.acc_qw[acc];
           valid[k] = u < nunits && od < P.Do && oh < P.Ho && ow < P.Wo;
@@ -881,9 +903,14 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const int split = in_dtype == TTA_F16_HI ? 0 : 1;
   const bool query = q_ksplit != nullptr;  // shape the launch only: report split-K factor and grid
   TTA_REQUIRE(query || (in_hi && (in_lo || !split) && wpacked && out), "tta_conv_tc: null pointer");
-  const int geom = geom_of(mode, K, stride);
+  int geom = geom_of(mode, K, stride);
   TTA_REQUIRE(geom != GEOM_NONE, "tta_conv_tc: unsupported geometry mode=%d K=%d stride=%d", mode, K, stride);
   TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_tc: bad dtype");
+  // small planes (8^3 level): two d-planes per 128-row tile (see issue_group); flags bit5 keeps the
+  // one-plane tiles (testing: both must agree)
+  const bool pl2 = (geom == GEOM_S1 || geom == GEOM_S1T) && Ho <= 8 && Do >= 2 && !(flags & 32);
+  if (pl2) geom = geom == GEOM_S1 ? GEOM_S1P : GEOM_S1TP;
+  const int ppa = pl2 ? 2 : 1;  // d-planes per accumulator
   const long long Vi = (long long)Di * Hi * Wi;
   TTA_REQUIRE(in_ns % (Vi * 8) == 0, "tta_conv_tc: n_stride must be a whole number of channel chunks");
   const int c8_pitch = (int)(in_ns / (Vi * 8));
@@ -920,25 +947,28 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   int Td, Th, Tw;  // extents of the tile space
   if (geom == GEOM_T2) { Td = Di; Th = Hi; Tw = Wi; } else { Td = Do; Th = Ho; Tw = Wo; }
   int hx, wx;      // halo extents of the single-box geometries
-  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else { hx = 18; wx = 10; }
-  const int gmax = tta_conv_tc_gmax(mode, K, stride);
-  P.ngroups = tta_conv_tc_ngroups(mode, K, stride);
+  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else if (pl2) { hx = 8; wx = 10; } else { hx = 18; wx = 10; }
+  // small-plane tiles regroup the SAME packed weights: 9 (kd, kh) groups of 3 kw entries instead of 3 kd groups of 9
+  const int gmax = pl2 ? 3 : tta_conv_tc_gmax(mode, K, stride);
+  P.ngroups = pl2 ? 9 : tta_conv_tc_ngroups(mode, K, stride);
+  P.pl2 = pl2 ? 1 : 0;
   const int acc_cols = split ? 2 * P.ntile : P.ntile;
   P.b_entry_bytes = 2 * acc_cols * 16;  // [kchunk 2][hi NT (| lo NT) rows][16 B]
   P.b_blob_bytes = gmax * P.b_entry_bytes;
 
   // ---- shape the work item: TD d-planes (B-operand reuse), TMEM double buffering, pipeline depth.
   // TMEM columns: nbuf * nacc * 2*NT <= 512.
-  const bool conv_like = geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1;
+  const bool conv_like = geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1 || pl2;
+  // td = accumulators per work item (each ppa d-planes)
   int td_max = 1;
   if (conv_like) {
     td_max = 512 / acc_cols;
     if (td_max > 4) td_max = 4;
-    if (td_max > Td) td_max = Td;
+    if (td_max > (Td + ppa - 1) / ppa) td_max = (Td + ppa - 1) / ppa;
     if (td_max < 1) td_max = 1;
     if (flags & 1) td_max = 1;
   }
-  auto a_plane_of = [&](int td_) { return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * 16); };
+  auto a_plane_of = [&](int td_) { return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * ppa * 16); };
   const int a_planes = split ? 2 : 1;
   // small-channel layers (C <= 32: the full-resolution levels, where items are many): keep ALL
   // weights of the single n-tile resident -> the per-stage B re-fetch (up to 2/3 of the L2->SM fill
@@ -954,7 +984,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   int nbuf = (2 * nacc * acc_cols <= 512) ? 2 : 1;
   {
     // many work items: trade TD for the second accumulator buffer (epilogue/main-loop overlap)
-    const long long tiles_now = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td - 1) / td);
+    const long long tiles_now = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td * ppa - 1) / (td * ppa));
     if (nbuf == 1 && conv_like && td > 1 && tiles_now * N * P.n_ntiles > 2LL * num_sms()) {
       const int t2 = td / 2;
       if (2 * t2 * acc_cols <= 512) { td = t2; nacc = td; nbuf = 2; }
@@ -964,7 +994,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     // SM-starved layers (16^3 / 8^3 levels): even with the split-K factor capped at ncblk/2 the grid
     // may fill less than half of the SMs -> fewer d-planes per item (more, shorter items) until it does
     auto items_of = [&](int td_) {
-      const long long it = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td_ - 1) / td_) * P.n_ntiles * N;
+      const long long it = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td_ * ppa - 1) / (td_ * ppa)) * P.n_ntiles * N;
       long long ks = 1;
       if (it < num_sms() && P.ncblk >= 4) {
         ks = (num_sms() + it - 1) / it;
@@ -976,11 +1006,11 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     nacc = td;
     nbuf = (2 * nacc * acc_cols <= 512) ? 2 : 1;
   }
-  P.td = td; P.nacc = nacc; P.nbuf = nbuf;
+  P.td = td * ppa; P.nacc = nacc; P.nbuf = nbuf;   // P.td: d-planes per work item
   P.a_plane_bytes = a_plane_of(td);
   P.stage_bytes = stage_bytes_of(td);
   P.b_off = a_planes * P.a_plane_bytes;
-  P.lbo16[0] = round128(hx * wx * td * 16) / 16;
+  P.lbo16[0] = round128(hx * wx * td * ppa * 16) / 16;
   // pipeline depth from what THIS instantiation leaves free (the statistics variants carry 8-10 KB of
   // static slots); td / split-K above were shaped with the most conservative budget so that
   // tta_conv_tc_query and the launch always agree on the grid
@@ -993,7 +1023,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   while (cols < nbuf * nacc * acc_cols) cols *= 2;
   TTA_REQUIRE(cols <= 512, "tta_conv_tc: %d accumulator columns exceed TMEM", nbuf * nacc * acc_cols);
   P.tmem_cols = cols;
-  P.tiles_w = (Tw + 7) / 8; P.tiles_h = (Th + 15) / 16; P.tiles_d = (Td + td - 1) / td;
+  P.tiles_w = (Tw + 7) / 8; P.tiles_h = (Th + 15) / 16; P.tiles_d = (Td + P.td - 1) / P.td;
 
   // ---- split-K over channel blocks when the tile grid cannot fill the SMs
   {
@@ -1109,8 +1139,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
         }
       }
   } else {
-    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? 1 : td);
-    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, geom == GEOM_T2 ? 1 : td);
+    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? 1 : td * ppa);
+    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, geom == GEOM_T2 ? 1 : td * ppa);
   }
   TTA_REQUIRE(ok, "tta_conv_tc: cuTensorMapEncodeTiled failed (dims %d,%d,%d C8 pitch %d)", Di, Hi, Wi, c8_pitch);
 
@@ -1123,6 +1153,16 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
       G.tx_bytes = 2 * G.ld[0].bytes;
     }
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
+  } else if (pl2) {
+    for (int g = 0; g < 9; ++g) {
+      const int kd = g / 3, kh = g % 3;
+      TcGroup& G = P.grp[g];
+      G.nloads = 1; G.nmma = 3;
+      G.ld[0] = {0, -1, geom == GEOM_S1P ? kh - 1 : 1 - kh, geom == GEOM_S1P ? kd - 1 : 1 - kd, 0,
+                 8 * 10 * td * ppa * 16, P.lbo16[0] * 16, 0};
+      G.tx_bytes = 2 * G.ld[0].bytes;
+    }
+    for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)(2 * p);
   } else if (geom == GEOM_K1) {
     TcGroup& G = P.grp[0];
     G.nloads = 1; G.nmma = 1;
@@ -1216,6 +1256,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     case GEOM_S1: TTA_TC_LAUNCH_TD(GEOM_S1); break;
     case GEOM_S1T: TTA_TC_LAUNCH_TD(GEOM_S1T); break;
     case GEOM_K1: TTA_TC_LAUNCH_TD(GEOM_K1); break;
+    case GEOM_S1P: TTA_TC_LAUNCH_TD(GEOM_S1P); break;
+    case GEOM_S1TP: TTA_TC_LAUNCH_TD(GEOM_S1TP); break;
     case GEOM_S2: TTA_TC_LAUNCH(GEOM_S2, 1); break;
     default: TTA_TC_LAUNCH(GEOM_T2, 1); break;
   }

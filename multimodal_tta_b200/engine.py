@@ -396,7 +396,7 @@ class TTAEngine:
         if use_tc:
             wp = cl.packed["tc_" + key]
             plan.keep.append(wp)
-            flags = (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0)
+            flags = (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0) | self.model.tc_flags
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
                     *odims, mode, cl.K, cl.stride, int(accumulate), flags)
             if stats_res is not None:

@@ -148,6 +148,8 @@ class UNetB200(nn.Module):
         self.use_cuda_graph = bool(get_config(cfg, "cuda_graph", True))
         # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
         self.deterministic = bool(get_config(cfg, "deterministic", False))
+        # extra tta_conv_tc flag bits for A/B experiments (include/tta_b200.h), e.g. 32 = one-plane tiles
+        self.tc_flags = int(get_config(cfg, "tc_flags", 0))
         # run a ResidualUnit's unit0 conv and its strided 3x3x3 shortcut conv as ONE launch
         self.fuse_shortcut = bool(get_config(cfg, "fuse_shortcut", True))
         # run the full-resolution tail (norm apply + 3x3x3 conv + entropy, and its backward) as two

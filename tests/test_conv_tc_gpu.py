@@ -24,7 +24,9 @@ GEOMS = [  # cin, cout, K, stride, transposed, dims
     (4, 32, 3, 2, False, (8, 32, 16)),      # stem: cin 4 -> one chunk + OOB k-chunk
     (32, 64, 3, 2, False, (8, 16, 16)),
     (64, 128, 3, 2, False, (4, 12, 12)),
-    (128, 256, 3, 1, False, (2, 6, 6)),     # n-tiles = 2, tiny spatial
+    (128, 256, 3, 1, False, (2, 6, 6)),     # n-tiles = 2, tiny spatial (two-plane tiles, ragged h/w)
+    (256, 512, 3, 1, False, (8, 8, 8)),     # bottleneck: two d-planes per 128-row tile, split-K
+    (64, 64, 3, 1, False, (5, 8, 16)),      # two-plane tiles, odd plane count, two w-tiles
     (48, 16, 3, 2, True, (3, 10, 6)),       # transposed s2, ragged
     (64, 3, 3, 2, True, (4, 16, 8)),        # head convT: cout 3 -> N=16 tile
     (3, 3, 3, 1, False, (8, 16, 16)),       # head conv 3->3
@@ -72,6 +74,14 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
         _tc(lib, hi, lo, *args, o_res, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2)
         _tc(lib, hi, lo, *args, o_str, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 16)
         assert torch.equal(o_res, o_str)
+    if K == 3 and s == 1 and dims[1] <= 8:
+        # small planes: two d-planes per 128-row tile (9 (kd, kh) groups) vs. one plane per tile (flags
+        # bit5): the same products enter every accumulator in the same order -> identical result
+        o_p2 = torch.zeros_like(out); o_p1 = torch.zeros_like(out)
+        args = (c8i * xv[0, 0].numel() * 8, TTA_F16, N, c8i, dims, wp, pack_bias(b.to(cuda)))
+        _tc(lib, hi, lo, *args, o_p2, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2)
+        _tc(lib, hi, lo, *args, o_p1, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 32)
+        assert torch.equal(o_p2, o_p1)
     if not tr and s == 2:
         # w-parity-split operand layout (flags bit3): same MMAs on the same bits -> identical result
         o_std = torch.zeros_like(out); o_ws = torch.zeros_like(out)
