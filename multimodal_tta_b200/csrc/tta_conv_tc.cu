@@ -57,6 +57,7 @@ struct TcParams {
   int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n, idesc0, pad_i;
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
+  int t2_jh16;  // GEOM_T2: offset (16 B units) of the h+1 halo rows inside a k-chunk: 9 = next row, or a second box
   int pl2;      // small-plane tiles (H <= 8): the 128 rows are 2 d-planes x 8 h x 8 w (GEOM_S1P / GEOM_S1TP)
   // fused norm statistics: per-CTA partial sums of y and y^2 over the leading stats_c8 chunks of the
   // output, layout [n][chunk][cta][16] (0..7 sum, 8..15 sum of squares) = what tta_norm_apply
@@ -297,7 +298,7 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
                                {5, 1, 0, 1}, {7, 1, 0, 1}, {3, 1, 1, 1}, {7, 1, 1, 1}};  // {acc0, k, jh, jw}
     constexpr int kG1[5][4] = {{4, 4, 0, 0}, {6, 2, 1, 0}, {5, 1, 0, 1}, {7, 1, 0, 1}, {7, 1, 1, 1}};
     auto stack = [&](int acc0, int k, int jh, int jw, uint32_t tap_off, bool overwrite) {
-      const uint32_t ao = (uint32_t)(jh * 9 + jw);
+      const uint32_t ao = (uint32_t)jh * (uint32_t)P.t2_jh16 + (uint32_t)jw;  // two-plane tiles: the jh = 1 rows are a second box
       const uint32_t lbo_b = ((uint32_t)k * acc_cols) << 16;          // rows of the whole stack per k-chunk
       const uint32_t sbase = (bsrc >> 4) + tap_off * b_ent;
       const uint32_t kk = (uint32_t)k > maxk ? maxk : (uint32_t)k;
@@ -910,7 +911,10 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   // one-plane tiles (testing: both must agree)
   const bool pl2 = (geom == GEOM_S1 || geom == GEOM_S1T) && Ho <= 8 && Do >= 2 && !(flags & 32);
   if (pl2) geom = geom == GEOM_S1 ? GEOM_S1P : GEOM_S1TP;
-  const int ppa = pl2 ? 2 : 1;  // d-planes per accumulator
+  // transposed stride-2 conv over small INPUT planes: same idea, rows 64..127 = input plane d0 + 1;
+  // the (jh = 0, jh = 1) halo rows become two 8-row boxes so that the plane pitch stays 8 rows
+  const bool pl2t = geom == GEOM_T2 && Hi <= 8 && Di >= 2 && !(flags & 32);
+  const int ppa = (pl2 || pl2t) ? 2 : 1;  // d-planes per accumulator
   const long long Vi = (long long)Di * Hi * Wi;
   TTA_REQUIRE(in_ns % (Vi * 8) == 0, "tta_conv_tc: n_stride must be a whole number of channel chunks");
   const int c8_pitch = (int)(in_ns / (Vi * 8));
@@ -947,17 +951,39 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   int Td, Th, Tw;  // extents of the tile space
   if (geom == GEOM_T2) { Td = Di; Th = Hi; Tw = Wi; } else { Td = Do; Th = Ho; Tw = Wo; }
   int hx, wx;      // halo extents of the single-box geometries
-  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else if (pl2) { hx = 8; wx = 10; } else { hx = 18; wx = 10; }
+  if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (pl2t) { hx = 8; wx = 9; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else if (pl2) { hx = 8; wx = 10; } else { hx = 18; wx = 10; }
   // small-plane tiles regroup the SAME packed weights: 9 (kd, kh) groups of 3 kw entries instead of 3 kd groups of 9
   const int gmax = pl2 ? 3 : tta_conv_tc_gmax(mode, K, stride);
   P.ngroups = pl2 ? 9 : tta_conv_tc_ngroups(mode, K, stride);
-  P.pl2 = pl2 ? 1 : 0;
+  P.pl2 = (pl2 || pl2t) ? 1 : 0;
+  P.t2_jh16 = pl2t ? 144 : 9;
   const int acc_cols = split ? 2 * P.ntile : P.ntile;
   P.b_entry_bytes = 2 * acc_cols * 16;  // [kchunk 2][hi NT (| lo NT) rows][16 B]
   P.b_blob_bytes = gmax * P.b_entry_bytes;
 
   // ---- shape the work item: TD d-planes (B-operand reuse), TMEM double buffering, pipeline depth.
   // TMEM columns: nbuf * nacc * 2*NT <= 512.
+  // split-K factor for `items` tile-level work items: the one that minimises (waves of CTAs) x (channel
+  // blocks per split + ~2 blocks' worth of pipeline fill / epilogue per wave).  Rounding the factor UP
+  // to fill the SMs (e.g. 64 items x 3 = 192 CTAs on 148 SMs) costs a second wave.
+  auto choose_ks = [&](long long items) -> int {
+    if ((flags & 2) || items >= num_sms() || P.ncblk < 4) return 1;
+    if (flags & 64) {  // A/B switch: round the factor up to fill the SMs
+      long long k = (num_sms() + items - 1) / items;
+      if (k > P.ncblk / 2) k = P.ncblk / 2;
+      const int cbs = (P.ncblk + (int)k - 1) / (int)k;
+      return (P.ncblk + cbs - 1) / cbs;
+    }
+    int best = 1;
+    long long best_cost = -1;
+    for (int k = 1; k <= P.ncblk / 2; ++k) {
+      const int cbs = (P.ncblk + k - 1) / k, real = (P.ncblk + cbs - 1) / cbs;
+      const long long waves = (items * real + num_sms() - 1) / num_sms();
+      const long long cost = waves * (cbs + 2);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = real; }
+    }
+    return best;
+  };
   const bool conv_like = geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1 || pl2;
   // td = accumulators per work item (each ppa d-planes)
   int td_max = 1;
@@ -968,7 +994,10 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     if (td_max < 1) td_max = 1;
     if (flags & 1) td_max = 1;
   }
-  auto a_plane_of = [&](int td_) { return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * ppa * 16); };
+  auto a_plane_of = [&](int td_) {
+    if (pl2t) return 2 * 4608;  // [kchunk 2][jh 2][2 planes][8 rows][9 w][16 B]
+    return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * ppa * 16);
+  };
   const int a_planes = split ? 2 : 1;
   // small-channel layers (C <= 32: the full-resolution levels, where items are many): keep ALL
   // weights of the single n-tile resident -> the per-stage B re-fetch (up to 2/3 of the L2->SM fill
@@ -995,12 +1024,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     // may fill less than half of the SMs -> fewer d-planes per item (more, shorter items) until it does
     auto items_of = [&](int td_) {
       const long long it = (long long)((Tw + 7) / 8) * ((Th + 15) / 16) * ((Td + td_ * ppa - 1) / (td_ * ppa)) * P.n_ntiles * N;
-      long long ks = 1;
-      if (it < num_sms() && P.ncblk >= 4) {
-        ks = (num_sms() + it - 1) / it;
-        if (ks > P.ncblk / 2) ks = P.ncblk / 2;
-      }
-      return it * ks;
+      return it * choose_ks(it);
     };
     while (td > 1 && items_of(td) * 2 <= num_sms()) td = (td + 1) / 2;
     nacc = td;
@@ -1010,7 +1034,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.a_plane_bytes = a_plane_of(td);
   P.stage_bytes = stage_bytes_of(td);
   P.b_off = a_planes * P.a_plane_bytes;
-  P.lbo16[0] = round128(hx * wx * td * ppa * 16) / 16;
+  P.lbo16[0] = pl2t ? 4608 / 16 : round128(hx * wx * td * ppa * 16) / 16;
   // pipeline depth from what THIS instantiation leaves free (the statistics variants carry 8-10 KB of
   // static slots); td / split-K above were shaped with the most conservative budget so that
   // tta_conv_tc_query and the launch always agree on the grid
@@ -1028,12 +1052,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   // ---- split-K over channel blocks when the tile grid cannot fill the SMs
   {
     const long long items = (long long)P.tiles_w * P.tiles_h * P.tiles_d * P.n_ntiles * N;
-    int ks = 1;
-    if (!(flags & 2) && items < num_sms() && P.ncblk >= 4) {
-      ks = (int)((num_sms() + items - 1) / items);
-      if (ks > P.ncblk / 2) ks = P.ncblk / 2;
-      if (ks < 1) ks = 1;
-    }
+    const int ks = choose_ks(items);
     P.cb_per_split = (P.ncblk + ks - 1) / ks;
     P.ksplit = (P.ncblk + P.cb_per_split - 1) / P.cb_per_split;
     P.work_items = (int)(items * P.ksplit);
@@ -1139,8 +1158,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
         }
       }
   } else {
-    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? 1 : td * ppa);
-    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, geom == GEOM_T2 ? 1 : td * ppa);
+    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? ppa : td * ppa);
+    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, geom == GEOM_T2 ? ppa : td * ppa);
   }
   TTA_REQUIRE(ok, "tta_conv_tc: cuTensorMapEncodeTiled failed (dims %d,%d,%d C8 pitch %d)", Di, Hi, Wi, c8_pitch);
 
@@ -1197,8 +1216,14 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
       TcGroup& G = P.grp[jd];
       G.nloads = 1;
       G.nmma = jd == 0 ? 18 : 9;
-      G.ld[0] = {0, 0, 0, jd, 0, 17 * 9 * 16, P.lbo16[0] * 16, 0};
-      G.tx_bytes = 2 * G.ld[0].bytes;
+      if (pl2t) {
+        G.nloads = 2;
+        for (int jh = 0; jh < 2; ++jh) G.ld[jh] = {0, 0, jh, jd, jh * 2304, 2304, 4608, 0};
+        G.tx_bytes = 2 * 2 * 2304;
+      } else {
+        G.ld[0] = {0, 0, 0, jd, 0, 17 * 9 * 16, P.lbo16[0] * 16, 0};
+        G.tx_bytes = 2 * G.ld[0].bytes;
+      }
     }
     for (int a = 0; a < 8; ++a) {
       P.acc_pd[a] = 0; P.acc_qd[a] = (signed char)(a >> 2); P.acc_qh[a] = (signed char)((a >> 1) & 1);

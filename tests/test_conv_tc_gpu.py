@@ -29,6 +29,8 @@ GEOMS = [  # cin, cout, K, stride, transposed, dims
     (64, 64, 3, 1, False, (5, 8, 16)),      # two-plane tiles, odd plane count, two w-tiles
     (48, 16, 3, 2, True, (3, 10, 6)),       # transposed s2, ragged
     (64, 3, 3, 2, True, (4, 16, 8)),        # head convT: cout 3 -> N=16 tile
+    (256, 64, 3, 2, True, (4, 8, 8)),       # transposed s2 over small planes: two input planes per tile
+    (40, 24, 3, 2, True, (3, 6, 5)),        # ... ragged, odd plane count
     (3, 3, 3, 1, False, (8, 16, 16)),       # head conv 3->3
     (256, 512, 1, 1, False, (4, 8, 8)),     # 1x1 shortcut
     (96, 40, 3, 1, False, (3, 9, 9)),       # odd chunk counts
@@ -74,7 +76,7 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
         _tc(lib, hi, lo, *args, o_res, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2)
         _tc(lib, hi, lo, *args, o_str, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 16)
         assert torch.equal(o_res, o_str)
-    if K == 3 and s == 1 and dims[1] <= 8:
+    if K == 3 and dims[1] <= 8 and (s == 1 or tr):
         # small planes: two d-planes per 128-row tile (9 (kd, kh) groups) vs. one plane per tile (flags
         # bit5): the same products enter every accumulator in the same order -> identical result
         o_p2 = torch.zeros_like(out); o_p1 = torch.zeros_like(out)
