@@ -219,7 +219,7 @@ def run_product(args):
     h2d = xs_host[0].numel() * 4
 
     # ---- live per-kernel-family timing (eager, CUDA events on the launching stream)
-    roof = kernel_family_times(torch, eng, tent, xs, min(K, 3))
+    roof = kernel_family_times(torch, eng, tent, xs, min(K, 3), args.per_op if rank == 0 else None)
     pk = peaks()
     conv_tflops = BATCH * CONV_GFLOP_PER_VOLUME / 1e3 / (roof["conv_ms"] / 1e3)
     # algorithmic HBM bytes (SURVEY 8d at s = 4 B/element): norm fwd 2*N*s + bwd 3*N*s, entropy 2*C*V*4
@@ -266,7 +266,7 @@ def run_product(args):
         dist.destroy_process_group()
 
 
-def kernel_family_times(torch, eng, tent, xs, reps: int):
+def kernel_family_times(torch, eng, tent, xs, reps: int, per_op_path=None):
     """Eager replay with a CUDA event pair around every op; returns per-step ms by family."""
     plan = eng.plans[(BATCH, *DIMS)]
     ops = [("stream", lambda: eng._pack_input(plan, xs[0]))]
@@ -274,6 +274,7 @@ def kernel_family_times(torch, eng, tent, xs, reps: int):
     ops += [("stream", plan.head_train)]
     ops += [("conv" if getattr(o, "__qualname__", "").find("_conv_call") >= 0 else "stream", o) for o in plan.bwd]
     acc = {"conv": 0.0, "stream": 0.0}
+    per_op = [0.0] * len(ops)
     nconv = sum(1 for k, _ in ops if k == "conv")
     for _ in range(reps):
         evs = []
@@ -287,8 +288,15 @@ def kernel_family_times(torch, eng, tent, xs, reps: int):
             a.record(); op(); b.record()
             evs.append((kind, a, b))
         torch.cuda.synchronize()
-        for kind, a, b in evs:
+        for i, (kind, a, b) in enumerate(evs):
             acc[kind] += a.elapsed_time(b)
+            per_op[i] += a.elapsed_time(b)
+    if per_op_path:
+        # in-stream duration of every op of the step (warm L2, back to back) -- what the graph replays
+        with open(per_op_path, "w") as f:
+            for i, (kind, op) in enumerate(ops):
+                lab = getattr(op, "label", getattr(op, "__qualname__", "?").split(".")[-1])
+                f.write(f"{i:3d} {kind:6s} {per_op[i] / reps * 1e3:8.1f} us  {lab}\n")
     return {"conv_ms": acc["conv"] / reps, "stream_ms": acc["stream"] / reps,
             "total_ms": (acc["conv"] + acc["stream"]) / reps, "conv_launches": nconv}
 
@@ -302,6 +310,7 @@ def main():
     ap.add_argument("--conv-backend", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--per-op", default=None, help="write the in-stream duration of every op of one step to this file")
     ap.add_argument("--set", action="append", help="model config override key=value (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":

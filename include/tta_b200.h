@@ -64,6 +64,9 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
  * weights, bit5 one d-plane per 128-row tile even when H <= 8 (default there: two planes per tile). */
 int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout);
 int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split);
+/* 1 when this layer runs kd-stacked (stride-1, single small n-tile, resident weights): its packed
+ * weight layout differs (layout.pack_weights_tc), so packer and kernel ask the same question. */
+int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int split);
 int tta_conv_tc_gmax(int mode, int K, int stride);
 int tta_conv_tc_ngroups(int mode, int K, int stride);
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout);

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "tta_conv_small": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, P]),
     "tta_conv_tc_supported": (I, [I, I, I, I, I]),
     "tta_conv_tc_ntile": (I, [I, I, I, I, I]),
+    "tta_conv_tc_stacked": (I, [I, I, I, I, I, I]),
     "tta_conv_tc_gmax": (I, [I, I, I]),
     "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),

@@ -27,6 +27,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "tta_common.cuh"
 
@@ -38,7 +40,7 @@ constexpr int kMaxLoads = 4;
 constexpr int kMaxAcc = 8;
 constexpr int kMaxStages = 8;
 
-enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2, GEOM_S1P, GEOM_S1TP };
+enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2, GEOM_S1P, GEOM_S1TP, GEOM_S1K, GEOM_S1TK };
 
 struct TcLoad {
   int map, dw, dh, dd, smem_off, bytes, chunk_pitch, pad;  // bytes / pitch are per k-chunk (8 channels)
@@ -57,6 +59,7 @@ struct TcParams {
   int out_mul, Do, Ho, Wo, C8out, accumulate, idesc_n, idesc_2n, idesc0, pad_i;
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
+  int b_nblob, b_cb_bytes, b_g_bytes;  // resident weights: blobs to copy; bytes per channel block / per group
   int t2_jh16;  // GEOM_T2: offset (16 B units) of the h+1 halo rows inside a k-chunk: 9 = next row, or a second box
   int pl2;      // small-plane tiles (H <= 8): the 128 rows are 2 d-planes x 8 h x 8 w (GEOM_S1P / GEOM_S1TP)
   // fused norm statistics: per-CTA partial sums of y and y^2 over the leading stats_c8 chunks of the
@@ -235,6 +238,54 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
         for (int p = 0; p < TD; ++p) {
           const uint32_t ao = (uint32_t)(rh * 10 + rw + p * 180);
           mma_pair<SPLIT>(leader, tmem_acc0 + p * acc_cols, ah + ao, al + ao, a_w1, bo, b_w1, i2n, in_, accum);
+        }
+      }
+  } else if (GEOM == GEOM_S1K || GEOM == GEOM_S1TK) {
+    // kd-STACKED stride-1 conv for small n-tiles.  A tcgen05.mma of M = 128, K = 16 costs
+    // max(64, N/2) cycles (measured: the N = 32 and N = 64 MMAs of the 32-channel layers ran ~70 cycles
+    // each), so one MMA per (plane, tap) wastes the tensor pipe when N = acc_cols < 128.  The input
+    // plane j = g of the (TD + 2)-plane halo feeds output planes j-2 .. j through the three kd taps of a
+    // (kh, kw) pair: ONE MMA over the stack of their weights (slot s -> accumulator j - 2 + s,
+    // accumulators contiguous in TMEM, N = k * acc_cols <= 192).  Stage = one halo plane (loaded once
+    // per channel block instead of once per kd); weights are resident, entry (kh, kw) =
+    // [kchunk][slot 0..2][hi NT | lo NT][8].  With split planes A_hi and A_lo both multiply the whole
+    // [B_hi | B_lo] stack (as GEOM_T2 does; the extra lo*lo term is below fp32 resolution).
+    const uint32_t a_w1 = 10u | (1u << 14);
+    const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
+    const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;
+    const int j = g;
+    const int s_lo = j < 2 ? 2 - j : 0, s_hi = (TD + 1 - j) < 2 ? (TD + 1 - j) : 2;
+    const uint32_t k = (uint32_t)(s_hi - s_lo + 1);
+    const uint32_t d0 = tmem_acc0 + (uint32_t)(j - 2 + s_lo) * acc_cols;
+    const uint32_t lbo_b = (3u * acc_cols) << 16;                      // rows of all three slots per k-chunk
+    const uint32_t sbase = (bsrc >> 4) + (uint32_t)s_lo * acc_cols;    // 16-byte rows
+    const uint32_t idesc_k = P.idesc0 | (((k * acc_cols) >> 3) << 17);
+    const uint32_t idesc_k1 = P.idesc0 | ((((k - 1u) * acc_cols) >> 3) << 17);
+    const uint32_t idesc_1 = P.idesc0 | ((acc_cols >> 3) << 17);
+    const bool fresh = first && j < TD;   // first channel block: accumulator j (the top slot) starts here
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int rh = GEOM == GEOM_S1K ? kh : 2 - kh, rw = GEOM == GEOM_S1K ? kw : 2 - kw;
+        const uint32_t ao = (uint32_t)(rh * 10 + rw);
+        const uint32_t bw0 = (sbase + (uint32_t)(kh * 3 + kw) * b_ent) | lbo_b;
+        const uint64_t bd = ((uint64_t)b_w1 << 32) | bw0;
+        const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | (ah + ao), ad_lo = ((uint64_t)a_w1 << 32) | (al + ao);
+        if (fresh && kh == 0 && kw == 0) {
+          // the older accumulators of the stack accumulate, the fresh one is overwritten
+          const uint64_t bd_top = ((uint64_t)b_w1 << 32) | ((bw0 + (k - 1u) * acc_cols));
+          if (leader) {
+            if (k > 1u) {
+              umma_f16(d0, ad_hi, bd, idesc_k1, 1u);
+              if (SPLIT) umma_f16(d0, ad_lo, bd, idesc_k1, 1u);
+            }
+            umma_f16(d0 + (k - 1u) * acc_cols, ad_hi, bd_top, idesc_1, 0u);
+            if (SPLIT) umma_f16(d0 + (k - 1u) * acc_cols, ad_lo, bd_top, idesc_1, 1u);
+          }
+        } else if (leader) {
+          umma_f16(d0, ad_hi, bd, idesc_k, 1u);
+          if (SPLIT) umma_f16(d0, ad_lo, bd, idesc_k, 1u);
         }
       }
   } else if (GEOM == GEOM_S1P || GEOM == GEOM_S1TP) {
@@ -478,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // ~300 cycles per copy on index arithmetic and constant-bank lookups).
     if (P.b_res && lane == 0 && warp == 0) {
       // weights never change: one copy per CTA lifetime instead of one per stage
-      const int nblob = P.ncblk * P.ngroups;
+      const int nblob = P.b_nblob;
       mbar_expect_tx(smem_u32(&bar_bres), (uint32_t)(nblob * P.b_blob_bytes));
       for (int b = 0; b < nblob; ++b)
         bulk_load(smem_base + P.b_res_off + b * P.b_blob_bytes, P.wpacked + (long long)b * P.b_blob_bytes,
@@ -547,17 +598,17 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc0 = tmem_base + buf * buf_cols;
       int g = 0;
-      uint32_t bres = smem_base + P.b_res_off + (uint32_t)(wi.cb0 * P.ngroups) * P.b_blob_bytes;
+      uint32_t bres = smem_base + P.b_res_off + (uint32_t)wi.cb0 * (uint32_t)P.b_cb_bytes;
       for (int it = 0; it < wi.nit; ++it) {
         mbar_wait(smem_u32(&bar_full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t stage = smem_base + s * P.stage_bytes;
-        const uint32_t bsrc = P.b_res ? bres : stage + P.b_off;
-        issue_group<GEOM, TD, SPLIT>(P, leader, g, stage, bsrc, acc0, it == 0);
+        const uint32_t bsrc = P.b_res ? bres + (uint32_t)g * (uint32_t)P.b_g_bytes : stage + P.b_off;
+        constexpr bool kStacked = GEOM == GEOM_S1K || GEOM == GEOM_S1TK;
+        issue_group<GEOM, TD, SPLIT>(P, leader, g, stage, bsrc, acc0, kStacked ? it < P.ngroups : it == 0);
         __syncwarp();
         if (leader) umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
-        bres += P.b_blob_bytes;
-        if (++g == P.ngroups) g = 0;
+        if (++g == P.ngroups) { g = 0; bres += P.b_cb_bytes; }
         if (++s == P.nstages) { s = 0; ph ^= 1; }
       }
       if (leader) umma_commit(smem_u32(&bar_acc_full[buf]));  // accumulators of this item complete
@@ -854,6 +905,20 @@ static int ntile_of(int geom, int cout, int split) {
 
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
+// kd-stacked stride-1 convs (GEOM_S1K / GEOM_S1TK, see issue_group): single n-tile, three accumulators
+// within one MMA (3 * acc_cols <= 256) and all weights resident in shared memory.  A function of the
+// layer alone, because the PACKED WEIGHT LAYOUT depends on it (layout.pack_weights_tc asks).
+static bool stacked_of(int geom, int cin, int cout, int split) {
+  if (geom != GEOM_S1 && geom != GEOM_S1T) return false;
+  const int cout_pad = (cout + 7) / 8 * 8;
+  const int nt = ntile_of(geom, cout_pad, split);
+  if ((cout_pad + nt - 1) / nt != 1) return false;
+  const int acc_cols = split ? 2 * nt : nt;
+  if (3 * acc_cols > 256) return false;
+  const int ncblk = (cin + 15) / 16;
+  return (long long)ncblk * 27 * 2 * acc_cols * 16 <= 112 * 1024;
+}
+
 static int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -878,6 +943,10 @@ int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout) {
 
 int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split) {
   return ntile_of(geom_of(mode, K, stride), cout, split);
+}
+
+int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int split) {
+  return stacked_of(geom_of(mode, K, stride), cin, cout, split) ? 1 : 0;
 }
 
 int tta_conv_tc_gmax(int mode, int K, int stride) {
@@ -909,6 +978,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_tc: bad dtype");
   // small planes (8^3 level): two d-planes per 128-row tile (see issue_group); flags bit5 keeps the
   // one-plane tiles (testing: both must agree)
+  const bool stacked = stacked_of(geom, C8in * 8, C8out * 8, in_dtype == TTA_F16_HI ? 0 : 1);
+  if (stacked) geom = geom == GEOM_S1 ? GEOM_S1K : GEOM_S1TK;
   const bool pl2 = (geom == GEOM_S1 || geom == GEOM_S1T) && Ho <= 8 && Do >= 2 && !(flags & 32);
   if (pl2) geom = geom == GEOM_S1 ? GEOM_S1P : GEOM_S1TP;
   // transposed stride-2 conv over small INPUT planes: same idea, rows 64..127 = input plane d0 + 1;
@@ -960,6 +1031,10 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const int acc_cols = split ? 2 * P.ntile : P.ntile;
   P.b_entry_bytes = 2 * acc_cols * 16;  // [kchunk 2][hi NT (| lo NT) rows][16 B]
   P.b_blob_bytes = gmax * P.b_entry_bytes;
+  if (stacked) {  // entry (kh, kw) = [kchunk 2][slot 3][hi NT (| lo NT)][16 B]; one blob per channel block
+    P.b_entry_bytes = 3 * 2 * acc_cols * 16;
+    P.b_blob_bytes = 9 * P.b_entry_bytes;
+  }
 
   // ---- shape the work item: TD d-planes (B-operand reuse), TMEM double buffering, pipeline depth.
   // TMEM columns: nbuf * nacc * 2*NT <= 512.
@@ -984,7 +1059,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     }
     return best;
   };
-  const bool conv_like = geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1 || pl2;
+  const bool conv_like = geom == GEOM_S1 || geom == GEOM_S1T || geom == GEOM_K1 || pl2 || stacked;
   // td = accumulators per work item (each ppa d-planes)
   int td_max = 1;
   if (conv_like) {
@@ -996,14 +1071,19 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   }
   auto a_plane_of = [&](int td_) {
     if (pl2t) return 2 * 4608;  // [kchunk 2][jh 2][2 planes][8 rows][9 w][16 B]
+    if (stacked) return 2 * round128(hx * wx * 16);  // a stage is ONE halo plane
     return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * ppa * 16);
   };
   const int a_planes = split ? 2 : 1;
   // small-channel layers (C <= 32: the full-resolution levels, where items are many): keep ALL
   // weights of the single n-tile resident -> the per-stage B re-fetch (up to 2/3 of the L2->SM fill
   // traffic of the stride-2 stem) disappears
-  const int b_total = P.ncblk * P.ngroups * P.b_blob_bytes;
-  const bool b_res = P.n_ntiles == 1 && geom != GEOM_T2 && b_total <= 112 * 1024 && !(flags & 16);
+  const int b_total = (stacked ? 1 : P.ngroups) * P.ncblk * P.b_blob_bytes;
+  // (transposed stride-2 convs: the head convT 64->3 re-fetched 28 KB of weights per 10 KB of A and ran at
+  // the L2->SM fill cap; its blobs reserve 18 entries per group, so the budget is what four A stages leave)
+  const int a_only_stage = round128((split ? 2 : 1) * a_plane_of(1));
+  const int b_res_cap = geom == GEOM_T2 ? 227 * 1024 - 14336 - 1024 - 4 * a_only_stage : 112 * 1024;
+  const bool b_res = stacked || (P.n_ntiles == 1 && b_total <= b_res_cap && !(flags & 16));
   P.b_res = b_res ? 1 : 0;
   auto stage_bytes_of = [&](int td_) { return round128(a_planes * a_plane_of(td_) + (b_res ? 0 : P.b_blob_bytes)); };
   const int smem_budget = 227 * 1024 - 14336 - (b_res ? b_total : 0);  // static smem: barriers, bias, statistics slots
@@ -1034,7 +1114,11 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.a_plane_bytes = a_plane_of(td);
   P.stage_bytes = stage_bytes_of(td);
   P.b_off = a_planes * P.a_plane_bytes;
-  P.lbo16[0] = pl2t ? 4608 / 16 : round128(hx * wx * td * ppa * 16) / 16;
+  P.lbo16[0] = pl2t ? 4608 / 16 : round128(hx * wx * (stacked ? 1 : td * ppa) * 16) / 16;
+  if (stacked) P.ngroups = td + 2;
+  P.b_nblob = stacked ? P.ncblk : P.ncblk * P.ngroups;
+  P.b_cb_bytes = stacked ? P.b_blob_bytes : P.ngroups * P.b_blob_bytes;
+  P.b_g_bytes = stacked ? 0 : P.b_blob_bytes;
   // pipeline depth from what THIS instantiation leaves free (the statistics variants carry 8-10 KB of
   // static slots); td / split-K above were shaped with the most conservative budget so that
   // tta_conv_tc_query and the launch always agree on the grid
@@ -1070,6 +1154,12 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     P.mg_tiles_w = magic((unsigned)P.tiles_w);
     P.mg_tiles_h = magic((unsigned)P.tiles_h);
   }
+  if (getenv("TTA_TC_DEBUG"))
+    fprintf(stderr, "tta_conv_tc: geom %d split %d N %d C8 %d->%d in %dx%dx%d | nt %d x%d ncblk %d | accs %d planes %d nbuf %d "
+            "stages %d x %d B bres %d | tiles %dx%dx%d ksplit %d (cb %d) items %d waves %.2f\n",
+            geom, split, N, C8in, C8out, Di, Hi, Wi, P.ntile, P.n_ntiles, P.ncblk, P.nacc, P.td, P.nbuf, P.nstages,
+            P.stage_bytes, P.b_res, P.tiles_d, P.tiles_h, P.tiles_w, P.ksplit, P.cb_per_split, P.work_items,
+            (double)P.work_items / num_sms());
   if (query) {
     *q_ksplit = P.ksplit;
     if (q_nbuf) *q_nbuf = P.nbuf;
@@ -1158,8 +1248,9 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
         }
       }
   } else {
-    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, geom == GEOM_T2 ? ppa : td * ppa);
-    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, geom == GEOM_T2 ? ppa : td * ppa);
+    const int box_d = geom == GEOM_T2 ? ppa : (stacked ? 1 : td * ppa);
+    ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, box_d);
+    if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, box_d);
   }
   TTA_REQUIRE(ok, "tta_conv_tc: cuTensorMapEncodeTiled failed (dims %d,%d,%d C8 pitch %d)", Di, Hi, Wi, c8_pitch);
 
@@ -1169,6 +1260,14 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
       TcGroup& G = P.grp[kd];
       G.nloads = 1; G.nmma = 9;
       G.ld[0] = {0, -1, -1, geom == GEOM_S1 ? kd - 1 : 1 - kd, 0, 18 * 10 * td * 16, P.lbo16[0] * 16, 0};
+      G.tx_bytes = 2 * G.ld[0].bytes;
+    }
+    for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
+  } else if (stacked) {
+    for (int j = 0; j < td + 2; ++j) {
+      TcGroup& G = P.grp[j];
+      G.nloads = 1; G.nmma = 9;
+      G.ld[0] = {0, -1, -1, j - 1, 0, 18 * 10 * 16, P.lbo16[0] * 16, 0};
       G.tx_bytes = 2 * G.ld[0].bytes;
     }
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
@@ -1281,6 +1380,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     case GEOM_S1: TTA_TC_LAUNCH_TD(GEOM_S1); break;
     case GEOM_S1T: TTA_TC_LAUNCH_TD(GEOM_S1T); break;
     case GEOM_K1: TTA_TC_LAUNCH_TD(GEOM_K1); break;
+    case GEOM_S1K: TTA_TC_LAUNCH_TD(GEOM_S1K); break;
+    case GEOM_S1TK: TTA_TC_LAUNCH_TD(GEOM_S1TK); break;
     case GEOM_S1P: TTA_TC_LAUNCH_TD(GEOM_S1P); break;
     case GEOM_S1TP: TTA_TC_LAUNCH_TD(GEOM_S1TP); break;
     case GEOM_S2: TTA_TC_LAUNCH(GEOM_S2, 1); break;

@@ -156,8 +156,11 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     const float* ys = y + (long long)n * y_ns + (long long)chunk * V * 8;
+    // gridDim.x > 1: a thread-block CLUSTER of gridDim.x CTAs owns the slab; every CTA reduces the
+    // voxels it will also apply (same stride as the apply loop -> its re-read hits L1/L2) and the
+    // per-CTA totals meet through distributed shared memory
 #pragma unroll 4
-    for (long long v = threadIdx.x; v < V; v += kThreads) {
+    for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V; v += (long long)gridDim.x * kThreads) {
       float x[8];
       load_f32x8(ys + v * 8, x);
 #pragma unroll
@@ -167,6 +170,7 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
       }
     }
     block_reduce_bcast<16>(acc, tot);
+    if (gridDim.x > 1) cluster_sum16(tot);
     const double M = (double)V;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -176,7 +180,7 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
       mu[i] = (float)m;
       rs[i] = (float)(1.0 / sqrt(var + (double)eps));
     }
-    if (threadIdx.x == 0) {  // keep them for the backward pass
+    if (threadIdx.x == 0 && blockIdx.x == 0) {  // keep them for the backward pass
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         mean_w[n * C + chunk * 8 + i] = mu[i];
@@ -382,7 +386,7 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
     const float* gs0 = g0 + (long long)n * g0_ns + sl;
     const float* gs1 = g1 ? g1 + (long long)n * g1_ns + sl : nullptr;
 #pragma unroll 2
-    for (long long v = threadIdx.x; v < V; v += kThreads) {
+    for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V; v += (long long)gridDim.x * kThreads) {
       float x[8], g[8];
       load_f32x8(ys + v * 8, x);
       load_f32x8(gs0 + v * 8, g);
@@ -401,13 +405,26 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
         acc[8 + i] = fmaf(dz, xh, acc[8 + i]);
       }
     }
-    block_reduce_bcast<16>(acc, tot, small_partial + (long long)(n * C8 + chunk) * 16);
+    if (gridDim.x == 1) {
+      block_reduce_bcast<16>(acc, tot, small_partial + (long long)(n * C8 + chunk) * 16);
+    } else {
+      // cluster of gridDim.x CTAs per slab: totals through distributed shared memory; CTA 0 of the
+      // cluster publishes them for the cross-sample dgamma / dbeta finalize
+      block_reduce_bcast<16>(acc, tot);
+      cluster_sum16(tot);
+      if (blockIdx.x == 0 && threadIdx.x < 16) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t = threadIdx.x == i ? tot[i] : t;
+        small_partial[(long long)(n * C8 + chunk) * 16 + threadIdx.x] = t;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       m1[i] = tot[i] * inv_m;
       m2[i] = tot[8 + i] * inv_m;
     }
-    if (last_block_of_chunk(small_counters, chunk, (unsigned int)N))
+    if (blockIdx.x == 0 && last_block_of_chunk(small_counters, chunk, (unsigned int)N))
       norm_bwd_finalize_tail(small_partial, C8, chunk, 1, N, 0, Creal, sums_w, dgamma, dbeta);
   } else if (partial != nullptr) {
     // reduction finalize fused here (no separate kernel): S1 = sum dz, S2 = sum dz*xhat
@@ -641,11 +658,20 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
   return tta_check_launch("tta_norm_bwd_apply");
 }
 
-// ---- small layers (V <= 4096 voxels per instance, per-instance statistics): statistics + apply,
-// and reduction + apply, as ONE launch each -- a CTA owns a whole (n, chunk) slab, reduces it, and
-// re-reads it from L1/L2.  The 8^3 / 16^3 levels are pure launch latency otherwise.
+// ---- small layers (V <= 65536 voxels per instance, per-instance statistics): statistics + apply,
+// and reduction + apply, as ONE launch each -- a CTA (V <= 512) or a thread-block cluster of up to 8
+// CTAs owns a whole (n, chunk) slab, reduces it (cluster: totals exchanged through distributed shared
+// memory), and re-reads it from L1/L2.  The 8^3 .. 32^3 levels are pure launch latency otherwise.
 int tta_norm_small_supported(int N, long long V, int batch_mode) {
-  return V >= 2 && V <= 4096 && !batch_mode && N >= 1;
+  return V >= 2 && V <= 65536 && !batch_mode && N >= 1;
+}
+
+// CTAs per (n, chunk) slab: 1 up to 512 voxels, else a thread-block cluster (<= 8, the portable
+// maximum) with >= 512 voxels per CTA, grown until the launch has ~2 CTAs per SM
+static inline int small_cluster(int N, int C8, long long V) {
+  int cs = 1;
+  while (cs < 8 && V / (cs * 2) >= 512 && (long long)N * C8 * cs < 2 * 148) cs *= 2;
+  return cs;
 }
 
 int tta_norm_fwd_small(const float* y, long long y_ns, int N, int C8, long long V, float eps, float* mean,
@@ -654,13 +680,14 @@ int tta_norm_fwd_small(const float* y, long long y_ns, int N, int C8, long long 
                        uint16_t* out_lo, long long out_ns, int out_dtype, uint16_t* ws_hi, uint16_t* ws_lo,
                        long long ws_ns, int W, cudaStream_t stream) {
   TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_fwd_small: null pointer");
-  TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_fwd_small: V=%lld unsupported (2..4096)", V);
+  TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_fwd_small: V=%lld unsupported (2..65536)", V);
   TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_fwd_small: res_kind %d", res_kind);
   TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_norm_fwd_small: bad dtype");
   TTA_REQUIRE(!ws_hi || (ws_lo && W > 0 && W % 2 == 0 && V % W == 0), "tta_norm_fwd_small: bad parity-split copy");
-  const dim3 grid(1, C8, N);
+  const int cs = small_cluster(N, C8, V);
+  const dim3 grid(cs, C8, N);
 #define LAUNCH(RES, DT)                                                                              \
-  tta_launch(norm_apply_kernel<RES, DT>, grid, kThreads, 0, stream, tta_pdl_family(2), y, y_ns, C8, V, mean, \
+  tta_launch_cluster(norm_apply_kernel<RES, DT>, grid, kThreads, 0, stream, cs, y, y_ns, C8, V, mean, \
              rstd, gamma, beta, relu, (const float*)res_a, (const uint16_t*)res_a, (const uint16_t*)res_b, \
              res_ns, out_hi, out_lo, out_ns, (const float*)nullptr, -1, N, 0, eps, mean, rstd, ws_hi, ws_lo, \
              ws_ns, W)
@@ -683,14 +710,15 @@ int tta_norm_bwd_small(const float* g0, long long g0_ns, const float* g1, long l
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dgamma && dbeta && dy_hi && workspace &&
                   (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_small: null pointer");
-  TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_bwd_small: V=%lld unsupported (2..4096)", V);
+  TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_bwd_small: V=%lld unsupported (2..65536)", V);
   TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_norm_bwd_small: bad dtype");
   TTA_REQUIRE(dy_wsplit_w == 0 || (dy_wsplit_w > 0 && dy_wsplit_w % 2 == 0 && V % dy_wsplit_w == 0),
               "tta_norm_bwd_small: bad parity-split row length %d", dy_wsplit_w);
   const float inv_m = (float)(1.0 / (double)V);
-  const dim3 grid(1, C8, N);
+  const int cs = small_cluster(N, C8, V);
+  const dim3 grid(cs, C8, N);
 #define LAUNCH(DT)                                                                                          \
-  tta_launch(norm_bwd_apply_kernel<DT>, grid, kThreads, 0, stream, tta_pdl_family(2), g0, g0_ns, g1, g1_ns, y, \
+  tta_launch_cluster(norm_bwd_apply_kernel<DT>, grid, kThreads, 0, stream, cs, g0, g0_ns, g1, g1_ns, y, \
              y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)nullptr, inv_m, dy_hi, dy_lo, dy_ns, aux_hi, \
              aux_lo, aux_ns, (const float*)nullptr, -1, N, 0, Creal, dgamma, dbeta, dy_wsplit_w, workspace + 1024,  \
              reinterpret_cast<unsigned int*>(workspace), sums)

@@ -54,6 +54,41 @@ __device__ __forceinline__ void block_reduce_bcast(float (&acc)[NV], float (&tot
   for (int i = 0; i < NV; ++i) tot[i] = tots[i];
 }
 
+// ---------------------------------------------------------------- cluster reduction (DSMEM)
+// tot[16] holds this CTA's block totals (identical in every thread); on return it holds the sum over
+// all CTAs of the thread-block cluster, accumulated in rank order in fp64 -> every CTA gets the same
+// bits.  Every thread of every CTA of the cluster must call it.
+__device__ __forceinline__ void cluster_sum16(float (&tot)[16]) {
+  __shared__ float cl_part[16];
+  __shared__ float cl_tot[16];
+  uint32_t nranks;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t = threadIdx.x == i ? tot[i] : t;
+    cl_part[threadIdx.x] = t;
+  }
+  // release/acquire cluster barrier: every CTA's partials are visible cluster-wide afterwards
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x < 16) {
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&cl_part[threadIdx.x]);
+    double a = 0.0;
+    for (uint32_t r = 0; r < nranks; ++r) {
+      uint32_t remote;
+      float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+      a += (double)v;
+    }
+    cl_tot[threadIdx.x] = (float)a;
+  }
+  // nobody leaves (or overwrites cl_part) while a peer may still be reading it
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tot[i] = cl_tot[i];
+}
+
 // ---------------------------------------------------------------- fused finalize (consumer prologue)
 // Sums the 16 per-block partial values of chunk `chunk` over splits (and over samples n0..n1)
 // in fp64 with all 256 threads; result in tot[16] (shared).  Deterministic order.

@@ -388,6 +388,7 @@ class TTAEngine:
 
             def run_small():
                 check(lib.tta_conv_small(*sargs, _stream()), f"conv_small {cl.name}")
+            run_small.label = f"conv_small {cl.name} {'bwd' if backward else 'fwd'}"
             return run_small
         use_tc = ("tc_" + key) in cl.packed and self.model.conv_backend in ("auto", "tc")
         if self.model.conv_backend == "tc" and not use_tc:
@@ -427,6 +428,7 @@ class TTAEngine:
                               f"conv_tc_bwd_norm {cl.name}")
                     else:
                         check(lib.tta_conv_tc(*args, 0, 0, _stream()), f"conv_tc {cl.name}")
+                run_bwd.label = f"conv_tc {cl.name} bwd {cin8 * 8}->{cout8 * 8} in {tuple(idims)}"
                 return run_bwd
 
             def run():
@@ -442,6 +444,8 @@ class TTAEngine:
 
             def run():
                 check(lib.tta_conv_simt(*args, _stream()), f"conv_simt {cl.name}")
+        run.label = (f"conv_{'tc' if use_tc else 'simt'} {cl.name} {'bwd' if backward else 'fwd'} "
+                     f"{cin8 * 8}->{cout8 * 8} in {tuple(idims)}")
         return run
 
     def build_plan(self, N: int, D: int, H: int, W: int) -> Plan:
@@ -563,6 +567,7 @@ class TTAEngine:
                     check(lib.tta_norm_stats(*st_args, plan.ws.data_ptr(), 1, _stream()), "norm_stats")
                     check(lib.tta_norm_apply(*ap_args, 0, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
                           "norm_apply")
+            run.label = f"norm fwd {nl.name} C={nl.C} V={y.V}"
             plan.fwd.append(run)
             ops.append(("norm", rec))
             return out
@@ -878,6 +883,7 @@ class TTAEngine:
                               "norm_bwd_reduce")
                     if ap_args is not None:
                         check(lib.tta_norm_bwd_apply(*ap_args, 0, nl.C, dg, db, dy_ws, _stream()), "norm_bwd_apply")
+                run.label = f"norm bwd {nl.name} C={nl.C} V={y.V}"
                 plan.bwd.append(run)
         n_conv = sum(1 for o in ops if o[0] == "conv")
         n_norm = sum(1 for o in ops if o[0] == "norm")

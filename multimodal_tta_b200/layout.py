@@ -153,6 +153,18 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
     gmax = max(len(g) for g in groups)
     ncb, nnt = cip // 16, cop // ntile
     out = torch.zeros((nnt, ncb, len(groups), gmax, 2, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+    if K == 3 and stride == 1 and lib.tta_conv_tc_stacked(mode, K, stride, ci, co, int(split)):
+        # kd-stacked stride-1 conv (small n-tile, resident weights; csrc/tta_conv_tc.cu GEOM_S1K): one
+        # blob per channel block, entry (kh, kw) = [kchunk][slot 0..2][hi NT | lo NT][8].  Slot s feeds
+        # the accumulator of output plane j - 2 + s from input plane j: kd = 2 - s for a conv, kd = s
+        # for its input-gradient dual (mirrored offsets).
+        st = torch.zeros((1, ncb, 9, 2, 3, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+        for sl in range(3):
+            kd = 2 - sl if mode == 0 else sl
+            for pi, plane in enumerate(planes):
+                sel = plane[kd * 9: kd * 9 + 9].reshape(9, ncb, 2, 8, nnt, ntile)   # [E][cb][kc][8][nt][n]
+                st[:, :, :, :, sl, pi] = sel.permute(4, 1, 0, 2, 5, 3)               # [nt][cb][E][kc][n][8]
+        return st.contiguous()
     if K == 3 and mode == 1 and stride == 2:
         # transposed stride-2: per group a sequence of stacks, each [kchunk][accumulators of the stack]
         # [hi NT | lo NT][8]: ONE MMA covers all accumulators of a stack (N = k * planes * NT)

@@ -167,9 +167,10 @@ class UNetB200(nn.Module):
         # layers with <= 4096 voxels per instance (8^3, 16^3): statistics + apply, and backward
         # reduction + apply, as one launch each
         self.fuse_small_norm = bool(get_config(cfg, "fuse_small_norm", True))
-        # ... up to this many voxels per instance: one CTA per (n, chunk) slab only pays while the slab
-        # is a few voxel-chunks per thread (measured: 16^3 slabs on 32 CTAs are slower than two launches)
-        self.small_norm_max_voxels = int(get_config(cfg, "small_norm_max_voxels", 512))
+        # ... up to this many voxels per instance.  Slabs above 512 voxels are owned by a thread-block
+        # cluster of up to 8 CTAs (totals through distributed shared memory).  Same-box A/B per step:
+        # 512 -> 2.645 ms, 4096 (16^3 level too) -> 2.628 ms, 65536 (32^3 too) -> 2.641 ms
+        self.small_norm_max_voxels = int(get_config(cfg, "small_norm_max_voxels", 4096))
         # OPT-IN: InstanceNorm backward sample by sample when one sample's gradient + conv result fit
         # the 126 MB L2 but the batch does not, hoping the apply pass re-reads them from L2.  Measured
         # on the four 64^3 layers (67 MB per sample): 2.578 ms vs 2.556 ms per step -- the second pass

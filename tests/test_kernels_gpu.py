@@ -107,7 +107,7 @@ def test_conv_small_forward_and_dgrad(lib, cuda, cin, cout, dims):
 
 
 @pytest.mark.parametrize("batch_mode", [0, 1])
-@pytest.mark.parametrize("C,dims", [(32, (8, 9, 10)), (3, (16, 16, 16)), (20, (5, 7, 3))])
+@pytest.mark.parametrize("C,dims", [(32, (8, 9, 10)), (3, (16, 16, 16)), (20, (5, 7, 3)), (16, (20, 24, 28))])
 def test_norm_forward_backward(lib, cuda, batch_mode, C, dims):
     torch.manual_seed(2)
     N = 2
