@@ -53,6 +53,67 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
   }
 }
 
+// Same, four consecutive-w voxels per thread (W % 4 == 0): one 128-bit load per real channel instead of
+// four scalar ones, 32-bit index arithmetic with two divisions per FOUR voxels.  Measured in-stream on
+// the 2 x 4 x 128^3 input: 87 us for the per-voxel kernel above (200 MB moved).
+__global__ void __launch_bounds__(kThreads)
+gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
+                    const int* win, const float* chan_scale, int D, int H,
+                    int W, int C8, uint16_t* hi, uint16_t* lo,
+                    long long o_ns, int wsplit) {
+  pdl_trigger();
+  pdl_wait();
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
+  const long long V = (long long)D * H * W;
+  const long long Vs = (long long)Ds * Hs * Ws;
+  const float* src = vol + (long long)vi * C * Vs;
+  float sc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = chunk * 8 + i;
+    sc[i] = (c < C) ? (chan_scale ? chan_scale[b * C + c] : 1.f) : 0.f;
+  }
+  const unsigned W4 = (unsigned)W >> 2, G = (unsigned)(V >> 2);
+  for (unsigned g = blockIdx.x * kThreads + threadIdx.x; g < G; g += gridDim.x * kThreads) {
+    const unsigned row = g / W4, w4 = g - row * W4;
+    const unsigned d = row / (unsigned)H, h = row - d * (unsigned)H;
+    const int sd = (int)d + d0, sh = (int)h + h0, sw = (int)(w4 * 4) + w0;
+    float x[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[k][i] = 0.f;
+    if (sd >= 0 && sd < Ds && sh >= 0 && sh < Hs && sw > -4 && sw < Ws) {
+      const float* rowp = src + ((long long)sd * Hs + sh) * Ws + sw;
+      const bool whole = sw >= 0 && sw + 3 < Ws;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = chunk * 8 + i;
+        if (c < C) {
+          const float* p = rowp + (long long)c * Vs;
+          if (whole && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0ull) {
+            const float4 v = *reinterpret_cast<const float4*>(p);
+            x[0][i] = v.x * sc[i]; x[1][i] = v.y * sc[i]; x[2][i] = v.z * sc[i]; x[3][i] = v.w * sc[i];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (sw + k >= 0 && sw + k < Ws) x[k][i] = p[k] * sc[i];
+          }
+        }
+      }
+    }
+    const long long rowbase = (long long)b * o_ns + ((long long)chunk * V + (long long)row * W) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int w = (int)(w4 * 4) + k;
+      // wsplit: the first conv is a stride-2 tcgen05 conv -> w-parity-split rows (tta_common.cuh)
+      const int wo = wsplit ? (w & 1) * (W >> 1) + (w >> 1) : w;
+      store_split8<TTA_F16>(hi, lo, rowbase + (long long)wo * 8, x[k]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- fused head
 // One pass: read the last conv's fp32 result (chunk 0, R <= 8 real channels), write logits in
 // the reference's NCDHW fp32 layout, the per-voxel entropy (block partial sums) and
@@ -250,8 +311,12 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
   TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
   const long long V = (long long)D * H * W;
-  tta_launch(gather_pack_kernel, dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream, tta_pdl_family(4), 
-      vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
+  if (W % 4 == 0 && V / 4 < 0x7fffffffLL)
+    tta_launch(gather_pack4_kernel, dim3(xblocks(V / 4, (long long)NB * C8), C8, NB), kThreads, 0, stream,
+               tta_pdl_family(4), vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
+  else
+    tta_launch(gather_pack_kernel, dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream, tta_pdl_family(4),
+               vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
   return tta_check_launch("tta_gather_pack");
 }
 

@@ -277,19 +277,21 @@ def test_adam_matches_torch(lib, cuda):
     assert int(step) == 5
 
 
-def test_gather_pack_windows_and_padding(lib, cuda):
+@pytest.mark.parametrize("vw,roi", [(11, (6, 8, 6)), (11, (6, 8, 8)), (12, (6, 8, 8)), (16, (5, 7, 12))])
+def test_gather_pack_windows_and_padding(lib, cuda, vw, roi):
+    # roi W % 4 == 0 takes the four-voxels-per-thread kernel: 128-bit loads where the source run is
+    # 16-byte aligned and inside the volume, per-element loads otherwise (vw = 11 / window w0 = 5, -3)
     torch.manual_seed(5)
-    vol = torch.randn(2, 3, 9, 10, 11)
-    wins = torch.tensor([[0, 0, 0, 0], [1, 3, 2, 5], [1, -2, -1, 4]], dtype=torch.int32)
-    roi = (6, 8, 6)
+    vol = torch.randn(2, 3, 9, 10, vw)
+    wins = torch.tensor([[0, 0, 0, 0], [1, 3, 2, 5], [1, -2, -1, -3]], dtype=torch.int32)
     scale = torch.tensor([[1., 1., 1.], [1., 0., 1.], [0., 1., 1.]])
     hi = torch.zeros((3, 1, *roi, 8), dtype=torch.int16, device=cuda); lo = torch.zeros_like(hi)
     vd, wd, sd = vol.to(cuda), wins.to(cuda), scale.to(cuda)   # keep alive across the async launch
-    check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, 11, wd.data_ptr(),
+    check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, vw, wd.data_ptr(),
                               sd.data_ptr(), 3, *roi, hi.data_ptr(), lo.data_ptr(),
                               roi[0] * roi[1] * roi[2] * 8, 1, 0, stream()))
     hw = torch.zeros_like(hi); lw = torch.zeros_like(hi)
-    check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, 11, wd.data_ptr(),
+    check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, vw, wd.data_ptr(),
                               sd.data_ptr(), 3, *roi, hw.data_ptr(), lw.data_ptr(),
                               roi[0] * roi[1] * roi[2] * 8, 1, 1, stream()))
     assert torch.equal(hw, wsplit(hi)) and torch.equal(lw, wsplit(lo))   # w-parity-split variant
