@@ -61,12 +61,18 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
 /* tcgen05/TMEM/TMA implicit GEMM.  wpacked: layout.pack_weights_tc blob for (mode,K,stride,dtype).
  * flags: bit0 force one d-plane per work item, bit1 no split-K (deterministic), bit2 non-persistent,
  * bit3 stride-2 conv input planes are w-parity-split ([N][C8][D][H][2][W/2][8]), bit4 no resident
- * weights, bit5 one d-plane per 128-row tile even when H <= 8 (default there: two planes per tile). */
+ * weights, bit5 one d-plane per 128-row tile even when H <= 8 (default there: two planes per tile),
+ * bit6 split-K factor rounded up (A/B switch), bits 8..10 real Cout of a small-Cout transposed conv
+ * packed for the dense-GEMM + col2im kernel (tta_conv_tc_t2s). */
 int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout);
 int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split);
 /* 1 when this layer runs kd-stacked (stride-1, single small n-tile, resident weights): its packed
  * weight layout differs (layout.pack_weights_tc), so packer and kernel ask the same question. */
 int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int split);
+/* 1 when a transposed stride-2 conv qualifies for the dense-GEMM + col2im kernel (Cout <= 4, Cin a
+ * multiple of 16 up to 64, split planes): pack with layout.pack_weights_tc(t2s=True) and pass the real
+ * Cout in flags bits 8..10 of tta_conv_tc. */
+int tta_conv_tc_t2s(int mode, int K, int stride, int cin, int cout, int split);
 int tta_conv_tc_gmax(int mode, int K, int stride);
 int tta_conv_tc_ngroups(int mode, int K, int stride);
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout);

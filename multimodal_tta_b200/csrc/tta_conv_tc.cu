@@ -871,6 +871,289 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   }
 }
 
+// =====================================================================================================
+// conv_t2s_kernel: transposed stride-2 3x3x3 conv with a TINY output-channel count (the UNet's head
+// convT 64 -> 3) as ONE dense GEMM per input plane + a shared-memory col2im.
+//
+// The generic GEOM_T2 path needs 28 small-N MMAs per 16-channel block and tile (every shifted A tile x
+// every parity class) and pads 3 output channels to 16: measured 156 .. 228 us for 5.4 GFLOP.  Here
+//     P[v, (tap, co)] = sum_ci X[v, ci] * W[ci, tap, co]          (M = 128 input voxels, N = 27*Cout)
+// is computed for every INPUT voxel of a 16(h) x 8(w) tile with 2 MMAs per 16-channel block
+// (A_hi x [B_hi | B_lo], A_lo x B_hi), the 27*Cout partial products of a voxel go TMEM -> registers ->
+// shared memory, and every output voxel gathers its 1 .. 8 contributions from the P rows of its input
+// voxel and of the +1 neighbours in h, w (same tile: the tile's last row / column is halo) and d (next
+// plane: a CTA walks a d-segment and keeps the P tiles of two consecutive planes):
+//     out[2d+qd, 2h+qh, 2w+qw] = b + sum over axes { q = 0: (shift 0, k = 1);  q = 1: (0, 2), (1, 0) }.
+// Roles: warp 0 TMA producer (one box [Cin/8 chunks][16 h][8 w] per plane and operand plane), warp 1
+// MMA issue, warps 2..5 epilogue; TMEM accumulators and the P tiles are double buffered.
+constexpr int kT2sThreads = 192;
+constexpr int kT2sStages = 3;  // at most
+
+struct T2sParams {
+  CUtensorMap amap[2];
+  int N, C8in, c8_view, nks;             // nks = Cin / 16 k-steps
+  int D, H, W;                           // input dims (output = 2x)
+  int tiles_h, tiles_w, dseg, seg_len, work_items;
+  int np;                                // padded GEMM N = round16(27 * Cout)
+  int stage_bytes, plane_bytes;          // plane_bytes = C8in * 2048 (one operand plane of a stage)
+  int w_bytes, tmem_cols, nstages;
+  unsigned idesc_2n, idesc_n;
+  long long out_ns;
+  const uint8_t* wpacked;
+  const float* bias;
+  float* out;
+  float* stats;                          // [n][1][grid][16] or nullptr
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kT2sThreads, 1)
+conv_t2s_kernel(const __grid_constant__ T2sParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[kT2sStages];
+  __shared__ __align__(8) uint64_t bar_empty[kT2sStages];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float red_s[4][8];
+  constexpr int NC = 27 * COUT;          // real GEMM columns
+  constexpr int PROW = NC | 1;           // odd row pitch of the P tiles: conflict-free column access
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.nstages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 4);
+    }
+    mbar_init(smem_u32(&bar_w), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t w_smem = smem_base + P.nstages * P.stage_bytes;
+  float* p_tiles = reinterpret_cast<float*>(smem + P.nstages * P.stage_bytes + P.w_bytes);  // [2][128][PROW]
+  const int per_n = P.dseg * P.tiles_h * P.tiles_w;
+
+  auto decode = [&](int item, int& n, int& ds, int& de, int& h0, int& w0) {
+    n = item / per_n;
+    int t = item - n * per_n;
+    const int sg = t / (P.tiles_h * P.tiles_w);
+    t -= sg * P.tiles_h * P.tiles_w;
+    const int th = t / P.tiles_w, tw = t - th * P.tiles_w;
+    ds = sg * P.seg_len;
+    de = min(P.D, ds + P.seg_len);
+    h0 = th * 15;
+    w0 = tw * 7;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bar_w), (uint32_t)P.w_bytes);
+      bulk_load(w_smem, P.wpacked, (uint32_t)P.w_bytes, smem_u32(&bar_w));
+      int s = 0, ph = 0;
+      for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
+        int n, ds, de, h0, w0;
+        decode(item, n, ds, de, h0, w0);
+        const int last = min(de, P.D - 1);   // plane de is the +1 halo of the segment (absent past the volume)
+        for (int p = ds; p <= last; ++p) {
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          const uint32_t stage = smem_base + s * P.stage_bytes;
+          mbar_expect_tx(full, 2u * (uint32_t)P.plane_bytes);
+          tma_load_4d(stage, &P.amap[0], full, w0 * 8, h0, p, n * P.c8_view);
+          tma_load_4d(stage + P.plane_bytes, &P.amap[1], full, w0 * 8, h0, p, n * P.c8_view);
+          if (++s == P.nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t leader = elect_one();
+    mbar_wait(smem_u32(&bar_w), 0);
+    int s = 0, ph = 0;
+    uint32_t step = 0;
+    const uint32_t a_w1 = 8u | (1u << 14), b_w1 = 8u | (1u << 14);           // SBO = 128 B
+    const uint32_t a_lbo = (2048u >> 4) << 16, b_lbo = ((2u * (uint32_t)P.np * 16u) >> 4) << 16;
+    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
+      int n, ds, de, h0, w0;
+      decode(item, n, ds, de, h0, w0);
+      const int last = min(de, P.D - 1);
+      for (int p = ds; p <= last; ++p, ++step) {
+        const uint32_t buf = step & 1u, use = step >> 1;
+        mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t stage = smem_base + s * P.stage_bytes;
+        const uint32_t d = tmem_base + buf * 2u * (uint32_t)P.np;
+        for (int ks = 0; ks < P.nks; ++ks) {
+          const uint32_t a_hi = ((stage + ks * 4096) >> 4) | a_lbo;
+          const uint32_t a_lo = ((stage + P.plane_bytes + ks * 4096) >> 4) | a_lbo;
+          const uint32_t b0 = ((w_smem + ks * (2 * 2 * P.np * 16)) >> 4) | b_lbo;
+          const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | a_hi, ad_lo = ((uint64_t)a_w1 << 32) | a_lo;
+          const uint64_t bd = ((uint64_t)b_w1 << 32) | b0;
+          if (leader) {
+            umma_f16(d, ad_hi, bd, P.idesc_2n, ks == 0 ? 0u : 1u);   // [hi*hi | hi*lo]
+            umma_f16(d, ad_lo, bd, P.idesc_n, 1u);                   // += lo*hi
+          }
+        }
+        __syncwarp();
+        if (leader) {
+          umma_commit(smem_u32(&bar_empty[s]));
+          umma_commit(smem_u32(&bar_acc_full[buf]));
+        }
+        __syncwarp();
+        if (++s == P.nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> P tile (smem) -> col2im gather -> HBM =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;           // input voxel of the tile = TMEM lane
+    const int hh = row >> 3, ww = row & 7;
+    const int et = threadIdx.x - 64;         // 0..127
+    const int Do = 2 * P.D, Ho = 2 * P.H, Wo = 2 * P.W;
+    float bias_r[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bias_r[c] = P.bias ? P.bias[c] : 0.f;
+    float s1[COUT], s2[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) s1[c] = s2[c] = 0.f;
+    int st_n = -1;
+    auto stats_flush = [&]() {
+      // fixed-order reduction of the 128 epilogue threads into this CTA's slot of sample st_n
+      float v[2 * COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        v[c] = warp_sum(s1[c]);
+        v[COUT + c] = warp_sum(s2[c]);
+        s1[c] = s2[c] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * COUT; ++i) red_s[q][i] = v[i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < 2 * COUT) {
+        const float tot = red_s[0][et] + red_s[1][et] + red_s[2][et] + red_s[3][et];
+        const int k = et < COUT ? et : 8 + (et - COUT);
+        P.stats[(((long long)st_n * gridDim.x) + blockIdx.x) * 16 + k] += tot;
+      }
+    };
+    if (P.stats) {
+      for (int t = et; t < P.N * 16; t += 128) P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    uint32_t step = 0;
+    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
+      int n, ds, de, h0, w0;
+      decode(item, n, ds, de, h0, w0);
+      if (P.stats && n != st_n) {
+        if (st_n >= 0) stats_flush();
+        st_n = n;
+      }
+      const bool mine = hh < 15 && ww < 7 && h0 + hh < P.H && w0 + ww < P.W;
+      const int ih = h0 + hh, iw = w0 + ww;
+      for (int p = ds; p <= de; ++p) {
+        const bool have = p < P.D;             // plane p exists (p == D: the halo past the volume is zero)
+        float* cur = p_tiles + (size_t)(p & 1) * 128 * PROW;
+        if (have) {
+          const uint32_t buf = step & 1u, use = step >> 1;
+          ++step;
+          mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tb = tmem_base + buf * 2u * (uint32_t)P.np + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int c16 = 0; c16 < (NC + 15) / 16; ++c16) {
+            uint32_t ra[16], rb[16];
+            tmem_ld16_nowait(tb + c16 * 16, ra);
+            tmem_ld16_nowait(tb + P.np + c16 * 16, rb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c16 * 16 + i < NC) cur[row * PROW + c16 * 16 + i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // P tile of plane p complete
+        if (p > ds && mine) {
+          const int d = p - 1;
+          const float* lo_t = p_tiles + (size_t)(d & 1) * 128 * PROW;   // P of plane d
+          const float* hi_t = cur;                                      // P of plane d + 1 (jd = 1)
+#pragma unroll
+          for (int qd = 0; qd < 2; ++qd)
+#pragma unroll
+            for (int qh = 0; qh < 2; ++qh) {
+              float o[2][COUT];
+#pragma unroll
+              for (int qw = 0; qw < 2; ++qw) {
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) o[qw][c] = bias_r[c];
+#pragma unroll
+                for (int ad = 0; ad <= qd; ++ad)
+#pragma unroll
+                  for (int ah = 0; ah <= qh; ++ah)
+#pragma unroll
+                    for (int aw = 0; aw <= qw; ++aw) {
+                      // shift j = a, tap k: q = 0 -> k = 1; q = 1 -> (j = 0, k = 2), (j = 1, k = 0)
+                      const int kd = qd ? (ad ? 0 : 2) : 1, kh = qh ? (ah ? 0 : 2) : 1, kw = qw ? (aw ? 0 : 2) : 1;
+                      if (ad && !have) continue;
+                      const float* src = (ad ? hi_t : lo_t) + (row + ah * 8 + aw) * PROW + (kd * 9 + kh * 3 + kw) * COUT;
+#pragma unroll
+                      for (int c = 0; c < COUT; ++c) o[qw][c] += src[c];
+                    }
+              }
+              const int od = 2 * d + qd, oh = 2 * ih + qh, ow = 2 * iw;
+              float* dst = P.out + (long long)n * P.out_ns + (((long long)od * Ho + oh) * Wo + ow) * 8;
+#pragma unroll
+              for (int qw = 0; qw < 2; ++qw) {
+                float rv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) rv[c] = 0.f;
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                  rv[c] = o[qw][c];
+                  s1[c] += o[qw][c];
+                  s2[c] = fmaf(o[qw][c], o[qw][c], s2[c]);
+                }
+                store_f32x8(dst + qw * 8, rv);
+              }
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // gathers done before the older P tile is overwritten
+      }
+    }
+    if (P.stats && st_n >= 0) stats_flush();
+    (void)Do;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -904,6 +1187,11 @@ static int ntile_of(int geom, int cout, int split) {
 }
 
 static int round128(int x) { return (x + 127) / 128 * 128; }
+
+// transposed stride-2 conv with <= 4 output channels: dense GEMM + col2im (conv_t2s_kernel)
+static bool t2s_of(int geom, int cin, int cout, int split) {
+  return geom == GEOM_T2 && split && cin % 16 == 0 && cin >= 16 && cin <= 64 && cout >= 1 && cout <= 4;
+}
 
 // kd-stacked stride-1 convs (GEOM_S1K / GEOM_S1TK, see issue_group): single n-tile, three accumulators
 // within one MMA (3 * acc_cols <= 256) and all weights resident in shared memory.  A function of the
@@ -949,6 +1237,10 @@ int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int spli
   return stacked_of(geom_of(mode, K, stride), cin, cout, split) ? 1 : 0;
 }
 
+int tta_conv_tc_t2s(int mode, int K, int stride, int cin, int cout, int split) {
+  return t2s_of(geom_of(mode, K, stride), cin, cout, split) ? 1 : 0;
+}
+
 int tta_conv_tc_gmax(int mode, int K, int stride) {
   const int g = geom_of(mode, K, stride);
   return g == GEOM_K1 ? 1 : (g == GEOM_T2 ? 18 : 9);
@@ -965,6 +1257,106 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
 // w-parity-split ([N][C8][D][H][2][W/2][8]: even-w voxels of a row first, then the odd ones).
 }  // extern "C"
 
+// ---- transposed stride-2 conv with <= 4 output channels: dense GEMM + col2im (conv_t2s_kernel)
+
+static int conv_t2s_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int N, int C8in, int Di, int Hi,
+                         int Wi, const void* wpacked, const float* bias, float* out, long long out_ns, int cout,
+                         int Do, int Ho, int Wo, int accumulate, float* stats_ws, int stats_c8, int* q_ksplit,
+                         int* q_grid, int* q_nbuf, cudaStream_t stream) {
+  const bool query = q_ksplit != nullptr;
+  TTA_REQUIRE(Do == 2 * Di && Ho == 2 * Hi && Wo == 2 * Wi, "tta_conv_tc: transposed s2 output dims");
+  TTA_REQUIRE(!accumulate, "tta_conv_tc: the small-Cout transposed conv does not accumulate");
+  const long long Vi = (long long)Di * Hi * Wi;
+  TTA_REQUIRE(in_ns % (Vi * 8) == 0, "tta_conv_tc: n_stride must be a whole number of channel chunks");
+  T2sParams P;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.C8in = C8in; P.c8_view = (int)(in_ns / (Vi * 8)); P.nks = C8in / 2;
+  P.D = Di; P.H = Hi; P.W = Wi;
+  P.tiles_h = (Hi + 14) / 15; P.tiles_w = (Wi + 6) / 7;
+  P.np = (27 * cout + 15) / 16 * 16;
+  P.plane_bytes = C8in * 2048;
+  P.stage_bytes = 2 * P.plane_bytes;
+  P.w_bytes = P.nks * 2 * 2 * P.np * 16;
+  const int p_bytes = 2 * 128 * ((27 * cout) | 1) * 4;
+  P.nstages = (227 * 1024 - 2048 - P.w_bytes - p_bytes) / P.stage_bytes;
+  if (P.nstages > kT2sStages) P.nstages = kT2sStages;
+  TTA_REQUIRE(P.nstages >= 2, "tta_conv_tc: small-Cout transposed conv does not fit shared memory (Cin %d, Cout %d)",
+              C8in * 8, cout);
+  P.tmem_cols = 32;
+  while (P.tmem_cols < 4 * P.np) P.tmem_cols *= 2;   // two buffers of [main np | corr np]
+  const int idesc0 = (1 << 4) | ((128 >> 4) << 24);  // fp16 operands, fp32 accumulate, M = 128
+  P.idesc_n = (unsigned)(idesc0 | ((P.np >> 3) << 17));
+  P.idesc_2n = (unsigned)(idesc0 | (((2 * P.np) >> 3) << 17));
+  {
+    // d-segments: every CTA walks a segment plane by plane (+1 halo plane); pick the count that
+    // minimises (waves of CTAs) x (planes per segment + halo + fill)
+    const long long cols = (long long)N * P.tiles_h * P.tiles_w;
+    int best_len = Di;
+    double best_cost = 1e30;
+    for (int k = 1; k <= Di; ++k) {
+      const int len = (Di + k - 1) / k, real = (Di + len - 1) / len;
+      const long long waves = (cols * real + num_sms() - 1) / num_sms();
+      const double cost = (double)waves * (len + 2.5);
+      if (cost < best_cost) { best_cost = cost; best_len = len; }
+    }
+    P.seg_len = best_len;
+    P.dseg = (Di + P.seg_len - 1) / P.seg_len;
+    P.work_items = (int)(cols * P.dseg);
+  }
+  const int grid_x = P.work_items < num_sms() ? P.work_items : num_sms();
+  if (getenv("TTA_TC_DEBUG"))
+    fprintf(stderr, "tta_conv_tc: t2s N %d Cin %d Cout %d in %dx%dx%d | np %d stages %d x %d B | tiles %dx%d dseg %d x %d "
+            "items %d waves %.2f\n", N, C8in * 8, cout, Di, Hi, Wi, P.np, P.nstages, P.stage_bytes, P.tiles_h, P.tiles_w,
+            P.dseg, P.seg_len, P.work_items, (double)P.work_items / num_sms());
+  if (query) {
+    *q_ksplit = 1;
+    *q_grid = grid_x;
+    if (q_nbuf) *q_nbuf = 2;
+    return TTA_OK;
+  }
+  TTA_REQUIRE(in_hi && in_lo && wpacked && out, "tta_conv_tc: null pointer");
+  EncodeTiledFn enc = get_encode();
+  TTA_REQUIRE(enc != nullptr, "tta_conv_tc: cuTensorMapEncodeTiled entry point not found");
+  P.out_ns = out_ns; P.wpacked = (const uint8_t*)wpacked; P.bias = bias; P.out = out;
+  P.stats = nullptr;
+  if (stats_ws != nullptr && stats_c8 > 0) {
+    TTA_REQUIRE(stats_c8 == 1, "tta_conv_tc: stats_c8 %d > 1 chunk", stats_c8);
+    P.stats = stats_ws + 1024;
+  }
+  const cuuint64_t nc_extent = (cuuint64_t)((long long)(N - 1) * P.c8_view + C8in);
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  bool ok = true;
+  for (int pl = 0; pl < 2; ++pl) {
+    cuuint64_t gdim[4] = {(cuuint64_t)Wi * 8, (cuuint64_t)Hi, (cuuint64_t)Di, nc_extent};
+    cuuint64_t gstr[3] = {(cuuint64_t)16 * Wi, (cuuint64_t)16 * Wi * Hi, (cuuint64_t)16 * Vi};
+    cuuint32_t box[4] = {64, 16, 1, (cuuint32_t)C8in};
+    ok = ok && enc(&P.amap[pl], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, (void*)(pl ? in_lo : in_hi), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  TTA_REQUIRE(ok, "tta_conv_tc: cuTensorMapEncodeTiled failed (t2s, dims %d,%d,%d)", Di, Hi, Wi);
+  const size_t smem = (size_t)P.nstages * P.stage_bytes + P.w_bytes + p_bytes + 1024;
+#define TTA_T2S_LAUNCH(CO)                                                                                      \
+  do {                                                                                                          \
+    static bool configured = false;                                                                             \
+    if (!configured) {                                                                                          \
+      if (cudaFuncSetAttribute(conv_t2s_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                               227 * 1024 - 1024) != cudaSuccess)                                               \
+        return tta_check_launch("tta_conv_tc(t2s cudaFuncSetAttribute)");                                       \
+      configured = true;                                                                                        \
+    }                                                                                                           \
+    tta_launch(conv_t2s_kernel<CO>, dim3(grid_x), kT2sThreads, smem, stream, tta_pdl_family(8), P);            \
+  } while (0)
+  switch (cout) {
+    case 1: TTA_T2S_LAUNCH(1); break;
+    case 2: TTA_T2S_LAUNCH(2); break;
+    case 3: TTA_T2S_LAUNCH(3); break;
+    default: TTA_T2S_LAUNCH(4); break;
+  }
+#undef TTA_T2S_LAUNCH
+  return tta_check_launch("tta_conv_tc(t2s)");
+}
+
 static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int C8in,
                         int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
                         int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
@@ -978,6 +1370,16 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_tc: bad dtype");
   // small planes (8^3 level): two d-planes per 128-row tile (see issue_group); flags bit5 keeps the
   // one-plane tiles (testing: both must agree)
+  // flags bits 8..10: real output-channel count (1..4) of a transposed stride-2 conv whose weights were
+  // packed for the dense-GEMM + col2im kernel (layout.pack_weights_tc(t2s=True)); 0 = generic path
+  const int t2s_small_cout = (flags >> 8) & 7;
+  TTA_REQUIRE(t2s_small_cout == 0 || t2s_of(geom, C8in * 8, t2s_small_cout, in_dtype == TTA_F16_HI ? 0 : 1),
+              "tta_conv_tc: flags ask for the small-Cout transposed kernel but the layer does not qualify");
+  if (t2s_small_cout > 0 && t2s_of(geom, C8in * 8, t2s_small_cout, in_dtype == TTA_F16_HI ? 0 : 1)) {
+    TTA_REQUIRE(C8out == 1 && segs == nullptr, "tta_conv_tc: small-Cout transposed conv writes one channel chunk");
+    return conv_t2s_impl(in_hi, in_lo, in_ns, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, t2s_small_cout, Do, Ho,
+                         Wo, accumulate, stats_ws, stats_c8, q_ksplit, q_grid, q_nbuf, stream);
+  }
   const bool stacked = stacked_of(geom, C8in * 8, C8out * 8, in_dtype == TTA_F16_HI ? 0 : 1);
   if (stacked) geom = geom == GEOM_S1 ? GEOM_S1K : GEOM_S1TK;
   const bool pl2 = (geom == GEOM_S1 || geom == GEOM_S1T) && Ho <= 8 && Do >= 2 && !(flags & 32);

@@ -170,7 +170,7 @@ class ConvLayer:
         self.cin, self.cout = holder.cin, holder.cout + (extra.cout if extra is not None else 0)
         self.packed = {}
 
-    def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16):
+    def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16, t2s: bool = True):
         """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05."""
         w = self.h.weight.detach().to(device=device, dtype=torch.float32)
         wf = wg_forward(w, self.h.transposed)
@@ -197,8 +197,14 @@ class ConvLayer:
             self.packed["small_fwd"] = pack_weights_small(wf, self.mode)
             self.packed["small_bwd"] = pack_weights_small(wd, 1 - self.mode)
         if want_tc:
+            self.tc_fwd_flags = 0
             if lib.tta_conv_tc_supported(self.mode, self.K, self.stride, self.cin, self.cout):
-                self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16)
+                # small-Cout transposed conv (the head convT): dense GEMM + col2im kernel, own weight
+                # layout, real Cout in flags bits 8..10 (include/tta_b200.h)
+                use_t2s = t2s and self.extra is None and bool(
+                    lib.tta_conv_tc_t2s(self.mode, self.K, self.stride, self.cin, self.cout, 1))
+                self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16, t2s=use_t2s)
+                self.tc_fwd_flags = (self.cout << 8) if use_t2s else 0
             bmode = 1 - self.mode
             if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.cin):
                 self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype)
@@ -318,9 +324,9 @@ class TTAEngine:
                 fused_members |= {id(fl.h), id(fl.extra)}
             for key, cl in self.conv_layers.items():
                 if key not in fused_members:
-                    cl.pack(device, want_tc, self.bwd_dtype)
+                    cl.pack(device, want_tc, self.bwd_dtype, t2s=self.model.t2s_head)
             for fl in self.fused_layers.values():
-                fl.pack(device, want_tc, self.bwd_dtype)
+                fl.pack(device, want_tc, self.bwd_dtype, t2s=self.model.t2s_head)
             self.model._params_dirty = False
 
     def _bind_params(self):
@@ -398,6 +404,8 @@ class TTAEngine:
             wp = cl.packed["tc_" + key]
             plan.keep.append(wp)
             flags = (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0) | self.model.tc_flags
+            if not backward:
+                flags |= getattr(cl, "tc_fwd_flags", 0)
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
                     *odims, mode, cl.K, cl.stride, int(accumulate), flags)
             if stats_res is not None:

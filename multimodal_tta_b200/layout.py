@@ -132,7 +132,22 @@ def t2_stacks() -> list[list[list[tuple[int, int]]]]:
     return [stacks(0, g0), stacks(1, g1)]
 
 
-def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int) -> torch.Tensor:
+def pack_weights_t2s(wg: torch.Tensor) -> torch.Tensor:
+    """Wg[27][ci][co] (transposed stride-2 conv, co <= 4, ci % 16 == 0) -> the resident B operand of
+    csrc/tta_conv_tc.cu:conv_t2s_kernel: [k-step ci/16][kchunk 2][hi NP rows | lo NP rows][8 ci] fp16,
+    row = tap * co + c (NP = 27*co rounded up to 16; pad rows zero)."""
+    T, ci, co = wg.shape
+    assert T == 27 and ci % 16 == 0 and 1 <= co <= 4
+    npad = (27 * co + 15) // 16 * 16
+    hi, lo = split_planes(wg.float(), TTA_F16)                       # [27][ci][co]
+    out = torch.zeros((ci // 16, 2, 2, npad, 8), dtype=torch.int16, device=wg.device)
+    for pi, plane in enumerate((hi, lo)):
+        rows = plane.permute(0, 2, 1).reshape(27 * co, ci // 16, 2, 8)   # [tap*co + c][ks][kc][8]
+        out[:, :, pi, : 27 * co] = rows.permute(1, 2, 0, 3)
+    return out.contiguous()
+
+
+def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int, t2s: bool = False) -> torch.Tensor:
     """Wg[T][ci][co] -> per-(n_tile, cblk, group) contiguous blobs
     [ntile][cblk][group][entry][kchunk 2][hi NT rows | lo NT rows][8 ci] of 16-bit values.
     A blob is what one pipeline stage of the tcgen05 kernel bulk-copies into shared memory as
@@ -141,6 +156,8 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
     from . import _lib
     T, ci, co = wg.shape
     lib = _lib.lib()
+    if t2s:   # dense-GEMM + col2im kernel for a small-Cout transposed conv (caller passes Cout in the flags)
+        return pack_weights_t2s(wg)
     split = dtype_tag != TTA_F16_HI      # TTA_F16_HI: single fp16 plane, B rows are not stacked
     ntile = lib.tta_conv_tc_ntile(mode, K, stride, co, int(split))
     cip = (ci + 15) // 16 * 16

@@ -150,6 +150,8 @@ class UNetB200(nn.Module):
         self.deterministic = bool(get_config(cfg, "deterministic", False))
         # extra tta_conv_tc flag bits for A/B experiments (include/tta_b200.h), e.g. 32 = one-plane tiles
         self.tc_flags = int(get_config(cfg, "tc_flags", 0))
+        # head convT (Cout <= 4) as dense GEMM + shared-memory col2im instead of 28 small MMAs per block
+        self.t2s_head = bool(get_config(cfg, "t2s_head", True))
         # run a ResidualUnit's unit0 conv and its strided 3x3x3 shortcut conv as ONE launch
         self.fuse_shortcut = bool(get_config(cfg, "fuse_shortcut", True))
         # run the full-resolution tail (norm apply + 3x3x3 conv + entropy, and its backward) as two

@@ -292,3 +292,57 @@ def test_conv_tc_fused_norm_backward_sums(lib, cuda, cin, cout, s, tr, dims, acc
         assert float((sm[:, :C, 1] - s2).abs().max()) < 2e-5 * scale
         assert float((db[:C].cpu() - s1.sum(0)).abs().max()) < 2e-5 * scale * N
         assert float((dg[:C].cpu() - s2.sum(0)).abs().max()) < 2e-5 * scale * N
+
+
+@pytest.mark.parametrize("cin,cout,dims", [(64, 3, (4, 16, 8)), (64, 3, (5, 17, 9)), (32, 1, (3, 8, 8)),
+                                            (16, 4, (2, 6, 5)), (64, 3, (20, 33, 20)), (48, 2, (9, 15, 7))])
+def test_conv_tc_small_cout_transposed_gemm_col2im(lib, cuda, cin, cout, dims):
+    """Transposed stride-2 conv with <= 4 output channels (the UNet head convT 64 -> 3) as a dense
+    GEMM per input plane + shared-memory col2im (conv_t2s_kernel; flags bits 8..10 = Cout, weights from
+    pack_weights_tc(t2s=True)): against torch conv_transpose3d on the same split-rounded operands
+    (rel-L2 <= 2e-5 as for every fp16 hi/lo conv), with the fused norm statistics, twice (slots are
+    re-zeroed by every launch), including tile edges (tiles advance by 15 x 7 input voxels) and
+    several d-segments."""
+    import ctypes
+    torch.manual_seed(21)
+    N = 2
+    assert lib.tta_conv_tc_t2s(1, 3, 2, cin, cout, 1) == 1
+    x = torch.randn(N, cin, *dims)
+    w = torch.randn(cin, cout, 3, 3, 3) * 0.1
+    b = torch.randn(cout)
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    whi, wlo = split_planes(w, TTA_F16)
+    ref = F.conv_transpose3d(xv.cpu(), join_planes(whi, wlo, TTA_F16), b, stride=2, padding=1, output_padding=1)
+    odims = tuple(ref.shape[2:])
+    c8i = cin // 8
+    Vi, Vo = dims[0] * dims[1] * dims[2], odims[0] * odims[1] * odims[2]
+    wp = pack_weights_tc(wg_forward(w.to(cuda), True), 1, 3, 2, TTA_F16, t2s=True)
+    flags = cout << 8
+    ks, grid = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.tta_conv_tc_query(TTA_F16, N, c8i, *dims, 1, *odims, 1, 3, 2, 0, flags, ctypes.byref(ks),
+                                ctypes.byref(grid), 0), "query")
+    assert ks.value == 1 and 1 <= grid.value <= 148
+    ws = torch.full((1024 + N * grid.value * 16,), 55.0, device=cuda)
+    out = torch.full((N, 1, *odims, 8), 9.0, device=cuda)
+    bias = pack_bias(b.to(cuda))
+    for _ in range(2):
+        check(lib.tta_conv_tc(hi.data_ptr(), lo.data_ptr(), c8i * Vi * 8, TTA_F16, N, c8i, *dims, wp.data_ptr(),
+                              bias.data_ptr(), out.data_ptr(), Vo * 8, 1, *odims, 1, 3, 2, 0, flags,
+                              ws.data_ptr(), 1, stream()), "conv_tc t2s")
+    torch.cuda.synchronize()
+    got = from_chunked(out, cout).cpu()
+    assert rel_l2(got, ref) < 2e-5, rel_l2(got, ref)
+    assert float(out[..., cout:].abs().max()) == 0.0                     # pad channels exactly zero
+    mean = torch.zeros(N * 8, device=cuda); rstd = torch.zeros_like(mean)
+    check(lib.tta_norm_stats_finalize(ws.data_ptr(), N, 1, grid.value, Vo, 0, 1e-5, mean.data_ptr(), rstd.data_ptr(),
+                                      stream()), "finalize")
+    y = from_chunked(out, cout).double()
+    mu = y.mean((2, 3, 4)); var = ((y - mu.view(N, cout, 1, 1, 1)) ** 2).mean((2, 3, 4))
+    assert float((mean.view(N, 8)[:, :cout].double() - mu).abs().max()) < 1e-5 * float(y.abs().max())
+    rs_ref = 1.0 / torch.sqrt(var + 1e-5)
+    assert float(((rstd.view(N, 8)[:, :cout].double() - rs_ref) / rs_ref).abs().max()) < 1e-5
+    # the generic parity-class path (no flag, generic packing) computes the same conv
+    wpg = pack_weights_tc(wg_forward(w.to(cuda), True), 1, 3, 2, TTA_F16)
+    out_g = torch.zeros_like(out)
+    _tc(lib, hi, lo, c8i * Vi * 8, TTA_F16, N, c8i, dims, wpg, bias, out_g, Vo * 8, 1, odims, 1, 3, 2)
+    assert rel_l2(out.cpu(), out_g.cpu()) < 2e-5
