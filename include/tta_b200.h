@@ -234,6 +234,19 @@ int tta_sw_normalise(const float* acc, const float* wsum, int n_vol, int R, long
 int tta_dice_counts(const float* logits, const float* label, int BR, long long V, float thr,
                     unsigned long long* counts, tta_stream_t stream);
 
+/* ---- input intensity policy on the device: per-channel clip + (masked) z-score, replaces
+ * `_normalize_img` of src/datasets/transforms.py:147-200 (configs/_global_patches/hecktor21.yaml:27-46).
+ * vol [n_vol][C][V] fp32.  rules [C][8] = {clip_on, lo, hi, z_mode, mask_gt, eps, mean, std}, z_mode 0 none,
+ * 1 masked z-score (falls back to all voxels when fewer than min_count pass the mask), 2 unmasked,
+ * 3 fixed (x - mean) / std.  tta_intensity_stats writes affine [n_vol][C][4] = {lo, hi, mu, 1/sd};
+ * tta_intensity_apply: out = (clamp(x, lo, hi) - mu) / sd (in place allowed).  workspace: zeroed once,
+ * tta_intensity_workspace_bytes. */
+long long tta_intensity_workspace_bytes(int n_vol, int C, long long V);
+int tta_intensity_stats(const float* vol, int n_vol, int C, long long V, const float* rules, int min_count,
+                        float* affine, void* workspace, tta_stream_t stream);
+int tta_intensity_apply(const float* vol, float* out, int n_vol, int C, long long V, const float* affine,
+                        tta_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

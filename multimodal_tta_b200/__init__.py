@@ -15,6 +15,7 @@ from .unet_b200 import UNetB200  # noqa: F401
 from .tent import TentB200  # noqa: F401
 from .sliding_window import SlidingWindowTTA  # noqa: F401
 from .evaluation import TTASegmentationEvaluationStrategy  # noqa: F401
+from .intensity import IntensityPolicy  # noqa: F401
 
-__all__ = ["UNetB200", "TentB200", "SlidingWindowTTA", "TTASegmentationEvaluationStrategy",
+__all__ = ["UNetB200", "TentB200", "SlidingWindowTTA", "TTASegmentationEvaluationStrategy", "IntensityPolicy",
            "get_model", "get_plugin", "get_evaluation_strategy"]

@@ -76,6 +76,9 @@ _SIGNATURES = {
     "tta_sw_blend": (I, [P, I, I, I, I, I, P, P, P, P, P, F, P, P, I, I, I, I, P]),
     "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),
     "tta_dice_counts": (I, [P, P, I, L, F, P, P]),
+    "tta_intensity_workspace_bytes": (L, [I, I, L]),
+    "tta_intensity_stats": (I, [P, I, I, L, P, I, P, P, P]),
+    "tta_intensity_apply": (I, [P, P, I, I, L, P, P]),
     "tta_conv_simt": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, P]),
     "tta_conv_small_supported": (I, [I, I, I, I]),
     "tta_conv_small": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, P]),
