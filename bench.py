@@ -67,18 +67,30 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch nvidia-smi (20 ms period) and wait for its first row, so that sampling is already
+        running when the timed region starts (its start-up alone outlasts a 50 ms timed region)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t = time.time()
+            while not self.rows and time.time() - t < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -86,7 +98,8 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t))]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 for n, v in zip(names, r[3:7]):
@@ -186,13 +199,13 @@ def run_product(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for i in range(K):
         tent.step(xs[i % NROT])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -212,6 +225,8 @@ def run_product(args):
         loss_host.copy_(tent.last_loss, non_blocking=False)
     e1.record()
     barrier()
+    sampler.mark_end()     # clocks are sampled over both timed regions (device-resident and end-to-end)
+    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
