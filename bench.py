@@ -246,9 +246,9 @@ def run_product(args):
         if args.skip_cpu:
             cpu = None
         else:
-            v, sec, cores, threads = cpu_oracle_rate(2, 1, batch=1)
+            v, sec, cores, threads = cpu_oracle_rate(8, 1, batch=1)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "threads": threads, "kind": "port",
-                   "sample": "oracle TENT step, B=1 4x128^3, 1 warm-up + 2 timed steps (median), all host threads"}
+                   "sample": "oracle TENT step, B=1 4x128^3, 1 warm-up + 8 timed steps (median), all host threads"}
         backends = sorted(set(eng.plans[(BATCH, *DIMS)].conv_backends.values()))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,

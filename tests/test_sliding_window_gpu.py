@@ -36,3 +36,29 @@ def test_missing_modality_dropout(cuda):
     sw = SlidingWindowTTA(tp, (32, 32, 32), sw_batch=2, overlap=0.5)
     got = sw(vol.cuda(), chan_scale_per_volume=keep).cpu()
     assert rel_l2(got, ref) < 1e-3
+
+
+def test_hecktor_pipeline_raw_intensities_to_blended_logits(cuda):
+    """BASELINE config 3 end to end on the device: RAW CT (HU) / PET (SUV) values -> intensity policy
+    (clip + masked z-score, configs/_global_patches/hecktor21.yaml:27-46) -> missing-modality dropout ->
+    sliding-window TENT -> Gaussian blend, against the oracle pipeline (oracle.intensity_oracle is pinned
+    to the reference's own transform).  Same tolerances as the other sliding-window cases."""
+    from multimodal_tta_b200 import IntensityPolicy
+    from oracle.intensity_oracle import normalize_img
+    from tests.golden.gen_intensity_golden import HECKTOR
+    oracle, prod = make_pair(HECKTOR_MODEL_CFG, seed=33)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"cuda_graph": True})
+    g = torch.Generator().manual_seed(9)
+    dims = (32, 48, 40)
+    raw = torch.stack([torch.stack([(torch.randn(dims, generator=g) * 300 - 200).clamp(-1500, 1500),
+                                    torch.empty(dims).exponential_(1.0 / 1.5, generator=g).clamp(0, 25)])
+                       for _ in range(2)])
+    keep = torch.tensor([[1.0, 0.0], [1.0, 1.0]])                      # volume 0 lost its PET
+    norm_ref = torch.stack([normalize_img(v, intensity_policy=HECKTOR) for v in raw])
+    ref = sliding_window_oracle(norm_ref * keep.view(2, 2, 1, 1, 1), (32, 32, 32), 2, lambda w: to.step(w)[0],
+                                overlap=0.5)
+    vol = IntensityPolicy(HECKTOR)(raw.cuda())
+    sw = SlidingWindowTTA(tp, (32, 32, 32), sw_batch=2, overlap=0.5)
+    got = sw(vol, chan_scale_per_volume=keep).cpu()
+    assert rel_l2(got, ref) < 1e-3
+    assert ((got >= 0) == (ref >= 0)).float().mean().item() >= 0.9999
