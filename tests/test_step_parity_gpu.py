@@ -167,3 +167,29 @@ def test_rejects_bad_inputs(cuda):
         tp.step(torch.zeros(1, 4, 24, 32, 32, device="cuda"))      # 24 not divisible by 16
     with pytest.raises(RuntimeError):
         tp.step(torch.zeros(1, 4, 32, 32, 32))                     # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_continual_domain_shift_stream(cuda, B):
+    """BASELINE config 5 (continual online TTA, non-episodic): a stream of batches whose synthetic
+    domain (per-channel gain / bias / noise, synthetic.domain_shift) switches every two batches; the
+    adapted state persists across batches and domains.  Every batch's pre-update logits and the
+    parameters after the whole stream are compared with the oracle run on the same stream (batch
+    sweep 1 / 2 / 4; the bench covers the 128^3 size, this the semantics)."""
+    from multimodal_tta_b200.synthetic import domain_shift
+    oracle, prod = make_pair(BRATS_MODEL_CFG, seed=41)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"entropy": "sigmoid", "cuda_graph": True})
+    stream = [domain_shift(brats_volume(B, (32, 32, 32), seed=300 + t), domain=t // 2, seed=7) for t in range(6)]
+    ref = [to.step(x)[0] for x in stream]
+    got = [o.clone().cpu() for o in tp.adapt_stream([x.pin_memory() for x in stream])]
+    for t, (a, b) in enumerate(zip(got, ref)):
+        assert rel_l2(a, b) < 1e-3, (t, rel_l2(a, b))
+        assert ((a >= 0) == (b >= 0)).float().mean().item() >= 0.999, t
+    # after SIX Adam steps (measured, scripts/stream_diag.py: median 2e-5, 5-8 % of the scalars beyond 1e-4 --
+    # the sign-flip mechanism of the header compounds over steps; logits 2e-4, agreement >= 99.986 %)
+    perr = (prod.engine.flat_params().cpu() - flat_gamma_beta(to.model)).abs()
+    assert float(perr.median()) < 1e-4                    # north-star tolerance on the typical scalar
+    assert float((perr > 1e-4).float().mean()) < 0.12
+    # episodic reset restores the source parameters
+    tp.reset()
+    assert torch.equal(prod.engine.flat_params().cpu(), tp._snapshot.cpu())
