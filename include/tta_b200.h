@@ -73,6 +73,8 @@ int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int spli
  * multiple of 16 up to 64, split planes): pack with layout.pack_weights_tc(t2s=True) and pass the real
  * Cout in flags bits 8..10 of tta_conv_tc. */
 int tta_conv_tc_t2s(int mode, int K, int stride, int cin, int cout, int split);
+/* 1 when a stride-2 conv reads a one-chunk input (<= 8 channels): taps are packed and issued in pairs. */
+int tta_conv_tc_s2pair(int mode, int K, int stride, int cin);
 int tta_conv_tc_gmax(int mode, int K, int stride);
 int tta_conv_tc_ngroups(int mode, int K, int stride);
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout);

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "tta_conv_tc_ntile": (I, [I, I, I, I, I]),
     "tta_conv_tc_stacked": (I, [I, I, I, I, I, I]),
     "tta_conv_tc_t2s": (I, [I, I, I, I, I, I]),
+    "tta_conv_tc_s2pair": (I, [I, I, I, I]),
     "tta_conv_tc_gmax": (I, [I, I, I]),
     "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),

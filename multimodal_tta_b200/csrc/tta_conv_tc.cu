@@ -60,6 +60,7 @@ struct TcParams {
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
   int b_nblob, b_cb_bytes, b_g_bytes;  // resident weights: blobs to copy; bytes per channel block / per group
+  int s2pair;   // GEOM_S2 with a one-chunk input: tap pairs share one K = 16 MMA (see issue_group)
   int t2_jh16;  // GEOM_T2: offset (16 B units) of the h+1 halo rows inside a k-chunk: 9 = next row, or a second box
   int pl2;      // small-plane tiles (H <= 8): the 128 rows are 2 d-planes x 8 h x 8 w (GEOM_S1P / GEOM_S1TP)
   // fused norm statistics: per-CTA partial sums of y and y^2 over the leading stats_c8 chunks of the
@@ -320,6 +321,27 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
   } else if (GEOM == GEOM_S2) {
     // parity sub-tiles [ph][pw] at fixed 128-aligned offsets: 16x8, 16x9, 17x8, 17x9 voxels
     constexpr int off16[4] = {0, 4096 / 16, 8704 / 16, 13056 / 16};
+    if (P.s2pair) {
+      // ONE-chunk inputs (stem: 4 channels; dgrad of the head convT: 3): half of every K = 16 MMA
+      // would multiply the all-zero second k-chunk.  Two taps of the same parity class differ only by
+      // an address offset (one voxel, or one sub-tile row), so the SECOND k-chunk of the descriptor is
+      // pointed at the second tap's window (LBO = that offset) and the weights of the pair are packed as
+      // the two k-chunks of one entry: 5 MMAs per kd instead of 9.  Entries (layout.s2_pairs):
+      // {class m, rh, rw, offset of the partner in 16 B units (0 = single tap (1,1), -1 = one row)}
+      constexpr int kPair[5][4] = {{3, 0, 0, 1}, {3, 1, 0, 1}, {2, 0, 0, -1}, {1, 0, 0, 1}, {0, 0, 0, 0}};
+#pragma unroll
+      for (int e = 0; e < 5; ++e) {
+        const int m = kPair[e][0], wx = (m & 1) ? 9 : 8;
+        const uint32_t a_w1 = (uint32_t)wx | (1u << 14);
+        const uint32_t dl = kPair[e][3] == 0 ? (uint32_t)P.lbo16[m] : (kPair[e][3] < 0 ? (uint32_t)wx : (uint32_t)kPair[e][3]);
+        const uint32_t ao = (uint32_t)(off16[m] + kPair[e][1] * wx + kPair[e][2]);
+        const uint32_t bo = b_w0 + (uint32_t)e * b_ent;
+        const uint32_t accum = (first && g == 0 && e == 0) ? 0u : 1u;
+        mma_pair<SPLIT>(leader, tmem_acc0, (a_hi0 + ao) | (dl << 16), (a_lo0 + ao) | (dl << 16), a_w1, bo, b_w1, i2n, in_,
+                        accum);
+      }
+      return;
+    }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -1193,6 +1215,9 @@ static bool t2s_of(int geom, int cin, int cout, int split) {
   return geom == GEOM_T2 && split && cin % 16 == 0 && cin >= 16 && cin <= 64 && cout >= 1 && cout <= 4;
 }
 
+// stride-2 conv over a one-chunk input (<= 8 channels): taps paired into the two k-chunks of one MMA
+static bool s2pair_of(int geom, int cin) { return geom == GEOM_S2 && cin <= 8; }
+
 // kd-stacked stride-1 convs (GEOM_S1K / GEOM_S1TK, see issue_group): single n-tile, three accumulators
 // within one MMA (3 * acc_cols <= 256) and all weights resident in shared memory.  A function of the
 // layer alone, because the PACKED WEIGHT LAYOUT depends on it (layout.pack_weights_tc asks).
@@ -1236,6 +1261,8 @@ int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split) {
 int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int split) {
   return stacked_of(geom_of(mode, K, stride), cin, cout, split) ? 1 : 0;
 }
+
+int tta_conv_tc_s2pair(int mode, int K, int stride, int cin) { return s2pair_of(geom_of(mode, K, stride), cin) ? 1 : 0; }
 
 int tta_conv_tc_t2s(int mode, int K, int stride, int cin, int cout, int split) {
   return t2s_of(geom_of(mode, K, stride), cin, cout, split) ? 1 : 0;
@@ -1429,6 +1456,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const int gmax = pl2 ? 3 : tta_conv_tc_gmax(mode, K, stride);
   P.ngroups = pl2 ? 9 : tta_conv_tc_ngroups(mode, K, stride);
   P.pl2 = (pl2 || pl2t) ? 1 : 0;
+  P.s2pair = s2pair_of(geom, C8in * 8) ? 1 : 0;
   P.t2_jh16 = pl2t ? 144 : 9;
   const int acc_cols = split ? 2 * P.ntile : P.ntile;
   P.b_entry_bytes = 2 * acc_cols * 16;  // [kchunk 2][hi NT (| lo NT) rows][16 B]
@@ -1701,7 +1729,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
       }
     for (int kd = 0; kd < 3; ++kd) {
       TcGroup& G = P.grp[kd];
-      G.nloads = 4; G.nmma = 9;
+      G.nloads = 4; G.nmma = P.s2pair ? 5 : 9;
       int abytes = 0;
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {

@@ -109,6 +109,13 @@ def tc_groups(mode: int, K: int, stride: int) -> list[list[int]]:
     return [taps([1, 2]), taps([0])]
 
 
+def s2_pairs() -> list[tuple[int, int | None]]:
+    """(kh*3 + kw) tap pairs of a stride-2 conv over a one-chunk input, in the kernel's entry order:
+    both taps of a pair read the same (h, w)-parity sub-tile, one voxel or one row apart."""
+    t = lambda kh, kw: kh * 3 + kw
+    return [(t(0, 0), t(0, 2)), (t(2, 0), t(2, 2)), (t(0, 1), t(2, 1)), (t(1, 0), t(1, 2)), (t(1, 1), None)]
+
+
 def t2_stacks() -> list[list[list[tuple[int, int]]]]:
     """Transposed stride-2 conv: per pipeline group, the weight STACKS the kernel multiplies with one
     shifted A tile (csrc/tta_conv_tc.cu, GEOM_T2 tables kG0 / kG1).  A stack is a list of
@@ -196,6 +203,18 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
                 blk = sel.permute(5, 2, 3, 1, 0, 6, 4).reshape(nnt, ncb, -1)     # [nt][cb][kc][k][P][n][8]
                 flat[:, :, gi, pos: pos + blk.shape[-1]] = blk
                 pos += blk.shape[-1]
+        return out.contiguous()
+    if K == 3 and lib.tta_conv_tc_s2pair(mode, K, stride, ci):
+        # stride-2 conv over a one-chunk input: entry = a PAIR of taps of one parity class, tap a in
+        # k-chunk 0 and tap b in k-chunk 1 (csrc/tta_conv_tc.cu, GEOM_S2 kPair); (1,1) stays single
+        for gi in range(3):
+            for e, (ta, tb) in enumerate(s2_pairs()):
+                for pi, plane in enumerate(planes):
+                    for kc, t in enumerate((ta, tb)):
+                        if t is None:
+                            continue
+                        sel = plane[gi * 9 + t][:8].reshape(8, nnt, ntile)            # [ci 8][nt][n]
+                        out[:, 0, gi, e, kc, pi] = sel.permute(1, 2, 0)
         return out.contiguous()
     for gi, taps in enumerate(groups):
         idx = torch.tensor(taps, device=wg.device)
