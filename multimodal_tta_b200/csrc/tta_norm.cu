@@ -10,6 +10,8 @@
 //   backward: dbeta = sum dz, dgamma = sum dz*xhat,
 //             dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dz = g * [z > 0]
 #include "tta_common.cuh"
+#include <cstdlib>
+
 #include "tta_reduce.cuh"
 
 namespace tta {
@@ -142,10 +144,15 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
                   uint16_t* out_hi, uint16_t* out_lo, long long out_ns,
                   const float* partial, int splits, int N, int batch_mode, float eps,
                   float* mean_w, float* rstd_w, uint16_t* ws_hi,
-                  uint16_t* ws_lo, long long ws_ns, int Wd) {
+                  uint16_t* ws_lo, long long ws_ns, int Wd, int rev) {
   pdl_trigger();
   pdl_wait();
-  const int chunk = blockIdx.y, n = blockIdx.z;
+  // rev: walk the slabs and the voxels of a slab in the REVERSE of the order in which the preceding
+  // statistics pass (or conv epilogue) touched them, so that this pass starts on what is still in L2
+  const bool rv = rev && splits >= 0;
+  const int chunk = rv ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int n = rv ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int bx = rv ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
   if (splits < 0) {
@@ -223,9 +230,12 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
   const float* yb = y + (long long)n * y_ns + slab;
   const long long ob = (long long)n * out_ns + slab;
   const long long rb = (long long)n * res_ns + slab;
+  const long long vstride = (long long)gridDim.x * kThreads, vfirst = (long long)bx * kThreads + threadIdx.x;
+  const long long vlast_it = vfirst < V ? (V - 1 - vfirst) / vstride : -1;
+  long long v = rv ? vfirst + vlast_it * vstride : vfirst;
+  const long long vstep = rv ? -vstride : vstride;
 #pragma unroll 2
-  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
-       v += (long long)gridDim.x * kThreads) {
+  for (long long it = 0; it <= vlast_it; ++it, v += vstep) {
     float x[8];
     load_f32x8(yb + v * 8, x);
 #pragma unroll
@@ -361,10 +371,14 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
                       uint16_t* aux_lo, long long aux_ns, const float* partial,
                       int splits, int N, int batch_mode, int Creal, float* dgamma,
                       float* dbeta, int dy_wsplit_w, float* small_partial, unsigned int* small_counters,
-                      float* sums_w) {
+                      float* sums_w, int rev) {
   pdl_trigger();
   pdl_wait();
-  const int chunk = blockIdx.y, n = blockIdx.z;
+  // rev: reverse of the reduction pass's order -> the tail of g / y it just streamed is still in L2
+  const bool rv = rev && splits >= 0;
+  const int chunk = rv ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int n = rv ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int bx = rv ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
 #pragma unroll
@@ -462,9 +476,12 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
   const float* g1b = g1 ? g1 + (long long)n * g1_ns + slab : nullptr;
   const long long ob = (long long)n * dy_ns + slab;
   const long long ab = (long long)n * aux_ns + slab;
+  const long long vstride = (long long)gridDim.x * kThreads, vfirst = (long long)bx * kThreads + threadIdx.x;
+  const long long vlast_it = vfirst < V ? (V - 1 - vfirst) / vstride : -1;
+  long long v = rv ? vfirst + vlast_it * vstride : vfirst;
+  const long long vstep = rv ? -vstride : vstride;
 #pragma unroll 2
-  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
-       v += (long long)gridDim.x * kThreads) {
+  for (long long it = 0; it <= vlast_it; ++it, v += vstep) {
     float x[8], g[8];
     load_f32x8(yb + v * 8, x);
     load_f32x8(g0b + v * 8, g);
@@ -510,6 +527,14 @@ split_f32_kernel(const float* g0, long long g0_ns, const float* g1,
     }
     store_split8<ODT>(hi, lo, (long long)n * o_ns + slab + v * 8, g);
   }
+}
+
+// apply passes walk the data in reverse of the pass before them (L2 reuse); TTA_NORM_FORWARD_ORDER=1
+// restores the forward order (A/B)
+static inline int norm_rev() {
+  static int v = -1;
+  if (v < 0) v = getenv("TTA_NORM_FORWARD_ORDER") ? 0 : 1;
+  return v;
 }
 
 static inline int pick_splits(int N, int C8, long long V) {
@@ -587,7 +612,7 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
       y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
       (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns,                       \
       partial ? partial + 1024 : nullptr, splits, N,                                                        \
-      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd), ws_hi, ws_lo, ws_ns, W)
+      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd), ws_hi, ws_lo, ws_ns, W, norm_rev())
   if (out_dtype == TTA_F16) {
     if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
   } else {
@@ -644,17 +669,17 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
     tta_launch(norm_bwd_apply_kernel<TTA_F16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr);
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev());
   else if (out_dtype == TTA_F16_HI)
     tta_launch(norm_bwd_apply_kernel<TTA_F16_HI>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr);
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev());
   else
     tta_launch(norm_bwd_apply_kernel<TTA_BF16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr);
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev());
   return tta_check_launch("tta_norm_bwd_apply");
 }
 
@@ -690,7 +715,7 @@ int tta_norm_fwd_small(const float* y, long long y_ns, int N, int C8, long long 
   tta_launch_cluster(norm_apply_kernel<RES, DT>, grid, kThreads, 0, stream, cs, y, y_ns, C8, V, mean, \
              rstd, gamma, beta, relu, (const float*)res_a, (const uint16_t*)res_a, (const uint16_t*)res_b, \
              res_ns, out_hi, out_lo, out_ns, (const float*)nullptr, -1, N, 0, eps, mean, rstd, ws_hi, ws_lo, \
-             ws_ns, W)
+             ws_ns, W, 0)
   if (out_dtype == TTA_F16) {
     if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
   } else {
@@ -721,7 +746,7 @@ int tta_norm_bwd_small(const float* g0, long long g0_ns, const float* g1, long l
   tta_launch_cluster(norm_bwd_apply_kernel<DT>, grid, kThreads, 0, stream, cs, g0, g0_ns, g1, g1_ns, y, \
              y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)nullptr, inv_m, dy_hi, dy_lo, dy_ns, aux_hi, \
              aux_lo, aux_ns, (const float*)nullptr, -1, N, 0, Creal, dgamma, dbeta, dy_wsplit_w, workspace + 1024,  \
-             reinterpret_cast<unsigned int*>(workspace), sums)
+             reinterpret_cast<unsigned int*>(workspace), sums, 0)
   if (out_dtype == TTA_F16) LAUNCH(TTA_F16); else if (out_dtype == TTA_F16_HI) LAUNCH(TTA_F16_HI); else LAUNCH(TTA_BF16);
 #undef LAUNCH
   return tta_check_launch("tta_norm_bwd_small");
