@@ -22,10 +22,14 @@ __global__ void __launch_bounds__(kThreads, 4)
 norm_stats_partial_kernel(const float* y, long long n_stride, int C8, long long V,
                           int splits, float* partial, unsigned int* counters,
                           int N, int batch_mode, float eps, float* mean,
-                          float* rstd) {
+                          float* rstd, int rev) {
   pdl_trigger();
   pdl_wait();
-  const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  // rev: blocks take the slabs / ranges in reverse launch order (what the producing conv wrote last is
+  // still in L2); every block still sums its own range in ascending order -> same partial sums
+  const int split = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int chunk = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int n = rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
   const float* base = y + (long long)n * n_stride + (long long)chunk * V * 8;
   const long long per = (V + splits - 1) / splits;
   const long long v0 = (long long)split * per;
@@ -271,10 +275,12 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
                         const float* gamma, const float* beta, int relu,
                         int splits, float* partial, unsigned int* counters, int N,
                         int batch_mode, int Creal, float* sums, float* dgamma,
-                        float* dbeta, int acc_dgb) {
+                        float* dbeta, int acc_dgb, int rev) {
   pdl_trigger();
   pdl_wait();
-  const int split = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  const int split = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int chunk = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int n = rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
   const int C = C8 * 8;
   float mu[8], rs[8], ga[8], be[8];
 #pragma unroll
@@ -531,10 +537,20 @@ split_f32_kernel(const float* g0, long long g0_ns, const float* g1,
 
 // apply passes walk the data in reverse of the pass before them (L2 reuse); TTA_NORM_FORWARD_ORDER=1
 // restores the forward order (A/B)
-static inline int norm_rev() {
+// TTA_NORM_ORDER (A/B, ms per step on one box): 0 = every pass forward (2.321), 1 (default) = apply passes
+// reversed (2.293), 2 = reduction passes reversed (they follow a conv that wrote front to back), the apply
+// pass after a reduction forward again, the apply pass that follows a conv directly reversed (2.305)
+static inline int norm_order() {
   static int v = -1;
-  if (v < 0) v = getenv("TTA_NORM_FORWARD_ORDER") ? 0 : 1;
+  if (v < 0) {
+    const char* e = getenv("TTA_NORM_ORDER");
+    v = e ? atoi(e) : 1;
+  }
   return v;
+}
+static inline int norm_rev_reduce() { return norm_order() == 2; }
+static inline int norm_rev_apply(bool follows_reduction) {
+  return norm_order() == 1 || (norm_order() == 2 && !follows_reduction);
 }
 
 static inline int pick_splits(int N, int C8, long long V) {
@@ -579,7 +595,7 @@ int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, i
   // finalize = 1: the last block of every chunk turns the partial sums into mean/rstd (single pass)
   tta_launch(norm_stats_partial_kernel, dim3(splits, C8, N), kThreads, 0, stream, tta_pdl_family(2), 
       y, y_ns, C8, V, splits, workspace + 1024, finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N,
-      batch_mode, eps, mean, rstd);
+      batch_mode, eps, mean, rstd, norm_rev_reduce());
   return tta_check_launch("tta_norm_stats");
 }
 
@@ -612,7 +628,8 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
       y, y_ns, C8, V, mean, rstd, gamma, beta, relu, (const float*)res_a,                      \
       (const uint16_t*)res_a, (const uint16_t*)res_b, res_ns, out_hi, out_lo, out_ns,                       \
       partial ? partial + 1024 : nullptr, splits, N,                                                        \
-      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd), ws_hi, ws_lo, ws_ns, W, norm_rev())
+      batch_mode, eps, const_cast<float*>(mean), const_cast<float*>(rstd), ws_hi, ws_lo, ws_ns, W,                \
+      norm_rev_apply(partial_splits <= 0))
   if (out_dtype == TTA_F16) {
     if (res_kind == 0) LAUNCH(0, TTA_F16); else if (res_kind == 1) LAUNCH(1, TTA_F16); else LAUNCH(2, TTA_F16);
   } else {
@@ -645,7 +662,7 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
   tta_launch(norm_bwd_partial_kernel, dim3(splits, C8, N), kThreads, 0, stream, tta_pdl_family(2), 
       g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, splits, workspace + 1024,
       finalize ? reinterpret_cast<unsigned int*>(workspace) : nullptr, N, batch_mode, Creal, sums, dgamma, dbeta,
-      accumulate_dgb);
+      accumulate_dgb, norm_rev_reduce());
   return tta_check_launch("tta_norm_bwd_reduce");
 }
 
@@ -669,17 +686,17 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
     tta_launch(norm_bwd_apply_kernel<TTA_F16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev());
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev_apply(true));
   else if (out_dtype == TTA_F16_HI)
     tta_launch(norm_bwd_apply_kernel<TTA_F16_HI>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev());
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev_apply(true));
   else
     tta_launch(norm_bwd_apply_kernel<TTA_BF16>, grid, kThreads, 0, stream, tta_pdl_family(2), 
         g0, g0_ns, g1, g1_ns, y, y_ns, C8, V, mean, rstd, gamma, beta, relu, sums, inv_m, dy_hi,
         dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, partial ? partial + 1024 : nullptr, splits, N, batch_mode, Creal, dgamma,
-        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev());
+        dbeta, dy_wsplit_w, nullptr, nullptr, nullptr, norm_rev_apply(true));
   return tta_check_launch("tta_norm_bwd_apply");
 }
 
