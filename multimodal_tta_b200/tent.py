@@ -108,15 +108,19 @@ class TentB200:
             self.reset()
         return eng, x
 
-    def _run(self, eng, plan, pack, gmul: float = 1.0) -> None:
+    def _run(self, eng, plan, pack, gmul: float = 1.0, input_key=None) -> None:
         """``steps`` x (forward, entropy, backward, [all-reduce], Adam); logits of the first forward
-        are kept in plan.logits_out."""
+        are kept in plan.logits_out.  ``input_key`` distinguishes graphs that bake different input
+        pointers (the two staging buffers of adapt_stream); at most four are kept per plan."""
         ws = self.world_size
         single = ws == 1
         for it in range(self.steps):
             if self.use_graph:
-                key = (single, eng.entropy_mode, tuple(sorted(eng.adam.items())))
-                if plan.graph is None or plan.graph_key != key:
+                key = (single, eng.entropy_mode, tuple(sorted(eng.adam.items())), input_key)
+                graphs = plan.__dict__.setdefault("graphs", {})
+                if plan.graph is None:          # invalidated by the caller (step_windows: pointers changed)
+                    graphs.clear()
+                if key not in graphs:
                     # warm-up run outside capture (also the first real step)
                     pack()
                     eng.run_step(plan, adam=False)
@@ -125,7 +129,10 @@ class TentB200:
                     with torch.cuda.graph(g):
                         pack()
                         eng.run_step(plan, adam=single)
-                    plan.graph, plan.graph_key = g, key
+                    if len(graphs) >= 4:
+                        graphs.clear()
+                    graphs[key] = g
+                plan.graph, plan.graph_key = graphs[key], key
                 plan.graph.replay()
                 if not single:
                     eng.adam_step(self._allreduce_grads(eng) * gmul)
@@ -142,11 +149,16 @@ class TentB200:
         self.gpu_launches_per_step = (plan.launches_fwd + plan.launches_bwd) * self.steps
         self.last_loss = plan.loss_out
 
-    def step(self, x: torch.Tensor) -> torch.Tensor:
+    def step(self, x: torch.Tensor, persistent_input: bool = False) -> torch.Tensor:
         """Adapt on one batch [B,C,D,H,W]; returns the pre-update logits [B,R,D,H,W] (a view of the
-        engine's static output buffer -- clone it to keep it across steps)."""
+        engine's static output buffer -- clone it to keep it across steps).  ``persistent_input``: the
+        caller keeps ``x`` alive at this address (a staging buffer it refills); the step then reads it
+        in place -- its own CUDA graph per buffer -- instead of copying it into the plan's static input."""
         eng, x = self._prepare(x)
         plan = eng.get_plan(*[int(s) for s in (x.shape[0], *x.shape[2:])])
+        if persistent_input:
+            self._run(eng, plan, lambda: eng._pack_input(plan, x), input_key=x.data_ptr())
+            return plan.logits_out
         if plan.x_static is None or plan.x_static.shape != x.shape:
             plan.x_static = torch.empty_like(x)
         if x.data_ptr() != plan.x_static.data_ptr():
@@ -220,7 +232,7 @@ class TentB200:
                     raise ValueError("adapt_stream: all batches must have the same shape")
                 enqueue(i + 1, following)
             cur.wait_event(ready[i % 2])
-            out = self.step(staging[i % 2])                   # D2D into the graph's static input + replay
+            out = self.step(staging[i % 2], persistent_input=True)   # the graph of this staging buffer reads it in place
             freed[i % 2].record(cur)
             yield out
             i, nxt = i + 1, following
