@@ -60,6 +60,7 @@ struct TcParams {
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
   int b_nblob, b_cb_bytes, b_g_bytes;  // resident weights: blobs to copy; bytes per channel block / per group
+  int pps;      // kd-stacked convs: halo planes per pipeline stage
   int s2pair;   // GEOM_S2 with a one-chunk input: tap pairs share one K = 16 MMA (see issue_group)
   int t2_jh16;  // GEOM_T2: offset (16 B units) of the h+1 halo rows inside a k-chunk: 9 = next row, or a second box
   int pl2;      // small-plane tiles (H <= 8): the 128 rows are 2 d-planes x 8 h x 8 w (GEOM_S1P / GEOM_S1TP)
@@ -242,53 +243,55 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
         }
       }
   } else if (GEOM == GEOM_S1K || GEOM == GEOM_S1TK) {
-    // kd-STACKED stride-1 conv for small n-tiles.  A tcgen05.mma of M = 128, K = 16 costs
-    // max(64, N/2) cycles (measured: the N = 32 and N = 64 MMAs of the 32-channel layers ran ~70 cycles
-    // each), so one MMA per (plane, tap) wastes the tensor pipe when N = acc_cols < 128.  The input
-    // plane j = g of the (TD + 2)-plane halo feeds output planes j-2 .. j through the three kd taps of a
-    // (kh, kw) pair: ONE MMA over the stack of their weights (slot s -> accumulator j - 2 + s,
-    // accumulators contiguous in TMEM, N = k * acc_cols <= 192).  Stage = one halo plane (loaded once
-    // per channel block instead of once per kd); weights are resident, entry (kh, kw) =
+    // kd-STACKED stride-1 conv for small n-tiles.  An M = 128, K = 16 MMA reads a 4 KB A tile (32 cycles
+    // of shared-memory operand bandwidth) but needs only N/2 tensor cycles, so one MMA per (plane, tap)
+    // with N = acc_cols < 128 leaves the tensor pipe mostly idle.  Input plane j of the (TD + 2)-plane
+    // halo feeds output planes j-2 .. j through the three kd taps of a (kh, kw) pair: ONE MMA over the
+    // stack of their weights (slot s -> accumulator j - 2 + s, accumulators contiguous in TMEM,
+    // N = k * acc_cols <= 192).  A stage holds P.pps consecutive halo planes (each loaded once per channel
+    // block instead of once per kd); weights are resident, entry (kh, kw) =
     // [kchunk][slot 0..2][hi NT | lo NT][8].  With split planes A_hi and A_lo both multiply the whole
     // [B_hi | B_lo] stack (as GEOM_T2 does; the extra lo*lo term is below fp32 resolution).
     const uint32_t a_w1 = 10u | (1u << 14);
     const uint32_t lbo = (uint32_t)P.lbo16[0] << 16;
-    const uint32_t ah = a_hi0 | lbo, al = a_lo0 | lbo;
-    const int j = g;
-    const int s_lo = j < 2 ? 2 - j : 0, s_hi = (TD + 1 - j) < 2 ? (TD + 1 - j) : 2;
-    const uint32_t k = (uint32_t)(s_hi - s_lo + 1);
-    const uint32_t d0 = tmem_acc0 + (uint32_t)(j - 2 + s_lo) * acc_cols;
     const uint32_t lbo_b = (3u * acc_cols) << 16;                      // rows of all three slots per k-chunk
-    const uint32_t sbase = (bsrc >> 4) + (uint32_t)s_lo * acc_cols;    // 16-byte rows
-    const uint32_t idesc_k = P.idesc0 | (((k * acc_cols) >> 3) << 17);
-    const uint32_t idesc_k1 = P.idesc0 | ((((k - 1u) * acc_cols) >> 3) << 17);
     const uint32_t idesc_1 = P.idesc0 | ((acc_cols >> 3) << 17);
-    const bool fresh = first && j < TD;   // first channel block: accumulator j (the top slot) starts here
+    for (int jj = 0; jj < P.pps; ++jj) {
+      const int j = g * P.pps + jj;
+      const uint32_t ah = (a_hi0 + (uint32_t)jj * 180u) | lbo, al = (a_lo0 + (uint32_t)jj * 180u) | lbo;
+      const int s_lo = j < 2 ? 2 - j : 0, s_hi = (TD + 1 - j) < 2 ? (TD + 1 - j) : 2;
+      const uint32_t k = (uint32_t)(s_hi - s_lo + 1);
+      const uint32_t d0 = tmem_acc0 + (uint32_t)(j - 2 + s_lo) * acc_cols;
+      const uint32_t sbase = (bsrc >> 4) + (uint32_t)s_lo * acc_cols;    // 16-byte rows
+      const uint32_t idesc_k = P.idesc0 | (((k * acc_cols) >> 3) << 17);
+      const uint32_t idesc_k1 = P.idesc0 | ((((k - 1u) * acc_cols) >> 3) << 17);
+      const bool fresh = first && j < TD;   // first channel block: accumulator j (the top slot) starts here
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int rh = GEOM == GEOM_S1K ? kh : 2 - kh, rw = GEOM == GEOM_S1K ? kw : 2 - kw;
-        const uint32_t ao = (uint32_t)(rh * 10 + rw);
-        const uint32_t bw0 = (sbase + (uint32_t)(kh * 3 + kw) * b_ent) | lbo_b;
-        const uint64_t bd = ((uint64_t)b_w1 << 32) | bw0;
-        const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | (ah + ao), ad_lo = ((uint64_t)a_w1 << 32) | (al + ao);
-        if (fresh && kh == 0 && kw == 0) {
-          // the older accumulators of the stack accumulate, the fresh one is overwritten
-          const uint64_t bd_top = ((uint64_t)b_w1 << 32) | ((bw0 + (k - 1u) * acc_cols));
-          if (leader) {
-            if (k > 1u) {
-              umma_f16(d0, ad_hi, bd, idesc_k1, 1u);
-              if (SPLIT) umma_f16(d0, ad_lo, bd, idesc_k1, 1u);
+        for (int kw = 0; kw < 3; ++kw) {
+          const int rh = GEOM == GEOM_S1K ? kh : 2 - kh, rw = GEOM == GEOM_S1K ? kw : 2 - kw;
+          const uint32_t ao = (uint32_t)(rh * 10 + rw);
+          const uint32_t bw0 = (sbase + (uint32_t)(kh * 3 + kw) * b_ent) | lbo_b;
+          const uint64_t bd = ((uint64_t)b_w1 << 32) | bw0;
+          const uint64_t ad_hi = ((uint64_t)a_w1 << 32) | (ah + ao), ad_lo = ((uint64_t)a_w1 << 32) | (al + ao);
+          if (fresh && kh == 0 && kw == 0) {
+            // the older accumulators of the stack accumulate, the fresh one is overwritten
+            const uint64_t bd_top = ((uint64_t)b_w1 << 32) | ((bw0 + (k - 1u) * acc_cols));
+            if (leader) {
+              if (k > 1u) {
+                umma_f16(d0, ad_hi, bd, idesc_k1, 1u);
+                if (SPLIT) umma_f16(d0, ad_lo, bd, idesc_k1, 1u);
+              }
+              umma_f16(d0 + (k - 1u) * acc_cols, ad_hi, bd_top, idesc_1, 0u);
+              if (SPLIT) umma_f16(d0 + (k - 1u) * acc_cols, ad_lo, bd_top, idesc_1, 1u);
             }
-            umma_f16(d0 + (k - 1u) * acc_cols, ad_hi, bd_top, idesc_1, 0u);
-            if (SPLIT) umma_f16(d0 + (k - 1u) * acc_cols, ad_lo, bd_top, idesc_1, 1u);
+          } else if (leader) {
+            umma_f16(d0, ad_hi, bd, idesc_k, 1u);
+            if (SPLIT) umma_f16(d0, ad_lo, bd, idesc_k, 1u);
           }
-        } else if (leader) {
-          umma_f16(d0, ad_hi, bd, idesc_k, 1u);
-          if (SPLIT) umma_f16(d0, ad_lo, bd, idesc_k, 1u);
         }
-      }
+    }
   } else if (GEOM == GEOM_S1P || GEOM == GEOM_S1TP) {
     // Small planes (H <= 8, the 8^3 level): a 16 x 8 tile of ONE plane would be half empty, so the
     // 128 rows are 2 d-planes x 8 h x 8 w.  The descriptor needs ONE stride between 8-row groups,
@@ -1499,9 +1502,17 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     if (td_max < 1) td_max = 1;
     if (flags & 1) td_max = 1;
   }
+  // kd-stacked convs: two halo planes per stage when the (td + 2)-plane halo splits evenly (fewer, longer
+  // stages: the per-stage barrier round trip was the critical path of the single-product dgrads);
+  // flags bit7 keeps one plane per stage (A/B)
+  auto pps_of = [&](int td_) {
+    if (!stacked || (flags & 128)) return 1;
+    if ((flags & 2048) && (td_ + 2) % 3 == 0) return 3;   // experiment: three planes per stage
+    return (td_ + 2) % 2 == 0 ? 2 : 1;
+  };
   auto a_plane_of = [&](int td_) {
     if (pl2t) return 2 * 4608;  // [kchunk 2][jh 2][2 planes][8 rows][9 w][16 B]
-    if (stacked) return 2 * round128(hx * wx * 16);  // a stage is ONE halo plane
+    if (stacked) return 2 * round128(hx * wx * pps_of(td_) * 16);  // a stage is pps halo planes
     return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * ppa * 16);
   };
   const int a_planes = split ? 2 : 1;
@@ -1544,8 +1555,9 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.a_plane_bytes = a_plane_of(td);
   P.stage_bytes = stage_bytes_of(td);
   P.b_off = a_planes * P.a_plane_bytes;
-  P.lbo16[0] = pl2t ? 4608 / 16 : round128(hx * wx * (stacked ? 1 : td * ppa) * 16) / 16;
-  if (stacked) P.ngroups = td + 2;
+  P.pps = pps_of(td);
+  P.lbo16[0] = pl2t ? 4608 / 16 : round128(hx * wx * (stacked ? P.pps : td * ppa) * 16) / 16;
+  if (stacked) P.ngroups = (td + 2) / P.pps;
   P.b_nblob = stacked ? P.ncblk : P.ncblk * P.ngroups;
   P.b_cb_bytes = stacked ? P.b_blob_bytes : P.ngroups * P.b_blob_bytes;
   P.b_g_bytes = stacked ? 0 : P.b_blob_bytes;
@@ -1678,7 +1690,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
         }
       }
   } else {
-    const int box_d = geom == GEOM_T2 ? ppa : (stacked ? 1 : td * ppa);
+    const int box_d = geom == GEOM_T2 ? ppa : (stacked ? P.pps : td * ppa);
     ok = ok && encode_row(&P.amap[0], in_hi, wx, hx, box_d);
     if (split) ok = ok && encode_row(&P.amap[1], in_lo, wx, hx, box_d);
   }
@@ -1694,10 +1706,10 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     }
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
   } else if (stacked) {
-    for (int j = 0; j < td + 2; ++j) {
+    for (int j = 0; j < P.ngroups; ++j) {
       TcGroup& G = P.grp[j];
       G.nloads = 1; G.nmma = 9;
-      G.ld[0] = {0, -1, -1, j - 1, 0, 18 * 10 * 16, P.lbo16[0] * 16, 0};
+      G.ld[0] = {0, -1, -1, j * P.pps - 1, 0, 18 * 10 * P.pps * 16, P.lbo16[0] * 16, 0};
       G.tx_bytes = 2 * G.ld[0].bytes;
     }
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
