@@ -1502,12 +1502,13 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     if (td_max < 1) td_max = 1;
     if (flags & 1) td_max = 1;
   }
-  // kd-stacked convs: two halo planes per stage when the (td + 2)-plane halo splits evenly (fewer, longer
-  // stages: the per-stage barrier round trip was the critical path of the single-product dgrads);
-  // flags bit7 keeps one plane per stage (A/B)
+  // kd-stacked convs: three (else two) halo planes per stage when the (td + 2)-plane halo splits evenly
+  // -- fewer, longer stages: the per-stage barrier round trip was on the critical path of the
+  // single-product dgrads.  Same-box A/B per step: 1 plane 2.285 ms, 2 planes 2.265 / 2.225, 3 planes 2.217.
+  // flags bit7: one plane per stage, bit11: at most two (A/B switches)
   auto pps_of = [&](int td_) {
     if (!stacked || (flags & 128)) return 1;
-    if ((flags & 2048) && (td_ + 2) % 3 == 0) return 3;   // experiment: three planes per stage
+    if (!(flags & 2048) && (td_ + 2) % 3 == 0) return 3;
     return (td_ + 2) % 2 == 0 ? 2 : 1;
   };
   auto a_plane_of = [&](int td_) {
