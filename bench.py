@@ -48,6 +48,17 @@ def measured_traffic():
     return d.get("conv_dram_bytes_per_step"), d.get("stream_dram_bytes_per_step")
 
 
+def measured_tensor_pipe():
+    """Duration-weighted tensor-pipe utilisation of the conv launches of one step (ncu, written by
+    scripts/summarize_tensor_pipe.py to profiles/tensor_pipe_r1.json); None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "tensor_pipe_r1.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return {k: d.get(k) for k in ("tensor_pipe_active_pct", "tc_pipe_active_pct", "sm_ghz_under_load")}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -274,7 +285,10 @@ def run_product(args):
                          "achieved": conv_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": conv_tflops / pk["tf_sust"], "traffic": conv_traffic, "peak_source": pk["src"],
                          "traffic_note": "DRAM bytes of all conv launches of one step (ncu, profiles/traffic_r1.json)",
-                         "ms_per_step": roof["conv_ms"], "share_of_step": roof["conv_ms"] / roof["total_ms"]},
+                         "ms_per_step": roof["conv_ms"], "share_of_step": roof["conv_ms"] / roof["total_ms"],
+                         "algorithmic_note": "achieved = algorithmic conv FLOPs (190.8 GFLOP/volume); the fp32-equivalent "
+                                             "forward executes 3-4 fp16 products per algorithmic MAC",
+                         "ncu_tensor_pipe": measured_tensor_pipe()},
             "roofline_hbm": {"bound": "hbm", "kernel": "norm stats/apply/bwd + fused entropy head",
                              "achieved": hbm_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_gbs / pk["hbm"],
                              "traffic": stream_traffic, "algorithmic_bytes": hbm_bytes,
