@@ -20,10 +20,16 @@
 //    A_lo x B_hi (N = NT); the epilogue adds the two column halves.  That is hi*hi + hi*lo + lo*hi
 //    in fp32 -- ~fp32-equivalent products -- for 2/3 of the shared-memory operand traffic of three
 //    separate MMAs (small-N MMAs are bound by the 4 KB A-tile read, not by tensor math).
-//  * Persistent CTAs: grid = min(work items, #SMs); warp 0 = TMA producer, warp 1 = TMEM alloc +
-//    single-thread MMA issue, warps 2..5 = epilogue.  The smem stage ring (full/empty mbarriers)
-//    runs across work items; TMEM accumulators are double buffered when they fit, so the epilogue
-//    of item i overlaps the main loop of item i+1.
+//  * Persistent CTAs: grid = min(work items, #SMs), 352 threads: warps 0 and 10 = TMA producers
+//    (alternating ring positions), warp 1 = TMEM alloc + MMA issue (warp-uniform code, one elected lane
+//    issues), warps 2..9 = epilogue (two per TMEM lane quarter).  The smem stage ring (full/empty
+//    mbarriers) runs across work items; TMEM accumulators are double buffered when they fit, so the
+//    epilogue of item i overlaps the main loop of item i+1.
+//  * Geometry variants (issue_group<GEOM>): S1 / S1T / K1 / S2 / T2 as above; S1P / S1TP = two d-planes
+//    per 128-row tile on planes with H <= 8; S1K / S1TK = kd-stacked MMAs for small n-tiles with
+//    resident weights; S2 with a one-chunk input issues tap PAIRS as the two k-chunks of one MMA.
+//    conv_t2s_kernel (below) is a separate kernel: transposed stride-2 conv with <= 4 output channels as
+//    one dense GEMM per input plane + a shared-memory col2im.
 #include <cuda.h>
 
 #include <algorithm>

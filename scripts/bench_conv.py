@@ -43,10 +43,13 @@ for name, cin, cout, K, s, mode, S in LAYERS:
     hi = torch.randint(-3000, 3000, (N, c8i, S, S, S, 8), dtype=torch.int16, device=dev)
     lo = torch.zeros_like(hi)
     w = torch.randn(27 if K == 3 else 1, cin, cout, device=dev) * 0.05
-    wp = pack_weights_tc(w, mode, K, s, TTA_F16)
+    # flags bits 8..10 (real Cout) select the dense-GEMM + col2im kernel where the layer qualifies
+    t2s = bool(flags & 0x700) and bool(lib.tta_conv_tc_t2s(mode, K, s, cin, cout, 1))
+    lflags = (flags & ~0x700) | ((cout << 8) if t2s else 0)
+    wp = pack_weights_tc(w, mode, K, s, TTA_F16, t2s=t2s)
     out = torch.zeros((N, c8o, So, So, So, 8), device=dev)
     args = (hi.data_ptr(), lo.data_ptr(), c8i * S ** 3 * 8, TTA_F16, N, c8i, S, S, S, wp.data_ptr(), 0, out.data_ptr(),
-            c8o * So ** 3 * 8, c8o, So, So, So, mode, K, s, 0, flags)
+            c8o * So ** 3 * 8, c8o, So, So, So, mode, K, s, 0, lflags)
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         check(lib.tta_conv_tc(*args, 0, 0, st))
