@@ -33,6 +33,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 
@@ -917,7 +918,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
 //     out[2d+qd, 2h+qh, 2w+qw] = b + sum over axes { q = 0: (shift 0, k = 1);  q = 1: (0, 2), (1, 0) }.
 // Roles: warp 0 TMA producer (one box [Cin/8 chunks][16 h][8 w] per plane and operand plane), warp 1
 // MMA issue, warps 2..5 epilogue; TMEM accumulators and the P tiles are double buffered.
-constexpr int kT2sThreads = 192;
+constexpr int kT2sThreads = 320;  // TMA producer, MMA issuer, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kT2sStages = 3;  // at most
 
 struct T2sParams {
@@ -946,7 +947,7 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float red_s[4][8];
+  __shared__ float red_s[8][8];
   constexpr int NC = 27 * COUT;          // real GEMM columns
   constexpr int PROW = NC | 1;           // odd row pitch of the P tiles: conflict-free column access
 
@@ -959,7 +960,7 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[b]), 4);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 8);
     }
     mbar_init(smem_u32(&bar_w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1055,10 +1056,14 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
     }
   } else {
     // ===================== epilogue: TMEM -> P tile (smem) -> col2im gather -> HBM =====================
+    // two warps per TMEM lane quarter: both own the same 32 input voxels; warp `half` copies every second
+    // 16-column block of the P rows and gathers the output planes of parity qd = half
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;                 // 0..7
     const int row = q * 32 + lane;           // input voxel of the tile = TMEM lane
     const int hh = row >> 3, ww = row & 7;
-    const int et = threadIdx.x - 64;         // 0..127
+    const int et = threadIdx.x - 64;         // 0..255
     const int Do = 2 * P.D, Ho = 2 * P.H, Wo = 2 * P.W;
     float bias_r[COUT];
 #pragma unroll
@@ -1076,21 +1081,23 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
         v[COUT + c] = warp_sum(s2[c]);
         s1[c] = s2[c] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 2 * COUT; ++i) red_s[q][i] = v[i];
+        for (int i = 0; i < 2 * COUT; ++i) red_s[ew][i] = v[i];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et < 2 * COUT) {
-        const float tot = red_s[0][et] + red_s[1][et] + red_s[2][et] + red_s[3][et];
+        float tot = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) tot += red_s[w8][et];
         const int k = et < COUT ? et : 8 + (et - COUT);
         P.stats[(((long long)st_n * gridDim.x) + blockIdx.x) * 16 + k] += tot;
       }
     };
     if (P.stats) {
-      for (int t = et; t < P.N * 16; t += 128) P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int t = et; t < P.N * 16; t += 256) P.stats[((long long)(t >> 4) * gridDim.x + blockIdx.x) * 16 + (t & 15)] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     uint32_t step = 0;
     for (int item = blockIdx.x; item < P.work_items; item += gridDim.x) {
@@ -1112,7 +1119,7 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tb = tmem_base + buf * 2u * (uint32_t)P.np + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-          for (int c16 = 0; c16 < (NC + 15) / 16; ++c16) {
+          for (int c16 = half; c16 < (NC + 15) / 16; c16 += 2) {
             uint32_t ra[16], rb[16];
             tmem_ld16_nowait(tb + c16 * 16, ra);
             tmem_ld16_nowait(tb + P.np + c16 * 16, rb);
@@ -1125,15 +1132,16 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // P tile of plane p complete
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // P tile of plane p complete
         if (p > ds && mine) {
           const int d = p - 1;
           const float* lo_t = p_tiles + (size_t)(d & 1) * 128 * PROW;   // P of plane d
           const float* hi_t = cur;                                      // P of plane d + 1 (jd = 1)
+          // the output-plane parity this warp gathers is a compile-time constant inside the lambda
+          auto gather = [&](auto QD) {
+            constexpr int qd = decltype(QD)::value;
 #pragma unroll
-          for (int qd = 0; qd < 2; ++qd)
-#pragma unroll
-            for (int qh = 0; qh < 2; ++qh) {
+          for (int qh = 0; qh < 2; ++qh) {
               float o[2][COUT];
 #pragma unroll
               for (int qw = 0; qw < 2; ++qw) {
@@ -1169,8 +1177,10 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
                 store_f32x8(dst + qw * 8, rv);
               }
             }
+          };
+          if (half == 0) gather(std::integral_constant<int, 0>{}); else gather(std::integral_constant<int, 1>{});
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // gathers done before the older P tile is overwritten
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // gathers done before the older P tile is overwritten
       }
     }
     if (P.stats && st_n >= 0) stats_flush();
