@@ -233,8 +233,9 @@ class Plan:
     launches_fwd: int = 0
     launches_bwd: int = 0
     conv_backends: dict = field(default_factory=dict)
-    graph: Optional[torch.cuda.CUDAGraph] = None
+    graph: Optional[torch.cuda.CUDAGraph] = None      # the graph replayed last (None: invalidated)
     graph_key: Optional[tuple] = None
+    graphs: dict = field(default_factory=dict)        # key (mode, Adam, input pointer) -> captured step
     sample_w: Optional[torch.Tensor] = None
     win: Optional[torch.Tensor] = None
     chan_scale: Optional[torch.Tensor] = None

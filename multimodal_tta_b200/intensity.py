@@ -98,7 +98,8 @@ class IntensityPolicy:
         V = int(v5[0, 0].numel())
         key = (v5.device, C)
         if key not in self._rules:
-            self._rules[key] = (self.rules(C)[0].to(v5.device), self.rules(C)[1])
+            table, mc = self.rules(C)
+            self._rules[key] = (table.to(v5.device), mc)
         rules, min_count = self._rules[key]
         lib = _load_lib()
         nbytes = int(lib.tta_intensity_workspace_bytes(B, C, V))

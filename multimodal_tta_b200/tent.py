@@ -117,7 +117,7 @@ class TentB200:
         for it in range(self.steps):
             if self.use_graph:
                 key = (single, eng.entropy_mode, tuple(sorted(eng.adam.items())), input_key)
-                graphs = plan.__dict__.setdefault("graphs", {})
+                graphs = plan.graphs
                 if plan.graph is None:          # invalidated by the caller (step_windows: pointers changed)
                     graphs.clear()
                 if key not in graphs:
