@@ -49,6 +49,11 @@ int tta_device_sm(void); /* compute capability major*10+minor of the current dev
 int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                     const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi, uint16_t* lo,
                     long long out_n_stride, int C8, int wsplit, tta_stream_t stream);
+/* same, with the intensity policy applied on the fly: affine [n_vol][C][4] = {lo, hi, mu, 1/sd} from
+ * tta_intensity_stats (NULL: identity).  Bit-identical to tta_intensity_apply followed by tta_gather_pack. */
+int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                         const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
+                         uint16_t* lo, long long o_n_stride, int C8, int wsplit, tta_stream_t stream);
 
 /* ---- convolution (forward and input gradient): replaces nn.Conv3d / nn.ConvTranspose3d inside
  * monai.networks.blocks.Convolution reached from src/models/unet.py:56-66, and autograd's

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "tta_norm_bwd_small": (I, [P, L, P, L, P, L, I, I, I, L, P, P, P, P, I, P, P, P, P, P, L, P, P, L, I, I, P, P]),
     "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
     "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, I, P]),
+    "tta_gather_pack_norm": (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, P, P, L, I, I, P]),
     "tta_head_entropy_blocks": (I, [I, L]),
     "tta_head_entropy": (I, [P, L, I, I, L, I, F, F, I, P, P, P, P, L, P, P, P]),
     "tta_head_fused_supported": (I, [I, I, I, I]),

@@ -12,12 +12,24 @@ namespace tta {
 
 constexpr int kThreads = 256;
 
+// Optional intensity policy folded into the gather (tta_intensity_stats: affine[n_vol][C][4] =
+// {lo, hi, mu, 1/sd}): x -> (clamp(x, lo, hi) - mu) / sd, the same expression as tta_intensity_apply, so
+// the fused and the two-pass paths give identical bits.  No table: identity.
+__device__ __forceinline__ void load_affine(const float* affine, int vi, int C, int c, float& lo, float& hi,
+                                            float& mu, float& inv) {
+  lo = -INFINITY; hi = INFINITY; mu = 0.f; inv = 1.f;
+  if (affine != nullptr && c < C) {
+    const float* A = affine + ((long long)vi * C + c) * 4;
+    lo = A[0]; hi = A[1]; mu = A[2]; inv = A[3];
+  }
+}
+
 // ---------------------------------------------------------------- gather / pack
 // win[b*4 + {0,1,2,3}] = {volume index, d0, h0, w0} of window b (origins may be negative or
 // run past the volume: those voxels read 0 = MONAI's constant pad).
 __global__ void __launch_bounds__(kThreads)
 gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
-                   const int* win, const float* chan_scale, int D, int H,
+                   const int* win, const float* chan_scale, const float* affine, int D, int H,
                    int W, int C8, uint16_t* hi, uint16_t* lo,
                    long long o_ns, int wsplit) {
   pdl_trigger();
@@ -27,11 +39,12 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
   const long long V = (long long)D * H * W;
   const long long Vs = (long long)Ds * Hs * Ws;
   const float* src = vol + (long long)vi * C * Vs;
-  float sc[8];
+  float sc[8], alo[8], ahi[8], amu[8], ainv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = chunk * 8 + i;
     sc[i] = (c < C) ? (chan_scale ? chan_scale[b * C + c] : 1.f) : 0.f;
+    load_affine(affine, vi, C, c, alo[i], ahi[i], amu[i], ainv[i]);
   }
   for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
        v += (long long)gridDim.x * kThreads) {
@@ -45,7 +58,7 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = chunk * 8 + i;
-      x[i] = (inside && c < C) ? src[(long long)c * Vs + so] * sc[i] : 0.f;
+      x[i] = (inside && c < C) ? (fminf(fmaxf(src[(long long)c * Vs + so], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i] : 0.f;
     }
     // wsplit: the first conv is a stride-2 tcgen05 conv -> w-parity-split rows (tta_common.cuh)
     const long long vo = wsplit ? v - w + (w & 1) * (W >> 1) + (w >> 1) : v;
@@ -58,7 +71,7 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
 // the 2 x 4 x 128^3 input: 87 us for the per-voxel kernel above (200 MB moved).
 __global__ void __launch_bounds__(kThreads)
 gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
-                    const int* win, const float* chan_scale, int D, int H,
+                    const int* win, const float* chan_scale, const float* affine, int D, int H,
                     int W, int C8, uint16_t* hi, uint16_t* lo,
                     long long o_ns, int wsplit) {
   pdl_trigger();
@@ -68,11 +81,12 @@ gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
   const long long V = (long long)D * H * W;
   const long long Vs = (long long)Ds * Hs * Ws;
   const float* src = vol + (long long)vi * C * Vs;
-  float sc[8];
+  float sc[8], alo[8], ahi[8], amu[8], ainv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = chunk * 8 + i;
     sc[i] = (c < C) ? (chan_scale ? chan_scale[b * C + c] : 1.f) : 0.f;
+    load_affine(affine, vi, C, c, alo[i], ahi[i], amu[i], ainv[i]);
   }
   const unsigned W4 = (unsigned)W >> 2, G = (unsigned)(V >> 2);
   for (unsigned g = blockIdx.x * kThreads + threadIdx.x; g < G; g += gridDim.x * kThreads) {
@@ -94,11 +108,13 @@ gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
           const float* p = rowp + (long long)c * Vs;
           if (whole && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0ull) {
             const float4 v = *reinterpret_cast<const float4*>(p);
-            x[0][i] = v.x * sc[i]; x[1][i] = v.y * sc[i]; x[2][i] = v.z * sc[i]; x[3][i] = v.w * sc[i];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k][i] = (fminf(fmaxf(vv[k], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (sw + k >= 0 && sw + k < Ws) x[k][i] = p[k] * sc[i];
+              if (sw + k >= 0 && sw + k < Ws) x[k][i] = (fminf(fmaxf(p[k], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
           }
         }
       }
@@ -304,19 +320,32 @@ using namespace tta;
 
 extern "C" {
 
+int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                         const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
+                         uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream);
+
+
 int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                     const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi,
                     uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
+  return tta_gather_pack_norm(vol, n_vol, C, Ds, Hs, Ws, win, chan_scale, nullptr, NB, D, H, W, hi, lo, o_ns, C8,
+                              wsplit, stream);
+}
+
+// same with the intensity policy applied on the fly: affine [n_vol][C][4] from tta_intensity_stats (or null)
+int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                         const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
+                         uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
   TTA_REQUIRE(vol && win && hi && lo, "tta_gather_pack: null pointer");
   TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
   const long long V = (long long)D * H * W;
   if (W % 4 == 0 && V / 4 < 0x7fffffffLL)
     tta_launch(gather_pack4_kernel, dim3(xblocks(V / 4, (long long)NB * C8), C8, NB), kThreads, 0, stream,
-               tta_pdl_family(4), vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
+               tta_pdl_family(4), vol, C, Ds, Hs, Ws, win, chan_scale, affine, D, H, W, C8, hi, lo, o_ns, wsplit);
   else
     tta_launch(gather_pack_kernel, dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream, tta_pdl_family(4),
-               vol, C, Ds, Hs, Ws, win, chan_scale, D, H, W, C8, hi, lo, o_ns, wsplit);
+               vol, C, Ds, Hs, Ws, win, chan_scale, affine, D, H, W, C8, hi, lo, o_ns, wsplit);
   return tta_check_launch("tta_gather_pack");
 }
 

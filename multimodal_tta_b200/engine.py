@@ -973,7 +973,8 @@ class TTAEngine:
                 h.num_batches_tracked += 1
 
     def _pack_input(self, plan: Plan, x: torch.Tensor, win: Optional[torch.Tensor] = None,
-                    chan_scale: Optional[torch.Tensor] = None, vol_dims=None, n_vol=None):
+                    chan_scale: Optional[torch.Tensor] = None, vol_dims=None, n_vol=None,
+                    affine: Optional[torch.Tensor] = None):
         N = plan.N
         D, H, W = plan.dims
         if win is None:
@@ -984,10 +985,12 @@ class TTAEngine:
             win = plan.win
             vol_dims, n_vol = (D, H, W), N
         a = plan.x
-        check(self.lib.tta_gather_pack(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
-                                       chan_scale.data_ptr() if chan_scale is not None else 0, N, D, H, W,
-                                       a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8,
-                                       int(a.wsplit), _stream()),
+        # affine [n_vol][C][4] (IntensityPolicy.stats): clip + z-score applied while gathering
+        check(self.lib.tta_gather_pack_norm(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
+                                            chan_scale.data_ptr() if chan_scale is not None else 0,
+                                            affine.data_ptr() if affine is not None else 0, N, D, H, W,
+                                            a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8,
+                                            int(a.wsplit), _stream()),
               "gather_pack")
 
     def _check_input(self, x: torch.Tensor):

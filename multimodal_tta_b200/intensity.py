@@ -91,8 +91,10 @@ class IntensityPolicy:
         return r, min_count
 
     # ------------------------------------------------------------------ device passes
-    def stats(self, vol: torch.Tensor) -> torch.Tensor:
-        """vol [B,C,D,H,W] (or [C,D,H,W]) fp32 CUDA -> affine [B,C,4] = (lo, hi, mu, 1/sd) on the device."""
+    def stats(self, vol: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """vol [B,C,D,H,W] (or [C,D,H,W]) fp32 CUDA -> affine [B,C,4] = (lo, hi, mu, 1/sd) on the device
+        (written into ``out`` when given: a persistent buffer for CUDA-graph consumers such as
+        ``SlidingWindowTTA(..., intensity_policy=...)``)."""
         v5 = self._check(vol)
         B, C = int(v5.shape[0]), int(v5.shape[1])
         V = int(v5[0, 0].numel())
@@ -106,7 +108,9 @@ class IntensityPolicy:
         wkey = (v5.device, nbytes)
         if wkey not in self._ws:
             self._ws[wkey] = torch.zeros(nbytes, dtype=torch.uint8, device=v5.device)
-        affine = torch.empty((B, C, 4), dtype=torch.float32, device=v5.device)
+        affine = torch.empty((B, C, 4), dtype=torch.float32, device=v5.device) if out is None else out
+        if tuple(affine.shape) != (B, C, 4) or affine.dtype != torch.float32 or not affine.is_cuda:
+            raise ValueError("intensity stats: out must be a CUDA float32 tensor of shape [B, C, 4]")
         check(lib.tta_intensity_stats(v5.data_ptr(), B, C, V, rules.data_ptr(), min_count, affine.data_ptr(),
                                       self._ws[wkey].data_ptr(), torch.cuda.current_stream(v5.device).cuda_stream),
               "intensity_stats")

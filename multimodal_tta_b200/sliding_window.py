@@ -112,9 +112,12 @@ class SlidingWindowTTA:
         return self._bufs[key]
 
     @torch.no_grad()
-    def __call__(self, vol: torch.Tensor, chan_scale_per_volume: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, vol: torch.Tensor, chan_scale_per_volume: Optional[torch.Tensor] = None,
+                 intensity_policy=None) -> torch.Tensor:
         """vol [B,C,Ds,Hs,Ws] fp32 cuda -> blended logits [B,R,Ds,Hs,Ws]; adapts window-batch by
-        window-batch (non-episodic unless the TentB200 is episodic)."""
+        window-batch (non-episodic unless the TentB200 is episodic).  ``intensity_policy``
+        (``IntensityPolicy``): ``vol`` holds RAW intensities; one statistics pass over the volume, then
+        clip + z-score are applied while the windows are gathered (no normalised copy of the volume)."""
         import torch.distributed as dist
 
         tent = self.tent
@@ -131,6 +134,12 @@ class SlidingWindowTTA:
         st = self._state(vol.device, (vol.device, NB))
         acc = torch.zeros((B, R, *padded), dtype=torch.float32, device=vol.device)
         wsum = torch.zeros((B, *padded), dtype=torch.float32, device=vol.device)
+        affine = None
+        if intensity_policy is not None:
+            akey = ("affine", vol.device, B, C)
+            if akey not in self._bufs:
+                self._bufs[akey] = torch.empty((B, C, 4), dtype=torch.float32, device=vol.device)
+            affine = intensity_policy.stats(vol, out=self._bufs[akey])
         cs_dev = None
         if chan_scale_per_volume is not None:
             cs_dev = torch.ones((NB, C), dtype=torch.float32, device=vol.device)
@@ -148,7 +157,7 @@ class SlidingWindowTTA:
             if cs_dev is not None:
                 cs_dev.copy_(chan_scale_per_volume.to(vol.device)[st["win_host"][:, 0].long()])
             logits = tent.step_windows(vol, st["win"], self.roi, sample_w=st["sw"], chan_scale=cs_dev,
-                                       n_valid_global=n_valid if ws > 1 else None)
+                                       n_valid_global=n_valid if ws > 1 else None, affine=affine)
             # blend needs origins in PADDED coordinates
             winp = st["win"].clone()
             winp[:, 1:] += torch.tensor(pad_lo, dtype=torch.int32, device=vol.device)

@@ -171,17 +171,21 @@ class TentB200:
     def step_windows(self, vol: torch.Tensor, win: torch.Tensor, roi: Sequence[int],
                      sample_w: Optional[torch.Tensor] = None,
                      chan_scale: Optional[torch.Tensor] = None,
-                     n_valid_global: Optional[int] = None) -> torch.Tensor:
+                     n_valid_global: Optional[int] = None,
+                     affine: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Adapt on a batch of sliding-window patches gathered on device from ``vol``
         [n_vol,C,Ds,Hs,Ws].  ``win`` int32 [NB,4] = (volume index, d0, h0, w0) -- must live in a
         persistent buffer when CUDA graphs are on; ``sample_w`` [NB] zero-weights padding windows
         (multi-rank tail batches only; ``n_valid_global`` = real windows over all ranks, so that the
-        all-reduced gradient equals the mean over the real windows)."""
+        all-reduced gradient equals the mean over the real windows); ``affine`` [n_vol,C,4] from
+        ``IntensityPolicy.stats`` normalises RAW intensities while the windows are gathered (persistent
+        buffer, like ``win``)."""
         eng, vol = self._prepare(vol)
         NB = int(win.shape[0])
         plan = eng.get_plan(NB, int(roi[0]), int(roi[1]), int(roi[2]))
         key = (vol.data_ptr(), tuple(vol.shape), win.data_ptr(),
-               None if chan_scale is None else chan_scale.data_ptr())
+               None if chan_scale is None else chan_scale.data_ptr(),
+               None if affine is None else affine.data_ptr())
         if getattr(plan, "win_key", None) != key:
             plan.graph = None  # pointers baked into the graph changed
             plan.win_key = key
@@ -192,7 +196,7 @@ class TentB200:
             gmul = NB * self.world_size / float(n_valid_global)
         vd = tuple(int(s) for s in vol.shape[2:])
         self._run(eng, plan, lambda: eng._pack_input(plan, vol, win=win, chan_scale=chan_scale,
-                                                     vol_dims=vd, n_vol=int(vol.shape[0])), gmul)
+                                                     vol_dims=vd, n_vol=int(vol.shape[0]), affine=affine), gmul)
         return plan.logits_out
 
     def adapt_stream(self, host_batches):

@@ -73,3 +73,32 @@ def test_cuda_intensity_policy_large_volume(cuda):
     ref = normalize_img(x, intensity_policy=HECKTOR)
     got = IntensityPolicy(HECKTOR)(x.to(cuda)).cpu()
     assert float((got - ref).abs().max()) <= 5e-6 * float(ref.abs().max())
+
+
+@pytest.mark.gpu
+def test_gather_with_fused_intensity_policy_is_bit_identical(cuda):
+    """tta_gather_pack_norm(raw volume, affine) == tta_gather_pack(tta_intensity_apply(raw volume)): window origins
+    inside / partly outside the volume, modality dropout scale, both the 4-wide and the scalar kernel."""
+    from multimodal_tta_b200._lib import check, lib as load
+    from multimodal_tta_b200.intensity import IntensityPolicy
+    lib = load()
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.from_numpy(GOLD["hecktor_in"])
+    raw = torch.stack([x, x.flip(-1) * 0.7 + 3.0]).to(cuda).contiguous()          # [2, 2, 10, 12, 14]
+    pol = IntensityPolicy(HECKTOR)
+    affine = pol.stats(raw)
+    norm = pol(raw)
+    wins = torch.tensor([[0, 0, 0, 0], [1, 2, 4, 6], [1, -3, -2, -5]], dtype=torch.int32, device=cuda)
+    scale = torch.tensor([[1., 1.], [1., 0.], [0.5, 1.]], device=cuda)
+    for roi in ((8, 8, 8), (8, 8, 6)):
+        V = roi[0] * roi[1] * roi[2]
+        outs = []
+        for vol, aff in ((raw, affine), (norm, None)):
+            hi = torch.zeros((3, 1, *roi, 8), dtype=torch.int16, device=cuda); lo = torch.zeros_like(hi)
+            check(lib.tta_gather_pack_norm(vol.data_ptr(), 2, 2, 10, 12, 14, wins.data_ptr(), scale.data_ptr(),
+                                           aff.data_ptr() if aff is not None else 0, 3, *roi, hi.data_ptr(),
+                                           lo.data_ptr(), V * 8, 1, 0, st), "gather_pack_norm")
+            outs.append((hi, lo))
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert int(outs[0][0].abs().max()) > 0

@@ -62,3 +62,11 @@ def test_hecktor_pipeline_raw_intensities_to_blended_logits(cuda):
     got = sw(vol, chan_scale_per_volume=keep).cpu()
     assert rel_l2(got, ref) < 1e-3
     assert ((got >= 0) == (ref >= 0)).float().mean().item() >= 0.9999
+    # fused variant: raw intensities in, clip + z-score applied inside the window gather.  The operand planes
+    # are bit-identical to the two-pass path (tests/test_intensity.py); the logits agree to the run-to-run
+    # noise of the split-K float atomics in the deep layers.
+    _, prod2 = make_pair(HECKTOR_MODEL_CFG, seed=33)
+    tp2 = TentB200(prod2, {"cuda_graph": True})
+    sw2 = SlidingWindowTTA(tp2, (32, 32, 32), sw_batch=2, overlap=0.5)
+    got2 = sw2(raw.cuda(), chan_scale_per_volume=keep, intensity_policy=IntensityPolicy(HECKTOR)).cpu()
+    assert rel_l2(got2, got) < 5e-4, rel_l2(got2, got)      # measured 3e-5 (atomics order x several Adam steps)
