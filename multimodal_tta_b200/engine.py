@@ -532,7 +532,8 @@ class TTAEngine:
             # of a fused unit0 || shortcut conv)
             q = y.root.tc_query
             # ... and double-buffered TMEM accumulators, so the reduction hides behind the next item's MMAs
-            fuse_st = (model.fuse_stats and q is not None and q[0] == 1 and q[2] == 2 and y.c8_off == 0
+            fuse_st = (model.fuse_stats and q is not None and q[0] == 1
+                       and (q[2] == 2 or model.fuse_stats_single_buffer) and y.c8_off == 0
                        and y.root.stats_c8 == 0)
             if fuse_st:
                 y.root.stats_c8, y.root.stats_grid = y.C8, q[1]

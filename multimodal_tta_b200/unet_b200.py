@@ -160,6 +160,10 @@ class UNetB200(nn.Module):
         # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
         # a separate pass over y (only where the conv runs without split-K)
         self.fuse_stats = bool(get_config(cfg, "fuse_stats", True))
+        # OPT-IN: also when the conv has a single TMEM accumulator buffer (the reduction is then not hidden
+        # behind the next item's MMAs, but a statistics pass over the conv result disappears).  Same-box A/B:
+        # 2.2936 vs 2.2968 ms per step -- within noise, so the default stays off
+        self.fuse_stats_single_buffer = bool(get_config(cfg, "fuse_stats_single_buffer", False))
         # ... and, OPT-IN, the norm-BACKWARD reductions (sum dz, sum dz*xhat) out of the epilogue of
         # the dgrad conv that completes the layer's incoming gradient.  Measured on B200 (2x4x128^3):
         # the four 64^3 / 32^3 layers it applies to lose 162 us in their dgrads (the epilogue has
