@@ -67,6 +67,9 @@ struct TcParams {
   int ksplit, cb_per_split, work_items, b_off;  // b_off: byte offset of the B blob inside a stage
   int s2_rows;  // stride-2 input stored w-parity-split: sub-tiles are whole-row 4-D TMA boxes
   int b_nblob, b_cb_bytes, b_g_bytes;  // resident weights: blobs to copy; bytes per channel block / per group
+  // CTA PAIRS (cluster of 2, opt-in): the two CTAs work on neighbouring tiles of the same (n-tile, split)
+  // and each fetches HALF of every weight blob, multicast into both; cl2 = 2 when active
+  int cl2, pair_items;
   int pps;      // kd-stacked convs: halo planes per pipeline stage
   int s2pair;   // GEOM_S2 with a one-chunk input: tap pairs share one K = 16 MMA (see issue_group)
   int t2_jh16;  // GEOM_T2: offset (16 B units) of the h+1 halo rows inside a k-chunk: 9 = next row, or a second box
@@ -175,6 +178,25 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// 2-CTA cluster variants: a bulk copy delivered to the same offset of both CTAs (complete_tx on both
+// full barriers), and a commit that arrives on the same barrier of both CTAs
+__device__ __forceinline__ void bulk_load_mc2(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -225,6 +247,10 @@ __device__ __forceinline__ void mma_pair(uint32_t leader, uint32_t d, uint32_t a
 template <int GEOM, int TD, int SPLIT>
 __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, int g, uint32_t stage,
                                             uint32_t bsrc, uint32_t tmem_acc0, bool first) {
+  // shared-memory addresses carry the CTA's rank in the cluster in bits 24+ (pair mode); the matrix
+  // descriptors take the 18-bit offset inside the CTA's own window
+  stage &= 0x3FFFFu;
+  bsrc &= 0x3FFFFu;
   const uint32_t nt = P.ntile;
   const uint32_t acc_cols = SPLIT ? 2u * nt : nt;
   const uint32_t a_hi0 = stage >> 4, a_lo0 = (stage + P.a_plane_bytes) >> 4;
@@ -512,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), P.cl2 == 2 ? 2 : 1);   // pair mode: this CTA's and the peer's MMAs release a stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
@@ -537,6 +563,18 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (P.cl2) cluster_sync_all();   // the peer's barriers exist before anything is multicast into them
+  // pair mode: CTA r of pair p takes tile 2*tpair + r of every (tile pair, n-tile, split) work unit
+  const int it_first = P.cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_stride = P.cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int it_count = P.cl2 ? P.pair_items : P.work_items;
+  const int pair_r = (int)(blockIdx.x & 1);
+  auto item_of = [&](int q) -> int {
+    if (!P.cl2) return q;
+    const int per_tile = P.n_ntiles * P.ksplit;
+    const int tpair = fast_div(q, P.mg_per_tile);
+    return (2 * tpair + pair_r) * per_tile + (q - tpair * per_tile);
+  };
   // everything above (barriers, TMEM allocation, smem clear) overlapped the previous kernel's tail;
   // activations / gradients written by it are only touched from here on
   pdl_wait();
@@ -575,7 +613,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     // item -- all advanced by compare-and-wrap: an integer division costs ~100 dependent cycles and
     // this loop is the critical path of every layer with few MMAs per stage
     int s = 0, ph = 0, par = 0;
-    for (int item = (two_prod || warp == 0) ? blockIdx.x : P.work_items; item < P.work_items; item += gridDim.x) {
+    for (int q = (two_prod || warp == 0) ? it_first : it_count; q < it_count; q += it_stride) {
+      const int item = item_of(q);
       const WorkItem wi = decode_item(P, item);
       int g = 0, cb = wi.cb0;
       for (int it = 0; it < wi.nit; ++it, par ^= 1) {
@@ -597,7 +636,12 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
           if (!P.b_res) {
             // every (nt, cb, g) blob reserves gmax entries; only this group's nmma entries are copied
             const long long blob = ((long long)wi.nt * P.ncblk + cb) * P.ngroups + g;
-            bulk_load(stage + P.b_off, P.wpacked + blob * P.b_blob_bytes, bbytes, full);
+            if (P.cl2 == 2) {   // this CTA's half of the blob, delivered to both CTAs of the pair
+              const uint32_t hb = bbytes >> 1;
+              bulk_load_mc2(stage + P.b_off + pair_r * hb, P.wpacked + blob * P.b_blob_bytes + pair_r * hb, hb, full);
+            } else {
+              bulk_load(stage + P.b_off, P.wpacked + blob * P.b_blob_bytes, bbytes, full);
+            }
           }
         }
         __syncwarp();
@@ -623,7 +667,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
     uint32_t local = 0;
     int s = 0, ph = 0;
     if (P.b_res) mbar_wait(smem_u32(&bar_bres), 0);  // resident weights have landed
-    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
+    for (int q = it_first; q < it_count; q += it_stride, ++local) {
+      const int item = item_of(q);
       const WorkItem wi = decode_item(P, item);
       const uint32_t buf = P.nbuf == 2 ? (local & 1u) : 0u, use = P.nbuf == 2 ? (local >> 1) : local;
       mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);  // epilogue drained this buffer
@@ -639,7 +684,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
         constexpr bool kStacked = GEOM == GEOM_S1K || GEOM == GEOM_S1TK;
         issue_group<GEOM, TD, SPLIT>(P, leader, g, stage, bsrc, acc0, kStacked ? it < P.ngroups : it == 0);
         __syncwarp();
-        if (leader) umma_commit(smem_u32(&bar_empty[s]));  // frees the smem stage when these MMAs retire
+        if (leader) {  // frees the smem stage when these MMAs retire (pair mode: in both CTAs -- the peer's
+                       // half-blob copy lands in this CTA's stage too)
+          if (P.cl2 == 2) umma_commit_mc2(smem_u32(&bar_empty[s])); else umma_commit(smem_u32(&bar_empty[s]));
+        }
         if (++g == P.ngroups) { g = 0; bres += P.b_cb_bytes; }
         if (++s == P.nstages) { s = 0; ph ^= 1; }
       }
@@ -711,7 +759,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    for (int item = blockIdx.x; item < P.work_items; item += gridDim.x, ++local) {
+    for (int q = it_first; q < it_count; q += it_stride, ++local) {
+      const int item = item_of(q);
       const WorkItem wi = decode_item(P, item);
       const uint32_t buf = P.nbuf == 2 ? (local & 1u) : 0u, use = P.nbuf == 2 ? (local >> 1) : local;
       if (do_stats && (wi.n != st_n || wi.nt != st_nt)) {
@@ -901,6 +950,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                  "r"((uint32_t)P.tmem_cols)
                  : "memory");
   }
+  if (P.cl2) cluster_sync_all();   // the peer may still arrive on this CTA's barriers until it is done too
 }
 
 // =====================================================================================================
@@ -1601,6 +1651,15 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     P.work_items = (int)(items * P.ksplit);
   }
   {
+    // OPT-IN (flags bit12): CTA pairs (cluster of 2) with multicast weight blobs, where weights are streamed
+    // per stage and every tile has a partner.  Bit-identical results; measured on the whole step 2.540 ms
+    // with pairs vs 2.531 ms without -- halving the weight fetch per CTA does not pay, the layers without
+    // resident weights are not L2->SM bandwidth bound, and the lockstep of the pair costs a little.
+    const long long tiles_all = (long long)P.tiles_w * P.tiles_h * P.tiles_d * N;
+    P.cl2 = (!P.b_res && (flags & 4096) && !(flags & 4) && tiles_all % 2 == 0 && tiles_all >= 2 && num_sms() % 2 == 0) ? 2 : 0;
+    P.pair_items = (int)(tiles_all / 2) * P.n_ntiles * P.ksplit;
+  }
+  {
     // magic(d) = floor(2^32 / d) + 1: __umulhi(x, magic) == x / d whenever x * d < 2^32; d == 1 -> 0 (identity)
     auto magic = [](unsigned d) -> unsigned { return d <= 1 ? 0u : (unsigned)((0x100000000ull / d) + 1ull); };
     const unsigned dmax = (unsigned)std::max(std::max(P.n_ntiles * P.ksplit, P.tiles_w * P.tiles_h * P.tiles_d),
@@ -1615,14 +1674,15 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   }
   if (getenv("TTA_TC_DEBUG"))
     fprintf(stderr, "tta_conv_tc: geom %d split %d N %d C8 %d->%d in %dx%dx%d | nt %d x%d ncblk %d | accs %d planes %d nbuf %d "
-            "stages %d x %d B bres %d | tiles %dx%dx%d ksplit %d (cb %d) items %d waves %.2f\n",
+            "stages %d x %d B bres %d cl2 %d | tiles %dx%dx%d ksplit %d (cb %d) items %d waves %.2f\n",
             geom, split, N, C8in, C8out, Di, Hi, Wi, P.ntile, P.n_ntiles, P.ncblk, P.nacc, P.td, P.nbuf, P.nstages,
-            P.stage_bytes, P.b_res, P.tiles_d, P.tiles_h, P.tiles_w, P.ksplit, P.cb_per_split, P.work_items,
+            P.stage_bytes, P.b_res, P.cl2, P.tiles_d, P.tiles_h, P.tiles_w, P.ksplit, P.cb_per_split, P.work_items,
             (double)P.work_items / num_sms());
   if (query) {
     *q_ksplit = P.ksplit;
     if (q_nbuf) *q_nbuf = P.nbuf;
     *q_grid = (flags & 4) ? P.work_items : (P.work_items < num_sms() ? P.work_items : num_sms());
+    if (P.cl2) *q_grid = 2 * (P.pair_items < num_sms() / 2 ? P.pair_items : num_sms() / 2);
     return TTA_OK;
   }
   // ---- fused norm statistics (see the epilogue): needs the whole K sum in one CTA and plain stores
@@ -1800,6 +1860,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   }
   int grid_x = P.work_items < num_sms() ? P.work_items : num_sms();
   if (flags & 4) grid_x = P.work_items;
+  if (P.cl2) grid_x = 2 * (P.pair_items < num_sms() / 2 ? P.pair_items : num_sms() / 2);
   const dim3 grid(grid_x, 1, 1);
 #define TTA_TC_LAUNCH_ST(G, T, S, ST)                                                                         \
   do {                                                                                                     \
@@ -1814,7 +1875,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
         return tta_check_launch("tta_conv_tc(cudaFuncSetAttribute)");                                      \
       configured = true;                                                                                   \
     }                                                                                                      \
-    tta_launch(conv_tc_kernel<G, T, S, ST>, grid, kTcThreads, smem, stream, pdl_ok && tta_pdl_family(8), P);                                           \
+    if (P.cl2) tta_launch_cluster(conv_tc_kernel<G, T, S, ST>, grid, kTcThreads, smem, stream, 2, P);      \
+    else tta_launch(conv_tc_kernel<G, T, S, ST>, grid, kTcThreads, smem, stream, pdl_ok && tta_pdl_family(8), P); \
   } while (0)
 #define TTA_TC_LAUNCH(G, T)                                                                                \
   do {                                                                                                     \

@@ -84,6 +84,14 @@ def test_conv_tc_forward_and_dgrad(lib, cuda, cin, cout, K, s, tr, dims):
         _tc(lib, hi, lo, *args, o_p2, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2)
         _tc(lib, hi, lo, *args, o_p1, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 32)
         assert torch.equal(o_p2, o_p1)
+    if K == 3:
+        # CTA pairs (flags bit12: 2-CTA clusters, each CTA fetches half of every streamed weight blob, multicast
+        # into both): same MMAs on the same bits -> identical result (no resident weights: bit4)
+        o_one = torch.zeros_like(out); o_pair = torch.zeros_like(out)
+        args = (c8i * xv[0, 0].numel() * 8, TTA_F16, N, c8i, dims, wp, pack_bias(b.to(cuda)))
+        _tc(lib, hi, lo, *args, o_one, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 16)
+        _tc(lib, hi, lo, *args, o_pair, c8o * ref[0, 0].numel() * 8, c8o, odims, mode, K, s, flags=2 | 16 | 4096)
+        assert torch.equal(o_one, o_pair)
     if not tr and s == 2:
         # w-parity-split operand layout (flags bit3): same MMAs on the same bits -> identical result
         o_std = torch.zeros_like(out); o_ws = torch.zeros_like(out)
