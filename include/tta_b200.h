@@ -68,7 +68,8 @@ int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int
  * bit3 stride-2 conv input planes are w-parity-split ([N][C8][D][H][2][W/2][8]), bit4 no resident
  * weights, bit5 one d-plane per 128-row tile even when H <= 8 (default there: two planes per tile),
  * bit6 split-K factor rounded up (A/B switch), bit7 / bit11 kd-stacked convs with one / at most two halo planes per stage (A/B),
- bit12 CTA pairs: 2-CTA clusters with multicast weight blobs (opt-in; measured neutral),
+ bit12 CTA pairs: 2-CTA clusters with multicast weight blobs (opt-in; measured neutral), bit13 nine (kd, kh)
+ * pipeline groups for ordinary planes (opt-in; measured slower),
  * bits 8..10 real Cout of a small-Cout transposed conv
  * packed for the dense-GEMM + col2im kernel (tta_conv_tc_t2s). */
 int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout);
