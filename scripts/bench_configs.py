@@ -51,3 +51,24 @@ assert out.shape == (1, 3, 155, 240, 240) and bool(torch.isfinite(out).all())
 assert sw.last_num_windows == 18
 print(f"config 4  BraTS 4x155x240x240 roi 128^3 overlap 0.5: {sw.last_num_windows} windows, {sw.last_steps} TENT steps, "
       f"{ms:.1f} ms per volume ({1e3 / ms:.2f} volumes/s, {sw.last_num_windows * 1e3 / ms:.0f} adapted windows/s)")
+
+# ---- config 5 (per-GPU part): continual TENT over a domain-shift stream, batch sweep
+from multimodal_tta_b200.synthetic import domain_shift
+for B in (1, 2, 4, 8, 16):
+    model = UNetB200(dict(BRATS_MODEL_CFG)).to(dev)
+    tent = TentB200(model, {"entropy": "sigmoid"})
+    xs = [domain_shift(brats_volume(B, (128, 128, 128), seed=50 + t), domain=t // 2, seed=5).to(dev) for t in range(2)]
+    for x in xs:
+        tent.step(x)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 10
+    a.record()
+    for t in range(K):
+        tent.step(xs[t % 2])
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / K
+    assert bool(torch.isfinite(tent.last_loss).all())
+    print(f"config 5  stream batch {B:2d} x 4x128^3: {ms:.2f} ms per step = {B * 1e3 / ms:.0f} adapted volumes/s per GPU")
+    del model, tent, xs
+    torch.cuda.empty_cache()
