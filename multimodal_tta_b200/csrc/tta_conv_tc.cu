@@ -1859,9 +1859,16 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   if (P.ksplit > 1 && !accumulate) {
     // partial sums are combined with float4 atomics: start from zero
     const long long Vo = (long long)Do * Ho * Wo;
-    for (int nn = 0; nn < N; ++nn)
-      if (cudaMemsetAsync(out + nn * out_ns, 0, (size_t)C8out * Vo * 8 * sizeof(float), stream) != cudaSuccess)
+    const long long per_n = (long long)C8out * Vo * 8;
+    static const bool per_sample_memset = getenv("TTA_MEMSET_PER_SAMPLE") != nullptr;   // A/B switch
+    if (out_ns == per_n && !per_sample_memset) {   // the view is the whole buffer: one memset node instead of one per sample
+      if (cudaMemsetAsync(out, 0, (size_t)N * per_n * sizeof(float), stream) != cudaSuccess)
         return tta_check_launch("tta_conv_tc(memset)");
+    } else {
+      for (int nn = 0; nn < N; ++nn)
+        if (cudaMemsetAsync(out + nn * out_ns, 0, (size_t)per_n * sizeof(float), stream) != cudaSuccess)
+          return tta_check_launch("tta_conv_tc(memset)");
+    }
   }
   int grid_x = P.work_items < num_sms() ? P.work_items : num_sms();
   if (flags & 4) grid_x = P.work_items;
