@@ -565,6 +565,10 @@ class TTAEngine:
                     # eval-mode BatchNorm: mean/rstd were filled from the running buffers
                     check(lib.tta_norm_apply(*ap_args, 0, 0, nl.batch, float(nl.h.eps), *ws_args(), _stream()),
                           "norm_apply")
+                elif fuse_st and model.stats_finalize_in_apply:
+                    # ... finalized by every block of the apply pass in its prologue (one launch less)
+                    check(lib.tta_norm_apply(*ap_args, plan.ws.data_ptr(), y.root.stats_grid, nl.batch,
+                                             float(nl.h.eps), *ws_args(), _stream()), "norm_apply")
                 elif fuse_st:
                     # partial sums were left in the workspace by the conv epilogue: tiny parallel finalize
                     check(lib.tta_norm_stats_finalize(plan.ws.data_ptr(), N, y.C8, y.root.stats_grid, y.V, nl.batch,

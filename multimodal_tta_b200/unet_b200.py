@@ -160,6 +160,9 @@ class UNetB200(nn.Module):
         # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
         # a separate pass over y (only where the conv runs without split-K)
         self.fuse_stats = bool(get_config(cfg, "fuse_stats", True))
+        # OPT-IN: statistics from a conv epilogue finalized inside the apply pass's prologue instead of a separate
+        # launch.  Measured slower (2.337 vs 2.326 ms per step: every apply block re-reduces 148 slots)
+        self.stats_finalize_in_apply = bool(get_config(cfg, "stats_finalize_in_apply", False))
         # OPT-IN: also when the conv has a single TMEM accumulator buffer (the reduction is then not hidden
         # behind the next item's MMAs, but a statistics pass over the conv result disappears).  Same-box A/B:
         # 2.2936 vs 2.2968 ms per step -- within noise, so the default stays off
