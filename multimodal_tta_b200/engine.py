@@ -13,6 +13,7 @@ producers write into channel slices of one buffer.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 from dataclasses import dataclass, field
@@ -27,8 +28,12 @@ from .layout import pack_bias, pack_weights_simt, pack_weights_small, pack_weigh
 from .unet_b200 import (ConvHolder, ConvolutionH, NormHolder, ResidualUnitH, SkipConnectionH, UNetB200)
 
 
+_DEVICE: Optional[torch.device] = None   # device of the engine that is launching (set by TTAEngine._on_device)
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream ON THE ENGINE'S DEVICE (not the process-wide current device)."""
+    return torch.cuda.current_stream(_DEVICE).cuda_stream
 
 
 class NormBwdSeg(ctypes.Structure):
@@ -171,25 +176,29 @@ class ConvLayer:
         self.packed = {}
 
     def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16, t2s: bool = True):
-        """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05."""
-        w = self.h.weight.detach().to(device=device, dtype=torch.float32)
+        """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05.
+        Packing runs on the HOST (a few hundred small index ops per layer, once per weight load) and every
+        blob reaches the device as one H2D copy -- the device only ever executes this library's kernels."""
+        host = torch.device("cpu")
+        w = self.h.weight.detach().to(device=host, dtype=torch.float32)
         wf = wg_forward(w, self.h.transposed)
         wd = wg_dgrad(w, self.h.transposed)
-        b = self.h.bias.detach().to(device=device, dtype=torch.float32)
+        b = self.h.bias.detach().to(device=host, dtype=torch.float32)
         if self.extra is not None:
-            w2 = self.extra.weight.detach().to(device=device, dtype=torch.float32)
+            w2 = self.extra.weight.detach().to(device=host, dtype=torch.float32)
             wf = torch.cat([wf, wg_forward(w2, False)], dim=2)      # [T][ci][co0 + co1]
             wd = torch.cat([wd, wg_dgrad(w2, False)], dim=1)        # [T][ci = dy0 || dy1][co = cin]
-            b = torch.cat([b, self.extra.bias.detach().to(device=device, dtype=torch.float32)])
+            b = torch.cat([b, self.extra.bias.detach().to(device=host, dtype=torch.float32)])
         if self.fold_identity:
             c = self.K ** 3 // 2
-            eye = torch.eye(self.cin, device=device)
+            eye = torch.eye(self.cin)
             wf = wf.clone(); wd = wd.clone()
             wf[c] += eye
             wd[c] += eye
+        self.wg_fwd_host = wf          # canonical Wg[T][ci][co] (fp32, host): weight-gradient tests, diagnostics
         self.packed = {
-            "simt_fwd": pack_weights_simt(wf), "simt_bwd": pack_weights_simt(wd),
-            "bias": pack_bias(b),
+            "simt_fwd": pack_weights_simt(wf).to(device), "simt_bwd": pack_weights_simt(wd).to(device),
+            "bias": pack_bias(b).to(device),
         }
         lib = _lib.lib()
         if lib.tta_conv_small_supported(self.K, self.stride, self.cin, self.cout):
@@ -203,11 +212,12 @@ class ConvLayer:
                 # layout, real Cout in flags bits 8..10 (include/tta_b200.h)
                 use_t2s = t2s and self.extra is None and bool(
                     lib.tta_conv_tc_t2s(self.mode, self.K, self.stride, self.cin, self.cout, 1))
-                self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16, t2s=use_t2s)
+                self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16,
+                                                        t2s=use_t2s).to(device)
                 self.tc_fwd_flags = (self.cout << 8) if use_t2s else 0
             bmode = 1 - self.mode
             if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.cin):
-                self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype)
+                self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype).to(device)
 
 
 class NormLayer:
@@ -296,6 +306,19 @@ class TTAEngine:
     def invalidate(self):
         self.model._params_dirty = True
 
+    @contextlib.contextmanager
+    def on_device(self):
+        """Every launch of this engine runs with ITS device current and on that device's current stream, whatever
+        the process-wide current device is (reference ``gpu_ids=[1]``, ``evaluate_epoch(device='cuda:1')``)."""
+        global _DEVICE
+        prev = _DEVICE
+        _DEVICE = self.device
+        try:
+            with torch.cuda.device(self.device):
+                yield
+        finally:
+            _DEVICE = prev
+
     @property
     def n_adaptable(self) -> int:
         return 2 * sum(n.C for n in self.norm_layers)
@@ -305,9 +328,12 @@ class TTAEngine:
         be launched from such a plan."""
         if device.type != "cuda" and not dry:
             raise RuntimeError("multimodal_tta_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         if self.device is not None and self.device != device:
             self.plans.clear()
             self.gb = None
+            self._packed_fp = None
         self.device = device
         if self.gb is None:
             P = self.P
@@ -319,6 +345,17 @@ class TTAEngine:
             self.model._params_dirty = True
         if self.model._params_dirty:
             self._bind_params()
+            # conv weights are baked into the plans (packed device blobs, host kernel parameters of the small /
+            # head kernels, captured CUDA graphs): repack only when a weight tensor really changed
+            # (storage, in-place version, device) and then drop every plan built on the old blobs
+            fp = tuple((id(h), h.weight.data_ptr(), h.weight._version, h.bias.data_ptr(), h.bias._version,
+                        str(h.weight.device)) for h in self.model.conv_holders())
+            fp = (fp, self.model.conv_backend, self.model.t2s_head, self.bwd_dtype)
+            if fp == getattr(self, "_packed_fp", None):
+                self.model._params_dirty = False
+                return
+            self._packed_fp = fp
+            self.plans.clear()
             want_tc = self.model.conv_backend in ("auto", "tc")
             fused_members = set()
             for fl in self.fused_layers.values():
@@ -1012,14 +1049,15 @@ class TTAEngine:
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = self._check_input(x)
         self._ensure_device(x.device)
-        plan = self.get_plan(*[int(s) for s in (x.shape[0], *x.shape[2:])])
-        self._load_running_stats(plan)
-        self._pack_input(plan, x)
-        for op in plan.fwd:
-            op()
-        plan.head_infer()
-        self._update_running_stats(plan)
-        return plan.logits.clone()
+        with self.on_device():
+            plan = self.get_plan(*[int(s) for s in (x.shape[0], *x.shape[2:])])
+            self._load_running_stats(plan)
+            self._pack_input(plan, x)
+            for op in plan.fwd:
+                op()
+            plan.head_infer()
+            self._update_running_stats(plan)
+            return plan.logits.clone()
 
     def run_step(self, plan: Plan, adam: bool = True, gscale: float = 1.0):
         """forward + fused head + backward (+ Adam) on whatever is in plan.x."""

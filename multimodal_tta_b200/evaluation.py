@@ -44,19 +44,47 @@ def device_dice_counts(logits: torch.Tensor, labels: torch.Tensor, threshold: fl
     V = logits[0, 0].numel()
     counts = torch.zeros((B, R, 3), dtype=torch.int64, device=logits.device)
     lab = labels.to(device=logits.device, dtype=torch.float32).contiguous()
-    check(_lib.lib().tta_dice_counts(logits.contiguous().data_ptr(), lab.data_ptr(), B * R, V, float(threshold),
-                                     counts.data_ptr(), torch.cuda.current_stream().cuda_stream), "dice_counts")
+    if not logits.is_cuda:
+        raise RuntimeError("multimodal_tta_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    with torch.cuda.device(logits.device):
+        check(_lib.lib().tta_dice_counts(logits.contiguous().data_ptr(), lab.data_ptr(), B * R, V, float(threshold),
+                                         counts.data_ptr(), torch.cuda.current_stream(logits.device).cuda_stream),
+              "dice_counts")
     return counts
 
 
 def _as_list_str(x, batch_size: int) -> List[str]:
+    """'domain' batch entry -> one string per sample, with the reference's cases (seg_eval.py:20-38): missing -> ""
+    (reported as ``unknown``), list/tuple -> str of every item, one str -> repeated, 0-d tensor -> its int for the
+    whole batch, B-element tensor -> one int per sample, anything else -> str(x) repeated."""
     if x is None:
-        return ["unknown"] * batch_size
+        return [""] * batch_size
     if isinstance(x, (list, tuple)):
         return [str(v) for v in x]
     if isinstance(x, str):
         return [x] * batch_size
+    if torch.is_tensor(x):
+        if x.ndim == 0:
+            return [str(int(x.item()))] * batch_size
+        if x.numel() == batch_size:
+            return [str(int(v.item())) for v in x.reshape(-1)]
     return [str(x)] * batch_size
+
+
+def load_source_checkpoint(model: UNetB200, path: str, trusted: bool = False) -> None:
+    """``method.checkpoint``: source-model weights written by the reference's CheckpointHook
+    (/root/reference/src/core/hooks.py:53-70: ``{"epoch", "model_state_dict", "optimizer_state_dict",
+    "best_metrics"}``; keys carry a ``module.`` prefix when the trainer wrapped the model in nn.DataParallel,
+    experiment_manager.py:95-96).  A bare state dict is accepted too.  Unlike the reference's loader
+    (hooks.py:72-76, warning + train from scratch) a missing file is an error: adapting random weights at
+    test time is never what the user meant."""
+    import os
+
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"method.checkpoint: {path} does not exist")
+    ck = torch.load(path, map_location="cpu", weights_only=not trusted)
+    sd = ck["model_state_dict"] if isinstance(ck, dict) and "model_state_dict" in ck else ck
+    model.load_state_dict(sd)
 
 
 @register_evaluation_strategy("tta_seg_eval")
@@ -72,6 +100,8 @@ class TTASegmentationEvaluationStrategy:
         self.sw_roi = list(get_config(sw, "roi", [128, 128, 128]))
         self.sw_batch = int(get_config(sw, "sw_batch", 1))
         self.sw_overlap = float(get_config(sw, "overlap", 0.5))
+        self.checkpoint = get_config(self.method_cfg, "checkpoint", None)
+        self.checkpoint_trusted = bool(get_config(self.method_cfg, "checkpoint_trusted", False))
         self._tent: Optional[TentB200] = None
         self._sw: Optional[SlidingWindowTTA] = None
 
@@ -81,6 +111,8 @@ class TTASegmentationEvaluationStrategy:
             raise TypeError("tta_seg_eval needs model.name=unet_b200 (got "
                             f"{type(core).__name__}); see configs/method/tent_b200.yaml")
         if self._tent is None or self._tent.model is not core:
+            if self.checkpoint:      # source weights first: TENT snapshots the parameters it starts from
+                load_source_checkpoint(core, str(self.checkpoint), self.checkpoint_trusted)
             self._tent = TentB200(core, self.method_cfg)
             self._sw = SlidingWindowTTA(self._tent, self.sw_roi, self.sw_batch, self.sw_overlap) \
                 if self.sw_enabled else None

@@ -111,9 +111,10 @@ class IntensityPolicy:
         affine = torch.empty((B, C, 4), dtype=torch.float32, device=v5.device) if out is None else out
         if tuple(affine.shape) != (B, C, 4) or affine.dtype != torch.float32 or not affine.is_cuda:
             raise ValueError("intensity stats: out must be a CUDA float32 tensor of shape [B, C, 4]")
-        check(lib.tta_intensity_stats(v5.data_ptr(), B, C, V, rules.data_ptr(), min_count, affine.data_ptr(),
-                                      self._ws[wkey].data_ptr(), torch.cuda.current_stream(v5.device).cuda_stream),
-              "intensity_stats")
+        with torch.cuda.device(v5.device):
+            check(lib.tta_intensity_stats(v5.data_ptr(), B, C, V, rules.data_ptr(), min_count, affine.data_ptr(),
+                                          self._ws[wkey].data_ptr(), torch.cuda.current_stream(v5.device).cuda_stream),
+                  "intensity_stats")
         return affine
 
     def __call__(self, vol: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -122,9 +123,10 @@ class IntensityPolicy:
         affine = self.stats(v5)
         o5 = torch.empty_like(v5) if out is None else self._check(out)
         B, C = int(v5.shape[0]), int(v5.shape[1])
-        check(_load_lib().tta_intensity_apply(v5.data_ptr(), o5.data_ptr(), B, C, int(v5[0, 0].numel()),
-                                              affine.data_ptr(), torch.cuda.current_stream(v5.device).cuda_stream),
-              "intensity_apply")
+        with torch.cuda.device(v5.device):
+            check(_load_lib().tta_intensity_apply(v5.data_ptr(), o5.data_ptr(), B, C, int(v5[0, 0].numel()),
+                                                  affine.data_ptr(), torch.cuda.current_stream(v5.device).cuda_stream),
+                  "intensity_apply")
         return o5.view(vol.shape) if out is None else out
 
     @staticmethod

@@ -10,8 +10,12 @@ Gaussian importance sigma = 0.125*roi clamped at max(min, 1e-3), out = sum(w*pre
 Patches are gathered straight from the resident volume into the conv operand layout
 (tta_gather_pack), predictions are blended by a deterministic gather-form kernel (tta_sw_blend).
 Multi-GPU: every global step adapts on ``sw_batch * world`` consecutive windows, rank r taking
-the r-th block of ``sw_batch``; the tail is padded with zero-weight windows so all ranks join the
-gradient all-reduce; blended accumulators are all-reduced once per volume batch.
+the r-th block of ``sw_batch``; the tail batch (single rank too: the plan has a fixed batch of
+``sw_batch`` windows) is padded with zero-weight windows, the loss/gradient are rescaled to the
+mean over the REAL windows (``n_valid_global``), and all ranks join the gradient all-reduce;
+blended accumulators are all-reduced once per volume batch.  With BatchNorm the padding windows
+(copies of window 0) still enter the batch statistics -- InstanceNorm, the reference's setting,
+is unaffected.
 """
 from __future__ import annotations
 
@@ -98,6 +102,8 @@ class SlidingWindowTTA:
         self.lib = _lib.lib()
         self.last_num_windows = 0
         self.last_steps = 0
+        self.time_collectives = False        # bench: CUDA events around the accumulator all-reduce
+        self.last_allreduce_ms: Optional[float] = None
 
     def _state(self, device, key):
         if key not in self._bufs:
@@ -105,11 +111,37 @@ class SlidingWindowTTA:
             fs, wmin = gaussian_factors(self.roi, self.sigma_scale)
             self._bufs[key] = dict(
                 win=torch.zeros((NB, 4), dtype=torch.int32, device=device),
-                win_host=torch.zeros((NB, 4), dtype=torch.int32).pin_memory(),
                 sw=torch.ones(NB, dtype=torch.float32, device=device),
-                sw_host=torch.ones(NB, dtype=torch.float32).pin_memory(),
                 g=[f.to(device) for f in fs], wmin=wmin)
         return self._bufs[key]
+
+    def _schedule(self, device, B, C, vd, world, rank, chan_scale_per_volume):
+        """The whole window schedule of one call, uploaded ONCE: per step the gather origins (unpadded
+        volume coordinates), the blend origins (padded coordinates), the window weights (0 = padding) and
+        the per-(window, channel) modality scales.  The per-step loop then only issues stream-ordered
+        device copies into the persistent buffers the CUDA graph reads -- no pinned buffer is reused
+        while a copy may still be in flight, no host synchronisation per window batch."""
+        padded, pad_lo, starts = plan_windows(vd, self.roi, self.overlap)
+        nwin, NB = len(starts), self.sw_batch
+        total = nwin * B
+        rows_g, rows_b, rows_w, n_valid = [], [], [], []
+        for idxs, nv in shard_schedule(total, NB, world, rank):
+            for idx in idxs:
+                valid = idx is not None
+                b, s = (idx // nwin, starts[idx % nwin]) if valid else (0, starts[0])
+                rows_g.append([b, s[0] - pad_lo[0], s[1] - pad_lo[1], s[2] - pad_lo[2]])
+                rows_b.append([b, s[0], s[1], s[2]])
+                rows_w.append(1.0 if valid else 0.0)
+            n_valid.append(nv)
+        steps = len(n_valid)
+        win_g = torch.tensor(rows_g, dtype=torch.int32).view(steps, NB, 4)
+        cs = None
+        if chan_scale_per_volume is not None:
+            cs = chan_scale_per_volume.detach().to("cpu", torch.float32)[win_g[..., 0].long()].contiguous()
+            cs = cs.to(device)                                             # [steps][NB][C]
+        return dict(padded=padded, pad_lo=pad_lo, total=total, steps=steps, n_valid=n_valid,
+                    win_g=win_g.to(device), win_b=torch.tensor(rows_b, dtype=torch.int32).view(steps, NB, 4).to(device),
+                    sw=torch.tensor(rows_w, dtype=torch.float32).view(steps, NB).to(device), cs=cs)
 
     @torch.no_grad()
     def __call__(self, vol: torch.Tensor, chan_scale_per_volume: Optional[torch.Tensor] = None,
@@ -123,58 +155,71 @@ class SlidingWindowTTA:
         tent = self.tent
         eng = tent.model.engine
         vol = eng._check_input(vol)
+        eng._ensure_device(vol.device)
+        with eng.on_device():
+            return self._sweep(vol, chan_scale_per_volume, intensity_policy, dist)
+
+    def _sweep(self, vol, chan_scale_per_volume, intensity_policy, dist):
+        tent = self.tent
         B, C = int(vol.shape[0]), int(vol.shape[1])
         vd = [int(s) for s in vol.shape[2:]]
-        padded, pad_lo, starts = plan_windows(vd, self.roi, self.overlap)
-        nwin = len(starts)
-        total = nwin * B
         ws = tent.world_size
         rank = dist.get_rank(tent.pg) if ws > 1 else 0
         NB, R = self.sw_batch, tent.model.out_channels
-        st = self._state(vol.device, (vol.device, NB))
-        acc = torch.zeros((B, R, *padded), dtype=torch.float32, device=vol.device)
-        wsum = torch.zeros((B, *padded), dtype=torch.float32, device=vol.device)
+        dev = vol.device
+        st = self._state(dev, (dev, NB))
+        sched = self._schedule(dev, B, C, vd, ws, rank, chan_scale_per_volume)
+        padded, pad_lo = sched["padded"], sched["pad_lo"]
+        # the captured step bakes the volume pointer in: keep ONE resident volume buffer per shape and copy
+        # the caller's tensor into it (143 MB for a BraTS volume, ~50 us) instead of re-capturing per volume
+        vkey = ("vol", dev, tuple(vol.shape))
+        if vkey not in self._bufs:
+            self._bufs[vkey] = torch.empty_like(vol)
+        if vol.data_ptr() != self._bufs[vkey].data_ptr():
+            self._bufs[vkey].copy_(vol, non_blocking=True)
+        vol = self._bufs[vkey]
+        acc = torch.zeros((B, R, *padded), dtype=torch.float32, device=dev)
+        wsum = torch.zeros((B, *padded), dtype=torch.float32, device=dev)
         affine = None
         if intensity_policy is not None:
-            akey = ("affine", vol.device, B, C)
+            akey = ("affine", dev, B, C)
             if akey not in self._bufs:
-                self._bufs[akey] = torch.empty((B, C, 4), dtype=torch.float32, device=vol.device)
+                self._bufs[akey] = torch.empty((B, C, 4), dtype=torch.float32, device=dev)
             affine = intensity_policy.stats(vol, out=self._bufs[akey])
         cs_dev = None
-        if chan_scale_per_volume is not None:
-            cs_dev = torch.ones((NB, C), dtype=torch.float32, device=vol.device)
-        steps = 0
-        for idxs, n_valid in shard_schedule(total, NB, ws, rank):
-            for j, idx in enumerate(idxs):
-                valid = idx is not None
-                b, s = (idx // nwin, starts[idx % nwin]) if valid else (0, starts[0])
-                # origins in UNPADDED volume coordinates (gather zero-fills outside the volume)
-                st["win_host"][j] = torch.tensor([b, s[0] - pad_lo[0], s[1] - pad_lo[1], s[2] - pad_lo[2]],
-                                                 dtype=torch.int32)
-                st["sw_host"][j] = 1.0 if valid else 0.0
-            st["win"].copy_(st["win_host"], non_blocking=True)
-            st["sw"].copy_(st["sw_host"], non_blocking=True)
+        if sched["cs"] is not None:
+            ckey = ("cs", dev, NB, C)
+            if ckey not in self._bufs:
+                self._bufs[ckey] = torch.ones((NB, C), dtype=torch.float32, device=dev)
+            cs_dev = self._bufs[ckey]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for t in range(sched["steps"]):
+            st["win"].copy_(sched["win_g"][t], non_blocking=True)
+            st["sw"].copy_(sched["sw"][t], non_blocking=True)
             if cs_dev is not None:
-                cs_dev.copy_(chan_scale_per_volume.to(vol.device)[st["win_host"][:, 0].long()])
+                cs_dev.copy_(sched["cs"][t], non_blocking=True)
             logits = tent.step_windows(vol, st["win"], self.roi, sample_w=st["sw"], chan_scale=cs_dev,
-                                       n_valid_global=n_valid if ws > 1 else None, affine=affine)
-            # blend needs origins in PADDED coordinates
-            winp = st["win"].clone()
-            winp[:, 1:] += torch.tensor(pad_lo, dtype=torch.int32, device=vol.device)
-            check(self.lib.tta_sw_blend(logits.data_ptr(), NB, R, *self.roi, winp.data_ptr(),
+                                       n_valid_global=sched["n_valid"][t], affine=affine)
+            check(self.lib.tta_sw_blend(logits.data_ptr(), NB, R, *self.roi, sched["win_b"][t].data_ptr(),
                                         st["sw"].data_ptr(), st["g"][0].data_ptr(), st["g"][1].data_ptr(),
                                         st["g"][2].data_ptr(), float(st["wmin"]), acc.data_ptr(),
-                                        wsum.data_ptr(), B, *padded,
-                                        torch.cuda.current_stream().cuda_stream), "sw_blend")
-            steps += 1
+                                        wsum.data_ptr(), B, *padded, stream), "sw_blend")
         if ws > 1:
+            ev = None
+            if self.time_collectives:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             dist.all_reduce(acc, group=tent.pg)
             dist.all_reduce(wsum, group=tent.pg)
+            if ev is not None:
+                ev[1].record()
+                ev[1].synchronize()
+                self.last_allreduce_ms = ev[0].elapsed_time(ev[1])
         out = torch.empty_like(acc)
         Vs = padded[0] * padded[1] * padded[2]
-        check(self.lib.tta_sw_normalise(acc.data_ptr(), wsum.data_ptr(), B, R, Vs, out.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream), "sw_normalise")
-        self.last_num_windows, self.last_steps = total, steps
+        check(self.lib.tta_sw_normalise(acc.data_ptr(), wsum.data_ptr(), B, R, Vs, out.data_ptr(), stream),
+              "sw_normalise")
+        self.last_num_windows, self.last_steps = sched["total"], sched["steps"]
         if padded != vd:
             out = out[:, :, pad_lo[0]:pad_lo[0] + vd[0], pad_lo[1]:pad_lo[1] + vd[1],
                       pad_lo[2]:pad_lo[2] + vd[2]].contiguous()

@@ -112,11 +112,18 @@ class TentB200:
         """``steps`` x (forward, entropy, backward, [all-reduce], Adam); logits of the first forward
         are kept in plan.logits_out.  ``input_key`` distinguishes graphs that bake different input
         pointers (the two staging buffers of adapt_stream); at most four are kept per plan."""
+        with eng.on_device():
+            self._run_on_device(eng, plan, pack, gmul, input_key)
+
+    def _run_on_device(self, eng, plan, pack, gmul, input_key) -> None:
         ws = self.world_size
         single = ws == 1
         for it in range(self.steps):
             if self.use_graph:
-                key = (single, eng.entropy_mode, tuple(sorted(eng.adam.items())), input_key)
+                # the key names everything a captured step bakes in: who runs Adam, the entropy / Adam constants,
+                # WHERE the input comes from (static copy, a caller-owned staging buffer, or a window gather with
+                # its volume / window-table pointers) and the gradient multiplier of a padded tail batch
+                key = (single, eng.entropy_mode, tuple(sorted(eng.adam.items())), input_key, round(float(gmul), 9))
                 graphs = plan.graphs
                 if plan.graph is None:          # invalidated by the caller (step_windows: pointers changed)
                     graphs.clear()
@@ -128,7 +135,7 @@ class TentB200:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         pack()
-                        eng.run_step(plan, adam=single)
+                        eng.run_step(plan, adam=single, gscale=gmul)
                     if len(graphs) >= 4:
                         graphs.clear()
                     graphs[key] = g
@@ -157,13 +164,14 @@ class TentB200:
         eng, x = self._prepare(x)
         plan = eng.get_plan(*[int(s) for s in (x.shape[0], *x.shape[2:])])
         if persistent_input:
-            self._run(eng, plan, lambda: eng._pack_input(plan, x), input_key=x.data_ptr())
+            self._run(eng, plan, lambda: eng._pack_input(plan, x), input_key=("staging", x.data_ptr()))
             return plan.logits_out
         if plan.x_static is None or plan.x_static.shape != x.shape:
             plan.x_static = torch.empty_like(x)
         if x.data_ptr() != plan.x_static.data_ptr():
             plan.x_static.copy_(x, non_blocking=True)
-        self._run(eng, plan, lambda: eng._pack_input(plan, plan.x_static))
+        self._run(eng, plan, lambda: eng._pack_input(plan, plan.x_static),
+                  input_key=("static", plan.x_static.data_ptr()))
         return plan.logits_out
 
     __call__ = step
@@ -175,9 +183,9 @@ class TentB200:
                      affine: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Adapt on a batch of sliding-window patches gathered on device from ``vol``
         [n_vol,C,Ds,Hs,Ws].  ``win`` int32 [NB,4] = (volume index, d0, h0, w0) -- must live in a
-        persistent buffer when CUDA graphs are on; ``sample_w`` [NB] zero-weights padding windows
-        (multi-rank tail batches only; ``n_valid_global`` = real windows over all ranks, so that the
-        all-reduced gradient equals the mean over the real windows); ``affine`` [n_vol,C,4] from
+        persistent buffer when CUDA graphs are on; ``sample_w`` [NB] zero-weights the padding windows of
+        a tail batch; ``n_valid_global`` = real windows of this step over all ranks, so that the
+        (all-reduced) gradient equals the mean over the real windows; ``affine`` [n_vol,C,4] from
         ``IntensityPolicy.stats`` normalises RAW intensities while the windows are gathered (persistent
         buffer, like ``win``)."""
         eng, vol = self._prepare(vol)
@@ -186,9 +194,7 @@ class TentB200:
         key = (vol.data_ptr(), tuple(vol.shape), win.data_ptr(),
                None if chan_scale is None else chan_scale.data_ptr(),
                None if affine is None else affine.data_ptr())
-        if getattr(plan, "win_key", None) != key:
-            plan.graph = None  # pointers baked into the graph changed
-            plan.win_key = key
+        plan.win_key = key     # (part of the graph key below: a graph is replayed only for the pointers it baked in)
         if sample_w is not None:
             plan.sample_w.copy_(sample_w, non_blocking=True)
         gmul = 1.0
@@ -196,7 +202,10 @@ class TentB200:
             gmul = NB * self.world_size / float(n_valid_global)
         vd = tuple(int(s) for s in vol.shape[2:])
         self._run(eng, plan, lambda: eng._pack_input(plan, vol, win=win, chan_scale=chan_scale,
-                                                     vol_dims=vd, n_vol=int(vol.shape[0]), affine=affine), gmul)
+                                                     vol_dims=vd, n_vol=int(vol.shape[0]), affine=affine), gmul,
+                  input_key=("win",) + key)
+        if gmul != 1.0:            # padded tail batch: report the mean over the real windows, as the gradient is
+            self.last_loss = plan.loss_out * gmul
         return plan.logits_out
 
     def adapt_stream(self, host_batches):

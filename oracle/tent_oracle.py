@@ -51,12 +51,13 @@ def configure_model(model: nn.Module) -> nn.Module:
     materialise gamma=1, beta=0 where affine=False; BatchNorm always uses batch statistics."""
     model.train()
     model.requires_grad_(False)
+    dev = next((p.device for p in model.parameters()), torch.device("cpu"))
     for m in model.modules():
         if isinstance(m, (nn.InstanceNorm3d, nn.BatchNorm3d)):
             c = m.num_features
             if m.weight is None:
-                m.weight = nn.Parameter(torch.ones(c))
-                m.bias = nn.Parameter(torch.zeros(c))
+                m.weight = nn.Parameter(torch.ones(c, device=dev))
+                m.bias = nn.Parameter(torch.zeros(c, device=dev))
                 m.affine = True
             m.weight.requires_grad_(True)
             m.bias.requires_grad_(True)

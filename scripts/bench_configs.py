@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from multimodal_tta_b200 import IntensityPolicy, SlidingWindowTTA, TentB200, UNetB200
 from multimodal_tta_b200.synthetic import brats_volume
-from oracle.unet_oracle import BRATS_MODEL_CFG, HECKTOR_MODEL_CFG   # config constants only
+from multimodal_tta_b200.presets import BRATS_MODEL_CFG, HECKTOR_MODEL_CFG
 from tests.golden.gen_intensity_golden import HECKTOR
 
 dev = torch.device("cuda")

@@ -246,3 +246,65 @@ def test_small_and_tc_pack_tables():
     assert [len(g) for g in tc_groups(0, 3, 1)] == [9, 9, 9] and [len(g) for g in tc_groups(1, 3, 2)] == [18, 9]
     assert tc_groups(1, 3, 2)[1] == list(range(9)) and tc_groups(0, 1, 1) == [[0]]
     assert sorted(sum(tc_groups(1, 3, 2), [])) == list(range(27))
+
+
+def test_domain_entry_formats_follow_the_reference():
+    """seg_eval.py:20-38: None -> "", list/tuple -> str per item, str -> repeated, 0-d tensor -> int for the batch,
+    B-element tensor -> one int per sample, anything else -> str(x) repeated."""
+    from multimodal_tta_b200.evaluation import _as_list_str
+    assert _as_list_str(None, 2) == ["", ""]
+    assert _as_list_str(["a", 3], 2) == ["a", "3"] and _as_list_str(("x", "y"), 2) == ["x", "y"]
+    assert _as_list_str("site", 3) == ["site"] * 3
+    assert _as_list_str(torch.tensor(4), 2) == ["4", "4"]
+    assert _as_list_str(torch.tensor([0, 1, 1]), 3) == ["0", "1", "1"]
+    assert _as_list_str(torch.tensor([[2.0], [5.0]]), 2) == ["2", "5"]
+    t = torch.tensor([0, 1, 2])
+    assert _as_list_str(t, 2) == [str(t)] * 2              # wrong length: falls through, like the reference
+    assert _as_list_str(7, 2) == ["7", "7"]
+
+
+def test_presets_equal_the_oracle_configs():
+    from multimodal_tta_b200 import presets
+    assert presets.BRATS_MODEL_CFG == BRATS_MODEL_CFG and presets.HECKTOR_MODEL_CFG == HECKTOR_MODEL_CFG
+    assert presets.BARE_DEFAULT_MODEL_CFG == BARE_DEFAULT_MODEL_CFG
+
+
+def test_load_source_checkpoint_formats(tmp_path):
+    """CheckpointHook format (hooks.py:53-70), with and without the DataParallel prefix, and a bare state dict."""
+    from multimodal_tta_b200.evaluation import load_source_checkpoint
+    torch.manual_seed(3)
+    o = OracleUNet.from_cfg(BRATS_MODEL_CFG)
+    k = "model.1.submodule.0.conv.unit1.conv.weight"
+    for name, payload in (("hook.pth", {"epoch": 1, "model_state_dict": o.state_dict(), "optimizer_state_dict": {},
+                                        "best_metrics": {"avg_dc": 0.1}}),
+                          ("dp.pth", {"epoch": 1, "model_state_dict": {"module." + n: v for n, v in o.state_dict().items()}}),
+                          ("bare.pth", o.state_dict())):
+        torch.save(payload, tmp_path / name)
+        m = UNetB200(dict(BRATS_MODEL_CFG))
+        assert not torch.equal(m.state_dict()[k], o.state_dict()[k])
+        load_source_checkpoint(m, str(tmp_path / name))
+        assert all(torch.equal(m.state_dict()[n], v) for n, v in o.state_dict().items())
+    with pytest.raises(FileNotFoundError):
+        load_source_checkpoint(UNetB200(dict(BRATS_MODEL_CFG)), str(tmp_path / "missing.pth"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference checkout not present (GPU box)")
+def test_registration_lands_in_the_reference_registry():
+    """Inside the reference checkout (``src.registry`` importable) the decorators must fill the reference's OWN
+    registries -- the maps ExperimentManager.setup_model / setup_evaluation read
+    (/root/reference/src/registry.py:60-66, src/core/experiment_manager.py:88-96,364-370)."""
+    import subprocess
+    import sys
+    code = (
+        "import multimodal_tta_b200 as pkg, multimodal_tta_b200.registry as r\n"
+        "from src.registry import MODELS, EVALUATION_STRATEGIES, PLUGINS, get_model, get_evaluation_strategy\n"
+        "assert r.USING_REFERENCE_REGISTRY and r.MODELS is MODELS and r.EVALUATION_STRATEGIES is EVALUATION_STRATEGIES\n"
+        "assert MODELS.has('unet_b200') and EVALUATION_STRATEGIES.has('tta_seg_eval') and PLUGINS.has('tent_b200')\n"
+        "assert get_model('unet_b200') is pkg.UNetB200\n"
+        "assert get_evaluation_strategy('tta_seg_eval') is pkg.TTASegmentationEvaluationStrategy\n"
+        "m = get_model('unet_b200')(pkg.create(dict(in_channels=4, num_classes=3, num_res_units=2, norm='INSTANCE')))\n"
+        "assert sum(p.numel() for p in m.parameters()) == 19223961\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(["/root/reference", ROOT]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr

@@ -59,6 +59,8 @@ def _check_step(cfg, x, mode, steps, use_graph, backend="auto", tight=False):
         # --- adapted parameters (north star: 1e-4 after N steps)
         perr = (prod.engine.flat_params().cpu() - flat_gamma_beta(to.model)).abs()
         frac_bad = float((perr > 1e-4).float().mean())
+        print(f"[{mode} {tuple(x.shape)} {backend} step {it}] logits {rel_l2(lp, lo):.1e} agree {agree:.6f} grad "
+              f"{rel_l2(g_p, g_o):.1e} flips {int(flip.sum())} params>1e-4 {100 * frac_bad:.2f} % median {float(perr.median()):.1e}")
         assert frac_bad < ((0.01 if it == 0 else 0.03) if tight else 0.12), (it, frac_bad)
         assert float(perr.median()) < 1e-5, (it, float(perr.median()))
     return to, tp, prod
