@@ -208,14 +208,22 @@ int tta_split_f32(const float* g0, long long g0_n_stride, const float* g1, long 
 int tta_head_fused_supported(int K, int stride, int cin, int cout);
 int tta_head_fused_tiles(int D, int H, int W);
 long long tta_head_fused_workspace_floats(int N, int D, int H, int W);
-int tta_head_fused_fwd(const float* y, long long y_n_stride, int N, int C, int D, int H, int W, const float* mean,
+int tta_head_fused_fwd(const float* y, long long y_n_stride, int y_cpv, int N, int C, int D, int H, int W, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, int relu, const float* W_host,
                        const float* bias, int mode, float inv_count, float grad_scale, const float* sample_w,
                        float* logits, float* dlogits, float* workspace, float* loss, tta_stream_t stream);
 int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, const float* W_host, const float* y,
-                       long long y_n_stride, const float* mean, const float* rstd, const float* gamma,
+                       long long y_n_stride, int y_cpv, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, int relu, int batch_mode, float* dz, long long dz_n_stride, float* sums,
                        float* dgamma, float* dbeta, float* workspace, tta_stream_t stream);
+/* COMPACT layout of the full-resolution tail (y_cpv = 4): the <= 4-channel tensors of the head otherwise carry
+ * five pad channels through every pass.  y is then fp32 [N][D][H][W][4] (written by tta_conv_tc with flags bit 14,
+ * y_n_stride in floats), dz is FP16 [N][D][H][W][4] (dz_n_stride in 16-bit elements), and the norm-backward apply
+ * of the head's norm layer is tta_norm_bwd_apply_c4 (dy leaves in the usual 8-channel operand layout). */
+int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_n_stride, const float* y, long long y_n_stride, int N,
+                          int Creal, long long V, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, int batch_mode, const float* sums, uint16_t* dy_hi, uint16_t* dy_lo,
+                          long long dy_n_stride, int out_dtype, int dy_wsplit_w, tta_stream_t stream);
 
 /* ---- fused head: logits + entropy loss + dlogits in one pass.  Replaces the loss + backward
  * entry of src/core/trainers/seg_trainer.py:141-142 with the TENT entropy (mode 0 softmax,

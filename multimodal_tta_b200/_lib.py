@@ -12,7 +12,8 @@ import subprocess
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtta_b200.so")
+# TTA_LIB selects a differently-built variant of the library (kernel A/B experiments inside one process launch)
+LIB_PATH = os.environ.get("TTA_LIB") or os.path.join(_HERE, "libtta_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,23 +22,24 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 TTA_F16, TTA_BF16, TTA_F16_HI = 0, 1, 2
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every csrc/*.cu into libtta_b200.so for sm_100a (cross-compiles without a GPU)."""
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """Compile every csrc/*.cu into libtta_b200.so for sm_100a (cross-compiles without a GPU).
+    ``out`` / ``defines``: build a variant (e.g. ``-DTTA_PDL_LATE``) next to the default library."""
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh")))
-    if not force and os.path.exists(LIB_PATH):
+    target = out or os.path.join(_HERE, "libtta_b200.so")
+    if not force and os.path.exists(target):
         newest = max(os.path.getmtime(p) for p in deps)
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+        if os.path.getmtime(target) >= newest:
+            return target
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *srcs, "-lcuda"] if _has_libcuda() else \
-          [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *srcs]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", target, *srcs]
     if verbose:
         print(" ".join(cmd))
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
-    return LIB_PATH
+    return target
 
 
 def _has_libcuda() -> bool:
@@ -71,8 +73,9 @@ _SIGNATURES = {
     "tta_head_fused_supported": (I, [I, I, I, I]),
     "tta_head_fused_tiles": (I, [I, I, I]),
     "tta_head_fused_workspace_floats": (L, [I, I, I, I]),
-    "tta_head_fused_fwd": (I, [P, L, I, I, I, I, I, P, P, P, P, I, P, P, I, F, F, P, P, P, P, P, P]),
-    "tta_head_fused_bwd": (I, [P, I, I, I, I, I, P, P, L, P, P, P, P, I, I, P, L, P, P, P, P, P]),
+    "tta_head_fused_fwd": (I, [P, L, I, I, I, I, I, I, P, P, P, P, I, P, P, I, F, F, P, P, P, P, P, P]),
+    "tta_head_fused_bwd": (I, [P, I, I, I, I, I, P, P, L, I, P, P, P, P, I, I, P, L, P, P, P, P, P]),
+    "tta_norm_bwd_apply_c4": (I, [P, L, P, L, I, I, L, P, P, P, P, I, P, P, P, L, I, I, P]),
     "tta_adam_step": (I, [P, P, P, P, I, F, F, F, F, F, P, P]),
     "tta_sw_blend": (I, [P, I, I, I, I, I, P, P, P, P, P, F, P, P, I, I, I, I, P]),
     "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),

@@ -985,6 +985,7 @@ struct T2sParams {
   const float* bias;
   float* out;
   float* stats;                          // [n][1][grid][16] or nullptr
+  int cpv;                               // floats per output voxel: 8 (chunk layout) or 4 (compact, flags bit 14)
 };
 
 template <int COUT>
@@ -1212,7 +1213,7 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
                     }
               }
               const int od = 2 * d + qd, oh = 2 * ih + qh, ow = 2 * iw;
-              float* dst = P.out + (long long)n * P.out_ns + (((long long)od * Ho + oh) * Wo + ow) * 8;
+              float* dst = P.out + (long long)n * P.out_ns + (((long long)od * Ho + oh) * Wo + ow) * P.cpv;
 #pragma unroll
               for (int qw = 0; qw < 2; ++qw) {
                 float rv[8];
@@ -1224,7 +1225,8 @@ conv_t2s_kernel(const __grid_constant__ T2sParams P) {
                   s1[c] += o[qw][c];
                   s2[c] = fmaf(o[qw][c], o[qw][c], s2[c]);
                 }
-                store_f32x8(dst + qw * 8, rv);
+                if (P.cpv == 8) store_f32x8(dst + qw * 8, rv);
+                else *reinterpret_cast<float4*>(dst + qw * 4) = make_float4(rv[0], rv[1], rv[2], rv[3]);
               }
             }
           };
@@ -1357,7 +1359,7 @@ int tta_conv_tc_ngroups(int mode, int K, int stride) {
 
 static int conv_t2s_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int N, int C8in, int Di, int Hi,
                          int Wi, const void* wpacked, const float* bias, float* out, long long out_ns, int cout,
-                         int Do, int Ho, int Wo, int accumulate, float* stats_ws, int stats_c8, int* q_ksplit,
+                         int Do, int Ho, int Wo, int accumulate, float* stats_ws, int stats_c8, int cpv, int* q_ksplit,
                          int* q_grid, int* q_nbuf, cudaStream_t stream) {
   const bool query = q_ksplit != nullptr;
   TTA_REQUIRE(Do == 2 * Di && Ho == 2 * Hi && Wo == 2 * Wi, "tta_conv_tc: transposed s2 output dims");
@@ -1414,6 +1416,7 @@ static int conv_t2s_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long
   EncodeTiledFn enc = get_encode();
   TTA_REQUIRE(enc != nullptr, "tta_conv_tc: cuTensorMapEncodeTiled entry point not found");
   P.out_ns = out_ns; P.wpacked = (const uint8_t*)wpacked; P.bias = bias; P.out = out;
+  P.cpv = cpv;
   P.stats = nullptr;
   if (stats_ws != nullptr && stats_c8 > 0) {
     TTA_REQUIRE(stats_c8 == 1, "tta_conv_tc: stats_c8 %d > 1 chunk", stats_c8);
@@ -1468,13 +1471,17 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   // one-plane tiles (testing: both must agree)
   // flags bits 8..10: real output-channel count (1..4) of a transposed stride-2 conv whose weights were
   // packed for the dense-GEMM + col2im kernel (layout.pack_weights_tc(t2s=True)); 0 = generic path
+  // flags bit 14 (with bits 8..10): that kernel writes the COMPACT fp32 layout [N][D][H][W][4] (out_n_stride in
+  // floats) instead of the 8-channel chunk layout -- for the fused full-resolution head, whose three tensors
+  // would otherwise carry five pad channels through every pass
   const int t2s_small_cout = (flags >> 8) & 7;
+  TTA_REQUIRE(!(flags & 16384) || t2s_small_cout > 0, "tta_conv_tc: flags bit 14 needs the small-Cout transposed kernel");
   TTA_REQUIRE(t2s_small_cout == 0 || t2s_of(geom, C8in * 8, t2s_small_cout, in_dtype == TTA_F16_HI ? 0 : 1),
               "tta_conv_tc: flags ask for the small-Cout transposed kernel but the layer does not qualify");
   if (t2s_small_cout > 0 && t2s_of(geom, C8in * 8, t2s_small_cout, in_dtype == TTA_F16_HI ? 0 : 1)) {
     TTA_REQUIRE(C8out == 1 && segs == nullptr, "tta_conv_tc: small-Cout transposed conv writes one channel chunk");
     return conv_t2s_impl(in_hi, in_lo, in_ns, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, t2s_small_cout, Do, Ho,
-                         Wo, accumulate, stats_ws, stats_c8, q_ksplit, q_grid, q_nbuf, stream);
+                         Wo, accumulate, stats_ws, stats_c8, (flags & 16384) ? 4 : 8, q_ksplit, q_grid, q_nbuf, stream);
   }
   const bool stacked = stacked_of(geom, C8in * 8, C8out * 8, in_dtype == TTA_F16_HI ? 0 : 1);
   if (stacked) geom = geom == GEOM_S1 ? GEOM_S1K : GEOM_S1TK;

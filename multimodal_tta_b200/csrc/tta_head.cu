@@ -50,7 +50,7 @@ __device__ __forceinline__ void tile_origin(const HeadGeom& G, int& d0, int& h0,
 // ---------------------------------------------------------------- forward
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 3)
-head_fwd_kernel(const float* y, long long y_ns, const HeadGeom G, const float* mean,
+head_fwd_kernel(const float* y, long long y_ns, const int cpv, const HeadGeom G, const float* mean,
                 const float* rstd, const float* gamma, const float* beta,
                 int relu, const __grid_constant__ HeadW<27 * CIN * COUT> Wc, const float* bias, int mode,
                 float inv_count, float grad_scale, const float* sample_w, float* logits,
@@ -84,7 +84,9 @@ head_fwd_kernel(const float* y, long long y_ns, const HeadGeom G, const float* m
         const int hh = p / kHW, ww = p - hh * kHW;
         const int gh = h0 + hh - 1, gw = w0 + ww - 1;
         const bool hw_in = gh >= 0 && gh < G.H && gw >= 0 && gw < G.W;
-        const float* src = yb + ((long long)gh * G.W + gw) * 8;
+        // cpv = floats per voxel of y: 8 (channel-chunk layout, 4 pad channels ride along in every sector) or
+        // 4 (the compact layout the small-Cout transposed conv writes for this kernel: dense 16-byte voxels)
+        const float* src = yb + ((long long)gh * G.W + gw) * cpv;
         float* dst = tile + hh * kPitch + ww;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -95,7 +97,7 @@ head_fwd_kernel(const float* y, long long y_ns, const HeadGeom G, const float* m
             const int gd = d0 + half * (kHD / 2) + j - 1;
             in[j] = hw_in && gd >= 0 && gd < G.D;
             x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in[j]) x[j] = __ldcg(reinterpret_cast<const float4*>(src + gd * HW * 8));
+            if (in[j]) x[j] = __ldcg(reinterpret_cast<const float4*>(src + gd * HW * cpv));
           }
 #pragma unroll
           for (int j = 0; j < kHD / 2; ++j) {
@@ -210,7 +212,7 @@ head_fwd_kernel(const float* y, long long y_ns, const HeadGeom G, const float* m
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 3)
 head_bwd_kernel(const float* dlogits, const HeadGeom G, const __grid_constant__ HeadW<27 * CIN * COUT> Wc,
-                const float* y, long long y_ns, const float* mean,
+                const float* y, long long y_ns, const int cpv, const float* mean,
                 const float* rstd, const float* gamma, const float* beta,
                 int relu, float* dz, long long dz_ns, float* partial,
                 unsigned int* counters, int N, int batch_mode, float* sums,
@@ -281,7 +283,7 @@ head_bwd_kernel(const float* dlogits, const HeadGeom G, const __grid_constant__ 
     if (dd >= 1 && dd <= kTD) {
       const int o = dd - 1, d = d0 + o;
       yv[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (d < G.D && hw_ok) yv[o] = __ldcg(reinterpret_cast<const float4*>(yb + (vbase + o * HWo) * 8));
+      if (d < G.D && hw_ok) yv[o] = __ldcg(reinterpret_cast<const float4*>(yb + (vbase + o * HWo) * cpv));
     }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
@@ -318,7 +320,18 @@ head_bwd_kernel(const float* dlogits, const HeadGeom G, const __grid_constant__ 
           red16[8 + c] = fmaf(dzv, xh, red16[8 + c]);
           r[c] = dzv;
         }
-        store_f32x8(ob + v * 8, r);
+        if (cpv == 8) {
+          store_f32x8(ob + v * 8, r);
+        } else {
+          // compact layout: the masked gradient leaves as four fp16 values per voxel (8 B instead of 32 B);
+          // its only consumer, tta_norm_bwd_apply_c4, rounds its own result to fp16 anyway
+          const __half2 h01 = __floats2half2_rn(fminf(fmaxf(r[0], -65504.f), 65504.f), fminf(fmaxf(r[1], -65504.f), 65504.f));
+          const __half2 h23 = __floats2half2_rn(fminf(fmaxf(r[2], -65504.f), 65504.f), fminf(fmaxf(r[3], -65504.f), 65504.f));
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned int*>(&h01);
+          pk.y = *reinterpret_cast<const unsigned int*>(&h23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dz) + ((long long)n * dz_ns + v * 4)) = pk;
+        }
       }
     }
     asm volatile("" ::: "memory");
@@ -371,14 +384,16 @@ long long tta_head_fused_workspace_floats(int N, int D, int H, int W) {
   return 1024 + (long long)N * tta_head_fused_tiles(D, H, W) * 16;
 }
 
-// y: fp32 chunk view [N][1][D][H][W][8] (the transposed conv's result, C <= 4 real channels);
+// y: fp32 chunk view [N][1][D][H][W][8] (the transposed conv's result, C <= 4 real channels), or with
+// y_cpv = 4 the compact view [N][D][H][W][4] written by tta_conv_tc(flags bit 14) (y_n_stride in floats);
 // mean/rstd: [N][8]; W_host: HOST fp32 [27][8][8] = Wg[tap][ci][co] of the 3x3x3 conv (identity
 // shortcut already folded into the centre tap); logits / dlogits: NCDHW fp32 [N][C][D][H][W]
 // (dlogits may be NULL: inference).  loss <- mean entropy * 1 (same scaling as tta_head_entropy).
-int tta_head_fused_fwd(const float* y, long long y_ns, int N, int C, int D, int H, int W, const float* mean,
+int tta_head_fused_fwd(const float* y, long long y_ns, int y_cpv, int N, int C, int D, int H, int W, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, int relu, const float* W_host,
                        const float* bias, int mode, float inv_count, float grad_scale, const float* sample_w,
                        float* logits, float* dlogits, float* workspace, float* loss, cudaStream_t stream) {
+  TTA_REQUIRE(y_cpv == 8 || y_cpv == 4, "tta_head_fused_fwd: y_cpv %d (8 = chunk layout, 4 = compact)", y_cpv);
   TTA_REQUIRE(y && mean && rstd && gamma && beta && W_host && workspace && loss, "tta_head_fused_fwd: null pointer");
   TTA_REQUIRE(tta_head_fused_supported(3, 1, C, C), "tta_head_fused_fwd: %d channels unsupported (1..4)", C);
   TTA_REQUIRE(mode == 0 || mode == 1, "tta_head_fused_fwd: mode %d", mode);
@@ -396,7 +411,7 @@ int tta_head_fused_fwd(const float* y, long long y_ns, int N, int C, int D, int 
       TTA_REQUIRE(set_smem(head_fwd_kernel<CC, CC>, smem), "tta_head_fused_fwd: cudaFuncSetAttribute failed"); \
       configured = true;                                                                                      \
     }                                                                                                         \
-    tta_launch(head_fwd_kernel<CC, CC>, grid, kThreads, smem, stream, tta_pdl_family(16), y, y_ns, G, mean, rstd, gamma, beta, relu, Wc, bias, \
+    tta_launch(head_fwd_kernel<CC, CC>, grid, kThreads, smem, stream, tta_pdl_family(16), y, y_ns, y_cpv, G, mean, rstd, gamma, beta, relu, Wc, bias, \
                                                               mode, inv_count, grad_scale, sample_w, logits,   \
                                                               dlogits, workspace + 1024, counter, loss);       \
   } while (0)
@@ -405,13 +420,15 @@ int tta_head_fused_fwd(const float* y, long long y_ns, int N, int C, int D, int 
   return tta_check_launch("tta_head_fused_fwd");
 }
 
-// dz: fp32 chunk view [N][1][D][H][W][8] <- masked gradient w.r.t. the norm output (pad channels 0);
+// dz: fp32 chunk view [N][1][D][H][W][8] <- masked gradient w.r.t. the norm output (pad channels 0); with
+// y_cpv = 4: FP16 [N][D][H][W][4] (dz_n_stride in 16-bit elements), consumed by tta_norm_bwd_apply_c4;
 // sums [N][8][2], dgamma/dbeta [C]: finalized by the last block (as tta_norm_bwd_reduce, finalize=1);
 // W_host: the SAME forward weights as tta_head_fused_fwd.
 int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, const float* W_host, const float* y,
-                       long long y_ns, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                       int relu, int batch_mode, float* dz, long long dz_ns, float* sums, float* dgamma, float* dbeta,
-                       float* workspace, cudaStream_t stream) {
+                       long long y_ns, int y_cpv, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int relu, int batch_mode, float* dz, long long dz_ns, float* sums,
+                       float* dgamma, float* dbeta, float* workspace, cudaStream_t stream) {
+  TTA_REQUIRE(y_cpv == 8 || y_cpv == 4, "tta_head_fused_bwd: y_cpv %d (8 = chunk layout, 4 = compact)", y_cpv);
   TTA_REQUIRE(dlogits && W_host && y && mean && rstd && gamma && beta && dz && sums && dgamma && dbeta && workspace,
               "tta_head_fused_bwd: null pointer");
   TTA_REQUIRE(tta_head_fused_supported(3, 1, C, C), "tta_head_fused_bwd: %d channels unsupported (1..4)", C);
@@ -428,7 +445,7 @@ int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, 
       TTA_REQUIRE(set_smem(head_bwd_kernel<CC, CC>, smem), "tta_head_fused_bwd: cudaFuncSetAttribute failed"); \
       configured = true;                                                                                      \
     }                                                                                                         \
-    tta_launch(head_bwd_kernel<CC, CC>, grid, kThreads, smem, stream, tta_pdl_family(16), dlogits, G, Wc, y, y_ns, mean, rstd, gamma, beta, \
+    tta_launch(head_bwd_kernel<CC, CC>, grid, kThreads, smem, stream, tta_pdl_family(16), dlogits, G, Wc, y, y_ns, y_cpv, mean, rstd, gamma, beta, \
                                                               relu, dz, dz_ns, workspace + 1024, counters, N,  \
                                                               batch_mode, sums, dgamma, dbeta);                \
   } while (0)

@@ -510,6 +510,52 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
   }
 }
 
+
+// Compact-layout variant for the fused full-resolution head (<= 4 channels): dz is the MASKED gradient as four
+// fp16 values per voxel (tta_head_fused_bwd, y_cpv = 4), y the conv result as four floats per voxel
+// (tta_conv_tc flags bit 14); dy leaves in the 8-channel chunk layout the dgrad conv's TMA boxes read.
+template <int ODT>
+__global__ void __launch_bounds__(kThreads, 4)
+norm_bwd_apply_c4_kernel(const uint16_t* dz, long long dz_ns, const float* y, long long y_ns, long long V,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         const float* sums, float inv_m, int Creal, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
+                         int dy_wsplit_w) {
+  pdl_trigger();
+  pdl_wait();
+  const int n = blockIdx.y;
+  float k0[4], k1[4], k2[4], mu[4], rs[4];   // dy = k0*dz - k1 - xhat*k2
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const bool live = c < Creal;
+    mu[c] = live ? mean[n * 8 + c] : 0.f;
+    rs[c] = live ? rstd[n * 8 + c] : 0.f;
+    const float gr = live ? gamma[c] * rs[c] : 0.f;
+    k0[c] = gr;
+    k1[c] = live ? gr * sums[(n * 8 + c) * 2 + 0] * inv_m : 0.f;
+    k2[c] = live ? gr * sums[(n * 8 + c) * 2 + 1] * inv_m : 0.f;
+  }
+  (void)beta;
+  const uint16_t* dzb = dz + (long long)n * dz_ns;
+  const float* yb = y + (long long)n * y_ns;
+  const long long ob = (long long)n * dy_ns;
+#pragma unroll 2
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V; v += (long long)gridDim.x * kThreads) {
+    const uint2 pk = *reinterpret_cast<const uint2*>(dzb + v * 4);
+    const float4 yv = *reinterpret_cast<const float4*>(yb + v * 4);
+    const __half2 h01 = *reinterpret_cast<const __half2*>(&pk.x), h23 = *reinterpret_cast<const __half2*>(&pk.y);
+    const float2 d01 = __half22float2(h01), d23 = __half22float2(h23);
+    const float dzv[4] = {d01.x, d01.y, d23.x, d23.y}, xv[4] = {yv.x, yv.y, yv.z, yv.w};
+    float x[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float xh = (xv[c] - mu[c]) * rs[c];
+      x[c] = fmaf(k0[c], dzv[c], -k1[c]) - xh * k2[c];
+      x[4 + c] = 0.f;
+    }
+    store_split8<ODT>(dy_hi, dy_lo, ob + (dy_wsplit_w > 0 ? wsplit_index(v, dy_wsplit_w) : v) * 8, x);
+  }
+}
+
 // plain fp32 (sum of up to two views) -> split planes; used where a gradient feeds a conv
 // directly without a norm in between.
 template <int ODT>
@@ -767,6 +813,33 @@ int tta_norm_bwd_small(const float* g0, long long g0_ns, const float* g1, long l
   if (out_dtype == TTA_F16) LAUNCH(TTA_F16); else if (out_dtype == TTA_F16_HI) LAUNCH(TTA_F16_HI); else LAUNCH(TTA_BF16);
 #undef LAUNCH
   return tta_check_launch("tta_norm_bwd_small");
+}
+
+// Compact-layout norm backward apply of the fused head (see norm_bwd_apply_c4_kernel): dz fp16 [N][V][4]
+// (n stride in 16-bit elements), y fp32 [N][V][4] (n stride in floats), mean/rstd [N][8], sums [N][8][2];
+// dy: one chunk per voxel in the usual operand layout.  InstanceNorm and BatchNorm alike (sums / mean / rstd are
+// already per (n, c)); inv_m = 1 / (voxels per normalisation group).
+int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_ns, const float* y, long long y_ns, int N, int Creal,
+                          long long V, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          int batch_mode, const float* sums, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
+                          int out_dtype, int dy_wsplit_w, cudaStream_t stream) {
+  TTA_REQUIRE(dz && y && mean && rstd && gamma && beta && sums && dy_hi && (dy_lo || out_dtype == TTA_F16_HI),
+              "tta_norm_bwd_apply_c4: null pointer");
+  TTA_REQUIRE(Creal >= 1 && Creal <= 4 && N > 0 && V > 0, "tta_norm_bwd_apply_c4: bad shape C=%d", Creal);
+  TTA_REQUIRE(dy_wsplit_w == 0 || (dy_wsplit_w > 0 && dy_wsplit_w % 2 == 0 && V % dy_wsplit_w == 0),
+              "tta_norm_bwd_apply_c4: bad parity-split row length %d", dy_wsplit_w);
+  TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_norm_bwd_apply_c4: bad dtype");
+  const float inv_m = (float)(1.0 / ((double)V * (batch_mode ? N : 1)));
+  long long xb = (V + kThreads - 1) / kThreads;
+  const long long want = (8LL * 148 + N - 1) / N;
+  if (xb > want) xb = want;
+  const dim3 grid((unsigned)xb, N);
+#define LAUNCH(DT)                                                                                                   \
+  tta_launch(norm_bwd_apply_c4_kernel<DT>, grid, kThreads, 0, stream, tta_pdl_family(2), dz, dz_ns, y, y_ns, V, mean, \
+             rstd, gamma, beta, sums, inv_m, Creal, dy_hi, dy_lo, dy_ns, dy_wsplit_w)
+  if (out_dtype == TTA_F16) LAUNCH(TTA_F16); else if (out_dtype == TTA_F16_HI) LAUNCH(TTA_F16_HI); else LAUNCH(TTA_BF16);
+#undef LAUNCH
+  return tta_check_launch("tta_norm_bwd_apply_c4");
 }
 
 int tta_split_f32(const float* g0, long long g0_ns, const float* g1, long long g1_ns, int N, int C8,

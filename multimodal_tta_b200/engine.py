@@ -123,6 +123,8 @@ class Res:
         self.stats_c8 = 0       # > 0: the producing tcgen05 conv also emits norm statistics partials
         self.stats_grid = 0     #      ... with this many slots (= its CTA count) per (n, chunk)
         self.tc_query = None    # (ksplit, grid) of the producing tcgen05 launch, None for other backends
+        self.c4 = False         # compact [N][D][H][W][4] fp32 layout (<= 4 channels, fused head only)
+        self.t2s = False        # produced by the small-Cout transposed kernel (the only writer of the compact layout)
         self.device = device
         self.root, self.c8_off = self, 0
 
@@ -452,6 +454,11 @@ class TTAEngine:
                                             int(accumulate), flags, ctypes.byref(ks), ctypes.byref(grid),
                                             ctypes.byref(nbuf)), "conv_tc_query")
                 stats_res.tc_query = (ks.value, grid.value, nbuf.value)
+                stats_res.t2s = bool((flags >> 8) & 7)
+                # the fused head may ask (later) for the compact layout of this result
+                odv = odims[0] * odims[1] * odims[2]
+                args_c4 = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, odv * 4, cout8,
+                           *odims, mode, cl.K, cl.stride, int(accumulate), flags | 16384)
             if bwd_rec is not None:
                 ks, grid, nbuf = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
                 check(lib.tta_conv_tc_query(src_dtype, N, cin8, *idims, cout8, *odims, mode, cl.K, cl.stride,
@@ -481,7 +488,8 @@ class TTAEngine:
                 # fused statistics are requested (later, by the norm that consumes this result) via the Res
                 st = (plan.ws.data_ptr(), stats_res.stats_c8) if (stats_res is not None and stats_res.stats_c8) \
                     else (0, 0)
-                check(lib.tta_conv_tc(*args, *st, _stream()), f"conv_tc {cl.name}")
+                a = args_c4 if (stats_res is not None and stats_res.c4) else args
+                check(lib.tta_conv_tc(*a, *st, _stream()), f"conv_tc {cl.name}")
         else:
             wp = cl.packed["simt_" + key]
             plan.keep.append(wp)
@@ -719,6 +727,16 @@ class TTAEngine:
                 fused_head = (hcl, hrec, hinp)
                 max_ws[0] = max(max_ws[0], lib.tta_head_fused_workspace_floats(N, *final_dims(final)))
         plan.fused_head = fused_head is not None
+        # compact layout of the head's tensors (conv result fp32 x4, masked gradient fp16 x4 per voxel instead of
+        # 8-channel chunks): when the small-Cout transposed kernel produces the result AND its statistics (no pass
+        # of the generic 8-channel norm kernels ever touches it)
+        head_c4 = False
+        if fused_head is not None and model.head_compact:
+            hrec_ = fused_head[1]
+            hy_ = hrec_["y"]
+            if isinstance(hy_, Res) and hy_.t2s and hrec_["fused_stats"]:
+                head_c4 = hy_.c4 = True
+        plan.head_c4 = head_c4
         plan.ws = torch.zeros(max_ws[0], dtype=torch.float32, device=dev)
         if fused_head is None:
             final.alloc_dy(nplanes)
@@ -763,7 +781,8 @@ class TTAEngine:
             def head(train: bool):  # noqa: F811  (fused variant replaces the streaming head)
                 def run():
                     check(lib.tta_head_fused_fwd(
-                        hy.ptr, hy.ns, N, R, hy.D, hy.H, hy.W, hrec["mean"].data_ptr(), hrec["rstd"].data_ptr(),
+                        hy.ptr, hy.V * 4 if head_c4 else hy.ns, 4 if head_c4 else 8, N, R, hy.D, hy.H, hy.W,
+                        hrec["mean"].data_ptr(), hrec["rstd"].data_ptr(),
                         hrec["gptr"], hrec["bptr"], int(hrec["relu"]), wp.data_ptr(),
                         hcl.packed["bias"].data_ptr(), self.entropy_mode, float(plan.inv_count),
                         float(plan.loss_scale), plan.sample_w.data_ptr(), plan.logits.data_ptr(),
@@ -790,9 +809,12 @@ class TTAEngine:
                     # fused tail: dgrad of the small conv + ReLU mask + norm-backward reduction in ONE
                     # kernel; the masked gradient lands in inp.g, sums/dgamma/dbeta are finalized
                     hrec, hnl = fused_head[1], fused_head[1]["nl"]
+                    hyv = hrec["y"].V
                     hb_args = (plan.dlogits.data_ptr(), N, R, y.D, y.H, y.W, cl.packed["small_fwd"].data_ptr(),
-                               hrec["y"].ptr, hrec["y"].ns, hrec["mean"].data_ptr(), hrec["rstd"].data_ptr(),
-                               hrec["gptr"], hrec["bptr"], int(hrec["relu"]), hnl.batch, inp.g, inp.ns,
+                               hrec["y"].ptr, hyv * 4 if head_c4 else hrec["y"].ns, 4 if head_c4 else 8,
+                               hrec["mean"].data_ptr(), hrec["rstd"].data_ptr(),
+                               hrec["gptr"], hrec["bptr"], int(hrec["relu"]), hnl.batch, inp.g,
+                               hyv * 4 if head_c4 else inp.ns,
                                hrec["sums"].data_ptr(), self.dgb.data_ptr() + hnl.off * 4,
                                self.dgb.data_ptr() + (P + hnl.off) * 4)
 
@@ -873,6 +895,11 @@ class TTAEngine:
                                aux.ns if aux else 0, bdt)
 
                 skip_reduce = fused_head is not None and rec is fused_head[1]   # done by tta_head_fused_bwd
+                c4_args = None
+                if skip_reduce and head_c4 and do_apply:
+                    c4_args = (g0, y.V * 4, y.ptr, y.V * 4, N, nl.C, y.V, rec["mean"].data_ptr(), rec["rstd"].data_ptr(),
+                               rec["gptr"], rec["bptr"], nl.batch, rec["sums"].data_ptr(), y.dy_ptr(0), y.dy_ptr(1), y.ns,
+                               bdt, dy_ws)
                 fin_args = None
                 if fuse_bwd is not None:
                     fin_args = (fuse_bwd[0].data_ptr(), N, y.C8, nl.C, fuse_bwd[1], nl.batch, rec["sums"].data_ptr(),
@@ -916,7 +943,10 @@ class TTAEngine:
                 rec["per_sample_bwd"] = per_n is not None
 
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db, dy_ws=dy_ws,
-                        skip_reduce=skip_reduce, fin_args=fin_args, sm_bwd=sm_bwd, per_n=per_n):
+                        skip_reduce=skip_reduce, fin_args=fin_args, sm_bwd=sm_bwd, per_n=per_n, c4_args=c4_args):
+                    if c4_args is not None:
+                        check(lib.tta_norm_bwd_apply_c4(*c4_args, _stream()), "norm_bwd_apply_c4")
+                        return
                     if per_n is not None:
                         for rd_n, ap_n, accum in per_n:
                             check(lib.tta_norm_bwd_reduce(*rd_n, plan.ws.data_ptr(), 1, accum, _stream()),

@@ -316,12 +316,15 @@ def test_dice_counts_match_reference_golden(lib, cuda):
         assert torch.equal(valid, torch.from_numpy(gold[f"valid{i}"]))
 
 
+@pytest.mark.parametrize("cpv", [8, 4])
 @pytest.mark.parametrize("mode,C,dims,batch_mode", [(1, 3, (9, 10, 37), 0), (0, 3, (8, 8, 32), 0), (1, 1, (5, 17, 6), 0),
                                                      (1, 2, (16, 8, 40), 1), (0, 4, (3, 9, 33), 0)])
-def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode):
+def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode, cpv):
     """tta_head_fused_{fwd,bwd} (norm apply + 3x3x3 conv + entropy, and its backward up to the
     norm-backward reduction) against torch fp32 autograd on the CPU; ragged tiles (dims are not
-    multiples of the 8x8x32 tile).  fp32 FMA chains in a different order: 3e-6 relative."""
+    multiples of the 8x8x32 tile).  fp32 FMA chains in a different order: 3e-6 relative.
+    cpv = 8: y / dz in the 8-channel chunk layout; cpv = 4: the compact layout (y fp32 [N][V][4], dz fp16 [N][V][4],
+    tta_norm_bwd_apply_c4) -- same math, half / a quarter of the bytes."""
     from multimodal_tta_b200.layout import pack_weights_small
     from oracle.tent_oracle import entropy_loss
     torch.manual_seed(11)
@@ -353,11 +356,17 @@ def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode):
     bp = torch.zeros(8, device=cuda); bp[:C] = beta.to(cuda)
     check(lib.tta_norm_stats(ych.data_ptr(), ns, N, 1, V, batch_mode, 1e-5, mean.data_ptr(), rstd.data_ptr(),
                              ws.data_ptr(), 1, stream()))
+    ych8 = ych
+    if cpv == 4:
+        ych = ych8[:, 0, ..., :4].contiguous()                  # [N][D][H][W][4]
+        ns_y = V * 4
+    else:
+        ns_y = ns
     wh = pack_weights_small(wg_forward(w, False), 0)            # HOST [27][8][8]
     bias = pack_bias(b.to(cuda))
     logits = torch.zeros(N, C, *dims, device=cuda); dlog = torch.zeros_like(logits)
     lossd = torch.zeros(1, device=cuda)
-    check(lib.tta_head_fused_fwd(ych.data_ptr(), ns, N, C, *dims, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
+    check(lib.tta_head_fused_fwd(ych.data_ptr(), ns_y, cpv, N, C, *dims, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
                                  bp.data_ptr(), 1, wh.data_ptr(), bias.data_ptr(), mode, 1.0 / (N * V), S, 0,
                                  logits.data_ptr(), dlog.data_ptr(), ws.data_ptr(), lossd.data_ptr(), stream()))
     assert rel_l2(logits.cpu(), z.detach()) < 3e-6
@@ -365,28 +374,43 @@ def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode):
     assert rel_l2(dlog.cpu() / S, z.grad) < 1e-5
     # inference variant: no dlogits, same logits; a second call also proves the block counter reset
     logits2 = torch.zeros_like(logits); loss2 = torch.zeros(1, device=cuda)
-    check(lib.tta_head_fused_fwd(ych.data_ptr(), ns, N, C, *dims, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
+    check(lib.tta_head_fused_fwd(ych.data_ptr(), ns_y, cpv, N, C, *dims, mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(),
                                  bp.data_ptr(), 1, wh.data_ptr(), bias.data_ptr(), mode, 1.0 / (N * V), S, 0,
                                  logits2.data_ptr(), 0, ws.data_ptr(), loss2.data_ptr(), stream()))
     assert torch.equal(logits2, logits) and torch.equal(loss2, lossd)
     # ---- backward: masked gradient w.r.t. the norm output + reductions
     dz = torch.full((N, 1, *dims, 8), 7.0, device=cuda)
+    dz4 = torch.full((N, *dims, 4), 7.0, dtype=torch.float16, device=cuda)
     sums = torch.zeros(N * 8 * 2, device=cuda)
     dg = torch.zeros(8, device=cuda); db = torch.zeros(8, device=cuda)
     for _ in range(2):                               # twice: self-resetting counters
-        check(lib.tta_head_fused_bwd(dlog.data_ptr(), N, C, *dims, wh.data_ptr(), ych.data_ptr(), ns,
+        check(lib.tta_head_fused_bwd(dlog.data_ptr(), N, C, *dims, wh.data_ptr(), ych.data_ptr(), ns_y, cpv,
                                      mean.data_ptr(), rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode,
-                                     dz.data_ptr(), ns, sums.data_ptr(), dg.data_ptr(), db.data_ptr(),
-                                     ws.data_ptr(), stream()))
+                                     (dz if cpv == 8 else dz4).data_ptr(), ns if cpv == 8 else V * 4, sums.data_ptr(),
+                                     dg.data_ptr(), db.data_ptr(), ws.data_ptr(), stream()))
     dz_ref = a.grad * (zn.detach() > 0)
-    assert rel_l2(from_chunked(dz, C).cpu() / S, dz_ref) < 1e-5
-    assert float(dz[..., C:].abs().max()) == 0.0     # pad channels exactly zero
+    if cpv == 8:
+        assert rel_l2(from_chunked(dz, C).cpu() / S, dz_ref) < 1e-5
+        assert float(dz[..., C:].abs().max()) == 0.0     # pad channels exactly zero
+    else:
+        got = dz4.float().permute(0, 4, 1, 2, 3)[:, :C].cpu() / S
+        assert rel_l2(got, dz_ref) < 5e-4                # one fp16 rounding
+        assert C == 4 or float(dz4[..., C:].abs().max()) == 0.0
     assert rel_l2(dg[:C].cpu() / S, gr.grad) < 2e-5
     assert rel_l2(db[:C].cpu() / S, br.grad) < 2e-5
-    # the existing norm-backward apply consumes dz as its gradient source: dy = autograd's dL/dy
+    # the norm-backward apply consumes dz as its gradient source: dy = autograd's dL/dy
     dhi = torch.zeros((N, 1, *dims, 8), dtype=torch.int16, device=cuda); dlo = torch.zeros_like(dhi)
-    check(lib.tta_norm_bwd_apply(dz.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, 1, V, mean.data_ptr(),
-                                 rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
-                                 dhi.data_ptr(), dlo.data_ptr(), ns, 0, 0, 0, TTA_BF16, 0, C, 0, 0, 0, stream()))
+    if cpv == 8:
+        check(lib.tta_norm_bwd_apply(dz.data_ptr(), ns, 0, 0, ych.data_ptr(), ns, N, 1, V, mean.data_ptr(),
+                                     rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), 1, batch_mode, sums.data_ptr(),
+                                     dhi.data_ptr(), dlo.data_ptr(), ns, 0, 0, 0, TTA_BF16, 0, C, 0, 0, 0, stream()))
+    else:
+        check(lib.tta_norm_bwd_apply_c4(dz4.data_ptr(), V * 4, ych.data_ptr(), ns_y, N, C, V, mean.data_ptr(),
+                                        rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), batch_mode, sums.data_ptr(),
+                                        dhi.data_ptr(), dlo.data_ptr(), ns, TTA_BF16, 0, stream()))
+        dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu() / S
+        assert rel_l2(dy, yr.grad) < 6e-4                # dz went through fp16 (11 bits) first
+        assert float(join_planes(dhi, dlo, TTA_BF16)[..., C:].abs().max()) == 0.0
+        return
     dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu() / S
     assert rel_l2(dy, yr.grad) < 5e-5                # bf16x2 storage (~16 bits)
