@@ -265,6 +265,22 @@ int tta_intensity_stats(const float* vol, int n_vol, int C, long long V, const f
 int tta_intensity_apply(const float* vol, float* out, int n_vol, int C, long long V, const float* affine,
                         tta_stream_t stream);
 
+/* ---- multimodal model (MultimodalUNetDeepFusion, src/models/unet_multimodal_midfusion.py:139-267): modality mean
+ * of M operand tensors (pseudo-shared bottleneck feature :216, fused skips :221-224; rep > 1 writes one copy per
+ * modality for the batched fusion layer), its backward / gradient fan-in as a scaled sum of fp32 views, and
+ * MONAI UpSample("nontrainable") = nn.Upsample(trilinear, align_corners=True) (:114-120) forward and adjoint.
+ * Pointer arrays are HOST arrays of nsrc <= 8 device pointers. */
+int tta_mean_planes(const uint16_t* const* in_hi, const uint16_t* const* in_lo, const long long* in_n_stride, int nsrc,
+                    int N, int C8, long long V, float scale, uint16_t* out_hi, uint16_t* out_lo, long long out_n_stride,
+                    int rep, tta_stream_t stream);
+int tta_sum_f32(const float* const* src, const long long* src_n_stride, int nsrc, int rep, int N, int C8, long long V,
+                float scale, float* out, long long out_n_stride, int accumulate, tta_stream_t stream);
+int tta_upsample_fwd(const float* in, long long in_n_stride, int N, int C8, int Di, int Hi, int Wi, int Do, int Ho,
+                     int Wo, uint16_t* out_hi, uint16_t* out_lo, long long out_n_stride, int out_dtype,
+                     tta_stream_t stream);
+int tta_upsample_bwd(const float* g, long long g_n_stride, int N, int C8, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                     uint16_t* dy_hi, uint16_t* dy_lo, long long dy_n_stride, int out_dtype, tta_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,4 +1,4 @@
-"""Execution engine: turns the ``UNetB200`` module tree into a static list of C-ABI kernel
+"""Execution engine: turns a ``B200Model`` module tree (``UNetB200``, ``MultimodalUNetB200``) into a static list of C-ABI kernel
 launches (forward, fused head, backward, Adam) over pre-allocated HBM buffers, optionally
 replayed as one CUDA graph.
 
@@ -25,7 +25,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
 from .layout import pack_bias, pack_weights_simt, pack_weights_small, pack_weights_tc, wg_dgrad, wg_forward
-from .unet_b200 import (ConvHolder, ConvolutionH, NormHolder, ResidualUnitH, SkipConnectionH, UNetB200)
+from .unet_b200 import (B200Model, ConvHolder, ConvolutionH, NormHolder, ResidualUnitH, SkipConnectionH)
 
 
 _DEVICE: Optional[torch.device] = None   # device of the engine that is launching (set by TTAEngine._on_device)
@@ -65,6 +65,32 @@ class Act:
         self.wsplit = False
         self.ws_planes: Optional[torch.Tensor] = None
         self.device = device
+        self.peers: List["Act"] = []    # other shapes of the SAME storage (batched aliases): written-state is shared
+
+    def batched_alias(self, factor: int, name: str = "") -> "Act":
+        """The same storage seen as [N * factor][C / factor] instead of [N][C]: index ((n*f + m)*C8' + c)*V*8 equals
+        (n*C8 + m*C8' + c)*V*8, so modality m of sample n is instance n*f + m.  Used where ONE layer (shared weights
+        and norm parameters) is applied to every modality: the modalities become batch entries of a single launch."""
+        if self.C8 % factor:
+            raise ValueError("batched_alias: channel chunks not divisible")
+        a = Act.__new__(Act)
+        a.N, a.C8, a.D, a.H, a.W, a.V = self.N * factor, self.C8 // factor, self.D, self.H, self.W, self.V
+        a.C = a.C8 * 8
+        a.name, a.needs_grad = name or self.name + "/batched", self.needs_grad
+        a.planes = self.planes.view(2, a.N, a.C8, self.D, self.H, self.W, 8)
+        a.grad = self.grad.view(a.N, a.C8, self.D, self.H, self.W, 8) if self.grad is not None else None
+        a.ns = a.C8 * a.V * 8
+        a.written, a.extra, a.writers = set(), [], []
+        a.wsplit, a.ws_planes, a.device = False, None, self.device
+        a.peers = [self]
+        self.peers.append(a)
+        return a
+
+    def mark_written(self, chunks: set):
+        self.written |= chunks
+        if len(self.written) == self.C8:          # fully written: so is every other shape of the storage
+            for p in self.peers:
+                p.written = set(range(p.C8))
 
     def need_ws_copy(self):
         if self.ws_planes is None:
@@ -176,6 +202,10 @@ class ConvLayer:
         self.mode = 1 if holder.transposed else 0
         self.cin, self.cout = holder.cin, holder.cout + (extra.cout if extra is not None else 0)
         self.packed = {}
+        # effective-weight hook (multimodal model): maps the holder's weight [co][ci][k,k,k] to the weight the
+        # launch uses, e.g. a 1-channel encoder stem conv -> 4 input channels with one non-zero; sets self.cin
+        self.w_map: Optional[Callable[[torch.Tensor], torch.Tensor]] = None
+        self.dgrad_cin: Optional[int] = None    # input gradient only for the leading channels (rest needs none)
 
     def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16, t2s: bool = True):
         """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05.
@@ -183,11 +213,16 @@ class ConvLayer:
         blob reaches the device as one H2D copy -- the device only ever executes this library's kernels."""
         host = torch.device("cpu")
         w = self.h.weight.detach().to(device=host, dtype=torch.float32)
+        if self.w_map is not None:
+            w = self.w_map(w)
         wf = wg_forward(w, self.h.transposed)
         wd = wg_dgrad(w, self.h.transposed)
-        b = self.h.bias.detach().to(device=host, dtype=torch.float32)
+        b = self.h.bias.detach().to(device=host, dtype=torch.float32) if self.h.bias is not None else \
+            torch.zeros(self.h.cout, dtype=torch.float32)        # nn.Conv3d(bias=False)
         if self.extra is not None:
             w2 = self.extra.weight.detach().to(device=host, dtype=torch.float32)
+            if self.w_map is not None:
+                w2 = self.w_map(w2)
             wf = torch.cat([wf, wg_forward(w2, False)], dim=2)      # [T][ci][co0 + co1]
             wd = torch.cat([wd, wg_dgrad(w2, False)], dim=1)        # [T][ci = dy0 || dy1][co = cin]
             b = torch.cat([b, self.extra.bias.detach().to(device=host, dtype=torch.float32)])
@@ -197,6 +232,8 @@ class ConvLayer:
             wf = wf.clone(); wd = wd.clone()
             wf[c] += eye
             wd[c] += eye
+        if self.dgrad_cin is not None:
+            wd = wd[:, :, : self.dgrad_cin].contiguous()
         self.wg_fwd_host = wf          # canonical Wg[T][ci][co] (fp32, host): weight-gradient tests, diagnostics
         self.packed = {
             "simt_fwd": pack_weights_simt(wf).to(device), "simt_bwd": pack_weights_simt(wd).to(device),
@@ -218,7 +255,7 @@ class ConvLayer:
                                                         t2s=use_t2s).to(device)
                 self.tc_fwd_flags = (self.cout << 8) if use_t2s else 0
             bmode = 1 - self.mode
-            if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.cin):
+            if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.dgrad_cin or self.cin):
                 self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype).to(device)
 
 
@@ -258,7 +295,7 @@ class Plan:
 class TTAEngine:
     """Owns packed weights, the flat norm-affine parameter/optimizer state and per-shape plans."""
 
-    def __init__(self, model: UNetB200):
+    def __init__(self, model: B200Model):
         self.model = model
         self.lib = _lib.lib()  # raises if the CUDA library is missing
         self.plans = {}
@@ -304,6 +341,7 @@ class TTAEngine:
                 self.norm_layers.append(nl)
                 off += nl.C8 * 8
         self.P = off
+        self.model.configure_layers(self)
 
     def invalidate(self):
         self.model._params_dirty = True
@@ -350,7 +388,8 @@ class TTAEngine:
             # conv weights are baked into the plans (packed device blobs, host kernel parameters of the small /
             # head kernels, captured CUDA graphs): repack only when a weight tensor really changed
             # (storage, in-place version, device) and then drop every plan built on the old blobs
-            fp = tuple((id(h), h.weight.data_ptr(), h.weight._version, h.bias.data_ptr(), h.bias._version,
+            fp = tuple((id(h), h.weight.data_ptr(), h.weight._version,
+                        h.bias.data_ptr() if h.bias is not None else 0, h.bias._version if h.bias is not None else 0,
                         str(h.weight.device)) for h in self.model.conv_holders())
             fp = (fp, self.model.conv_backend, self.model.t2s_head, self.bwd_dtype)
             if fp == getattr(self, "_packed_fp", None):
@@ -507,6 +546,7 @@ class TTAEngine:
         lib = self.lib
         model = self.model
         P = self.P
+        NB = N                       # the plan's batch (N is rebound per tensor further down: batched aliases)
         R = model.out_channels
         x = Act(N, model.in_channels, D, H, W, dev, needs_grad=False, name="x")
         plan = Plan(N=N, dims=(D, H, W), x=x,
@@ -516,6 +556,7 @@ class TTAEngine:
         max_ws = [1]
 
         def conv(cl: ConvLayer, inp: ActView) -> Res:
+            N = inp.parent.N            # instances of THIS tensor (a batched alias has N * modalities)
             d, h, w = inp.dims
             s = cl.stride
             if cl.mode == 0:
@@ -548,11 +589,12 @@ class TTAEngine:
             return y
 
         def normact(nl: NormLayer, y: Res, relu: bool, residual, out: Optional[ActView]) -> ActView:
+            N = y.N
             if out is None:
                 a = Act(N, y.C, y.D, y.H, y.W, dev, needs_grad=True, name=nl.name)
                 plan.keep.append(a)
                 out = a.view()
-            if (out.C8, *out.dims) != (y.C8, y.D, y.H, y.W):
+            if (out.C8, *out.dims) != (y.C8, y.D, y.H, y.W) or out.parent.N != N:
                 raise ValueError(f"{nl.name}: output view shape mismatch")
             if y.V * (N if nl.batch else 1) == 1:
                 plan.single_element_norm = nl.name
@@ -674,45 +716,72 @@ class TTAEngine:
                 return cur
             raise TypeError(type(mod))
 
-        def out_channels(mod) -> int:
-            if isinstance(mod, ResidualUnitH):
-                return list(mod.conv.children())[-1].conv.cout
-            if isinstance(mod, ConvolutionH):
-                return mod.conv.cout
-            return out_channels(list(mod.children())[-1])
+        # ---- ops beyond the plain UNet (multimodal model): modality mean, trilinear upsample, fp32 -> operand cast
+        def new_act(C, dims, needs_grad=True, name="", n=None) -> Act:
+            a = Act(N if n is None else n, C, *dims, dev, needs_grad=needs_grad, name=name)
+            plan.keep.append(a)
+            return a
 
-        def block(seq: nn.Sequential, inp: ActView, out: Optional[ActView]):
-            down, skip, up = seq[0], seq[1], seq[2]
-            sub = skip.submodule
-            c, cs = out_channels(down), out_channels(sub)
-            if c % 8 or cs % 8:
-                raise ValueError("unet_b200: skip-connection channel counts must be multiples of 8")
-            d, h, w = inp.dims
-            if isinstance(down, ResidualUnitH):
-                s = list(down.conv.children())[0].conv.stride
-            else:
-                s = down.conv.stride
-            if d % s or h % s or w % s:
-                raise ValueError(f"unet_b200: spatial size {(d, h, w)} not divisible by stride {s} "
-                                 "(the skip concat would mismatch, as in the reference)")
-            od, oh, ow = d // s, h // s, w // s
-            cat = Act(N, c + cs, od, oh, ow, dev, needs_grad=True, name="cat")
-            plan.keep.append(cat)
-            dv = cat.view(0, c // 8)
-            layer(down, inp, dv)
-            sv = cat.view(c // 8, cs // 8)
-            if isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], SkipConnectionH):
-                block(sub, dv, sv)
-            else:
-                layer(sub, dv, sv)
-            return layer(up, cat.view(), out)
+        def mean(inputs: List[ActView], dst: ActView, rep: int = 1):
+            """dst[(n*rep + r)] = mean_k inputs[k][n] for r < rep (operand planes)."""
+            k = len(inputs)
+            n_in = inputs[0].parent.N
+            if any((v.C8, *v.dims, v.parent.N) != (dst.C8, *dst.dims, n_in) for v in inputs) or dst.parent.N != n_in * rep:
+                raise ValueError("mean: shape mismatch")
+            his = (ctypes.c_void_p * k)(*[v.hi for v in inputs])
+            los = (ctypes.c_void_p * k)(*[v.lo for v in inputs])
+            nss = (ctypes.c_longlong * k)(*[v.ns for v in inputs])
+            V = dst.parent.V
+            args = (his, los, nss, k, n_in, dst.C8, V, 1.0 / k, dst.hi, dst.lo, dst.ns, rep)
+
+            def run():
+                check(lib.tta_mean_planes(*args, _stream()), "mean_planes")
+            run.label = f"mean of {k} x C={dst.C8 * 8} V={V} rep={rep}"
+            run.launches = 1
+            plan.fwd.append(run)
+            plan.keep += [his, los, nss]
+            ops.append(("mean", inputs, dst, rep))
+
+        def upsample(y: Res, dst: ActView):
+            """nn.Upsample(trilinear, align_corners=True) of a conv-only fp32 result into operand planes."""
+            if y.C8 != dst.C8 or y.N != dst.parent.N:
+                raise ValueError("upsample: shape mismatch")
+            od = dst.dims
+            args = (y.ptr, y.ns, y.N, y.C8, y.D, y.H, y.W, *od, dst.hi, dst.lo, dst.ns, TTA_F16)
+
+            def run():
+                check(lib.tta_upsample_fwd(*args, _stream()), "upsample_fwd")
+            run.label = f"upsample C={y.C8 * 8} {(y.D, y.H, y.W)} -> {tuple(od)}"
+            run.launches = 1
+            plan.fwd.append(run)
+            ops.append(("upsample", y, dst))
+
+        def cast(y: Res, dst: Optional[ActView] = None) -> ActView:
+            """fp32 conv-only result -> operand planes (two consecutive linear layers, no norm in between)."""
+            if dst is None:
+                dst = new_act(y.C, (y.D, y.H, y.W), name=y.name + "/cast", n=y.N).view()
+            args = (y.ptr, y.ns, 0, 0, y.N, y.C8, y.V, dst.hi, dst.lo, dst.ns, TTA_F16)
+
+            def run():
+                check(lib.tta_split_f32(*args, _stream()), "split_f32")
+            run.label = f"cast C={y.C8 * 8} V={y.V}"
+            run.launches = 1
+            plan.fwd.append(run)
+            ops.append(("cast", y, dst))
+            return dst
+
+        import types
+        G = types.SimpleNamespace(N=N, dims=(D, H, W), x=x, plan=plan, engine=self, conv=conv, normact=normact,
+                                  convolution=convolution, residual_unit=residual_unit, layer=layer, new_act=new_act,
+                                  mean=mean, upsample=upsample, cast=cast, conv_layer=lambda h: self.conv_layers[id(h)],
+                                  norm_layer=self._nl)
 
         def final_dims(r):
             return r.D, r.H, r.W
 
-        final = block(model.model, x.view(), None)
+        final = model.build_graph(G)        # the model walks its own module tree with the emitters above
         if not isinstance(final, Res):
-            raise ValueError("unet_b200: the top-level up layer must end in a conv (MONAI UNet does)")
+            raise ValueError("unet_b200: the network must end in a conv (MONAI UNet does)")
         bdt = self.bwd_dtype
         nplanes = 1 if bdt == TTA_F16_HI else 2
         # ---- fused full-resolution tail: [norm apply -> small 3x3x3 conv -> entropy] as one kernel
@@ -794,17 +863,69 @@ class TTAEngine:
         # ------------------------------------------------------------ backward emission
         bwd_apply_flags = []
         for op in reversed(ops):
+            if op[0] == "mean":
+                # d(mean)/d(input k) = g / K for every input; g = sum over the (replicated) destination's gradient
+                # sources: its own grad slice (written by the dgrads of its consumers) and identity-residual extras
+                _, inputs, dst, rep = op
+                par = dst.parent
+                chunks = set(range(dst.c8_off, dst.c8_off + dst.C8))
+                srcs = []
+                if chunks <= par.written:
+                    srcs.append((dst.g, dst.ns))
+                srcs += [(ev[0], ev[1]) for ev in par.extra if (ev[2], ev[3]) == (dst.c8_off, dst.C8)]
+                if not srcs:
+                    raise RuntimeError("mean: no gradient reaches the destination")
+                n_in, V = inputs[0].parent.N, par.V
+                tmp = torch.zeros((n_in, dst.C8, V, 8), dtype=torch.float32, device=dev)
+                plan.keep.append(tmp)
+                ps = (ctypes.c_void_p * len(srcs))(*[p_ for p_, _ in srcs])
+                nss = (ctypes.c_longlong * len(srcs))(*[n_ for _, n_ in srcs])
+                plan.keep += [ps, nss]
+                sm_args = (ps, nss, len(srcs), rep, n_in, dst.C8, V, 1.0 / len(inputs), tmp.data_ptr(), dst.C8 * V * 8, 0)
+
+                def run_mean_bwd(sm_args=sm_args):
+                    check(lib.tta_sum_f32(*sm_args, _stream()), "sum_f32")
+                run_mean_bwd.label = f"mean bwd C={dst.C8 * 8} V={V}"
+                run_mean_bwd.launches = 1
+                plan.bwd.append(run_mean_bwd)
+                for v in inputs:
+                    v.parent.extra.append((tmp.data_ptr(), dst.C8 * V * 8, v.c8_off, v.C8))
+                continue
+            if op[0] in ("upsample", "cast"):
+                # gradient of the operand tensor (fp32, complete) -> 16-bit gradient plane(s) of the conv-only result
+                _, y, dst = op
+                par = dst.parent
+                chunks = set(range(dst.c8_off, dst.c8_off + dst.C8))
+                if not chunks <= par.written or any((ev[2], ev[3]) == (dst.c8_off, dst.C8) for ev in par.extra):
+                    raise RuntimeError(f"{op[0]}: the destination's gradient must come from dgrads only")
+                y.alloc_dy(nplanes)
+                if op[0] == "upsample":
+                    u_args = (dst.g, dst.ns, y.N, y.C8, y.D, y.H, y.W, *dst.dims, y.dy_ptr(0), y.dy_ptr(1), y.ns, bdt)
+
+                    def run_up_bwd(u_args=u_args):
+                        check(lib.tta_upsample_bwd(*u_args, _stream()), "upsample_bwd")
+                else:
+                    u_args = (dst.g, dst.ns, 0, 0, y.N, y.C8, y.V, y.dy_ptr(0), y.dy_ptr(1), y.ns, bdt)
+
+                    def run_up_bwd(u_args=u_args):
+                        check(lib.tta_split_f32(*u_args, _stream()), "split_f32")
+                run_up_bwd.label = f"{op[0]} bwd C={y.C8 * 8} V={y.V}"
+                run_up_bwd.launches = 1
+                plan.bwd.append(run_up_bwd)
+                continue
             if op[0] == "conv":
                 _, cl, inp, y = op
                 if not inp.parent.needs_grad:
                     continue
+                N = y.N
                 par = inp.parent
-                chunks = set(range(inp.c8_off, inp.c8_off + inp.C8))
+                c8o = (cl.dgrad_cin + 7) // 8 if cl.dgrad_cin is not None else inp.C8
+                chunks = set(range(inp.c8_off, inp.c8_off + c8o))
                 done = chunks & par.written
                 if done and done != chunks:
                     raise RuntimeError("partial gradient accumulation state")
                 acc = bool(done)
-                par.written |= chunks
+                par.mark_written(chunks)
                 if fused_head is not None and cl is fused_head[0]:
                     # fused tail: dgrad of the small conv + ReLU mask + norm-backward reduction in ONE
                     # kernel; the masked gradient lands in inp.g, sums/dgamma/dbeta are finalized
@@ -826,12 +947,13 @@ class TTAEngine:
                 crec = dict(segs=[], info=None)
                 plan.bwd.append(self._conv_call(
                     plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.ns), bdt, N, y.C8,
-                    (y.D, y.H, y.W), inp.g, inp.ns, inp.C8, inp.dims, acc, wsplit_in=y.root.dy_wsplit,
+                    (y.D, y.H, y.W), inp.g, inp.ns, c8o, inp.dims, acc, wsplit_in=y.root.dy_wsplit,
                     bwd_rec=crec))
-                par.writers.append((inp.c8_off, inp.c8_off + inp.C8, crec, acc))
+                par.writers.append((inp.c8_off, inp.c8_off + c8o, crec, acc))
             else:
                 rec = op[1]
                 nl, y, out = rec["nl"], rec["y"], rec["out"]
+                N = y.N
                 par = out.parent
                 chunks = set(range(out.c8_off, out.c8_off + out.C8))
                 srcs = []
@@ -984,7 +1106,10 @@ class TTAEngine:
         plan.n_small_bwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("small_bwd"))
         plan.launches_fwd -= plan.n_small_fwd      # statistics + apply in one launch
         plan.launches_bwd -= plan.n_small_bwd      # reduction + apply in one launch
-        plan.launches_bwd += 2 * (N - 1) * sum(1 for o in ops if o[0] == "norm" and o[1].get("per_sample_bwd"))
+        plan.launches_bwd += 2 * (NB - 1) * sum(1 for o in ops if o[0] == "norm" and o[1].get("per_sample_bwd"))
+        n_extra = sum(1 for o in ops if o[0] in ("mean", "upsample", "cast"))   # one launch each way
+        plan.launches_fwd += n_extra + (1 if getattr(plan, "x2", None) is not None else 0)
+        plan.launches_bwd += n_extra
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:
@@ -1064,6 +1189,15 @@ class TTAEngine:
                                             a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8,
                                             int(a.wsplit), _stream()),
               "gather_pack")
+        x2 = getattr(plan, "x2", None)
+        if x2 is not None:
+            # a second consumer wants the other layout (multimodal model: the last decoder stage concatenates the
+            # input in plain layout while the encoder stems read it w-parity-split)
+            check(self.lib.tta_gather_pack_norm(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
+                                                chan_scale.data_ptr() if chan_scale is not None else 0,
+                                                affine.data_ptr() if affine is not None else 0, N, D, H, W,
+                                                x2.hi, x2.lo, x2.ns, x2.C8, 0, _stream()),
+                  "gather_pack")
 
     def _check_input(self, x: torch.Tensor):
         if x.dim() != 5:

@@ -24,7 +24,7 @@ from .config import DictConfig, create, get_config
 from .registry import register_evaluation_strategy
 from .sliding_window import SlidingWindowTTA
 from .tent import TentB200
-from .unet_b200 import UNetB200
+from .unet_b200 import B200Model
 
 
 def dice_iou_from_counts(counts: torch.Tensor, eps: float = 1e-7):
@@ -71,7 +71,7 @@ def _as_list_str(x, batch_size: int) -> List[str]:
     return [str(x)] * batch_size
 
 
-def load_source_checkpoint(model: UNetB200, path: str, trusted: bool = False) -> None:
+def load_source_checkpoint(model: B200Model, path: str, trusted: bool = False) -> None:
     """``method.checkpoint``: source-model weights written by the reference's CheckpointHook
     (/root/reference/src/core/hooks.py:53-70: ``{"epoch", "model_state_dict", "optimizer_state_dict",
     "best_metrics"}``; keys carry a ``module.`` prefix when the trainer wrapped the model in nn.DataParallel,
@@ -107,8 +107,8 @@ class TTASegmentationEvaluationStrategy:
 
     def _method(self, model) -> TentB200:
         core = model.module if hasattr(model, "module") else model  # nn.DataParallel wrapper
-        if not isinstance(core, UNetB200):
-            raise TypeError("tta_seg_eval needs model.name=unet_b200 (got "
+        if not isinstance(core, B200Model):
+            raise TypeError("tta_seg_eval needs model.name=unet_b200 / unet_multimodal_deepfusion_b200 (got "
                             f"{type(core).__name__}); see configs/method/tent_b200.yaml")
         if self._tent is None or self._tent.model is not core:
             if self.checkpoint:      # source weights first: TENT snapshots the parameters it starts from

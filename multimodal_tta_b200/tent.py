@@ -17,18 +17,18 @@ import torch
 
 from .config import DictConfig, create, get_config
 from .registry import register_plugin
-from .unet_b200 import NormHolder, UNetB200
+from .unet_b200 import B200Model, NormHolder
 
 _MODES = {"softmax": 0, "sigmoid": 1}
 
 
 @register_plugin("tent_b200")
 class TentB200:
-    def __init__(self, model: UNetB200, cfg: Optional[DictConfig | Dict[str, Any]] = None, *,
+    def __init__(self, model: B200Model, cfg: Optional[DictConfig | Dict[str, Any]] = None, *,
                  process_group=None):
-        if not isinstance(model, UNetB200):
-            raise TypeError("tent_b200 adapts a `unet_b200` model (set model.name=unet_b200); got "
-                            f"{type(model).__name__}")
+        if not isinstance(model, B200Model):
+            raise TypeError("tent_b200 adapts a B200 model (set model.name=unet_b200 or "
+                            f"unet_multimodal_deepfusion_b200); got {type(model).__name__}")
         cfg = cfg if isinstance(cfg, DictConfig) else create(dict(cfg or {}))
         self.model = model
         self.mode = str(get_config(cfg, "entropy", "auto"))

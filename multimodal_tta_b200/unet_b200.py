@@ -115,109 +115,25 @@ class SkipConnectionH(nn.Module):
         self.submodule = submodule
 
 
-@register_model("unet_b200")
-class UNetB200(nn.Module):
-    def __init__(self, cfg: DictConfig | Dict[str, Any], in_channels: Optional[int] = None,
-                 eps: Optional[float] = None):
-        super().__init__()
-        if not isinstance(cfg, DictConfig):
-            cfg = create(dict(cfg))
-        c_in_cfg = get_config(cfg, "in_channels", 3)
-        c_in = in_channels if in_channels is not None else (None if c_in_cfg == "auto" else int(c_in_cfg))
-        if c_in is None:
-            raise ValueError("[UNet] in_channels is 'auto'; please pass in_channels at construction time.")
-        self.in_channels = c_in
-        self.out_channels = int(get_config(cfg, "num_classes", 1))
-        self.channels = [int(c) for c in get_config(cfg, "channels", [32, 64, 128, 256, 512])]
-        self.strides = [int(s) for s in get_config(cfg, "strides", [2, 2, 2, 2])]
-        self.num_res_units = int(get_config(cfg, "num_res_units", 0))
-        self.act = get_config(cfg, "act", "relu")
-        self.norm = get_config(cfg, "norm", "BATCH")
-        self.dropout = float(get_config(cfg, "dropout", 0.0))
-        if int(get_config(cfg, "spatial_dims", 3)) != 3:
-            raise ValueError("unet_b200 implements the 3-D path only")
-        if len(self.channels) < 2:
-            raise ValueError("the length of `channels` should be no less than 2.")
-        if len(self.strides) < len(self.channels) - 1:
-            raise ValueError("the length of `strides` should equal to `len(channels) - 1`.")
-        for s in self.strides:
-            if s not in (1, 2):
-                raise ValueError(f"unet_b200: stride {s} unsupported (1 or 2)")
-        # backend options (not in the reference): conv kernel family and whole-step CUDA graph
-        self.conv_backend = str(get_config(cfg, "conv_backend", "auto"))
-        self.use_cuda_graph = bool(get_config(cfg, "cuda_graph", True))
-        # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
-        self.deterministic = bool(get_config(cfg, "deterministic", False))
-        # extra tta_conv_tc flag bits for A/B experiments (include/tta_b200.h), e.g. 32 = one-plane tiles
-        self.tc_flags = int(get_config(cfg, "tc_flags", 0))
-        # head convT (Cout <= 4) as dense GEMM + shared-memory col2im instead of 28 small MMAs per block
-        self.t2s_head = bool(get_config(cfg, "t2s_head", True))
-        # run a ResidualUnit's unit0 conv and its strided 3x3x3 shortcut conv as ONE launch
-        self.fuse_shortcut = bool(get_config(cfg, "fuse_shortcut", True))
-        # run the full-resolution tail (norm apply + 3x3x3 conv + entropy, and its backward) as two
-        # fused CUDA-core kernels instead of five streaming passes (csrc/tta_head.cu)
-        self.fuse_head = bool(get_config(cfg, "fuse_head", True))
-        # the <= 4-channel tensors of the fused head (convT result, masked gradient) in a compact 4-channel layout
-        # instead of 8-channel chunks: -0.4 GB of DRAM traffic per 2x4x128^3 step
-        self.head_compact = bool(get_config(cfg, "head_compact", True))
-        # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
-        # a separate pass over y (only where the conv runs without split-K)
-        self.fuse_stats = bool(get_config(cfg, "fuse_stats", True))
-        # OPT-IN: statistics from a conv epilogue finalized inside the apply pass's prologue instead of a separate
-        # launch.  Measured slower (2.337 vs 2.326 ms per step: every apply block re-reduces 148 slots)
-        self.stats_finalize_in_apply = bool(get_config(cfg, "stats_finalize_in_apply", False))
-        # OPT-IN: also when the conv has a single TMEM accumulator buffer (the reduction is then not hidden
-        # behind the next item's MMAs, but a statistics pass over the conv result disappears).  Same-box A/B:
-        # 2.2936 vs 2.2968 ms per step -- within noise, so the default stays off
-        self.fuse_stats_single_buffer = bool(get_config(cfg, "fuse_stats_single_buffer", False))
-        # ... and, OPT-IN, the norm-BACKWARD reductions (sum dz, sum dz*xhat) out of the epilogue of
-        # the dgrad conv that completes the layer's incoming gradient.  Measured on B200 (2x4x128^3):
-        # the four 64^3 / 32^3 layers it applies to lose 162 us in their dgrads (the epilogue has
-        # 8 warps per SM for ~100 instructions per voxel-chunk) and save 144 us of streaming passes
-        # (2048 threads per SM) -> default off; the streaming tta_norm_bwd_reduce stays the product path
-        self.fuse_bwd_stats = bool(get_config(cfg, "fuse_bwd_stats", False))
-        # layers with <= 4096 voxels per instance (8^3, 16^3): statistics + apply, and backward
-        # reduction + apply, as one launch each
-        self.fuse_small_norm = bool(get_config(cfg, "fuse_small_norm", True))
-        # ... up to this many voxels per instance.  Slabs above 512 voxels are owned by a thread-block
-        # cluster of up to 8 CTAs (totals through distributed shared memory).  Same-box A/B per step:
-        # 512 -> 2.645 ms, 4096 (16^3 level too) -> 2.628 ms, 65536 (32^3 too) -> 2.641 ms
-        self.small_norm_max_voxels = int(get_config(cfg, "small_norm_max_voxels", 4096))
-        # OPT-IN: InstanceNorm backward sample by sample when one sample's gradient + conv result fit
-        # the 126 MB L2 but the batch does not, hoping the apply pass re-reads them from L2.  Measured
-        # on the four 64^3 layers (67 MB per sample): 2.578 ms vs 2.556 ms per step -- the second pass
-        # does not hit, the two extra launches per layer cost more; default off
-        self.per_sample_norm_bwd = bool(get_config(cfg, "per_sample_norm_bwd", False))
-        # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
-        # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
-        self.bwd_precision = str(get_config(cfg, "bwd_precision", "fp16"))
-        if self.bwd_precision not in ("fp16", "bf16x2"):
-            raise ValueError("unet_b200: bwd_precision must be 'fp16' or 'bf16x2'")
-        k, nru, norm, act, dr = 3, self.num_res_units, self.norm, self.act, self.dropout
+class B200Model(nn.Module):
+    """Common part of the B200 model classes: backend options, holder plumbing, the lazily built TTAEngine.
+    A subclass builds its holder tree, then implements ``build_graph(G)`` (walk the tree with the engine's
+    emitters, return the final conv result) and optionally ``configure_layers(engine)``."""
 
-        def down(cin, cout, stride):
-            if nru > 0:
-                return ResidualUnitH(cin, cout, stride, k, nru, norm, act, dr)
-            return ConvolutionH(cin, cout, stride, k, norm, act, dr)
+    in_channels: int
+    out_channels: int
 
-        def up(cin, cout, stride, is_top):
-            conv: nn.Module = ConvolutionH(cin, cout, stride, k, norm, act, dr,
-                                           conv_only=is_top and nru == 0, transposed=True)
-            if nru > 0:
-                conv = nn.Sequential(conv, ResidualUnitH(cout, cout, 1, k, 1, norm, act, dr, last_conv_only=is_top))
-            return conv
-
-        def block(inc, outc, chs, sts, is_top):
-            c, s = chs[0], sts[0]
-            if len(chs) > 2:
-                sub, upc = block(c, c, chs[1:], sts[1:], False), c * 2
-            else:
-                sub, upc = down(c, chs[1], 1), c + chs[1]
-            return nn.Sequential(down(inc, c, s), SkipConnectionH(sub), up(upc, outc, s, is_top))
-
-        self.model = block(self.in_channels, self.out_channels, self.channels, self.strides, True)
+    def _init_backend(self, cfg) -> None:
+        get = lambda k, d: get_config(cfg, k, d)
         self._engine = None
         self._params_dirty = True
+        self._backend_options(get)
+
+    def build_graph(self, G):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def configure_layers(self, engine) -> None:
+        """Hook for per-layer launch options (effective-weight maps)."""
 
     # ------------------------------------------------------------------ plumbing
     def norm_holders(self) -> List[NormHolder]:
@@ -255,3 +171,147 @@ class UNetB200(nn.Module):
         """Raw logits [B,R,D,H,W].  train(): test-batch norm statistics; eval(): BatchNorm uses its
         running statistics (InstanceNorm always uses instance statistics, as in the reference)."""
         return self.engine.forward(x)
+
+    def _backend_options(self, get) -> None:
+        """Backend options (not in the reference): conv kernel family, whole-step CUDA graph, A/B switches."""
+        self.conv_backend = str(get("conv_backend", "auto"))
+        self.use_cuda_graph = bool(get("cuda_graph", True))
+        # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
+        self.deterministic = bool(get("deterministic", False))
+        # extra tta_conv_tc flag bits for A/B experiments (include/tta_b200.h), e.g. 32 = one-plane tiles
+        self.tc_flags = int(get("tc_flags", 0))
+        # head convT (Cout <= 4) as dense GEMM + shared-memory col2im instead of 28 small MMAs per block
+        self.t2s_head = bool(get("t2s_head", True))
+        # run a ResidualUnit's unit0 conv and its strided 3x3x3 shortcut conv as ONE launch
+        self.fuse_shortcut = bool(get("fuse_shortcut", True))
+        # run the full-resolution tail (norm apply + 3x3x3 conv + entropy, and its backward) as two
+        # fused CUDA-core kernels instead of five streaming passes (csrc/tta_head.cu)
+        self.fuse_head = bool(get("fuse_head", True))
+        # the <= 4-channel tensors of the fused head (convT result, masked gradient) in a compact 4-channel layout
+        # instead of 8-channel chunks: -0.4 GB of DRAM traffic per 2x4x128^3 step
+        self.head_compact = bool(get("head_compact", True))
+        # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
+        # a separate pass over y (only where the conv runs without split-K)
+        self.fuse_stats = bool(get("fuse_stats", True))
+        # OPT-IN: statistics from a conv epilogue finalized inside the apply pass's prologue instead of a separate
+        # launch.  Measured slower (2.337 vs 2.326 ms per step: every apply block re-reduces 148 slots)
+        self.stats_finalize_in_apply = bool(get("stats_finalize_in_apply", False))
+        # OPT-IN: also when the conv has a single TMEM accumulator buffer (the reduction is then not hidden
+        # behind the next item's MMAs, but a statistics pass over the conv result disappears).  Same-box A/B:
+        # 2.2936 vs 2.2968 ms per step -- within noise, so the default stays off
+        self.fuse_stats_single_buffer = bool(get("fuse_stats_single_buffer", False))
+        # ... and, OPT-IN, the norm-BACKWARD reductions (sum dz, sum dz*xhat) out of the epilogue of
+        # the dgrad conv that completes the layer's incoming gradient.  Measured on B200 (2x4x128^3):
+        # the four 64^3 / 32^3 layers it applies to lose 162 us in their dgrads (the epilogue has
+        # 8 warps per SM for ~100 instructions per voxel-chunk) and save 144 us of streaming passes
+        # (2048 threads per SM) -> default off; the streaming tta_norm_bwd_reduce stays the product path
+        self.fuse_bwd_stats = bool(get("fuse_bwd_stats", False))
+        # layers with <= 4096 voxels per instance (8^3, 16^3): statistics + apply, and backward
+        # reduction + apply, as one launch each
+        self.fuse_small_norm = bool(get("fuse_small_norm", True))
+        # ... up to this many voxels per instance.  Slabs above 512 voxels are owned by a thread-block
+        # cluster of up to 8 CTAs (totals through distributed shared memory).  Same-box A/B per step:
+        # 512 -> 2.645 ms, 4096 (16^3 level too) -> 2.628 ms, 65536 (32^3 too) -> 2.641 ms
+        self.small_norm_max_voxels = int(get("small_norm_max_voxels", 4096))
+        # OPT-IN: InstanceNorm backward sample by sample when one sample's gradient + conv result fit
+        # the 126 MB L2 but the batch does not, hoping the apply pass re-reads them from L2.  Measured
+        # on the four 64^3 layers (67 MB per sample): 2.578 ms vs 2.556 ms per step -- the second pass
+        # does not hit, the two extra launches per layer cost more; default off
+        self.per_sample_norm_bwd = bool(get("per_sample_norm_bwd", False))
+        # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
+        # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
+        self.bwd_precision = str(get("bwd_precision", "fp16"))
+        if self.bwd_precision not in ("fp16", "bf16x2"):
+            raise ValueError("unet_b200: bwd_precision must be 'fp16' or 'bf16x2'")
+
+
+@register_model("unet_b200")
+class UNetB200(B200Model):
+    def __init__(self, cfg: DictConfig | Dict[str, Any], in_channels: Optional[int] = None,
+                 eps: Optional[float] = None):
+        super().__init__()
+        if not isinstance(cfg, DictConfig):
+            cfg = create(dict(cfg))
+        c_in_cfg = get_config(cfg, "in_channels", 3)
+        c_in = in_channels if in_channels is not None else (None if c_in_cfg == "auto" else int(c_in_cfg))
+        if c_in is None:
+            raise ValueError("[UNet] in_channels is 'auto'; please pass in_channels at construction time.")
+        self.in_channels = c_in
+        self.out_channels = int(get_config(cfg, "num_classes", 1))
+        self.channels = [int(c) for c in get_config(cfg, "channels", [32, 64, 128, 256, 512])]
+        self.strides = [int(s) for s in get_config(cfg, "strides", [2, 2, 2, 2])]
+        self.num_res_units = int(get_config(cfg, "num_res_units", 0))
+        self.act = get_config(cfg, "act", "relu")
+        self.norm = get_config(cfg, "norm", "BATCH")
+        self.dropout = float(get_config(cfg, "dropout", 0.0))
+        if int(get_config(cfg, "spatial_dims", 3)) != 3:
+            raise ValueError("unet_b200 implements the 3-D path only")
+        if len(self.channels) < 2:
+            raise ValueError("the length of `channels` should be no less than 2.")
+        if len(self.strides) < len(self.channels) - 1:
+            raise ValueError("the length of `strides` should equal to `len(channels) - 1`.")
+        for s in self.strides:
+            if s not in (1, 2):
+                raise ValueError(f"unet_b200: stride {s} unsupported (1 or 2)")
+        self._init_backend(cfg)
+        k, nru, norm, act, dr = 3, self.num_res_units, self.norm, self.act, self.dropout
+
+        def down(cin, cout, stride):
+            if nru > 0:
+                return ResidualUnitH(cin, cout, stride, k, nru, norm, act, dr)
+            return ConvolutionH(cin, cout, stride, k, norm, act, dr)
+
+        def up(cin, cout, stride, is_top):
+            conv: nn.Module = ConvolutionH(cin, cout, stride, k, norm, act, dr,
+                                           conv_only=is_top and nru == 0, transposed=True)
+            if nru > 0:
+                conv = nn.Sequential(conv, ResidualUnitH(cout, cout, 1, k, 1, norm, act, dr, last_conv_only=is_top))
+            return conv
+
+        def block(inc, outc, chs, sts, is_top):
+            c, s = chs[0], sts[0]
+            if len(chs) > 2:
+                sub, upc = block(c, c, chs[1:], sts[1:], False), c * 2
+            else:
+                sub, upc = down(c, chs[1], 1), c + chs[1]
+            return nn.Sequential(down(inc, c, s), SkipConnectionH(sub), up(upc, outc, s, is_top))
+
+        self.model = block(self.in_channels, self.out_channels, self.channels, self.strides, True)
+
+    # ------------------------------------------------------------------ op graph
+    def build_graph(self, G):
+        """Walk MONAI's recursive ``_create_block`` structure (down, SkipConnection(sub), up) with the engine's
+        emitters; ``torch.cat`` of the skip connection = channel slices of one buffer.  Returns the final conv
+        result (src/models/unet.py:68-69 -> monai UNet.forward)."""
+        def out_channels(mod) -> int:
+            if isinstance(mod, ResidualUnitH):
+                return list(mod.conv.children())[-1].conv.cout
+            if isinstance(mod, ConvolutionH):
+                return mod.conv.cout
+            return out_channels(list(mod.children())[-1])
+
+        def block(seq: nn.Sequential, inp, out):
+            down, skip, up = seq[0], seq[1], seq[2]
+            sub = skip.submodule
+            c, cs = out_channels(down), out_channels(sub)
+            if c % 8 or cs % 8:
+                raise ValueError("unet_b200: skip-connection channel counts must be multiples of 8")
+            d, h, w = inp.dims
+            if isinstance(down, ResidualUnitH):
+                s = list(down.conv.children())[0].conv.stride
+            else:
+                s = down.conv.stride
+            if d % s or h % s or w % s:
+                raise ValueError(f"unet_b200: spatial size {(d, h, w)} not divisible by stride {s} "
+                                 "(the skip concat would mismatch, as in the reference)")
+            cat = G.new_act(c + cs, (d // s, h // s, w // s), name="cat")
+            dv = cat.view(0, c // 8)
+            G.layer(down, inp, dv)
+            sv = cat.view(c // 8, cs // 8)
+            if isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], SkipConnectionH):
+                block(sub, dv, sv)
+            else:
+                G.layer(sub, dv, sv)
+            return G.layer(up, cat.view(), out)
+
+        return block(self.model, G.x.view(), None)

@@ -308,3 +308,31 @@ def test_registration_lands_in_the_reference_registry():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join(["/root/reference", ROOT]))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr
+
+
+def test_multimodal_model_keys_counts_and_plan():
+    """holder tree of MultimodalUNetDeepFusion reproduces the oracle's (= the reference's) state-dict
+    keys and shapes; every InstanceNorm becomes adaptable; the op graph builds without a GPU."""
+    from multimodal_tta_b200 import MultimodalUNetB200
+    from oracle.multimodal_oracle import MULTIMODAL_MODEL_CFG, OracleMultimodalUNet
+    torch.manual_seed(0)
+    o = OracleMultimodalUNet.from_cfg(MULTIMODAL_MODEL_CFG)
+    m = MultimodalUNetB200(dict(MULTIMODAL_MODEL_CFG))
+    so, sm = o.state_dict(), m.state_dict()
+    assert list(so.keys()) == list(sm.keys()) and all(so[k].shape == sm[k].shape for k in so)
+    assert sum(p.numel() for p in m.parameters()) == sum(p.numel() for p in o.parameters()) == 83075815
+    assert "bottleneck_reduce.bias" not in sm and "decoder_stages.0.upsample.preconv.bias" in sm
+    m.load_state_dict({"module." + k: v for k, v in so.items()})
+    t = TentB200(m, {"cuda_graph": False})
+    assert len(t.adaptable_parameters()) == 98 and m.engine.n_adaptable == 18816
+    eng = m.engine
+    eng._ensure_device(torch.device("cpu"), dry=True)
+    plan = eng.build_plan(1, 32, 32, 32)
+    assert set(plan.conv_backends.values()) == {"tc"} and not plan.fused_head and plan.x2 is not None
+    # the four stems read the one packed input chunk through one-hot channel weights
+    cl = eng.fused_layers[id(m.specific_encoders[2].layers[0].conv.unit0.conv)]
+    assert cl.cin == 4 and float(cl.wg_fwd_host[:, [0, 1, 3]].abs().max()) == 0.0 and float(cl.wg_fwd_host[:, 2].abs().max()) > 0
+    with pytest.raises(ValueError):
+        MultimodalUNetB200(dict(MULTIMODAL_MODEL_CFG, norm="BATCH"))
+    with pytest.raises(ValueError):
+        eng.build_plan(1, 24, 32, 32)

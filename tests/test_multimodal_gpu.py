@@ -1,0 +1,142 @@
+"""the reference's multimodal model (MultimodalUNetDeepFusion,
+/root/reference/src/models/unet_multimodal_midfusion.py:139-267) on the B200 kernels -- the new streaming
+kernels against plain torch fp32 references, then forward and TENT-step parity against the CPU oracle
+(oracle/multimodal_oracle.py) at the north-star tolerances."""
+import copy
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from multimodal_tta_b200 import MultimodalUNetB200, SlidingWindowTTA, TentB200, get_model
+from multimodal_tta_b200._lib import TTA_BF16, TTA_F16, TTA_F16_HI, check
+from multimodal_tta_b200.layout import from_chunked, join_planes, split_planes, to_chunked
+from multimodal_tta_b200.synthetic import brats_volume
+from oracle.multimodal_oracle import MULTIMODAL_MODEL_CFG, OracleMultimodalUNet
+from oracle.tent_oracle import TentOracle, flat_gamma_beta
+from tests.util import rel_l2, stream
+
+pytestmark = pytest.mark.gpu
+
+SMALL_CFG = dict(MULTIMODAL_MODEL_CFG, channels=[8, 16, 32, 64, 128])      # same structure, test-sized
+
+
+def _pair(cfg, seed):
+    torch.manual_seed(seed)
+    oracle = OracleMultimodalUNet.from_cfg(cfg)
+    prod = MultimodalUNetB200(dict(cfg))
+    prod.load_state_dict(copy.deepcopy(oracle.state_dict()))
+    return oracle, prod.to("cuda")
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("K,rep,C,dims", [(4, 1, 16, (4, 6, 8)), (4, 4, 24, (2, 2, 2)), (2, 2, 8, (3, 5, 7)), (3, 1, 8, (4, 4, 4))])
+def test_mean_planes(lib, cuda, K, rep, C, dims):
+    torch.manual_seed(1)
+    N, V = 2, dims[0] * dims[1] * dims[2]
+    xs = [torch.randn(N, C, *dims, device=cuda) for _ in range(K)]
+    planes = [split_planes(to_chunked(x), TTA_F16) for x in xs]
+    vals = [from_chunked(join_planes(h, l, TTA_F16), C) for h, l in planes]
+    C8 = C // 8
+    ohi = torch.zeros((N * rep, C8, *dims, 8), dtype=torch.int16, device=cuda); olo = torch.zeros_like(ohi)
+    his = (ctypes.c_void_p * K)(*[h.data_ptr() for h, _ in planes])
+    los = (ctypes.c_void_p * K)(*[l.data_ptr() for _, l in planes])
+    nss = (ctypes.c_longlong * K)(*[C8 * V * 8] * K)
+    check(lib.tta_mean_planes(his, los, nss, K, N, C8, V, 1.0 / K, ohi.data_ptr(), olo.data_ptr(), C8 * V * 8, rep, stream()))
+    got = from_chunked(join_planes(ohi, olo, TTA_F16), C)
+    ref = torch.stack(vals).mean(0).repeat_interleave(rep, dim=0)
+    assert rel_l2(got.cpu(), ref.cpu()) < 2e-6                           # fp16 hi/lo storage of the result
+
+
+@pytest.mark.parametrize("K,rep,acc", [(1, 1, 0), (2, 4, 0), (3, 2, 1), (8, 1, 0)])
+def test_sum_f32(lib, cuda, K, rep, acc):
+    torch.manual_seed(2)
+    N, C8, dims = 2, 2, (3, 4, 5)
+    V = 60
+    srcs = [torch.randn(N * rep, C8, *dims, 8, device=cuda) for _ in range(K)]
+    out = torch.randn(N, C8, *dims, 8, device=cuda)
+    ref = (out if acc else 0) + 0.25 * sum(s.view(N, rep, C8, *dims, 8).sum(1) for s in srcs)
+    ps = (ctypes.c_void_p * K)(*[s.data_ptr() for s in srcs])
+    nss = (ctypes.c_longlong * K)(*[C8 * V * 8] * K)
+    check(lib.tta_sum_f32(ps, nss, K, rep, N, C8, V, 0.25, out.data_ptr(), C8 * V * 8, acc, stream()))
+    assert rel_l2(out.cpu(), ref.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("dims,scale", [((4, 4, 4), 2), ((2, 3, 5), 2), ((1, 2, 2), 2), ((8, 8, 8), 2), ((3, 3, 3), 1)])
+@pytest.mark.parametrize("bdt", [TTA_F16_HI, TTA_BF16])
+def test_trilinear_upsample_forward_and_adjoint(lib, cuda, dims, scale, bdt):
+    """nn.Upsample(scale_factor, mode="trilinear", align_corners=True) and its autograd adjoint (CPU fp32)."""
+    torch.manual_seed(3)
+    N, C = 2, 16
+    C8 = C // 8
+    od = tuple(d * scale for d in dims)
+    x = torch.randn(N, C, *dims)
+    xr = x.clone().requires_grad_(True)
+    up = torch.nn.Upsample(scale_factor=scale, mode="trilinear", align_corners=True)
+    y = up(xr)
+    g = torch.randn_like(y)
+    y.backward(g)
+    Vi, Vo = dims[0] * dims[1] * dims[2], od[0] * od[1] * od[2]
+    xin = to_chunked(x.to(cuda))
+    ohi = torch.zeros((N, C8, *od, 8), dtype=torch.int16, device=cuda); olo = torch.zeros_like(ohi)
+    check(lib.tta_upsample_fwd(xin.data_ptr(), C8 * Vi * 8, N, C8, *dims, *od, ohi.data_ptr(), olo.data_ptr(),
+                               C8 * Vo * 8, TTA_F16, stream()))
+    got = from_chunked(join_planes(ohi, olo, TTA_F16), C).cpu()
+    assert rel_l2(got, y.detach()) < 2e-6
+    gd = to_chunked(g.to(cuda))
+    dhi = torch.zeros((N, C8, *dims, 8), dtype=torch.int16, device=cuda); dlo = torch.zeros_like(dhi)
+    check(lib.tta_upsample_bwd(gd.data_ptr(), C8 * Vo * 8, N, C8, *dims, *od, dhi.data_ptr(), dlo.data_ptr(),
+                               C8 * Vi * 8, bdt, stream()))
+    dx = from_chunked(join_planes(dhi, dlo, bdt), C).cpu()
+    assert rel_l2(dx, xr.grad) < (6e-4 if bdt == TTA_F16_HI else 2e-5)   # one fp16 plane / bf16 hi+lo
+
+
+# ------------------------------------------------------------------------------------------ model
+def test_registry_names_and_forward_matches_oracle(cuda):
+    assert get_model("unet_multimodal_deepfusion_b200") is MultimodalUNetB200
+    assert get_model("unet_multimodal_midfusion_b200") is MultimodalUNetB200
+    oracle, prod = _pair(SMALL_CFG, seed=5)
+    x = brats_volume(2, (32, 32, 48), seed=1)
+    for train in (True, False):                                          # InstanceNorm: identical either way
+        oracle.train(train); prod.train(train)
+        with torch.no_grad():
+            ref = oracle(x)
+        got = prod(x.cuda()).cpu()
+        assert got.shape == ref.shape == (2, 3, 32, 32, 48)
+        assert rel_l2(got, ref) < 1e-4, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("cfg,dims,B,use_graph", [(SMALL_CFG, (32, 32, 32), 2, True), (SMALL_CFG, (48, 32, 32), 1, False),
+                                                  (MULTIMODAL_MODEL_CFG, (32, 32, 32), 1, True)])
+def test_tent_step_matches_oracle(cuda, cfg, dims, B, use_graph):
+    oracle, prod = _pair(dict(cfg, deterministic=True), seed=7)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"entropy": "sigmoid", "cuda_graph": use_graph})
+    assert len(tp.adaptable_parameters()) == 2 * 49
+    for it in range(2):
+        x = brats_volume(B, dims, seed=20 + it)
+        lo, loss_o = to.step(x)
+        lp = tp.step(x.cuda()).cpu()
+        g_o, g_p = to.last_grads, prod.engine.flat_grads().cpu()
+        agree = ((lp >= 0) == (lo >= 0)).float().mean().item()
+        perr = (prod.engine.flat_params().cpu() - flat_gamma_beta(to.model)).abs()
+        print(f"[multimodal {dims} B={B} step {it}] logits {rel_l2(lp, lo):.1e} agree {agree:.6f} grad {rel_l2(g_p, g_o):.1e} "
+              f"params>1e-4 {100 * float((perr > 1e-4).float().mean()):.2f} % median {float(perr.median()):.1e}")
+        assert rel_l2(lp, lo) < 1e-3
+        assert abs(float(tp.last_loss) - loss_o) < 1e-4 * max(1.0, abs(loss_o))
+        assert agree >= 0.999
+        # step 0 starts from identical parameters: the gradient itself is compared; later steps start from parameters
+        # that already differ by Adam sign flips of noise-floor gradients (header of test_step_parity_gpu.py)
+        assert rel_l2(g_p, g_o) < (1e-3 if it == 0 else 1e-2)
+        assert float(perr.median()) < 1e-5 and float((perr > 1e-4).float().mean()) < 0.12
+
+
+def test_sliding_window_over_the_multimodal_model(cuda):
+    from oracle.sliding_window_oracle import sliding_window_oracle
+    oracle, prod = _pair(dict(SMALL_CFG, deterministic=True), seed=9)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"cuda_graph": True})
+    vol = brats_volume(1, (32, 48, 40), seed=4)
+    ref = sliding_window_oracle(vol, (32, 32, 32), 2, lambda w: to.step(w)[0], overlap=0.5)
+    got = SlidingWindowTTA(tp, (32, 32, 32), sw_batch=2, overlap=0.5)(vol.cuda()).cpu()
+    assert rel_l2(got, ref) < 1e-3
+    assert ((got >= 0) == (ref >= 0)).float().mean().item() >= 0.999
