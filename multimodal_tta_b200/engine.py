@@ -810,7 +810,8 @@ class TTAEngine:
         if fused_head is None:
             final.alloc_dy(nplanes)
         # power-of-two loss scale keeps the fp16 gradient planes in range; Adam divides it out
-        plan.loss_scale = float(2 ** math.ceil(math.log2(4.0 * N * final.V))) if bdt == TTA_F16_HI else 1.0
+        plan.loss_scale = float(2 ** math.ceil(math.log2(4.0 * N * final.V * model.loss_scale_mult))) \
+            if bdt == TTA_F16_HI else 1.0
         nblk = lib.tta_head_entropy_blocks(N, final.V)
         plan.partial = torch.zeros(nblk * N, dtype=torch.float32, device=dev)
         plan.sample_w = torch.ones(N, dtype=torch.float32, device=dev)

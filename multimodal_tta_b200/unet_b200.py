@@ -221,6 +221,9 @@ class B200Model(nn.Module):
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get("bwd_precision", "fp16"))
+        # the fp16 gradient planes carry the loss times 2^ceil(log2(4 * voxels * loss_scale_mult)): large enough that
+        # the deep layers' gradients stay out of the fp16 subnormals, small enough that the head's do not saturate
+        self.loss_scale_mult = float(get("loss_scale_mult", 1.0))
         if self.bwd_precision not in ("fp16", "bf16x2"):
             raise ValueError("unet_b200: bwd_precision must be 'fp16' or 'bf16x2'")
 

@@ -107,9 +107,12 @@ def test_registry_names_and_forward_matches_oracle(cuda):
         assert rel_l2(got, ref) < 1e-4, rel_l2(got, ref)
 
 
-@pytest.mark.parametrize("cfg,dims,B,use_graph", [(SMALL_CFG, (32, 32, 32), 2, True), (SMALL_CFG, (48, 32, 32), 1, False),
-                                                  (MULTIMODAL_MODEL_CFG, (32, 32, 32), 1, True)])
-def test_tent_step_matches_oracle(cuda, cfg, dims, B, use_graph):
+@pytest.mark.parametrize("cfg,dims,B,use_graph,gtol", [
+    (SMALL_CFG, (32, 32, 32), 2, True, 1e-3), (SMALL_CFG, (48, 32, 32), 1, False, 1e-3),
+    # reference channel counts: at 32^3 the 512-channel bottleneck normalises over 2^3 = 8 voxels (ill-conditioned:
+    # a looser structural check, as for the plain UNet); 64^3 is the tight case
+    (MULTIMODAL_MODEL_CFG, (32, 32, 32), 1, True, 3e-3), (MULTIMODAL_MODEL_CFG, (64, 64, 64), 1, True, 1e-3)])
+def test_tent_step_matches_oracle(cuda, cfg, dims, B, use_graph, gtol):
     oracle, prod = _pair(dict(cfg, deterministic=True), seed=7)
     to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"entropy": "sigmoid", "cuda_graph": use_graph})
     assert len(tp.adaptable_parameters()) == 2 * 49
@@ -127,7 +130,7 @@ def test_tent_step_matches_oracle(cuda, cfg, dims, B, use_graph):
         assert agree >= 0.999
         # step 0 starts from identical parameters: the gradient itself is compared; later steps start from parameters
         # that already differ by Adam sign flips of noise-floor gradients (header of test_step_parity_gpu.py)
-        assert rel_l2(g_p, g_o) < (1e-3 if it == 0 else 1e-2)
+        assert rel_l2(g_p, g_o) < (gtol if it == 0 else 1e-2)
         assert float(perr.median()) < 1e-5 and float((perr > 1e-4).float().mean()) < 0.12
 
 
