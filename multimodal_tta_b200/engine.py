@@ -1040,30 +1040,45 @@ class TTAEngine:
                               dy_ws)
                 rec["small_bwd"] = sm_bwd is not None
 
-                # per-sample reduce -> apply: bytes one sample's pass reads (g sources + y) must fit L2 with
-                # room to spare, while the whole batch must not (otherwise the batched form hits L2 anyway)
+                # L2-sized groups: reduce -> apply over one (sample, channel-chunk range) at a time, so that the apply
+                # pass re-reads g and y from the 126 MB L2 instead of HBM.  per_sample_norm_bwd (round 1) used whole
+                # samples (67 MB at the 64^3 level: the second pass did not hit); norm_bwd_l2_mb bounds the bytes a
+                # group's reduction pass reads (g sources + y)
                 per_n = None
                 nsrc = 1 + (1 if g1 else 0)
                 bytes_n = (nsrc + 1) * y.C8 * y.V * 32
-                if (model.per_sample_norm_bwd and do_apply and fin_args is None and not skip_reduce and sm_bwd is None
-                        and not nl.batch and N > 1 and bytes_n <= 96e6 and N * bytes_n > 100e6):
-                    per_n = []
-                    Cp = y.C8 * 8
-                    for n_ in range(N):
-                        rd_n = (g0 + n_ * g0ns * 4, g0ns, (g1 + n_ * g1ns * 4) if g1 else 0, g1ns, y.ptr + n_ * y.ns * 4,
-                                y.ns, 1, y.C8, nl.C, y.V, rec["mean"].data_ptr() + n_ * Cp * 4,
-                                rec["rstd"].data_ptr() + n_ * Cp * 4, rec["gptr"], rec["bptr"], int(rec["relu"]),
-                                nl.batch, rec["sums"].data_ptr() + n_ * Cp * 8, dg, db)
-                        ap_n = (g0 + n_ * g0ns * 4, g0ns, (g1 + n_ * g1ns * 4) if g1 else 0, g1ns, y.ptr + n_ * y.ns * 4,
-                                y.ns, 1, y.C8, y.V, rec["mean"].data_ptr() + n_ * Cp * 4,
-                                rec["rstd"].data_ptr() + n_ * Cp * 4, rec["gptr"], rec["bptr"], int(rec["relu"]),
-                                nl.batch, rec["sums"].data_ptr() + n_ * Cp * 8, y.dy_ptr(0) + n_ * y.ns * 2,
-                                (y.dy_ptr(1) + n_ * y.ns * 2) if nplanes == 2 else y.dy_ptr(1), y.ns,
-                                (aux.dy_ptr(0) + n_ * aux.ns * 2) if aux else 0,
-                                ((aux.dy_ptr(1) + n_ * aux.ns * 2) if nplanes == 2 else aux.dy_ptr(1)) if aux else 0,
-                                aux.ns if aux else 0, bdt)
-                        per_n.append((rd_n, ap_n, int(n_ > 0)))
-                rec["per_sample_bwd"] = per_n is not None
+                budget = model.norm_bwd_l2_mb * 1e6 if model.norm_bwd_l2_mb > 0 else (96e6 if model.per_sample_norm_bwd else 0)
+                if (budget > 0 and do_apply and fin_args is None and not skip_reduce and sm_bwd is None
+                        and not nl.batch and N * bytes_n > model.norm_bwd_l2_min_mb * 1e6):
+                    parts = 1
+                    while bytes_n / parts > budget and parts < y.C8:
+                        parts += 1
+                    while y.C8 % parts:
+                        parts += 1
+                    cc = y.C8 // parts
+                    if parts * N > 1:
+                        per_n = []
+                        Cp = y.C8 * 8
+                        for n_ in range(N):
+                            for c0 in range(0, y.C8, cc):
+                                o4, o2, oc = c0 * y.V * 8 * 4, c0 * y.V * 8 * 2, c0 * 8
+                                mo = (n_ * Cp + oc) * 4
+                                creal = max(0, min(nl.C - oc, cc * 8))
+                                gp, bp = rec["gptr"] + oc * 4, rec["bptr"] + oc * 4
+                                rd_n = (g0 + n_ * g0ns * 4 + o4, g0ns, (g1 + n_ * g1ns * 4 + o4) if g1 else 0, g1ns,
+                                        y.ptr + n_ * y.ns * 4 + o4, y.ns, 1, cc, creal, y.V, rec["mean"].data_ptr() + mo,
+                                        rec["rstd"].data_ptr() + mo, gp, bp, int(rec["relu"]), nl.batch,
+                                        rec["sums"].data_ptr() + 2 * mo, dg + oc * 4, db + oc * 4)
+                                ap_n = (g0 + n_ * g0ns * 4 + o4, g0ns, (g1 + n_ * g1ns * 4 + o4) if g1 else 0, g1ns,
+                                        y.ptr + n_ * y.ns * 4 + o4, y.ns, 1, cc, y.V, rec["mean"].data_ptr() + mo,
+                                        rec["rstd"].data_ptr() + mo, gp, bp, int(rec["relu"]), nl.batch,
+                                        rec["sums"].data_ptr() + 2 * mo, y.dy_ptr(0) + n_ * y.ns * 2 + o2,
+                                        (y.dy_ptr(1) + n_ * y.ns * 2 + o2) if nplanes == 2 else y.dy_ptr(1), y.ns,
+                                        (aux.dy_ptr(0) + n_ * aux.ns * 2 + o2) if aux else 0,
+                                        ((aux.dy_ptr(1) + n_ * aux.ns * 2 + o2) if nplanes == 2 else aux.dy_ptr(1)) if aux else 0,
+                                        aux.ns if aux else 0, bdt)
+                                per_n.append((rd_n, ap_n, int(n_ > 0), creal, dg + oc * 4, db + oc * 4))
+                rec["per_sample_bwd"] = len(per_n) if per_n is not None else 0
 
                 def run(rd_args=rd_args, ap_args=ap_args if do_apply else None, nl=nl, dg=dg, db=db, dy_ws=dy_ws,
                         skip_reduce=skip_reduce, fin_args=fin_args, sm_bwd=sm_bwd, per_n=per_n, c4_args=c4_args):
@@ -1071,10 +1086,10 @@ class TTAEngine:
                         check(lib.tta_norm_bwd_apply_c4(*c4_args, _stream()), "norm_bwd_apply_c4")
                         return
                     if per_n is not None:
-                        for rd_n, ap_n, accum in per_n:
+                        for rd_n, ap_n, accum, creal, dg_, db_ in per_n:
                             check(lib.tta_norm_bwd_reduce(*rd_n, plan.ws.data_ptr(), 1, accum, _stream()),
                                   "norm_bwd_reduce")
-                            check(lib.tta_norm_bwd_apply(*ap_n, 0, nl.C, dg, db, dy_ws, _stream()), "norm_bwd_apply")
+                            check(lib.tta_norm_bwd_apply(*ap_n, 0, creal, dg_, db_, dy_ws, _stream()), "norm_bwd_apply")
                         return
                     if sm_bwd is not None:
                         check(lib.tta_norm_bwd_small(*sm_bwd, plan.ws.data_ptr(), _stream()), "norm_bwd_small")
@@ -1107,7 +1122,7 @@ class TTAEngine:
         plan.n_small_bwd = sum(1 for o in ops if o[0] == "norm" and o[1].get("small_bwd"))
         plan.launches_fwd -= plan.n_small_fwd      # statistics + apply in one launch
         plan.launches_bwd -= plan.n_small_bwd      # reduction + apply in one launch
-        plan.launches_bwd += 2 * (NB - 1) * sum(1 for o in ops if o[0] == "norm" and o[1].get("per_sample_bwd"))
+        plan.launches_bwd += sum(2 * (o[1]["per_sample_bwd"] - 1) for o in ops if o[0] == "norm" and o[1].get("per_sample_bwd"))
         n_extra = sum(1 for o in ops if o[0] in ("mean", "upsample", "cast"))   # one launch each way
         plan.launches_fwd += n_extra + (1 if getattr(plan, "x2", None) is not None else 0)
         plan.launches_bwd += n_extra

@@ -218,6 +218,12 @@ class B200Model(nn.Module):
         # on the four 64^3 layers (67 MB per sample): 2.578 ms vs 2.556 ms per step -- the second pass
         # does not hit, the two extra launches per layer cost more; default off
         self.per_sample_norm_bwd = bool(get("per_sample_norm_bwd", False))
+        # OPT-IN generalisation: (sample, channel-chunk range) groups whose reduction pass reads at most this many MB
+        # (0 = off), small enough that the apply pass should find g and y in L2.  Measured (round 2, same box, ms per
+        # step): off 2.233, 70 MB 2.302, 40 MB 2.371, 20 MB 2.422 -- more, smaller launches cost more than the
+        # second pass gains; the re-read is not where the time goes
+        self.norm_bwd_l2_mb = float(get("norm_bwd_l2_mb", 0))
+        self.norm_bwd_l2_min_mb = float(get("norm_bwd_l2_min_mb", 100))   # only layers whose batch exceeds this
         # gradient operand format of the dgrad convs: "fp16" = one loss-scaled fp16 plane (1 MMA per
         # k-step), "bf16x2" = split bf16 planes (2 MMAs); DESIGN.md section 6 has the error budget
         self.bwd_precision = str(get("bwd_precision", "fp16"))

@@ -105,6 +105,26 @@ def test_unfused_shortcut_convs(cuda):
     _check_step(dict(BRATS_MODEL_CFG, fuse_shortcut=False), x, "sigmoid", steps=2, use_graph=True)
 
 
+def test_norm_backward_in_l2_sized_groups_is_bit_identical(cuda):
+    """norm_bwd_l2_mb: reduce -> apply per (sample, chunk range) group; same kernels, same per-slab arithmetic."""
+    x = brats_volume(2, (32, 32, 32), seed=47).cuda()
+    outs = []
+    for opts in ({}, {"norm_bwd_l2_mb": 0.2, "norm_bwd_l2_min_mb": 0}, {"per_sample_norm_bwd": True, "norm_bwd_l2_min_mb": 0}):
+        _, prod = make_pair(dict(BRATS_MODEL_CFG, deterministic=True, fuse_small_norm=False, **opts), seed=12)
+        tp = TentB200(prod, {"cuda_graph": False})
+        for _ in range(2):
+            lg = tp.step(x).clone()
+        outs.append((lg, prod.engine.flat_grads().clone(), prod.engine.flat_params().clone()))
+        if opts:
+            plan = next(iter(prod.engine.plans.values()))
+            assert plan.launches_bwd > base_launches          # the grouped path really ran
+        else:
+            base_launches = next(iter(prod.engine.plans.values())).launches_bwd
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[2], outs[0][2])
+        assert rel_l2(o[1].cpu(), outs[0][1].cpu()) < 1e-6      # dgamma accumulates over samples in another order
+
+
 def test_inference_forward_matches_oracle_eval_and_train(cuda):
     for cfg in (BRATS_MODEL_CFG, dict(BARE_DEFAULT_MODEL_CFG, in_channels=4)):
         oracle, prod = make_pair(cfg, seed=3)
