@@ -98,29 +98,48 @@ __global__ void norm_stats_finalize_kernel(const float* partial, int N, int C8,
   rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// one CTA per channel chunk: fp64 reduction of the `splits` partial slots with all 256 threads
+// one CTA per (channel chunk, normalisation group): fp64 reduction of the `splits` partial slots of both sums at
+// once -- thread (v, j) walks slots j, j+16, ... of value v with four independent loads in flight (the launch is
+// pure latency: ~150 slots of 64 B per group; one serial chain per sample and sum took 10 us)
 // (the partials may come from norm_stats_partial_kernel or from the tcgen05 conv epilogue)
 __global__ void __launch_bounds__(kThreads)
 norm_stats_finalize_chunk_kernel(const float* partial, int N, int C8, int splits, long long V, int batch_mode,
                                  float eps, float* mean, float* rstd) {
   pdl_trigger();
   pdl_wait();
+  __shared__ double red[16][17];
   const int chunk = blockIdx.x;
   const int C = C8 * 8;
   const double M = (double)V * (batch_mode ? N : 1);
-  for (int nn = 0; nn < (batch_mode ? 1 : N); ++nn) {
-    const int n0 = batch_mode ? 0 : nn, n1 = batch_mode ? N : nn + 1;
-    const double s1 = reduce_partials_one(partial, C8, chunk, splits, n0, n1, threadIdx.x & 7);
-    const double s2 = reduce_partials_one(partial, C8, chunk, splits, n0, n1, 8 + (threadIdx.x & 7));
-    if (threadIdx.x < 8) {
-      const double m = s1 / M;
-      double var = s2 / M - m * m;
-      if (var < 0.0) var = 0.0;
-      const float mu = (float)m, rs = (float)(1.0 / sqrt(var + (double)eps));
-      for (int n2 = n0; n2 < n1; ++n2) {
-        mean[n2 * C + chunk * 8 + threadIdx.x] = mu;
-        rstd[n2 * C + chunk * 8 + threadIdx.x] = rs;
-      }
+  const int n0 = batch_mode ? 0 : (int)blockIdx.y, n1 = batch_mode ? N : (int)blockIdx.y + 1;
+  const int v = threadIdx.x & 15, j = threadIdx.x >> 4;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int nn = n0; nn < n1; ++nn) {      // fixed order -> deterministic
+    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16 + v;
+    int sp = j;
+    for (; sp + 48 < splits; sp += 64) {
+      const float x0 = __ldcg(p + sp * 16), x1 = __ldcg(p + (sp + 16) * 16), x2 = __ldcg(p + (sp + 32) * 16),
+                  x3 = __ldcg(p + (sp + 48) * 16);
+      a0 += (double)x0; a1 += (double)x1; a2 += (double)x2; a3 += (double)x3;
+    }
+    for (; sp < splits; sp += 16) a0 += (double)__ldcg(p + sp * 16);
+  }
+  red[v][j] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      s1 += red[threadIdx.x][jj];
+      s2 += red[8 + threadIdx.x][jj];
+    }
+    const double m = s1 / M;
+    double var = s2 / M - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)m, rs = (float)(1.0 / sqrt(var + (double)eps));
+    for (int n2 = n0; n2 < n1; ++n2) {
+      mean[n2 * C + chunk * 8 + threadIdx.x] = mu;
+      rstd[n2 * C + chunk * 8 + threadIdx.x] = rs;
     }
   }
 }
@@ -650,8 +669,8 @@ int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, i
 int tta_norm_stats_finalize(const float* workspace, int N, int C8, int splits, long long V, int batch_mode,
                             float eps, float* mean, float* rstd, cudaStream_t stream) {
   TTA_REQUIRE(workspace && mean && rstd && splits > 0, "tta_norm_stats_finalize: bad argument");
-  tta_launch(norm_stats_finalize_chunk_kernel, C8, kThreads, 0, stream, tta_pdl_family(2), workspace + 1024, N, C8,
-             splits, V, batch_mode, eps, mean, rstd);
+  tta_launch(norm_stats_finalize_chunk_kernel, dim3(C8, batch_mode ? 1 : N), kThreads, 0, stream, tta_pdl_family(2),
+             workspace + 1024, N, C8, splits, V, batch_mode, eps, mean, rstd);
   return tta_check_launch("tta_norm_stats_finalize");
 }
 

@@ -117,11 +117,20 @@ __device__ __forceinline__ double reduce_partials_one(const float* partial, int 
                                                       int splits, int n0, int n1, int which) {
   __shared__ double red1[16][17];
   const int v = threadIdx.x & 15, j = threadIdx.x >> 4;
-  double a = 0.0;
+  double a = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   for (int nn = n0; nn < n1; ++nn) {
-    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16;
-    for (int sp = j; sp < splits; sp += 16) a += (double)__ldcg(p + sp * 16 + v);
+    // four independent loads in flight per thread: these tails are pure L2 latency (a serial chain of ~10
+    // dependent 600 ns loads per call otherwise)
+    const float* p = partial + (long long)(nn * C8 + chunk) * splits * 16 + v;
+    int sp = j;
+    for (; sp + 48 < splits; sp += 64) {
+      const float x0 = __ldcg(p + sp * 16), x1 = __ldcg(p + (sp + 16) * 16), x2 = __ldcg(p + (sp + 32) * 16),
+                  x3 = __ldcg(p + (sp + 48) * 16);
+      a += (double)x0; a1 += (double)x1; a2 += (double)x2; a3 += (double)x3;
+    }
+    for (; sp < splits; sp += 16) a += (double)__ldcg(p + sp * 16);
   }
+  a = (a + a1) + (a2 + a3);
   red1[v][j] = a;
   __syncthreads();
   double t = 0.0;
