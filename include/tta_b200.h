@@ -281,6 +281,22 @@ int tta_upsample_fwd(const float* in, long long in_n_stride, int N, int C8, int 
 int tta_upsample_bwd(const float* g, long long g_n_stride, int N, int C8, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
                      uint16_t* dy_hi, uint16_t* dy_lo, long long dy_n_stride, int out_dtype, tta_stream_t stream);
 
+/* ---- the step as a C object (plan_create / tta_step / workspace_bytes).  Build the launch list once
+ * per input shape by calling the ordinary tta_* entry points between tta_plan_begin(plan, section) and tta_plan_end():
+ * while a recording is active on the calling thread those calls store themselves (arguments by value; host pointer
+ * arguments must outlive the plan) instead of launching.  tta_plan_run enqueues a section on `stream`; tta_step =
+ * sections 0 (forward), 1 (training head: logits, entropy loss, dlogits) and 3 (backward).  Section 2 is the
+ * inference head; 4..7 are free for the caller (e.g. the input gather of a fixed staging buffer, Adam). */
+typedef struct tta_plan tta_plan;
+int tta_plan_create(tta_plan** out);
+int tta_plan_destroy(tta_plan* plan);
+int tta_plan_begin(tta_plan* plan, int section);
+int tta_plan_end(void);
+int tta_plan_num_launches(const tta_plan* plan, int section);
+int tta_plan_run(const tta_plan* plan, int section, tta_stream_t stream);
+int tta_step(const tta_plan* plan, tta_stream_t stream);
+long long tta_workspace_bytes(int N, int C8, long long V);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,14 @@ _SIGNATURES = {
     "tta_conv_tc": (I, [P, P, L, I, I, I, I, I, I, P, P, P, L, I, I, I, I, I, I, I, I, I, P, I, P]),
     "tta_conv_tc_bwd_norm": (I, [P, P, L, I, I, I, I, I, I, P, P, L, I, I, I, I, I, I, I, I, I, P, I, P]),
     "tta_norm_bwd_finalize": (I, [P, I, I, I, I, I, P, P, P, P]),
+    "tta_plan_create": (I, [P]),
+    "tta_plan_destroy": (I, [P]),
+    "tta_plan_begin": (I, [P, I]),
+    "tta_plan_end": (I, []),
+    "tta_plan_num_launches": (I, [P, I]),
+    "tta_plan_run": (I, [P, I, P]),
+    "tta_step": (I, [P, P]),
+    "tta_workspace_bytes": (L, [I, I, L]),
     "tta_mean_planes": (I, [P, P, P, I, I, I, L, F, P, P, L, I, P]),
     "tta_sum_f32": (I, [P, P, I, I, I, I, L, F, P, L, I, P]),
     "tta_upsample_fwd": (I, [P, L, I, I, I, I, I, I, I, I, P, P, L, I, P]),

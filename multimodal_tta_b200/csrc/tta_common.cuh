@@ -22,6 +22,8 @@
 #define TTA_F16 0
 #define TTA_BF16 1
 #define TTA_F16_HI 2  // single fp16 plane (no lo plane is written or read): scaled gradients in backward
+#define TTA_PLAN_SECTIONS 8
+extern "C" long long tta_norm_workspace_floats(int N, int C8, long long V);
 
 void tta_set_error(const char* fmt, ...);
 int tta_check_launch(const char* what);
@@ -40,6 +42,20 @@ int tta_check_launch(const char* what);
 // dependents cost more than the overlapped prologues save, so the default is OFF.
 bool tta_pdl_enabled();
 bool tta_pdl_family(int family_bit);  // TTA_PDL_OFF=<mask> switches PDL off per kernel family (debugging)
+
+// ---- launch recorder (csrc/tta_plan.cu): while a tta_plan section is being recorded on the calling thread, every
+// launching entry point stores itself (arguments by value) instead of launching; tta_plan_run / tta_step replay
+// the stored calls on a stream.  Host pointer arguments (W_host, pointer arrays, segment tables) must outlive the plan.
+#include <functional>
+bool tta_recording();
+void tta_record_push(std::function<int(cudaStream_t)> fn);
+#define TTA_RECORDABLE(call_with_s_)                                                   \
+  do {                                                                                 \
+    if (tta_recording()) {                                                             \
+      tta_record_push([=](cudaStream_t s_) -> int { return call_with_s_; });           \
+      return TTA_OK;                                                                   \
+    }                                                                                  \
+  } while (0)
 
 #define TTA_REQUIRE(cond, ...)              \
   do {                                      \

@@ -153,6 +153,7 @@ extern "C" int tta_conv_simt(const uint16_t* in_hi, const uint16_t* in_lo, long 
                              const float* Wp, const float* bias, float* out, long long out_ns,
                              int C8out, int Do, int Ho, int Wo, int mode, int K, int stride,
                              int accumulate, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_conv_simt(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, Wp, bias, out, out_ns, C8out, Do, Ho, Wo, mode, K, stride, accumulate, s_));
   TTA_REQUIRE(in_hi && (in_lo || in_dtype == TTA_F16_HI) && Wp && out, "tta_conv_simt: null pointer");
   TTA_REQUIRE(mode == 0 || mode == 1, "tta_conv_simt: mode %d", mode);
   TTA_REQUIRE(K == 1 || K == 3, "tta_conv_simt: kernel size %d unsupported (1 or 3)", K);

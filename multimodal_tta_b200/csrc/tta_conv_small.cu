@@ -156,6 +156,7 @@ int tta_conv_small_supported(int K, int stride, int cin, int cout) {
 int tta_conv_small(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, int in_dtype, int N, int cin,
                    int D, int H, int Wd, const float* W, const float* bias, float* out, long long out_ns, int cout,
                    int accumulate, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_conv_small(in_hi, in_lo, in_ns, in_dtype, N, cin, D, H, Wd, W, bias, out, out_ns, cout, accumulate, s_));
   TTA_REQUIRE(in_hi && (in_lo || in_dtype == TTA_F16_HI) && W && out, "tta_conv_small: null pointer");
   TTA_REQUIRE(tta_conv_small_supported(3, 1, cin, cout), "tta_conv_small: cin=%d cout=%d unsupported", cin, cout);
   TTA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "tta_conv_small: bad dtype");

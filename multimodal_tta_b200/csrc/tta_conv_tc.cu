@@ -1939,6 +1939,7 @@ int tta_conv_tc(const uint16_t* in_hi, const uint16_t* in_lo, long long in_ns, i
                 int Di, int Hi, int Wi, const void* wpacked, const float* bias, float* out, long long out_ns,
                 int C8out, int Do, int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
                 float* stats_ws, int stats_c8, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_conv_tc(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, C8out, Do, Ho, Wo, mode, K, stride, accumulate, flags, stats_ws, stats_c8, s_));
   return conv_tc_impl(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, C8out, Do, Ho,
                       Wo, mode, K, stride, accumulate, flags, stats_ws, stats_c8, nullptr, 0, nullptr, nullptr, nullptr,
                       stream);
@@ -1953,6 +1954,7 @@ int tta_conv_tc_bwd_norm(const uint16_t* in_hi, const uint16_t* in_lo, long long
                          int Di, int Hi, int Wi, const void* wpacked, float* out, long long out_ns, int C8out, int Do,
                          int Ho, int Wo, int mode, int K, int stride, int accumulate, int flags,
                          const tta_norm_bwd_seg* segs, int nsegs, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_conv_tc_bwd_norm(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, out, out_ns, C8out, Do, Ho, Wo, mode, K, stride, accumulate, flags, segs, nsegs, s_));
   return conv_tc_impl(in_hi, in_lo, in_ns, in_dtype, N, C8in, Di, Hi, Wi, wpacked, nullptr, out, out_ns, C8out, Do, Ho,
                       Wo, mode, K, stride, accumulate, flags, nullptr, 0, segs, nsegs, nullptr, nullptr, nullptr, stream);
 }

@@ -393,6 +393,7 @@ int tta_head_fused_fwd(const float* y, long long y_ns, int y_cpv, int N, int C, 
                        const float* rstd, const float* gamma, const float* beta, int relu, const float* W_host,
                        const float* bias, int mode, float inv_count, float grad_scale, const float* sample_w,
                        float* logits, float* dlogits, float* workspace, float* loss, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_head_fused_fwd(y, y_ns, y_cpv, N, C, D, H, W, mean, rstd, gamma, beta, relu, W_host, bias, mode, inv_count, grad_scale, sample_w, logits, dlogits, workspace, loss, s_));
   TTA_REQUIRE(y_cpv == 8 || y_cpv == 4, "tta_head_fused_fwd: y_cpv %d (8 = chunk layout, 4 = compact)", y_cpv);
   TTA_REQUIRE(y && mean && rstd && gamma && beta && W_host && workspace && loss, "tta_head_fused_fwd: null pointer");
   TTA_REQUIRE(tta_head_fused_supported(3, 1, C, C), "tta_head_fused_fwd: %d channels unsupported (1..4)", C);
@@ -428,6 +429,7 @@ int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, 
                        long long y_ns, int y_cpv, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, int relu, int batch_mode, float* dz, long long dz_ns, float* sums,
                        float* dgamma, float* dbeta, float* workspace, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_head_fused_bwd(dlogits, N, C, D, H, W, W_host, y, y_ns, y_cpv, mean, rstd, gamma, beta, relu, batch_mode, dz, dz_ns, sums, dgamma, dbeta, workspace, s_));
   TTA_REQUIRE(y_cpv == 8 || y_cpv == 4, "tta_head_fused_bwd: y_cpv %d (8 = chunk layout, 4 = compact)", y_cpv);
   TTA_REQUIRE(dlogits && W_host && y && mean && rstd && gamma && beta && dz && sums && dgamma && dbeta && workspace,
               "tta_head_fused_bwd: null pointer");

@@ -137,6 +137,7 @@ long long tta_intensity_workspace_bytes(int n_vol, int C, long long V) {
 
 int tta_intensity_stats(const float* vol, int n_vol, int C, long long V, const float* rules, int min_count,
                         float* affine, void* workspace, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_intensity_stats(vol, n_vol, C, V, rules, min_count, affine, workspace, s_));
   TTA_REQUIRE(vol && rules && affine && workspace, "tta_intensity_stats: null pointer");
   TTA_REQUIRE(n_vol > 0 && C > 0 && V > 0 && n_vol * C <= 1024, "tta_intensity_stats: bad shape n_vol=%d C=%d V=%lld",
               n_vol, C, V);
@@ -149,6 +150,7 @@ int tta_intensity_stats(const float* vol, int n_vol, int C, long long V, const f
 
 int tta_intensity_apply(const float* vol, float* out, int n_vol, int C, long long V, const float* affine,
                         cudaStream_t stream) {
+  TTA_RECORDABLE(tta_intensity_apply(vol, out, n_vol, C, V, affine, s_));
   TTA_REQUIRE(vol && out && affine, "tta_intensity_apply: null pointer");
   TTA_REQUIRE(n_vol > 0 && C > 0 && V > 0, "tta_intensity_apply: bad shape");
   long long xb = (V / 4 + kThreads - 1) / kThreads;

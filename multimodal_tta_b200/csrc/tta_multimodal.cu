@@ -224,6 +224,7 @@ extern "C" {
 int tta_mean_planes(const uint16_t* const* in_hi, const uint16_t* const* in_lo, const long long* in_ns, int nsrc, int N,
                     int C8, long long V, float scale, uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int rep,
                     cudaStream_t stream) {
+  TTA_RECORDABLE(tta_mean_planes(in_hi, in_lo, in_ns, nsrc, N, C8, V, scale, out_hi, out_lo, out_ns, rep, s_));
   TTA_REQUIRE(in_hi && in_lo && in_ns && out_hi && out_lo, "tta_mean_planes: null pointer");
   TTA_REQUIRE(nsrc >= 1 && nsrc <= kMaxSrc, "tta_mean_planes: %d sources (1..8)", nsrc);
   TTA_REQUIRE(N > 0 && C8 > 0 && V > 0 && rep >= 1, "tta_mean_planes: bad shape");
@@ -241,6 +242,7 @@ int tta_mean_planes(const uint16_t* const* in_hi, const uint16_t* const* in_lo, 
 // out[n] (=|+=) scale * sum_k sum_{r<rep} src_k[n*rep + r]   (fp32 chunk layout; src: HOST arrays of <= 8 entries)
 int tta_sum_f32(const float* const* src, const long long* src_ns, int nsrc, int rep, int N, int C8, long long V,
                 float scale, float* out, long long out_ns, int accumulate, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_sum_f32(src, src_ns, nsrc, rep, N, C8, V, scale, out, out_ns, accumulate, s_));
   TTA_REQUIRE(src && src_ns && out, "tta_sum_f32: null pointer");
   TTA_REQUIRE(nsrc >= 1 && nsrc <= kMaxSrc, "tta_sum_f32: %d sources (1..8)", nsrc);
   TTA_REQUIRE(N > 0 && C8 > 0 && V > 0 && rep >= 1, "tta_sum_f32: bad shape");
@@ -257,6 +259,7 @@ int tta_sum_f32(const float* const* src, const long long* src_ns, int nsrc, int 
 
 int tta_upsample_fwd(const float* in, long long in_ns, int N, int C8, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
                      uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int out_dtype, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_upsample_fwd(in, in_ns, N, C8, Di, Hi, Wi, Do, Ho, Wo, out_hi, out_lo, out_ns, out_dtype, s_));
   TTA_REQUIRE(in && out_hi && out_lo, "tta_upsample_fwd: null pointer");
   TTA_REQUIRE(out_dtype == TTA_F16 || out_dtype == TTA_BF16, "tta_upsample_fwd: bad dtype");
   TTA_REQUIRE(N > 0 && C8 > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do >= Di && Ho >= Hi && Wo >= Wi, "tta_upsample_fwd: bad shape");
@@ -274,6 +277,7 @@ int tta_upsample_fwd(const float* in, long long in_ns, int N, int C8, int Di, in
 // 16-bit plane(s) (dy_lo unused for TTA_F16_HI)
 int tta_upsample_bwd(const float* g, long long g_ns, int N, int C8, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
                      uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns, int out_dtype, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_upsample_bwd(g, g_ns, N, C8, Di, Hi, Wi, Do, Ho, Wo, dy_hi, dy_lo, dy_ns, out_dtype, s_));
   TTA_REQUIRE(g && dy_hi && (dy_lo || out_dtype == TTA_F16_HI), "tta_upsample_bwd: null pointer");
   TTA_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "tta_upsample_bwd: bad dtype");
   TTA_REQUIRE(N > 0 && C8 > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do >= Di && Ho >= Hi && Wo >= Wi, "tta_upsample_bwd: bad shape");

@@ -653,6 +653,7 @@ long long tta_norm_workspace_floats(int N, int C8, long long V) {
 int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, int batch_mode,
                    float eps, float* mean, float* rstd, float* workspace, int finalize,
                    cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_stats(y, y_ns, N, C8, V, batch_mode, eps, mean, rstd, workspace, finalize, s_));
   TTA_REQUIRE(y && workspace && (!finalize || (mean && rstd)), "tta_norm_stats: null pointer");
   TTA_REQUIRE(N > 0 && C8 > 0 && V > 0, "tta_norm_stats: empty shape N=%d C8=%d V=%lld", N, C8, V);
   TTA_REQUIRE(C8 <= 1024, "tta_norm_stats: more than 8192 channels unsupported");
@@ -668,6 +669,7 @@ int tta_norm_stats(const float* y, long long y_ns, int N, int C8, long long V, i
 // (tta_norm_stats with finalize = 0, or the fused statistics of tta_conv_tc with splits = its grid)
 int tta_norm_stats_finalize(const float* workspace, int N, int C8, int splits, long long V, int batch_mode,
                             float eps, float* mean, float* rstd, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_stats_finalize(workspace, N, C8, splits, V, batch_mode, eps, mean, rstd, s_));
   TTA_REQUIRE(workspace && mean && rstd && splits > 0, "tta_norm_stats_finalize: bad argument");
   tta_launch(norm_stats_finalize_chunk_kernel, dim3(C8, batch_mode ? 1 : N), kThreads, 0, stream, tta_pdl_family(2),
              workspace + 1024, N, C8, splits, V, batch_mode, eps, mean, rstd);
@@ -680,6 +682,7 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
                    uint16_t* out_hi, uint16_t* out_lo, long long out_ns, int out_dtype,
                    const float* partial, int partial_splits, int batch_mode, float eps, uint16_t* ws_hi,
                    uint16_t* ws_lo, long long ws_ns, int W, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_apply(y, y_ns, N, C8, V, mean, rstd, gamma, beta, relu, res_kind, res_a, res_b, res_ns, out_hi, out_lo, out_ns, out_dtype, partial, partial_splits, batch_mode, eps, ws_hi, ws_lo, ws_ns, W, s_));
   TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_apply: null pointer");
   TTA_REQUIRE(!ws_hi || (ws_lo && W > 0 && W % 2 == 0 && V % W == 0),
               "tta_norm_apply: w-parity-split copy needs an even row length W=%d dividing V", W);
@@ -708,6 +711,7 @@ int tta_norm_apply(const float* y, long long y_ns, int N, int C8, long long V, c
 // 1024-float counter prefix: `partial` points at the slots themselves)
 int tta_norm_bwd_finalize(const float* partial, int N, int C8, int Creal, int splits, int batch_mode, float* sums,
                           float* dgamma, float* dbeta, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_bwd_finalize(partial, N, C8, Creal, splits, batch_mode, sums, dgamma, dbeta, s_));
   TTA_REQUIRE(partial && sums && dgamma && dbeta && splits > 0, "tta_norm_bwd_finalize: bad argument");
   tta_launch(norm_bwd_finalize_chunk_kernel, C8, kThreads, 0, stream, tta_pdl_family(2), partial, N, C8, Creal, splits,
              batch_mode, sums, dgamma, dbeta);
@@ -719,6 +723,7 @@ int tta_norm_bwd_reduce(const float* g0, long long g0_ns, const float* g1, long 
                         const float* mean, const float* rstd, const float* gamma,
                         const float* beta, int relu, int batch_mode, float* sums, float* dgamma,
                         float* dbeta, float* workspace, int finalize, int accumulate_dgb, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_bwd_reduce(g0, g0_ns, g1, g1_ns, y, y_ns, N, C8, Creal, V, mean, rstd, gamma, beta, relu, batch_mode, sums, dgamma, dbeta, workspace, finalize, accumulate_dgb, s_));
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && workspace &&
                   (!finalize || (sums && dgamma && dbeta)),
               "tta_norm_bwd_reduce: null pointer");
@@ -738,6 +743,7 @@ int tta_norm_bwd_apply(const float* g0, long long g0_ns, const float* g1, long l
                        uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi, uint16_t* aux_lo,
                        long long aux_ns, int out_dtype, const float* partial, int Creal, float* dgamma,
                        float* dbeta, int dy_wsplit_w, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_bwd_apply(g0, g0_ns, g1, g1_ns, y, y_ns, N, C8, V, mean, rstd, gamma, beta, relu, batch_mode, sums, dy_hi, dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, out_dtype, partial, Creal, dgamma, dbeta, dy_wsplit_w, s_));
   TTA_REQUIRE(dy_wsplit_w == 0 || (dy_wsplit_w > 0 && dy_wsplit_w % 2 == 0 && V % dy_wsplit_w == 0),
               "tta_norm_bwd_apply: w-parity-split dy needs an even row length dividing V (got %d)", dy_wsplit_w);
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && (sums || (partial && dgamma && dbeta)) && dy_hi &&
@@ -786,6 +792,7 @@ int tta_norm_fwd_small(const float* y, long long y_ns, int N, int C8, long long 
                        const void* res_a, const void* res_b, long long res_ns, uint16_t* out_hi,
                        uint16_t* out_lo, long long out_ns, int out_dtype, uint16_t* ws_hi, uint16_t* ws_lo,
                        long long ws_ns, int W, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_fwd_small(y, y_ns, N, C8, V, eps, mean, rstd, gamma, beta, relu, res_kind, res_a, res_b, res_ns, out_hi, out_lo, out_ns, out_dtype, ws_hi, ws_lo, ws_ns, W, s_));
   TTA_REQUIRE(y && mean && rstd && gamma && beta && out_hi && out_lo, "tta_norm_fwd_small: null pointer");
   TTA_REQUIRE(tta_norm_small_supported(N, V, 0), "tta_norm_fwd_small: V=%lld unsupported (2..65536)", V);
   TTA_REQUIRE(res_kind >= 0 && res_kind <= 2, "tta_norm_fwd_small: res_kind %d", res_kind);
@@ -814,6 +821,7 @@ int tta_norm_bwd_small(const float* g0, long long g0_ns, const float* g1, long l
                        float* dgamma, float* dbeta, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
                        uint16_t* aux_hi, uint16_t* aux_lo, long long aux_ns, int out_dtype, int dy_wsplit_w,
                        float* workspace, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_bwd_small(g0, g0_ns, g1, g1_ns, y, y_ns, N, C8, Creal, V, mean, rstd, gamma, beta, relu, sums, dgamma, dbeta, dy_hi, dy_lo, dy_ns, aux_hi, aux_lo, aux_ns, out_dtype, dy_wsplit_w, workspace, s_));
   TTA_REQUIRE(g0 && y && mean && rstd && gamma && beta && sums && dgamma && dbeta && dy_hi && workspace &&
                   (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_small: null pointer");
@@ -842,6 +850,7 @@ int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_ns, const float* y, l
                           long long V, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           int batch_mode, const float* sums, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
                           int out_dtype, int dy_wsplit_w, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_bwd_apply_c4(dz, dz_ns, y, y_ns, N, Creal, V, mean, rstd, gamma, beta, batch_mode, sums, dy_hi, dy_lo, dy_ns, out_dtype, dy_wsplit_w, s_));
   TTA_REQUIRE(dz && y && mean && rstd && gamma && beta && sums && dy_hi && (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_apply_c4: null pointer");
   TTA_REQUIRE(Creal >= 1 && Creal <= 4 && N > 0 && V > 0, "tta_norm_bwd_apply_c4: bad shape C=%d", Creal);
@@ -864,6 +873,7 @@ int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_ns, const float* y, l
 int tta_split_f32(const float* g0, long long g0_ns, const float* g1, long long g1_ns, int N, int C8,
                   long long V, uint16_t* hi, uint16_t* lo, long long o_ns, int out_dtype,
                   cudaStream_t stream) {
+  TTA_RECORDABLE(tta_split_f32(g0, g0_ns, g1, g1_ns, N, C8, V, hi, lo, o_ns, out_dtype, s_));
   TTA_REQUIRE(g0 && hi && (lo || out_dtype == TTA_F16_HI), "tta_split_f32: null pointer");
   const dim3 grid(pick_xblocks(N, C8, V), C8, N);
   if (out_dtype == TTA_F16)

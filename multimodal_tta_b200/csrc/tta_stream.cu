@@ -336,6 +336,7 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
 int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                          const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
                          uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_gather_pack_norm(vol, n_vol, C, Ds, Hs, Ws, win, chan_scale, affine, NB, D, H, W, hi, lo, o_ns, C8, wsplit, s_));
   TTA_REQUIRE(vol && win && hi && lo, "tta_gather_pack: null pointer");
   TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
@@ -355,6 +356,7 @@ int tta_head_entropy(const float* y, long long y_ns, int N, int R, long long V, 
                      float inv_count, float grad_scale, int dz_dtype, const float* sample_w, float* logits,
                      uint16_t* dz_hi, uint16_t* dz_lo, long long dz_ns, float* partial, float* loss,
                      cudaStream_t stream) {
+  TTA_RECORDABLE(tta_head_entropy(y, y_ns, N, R, V, mode, inv_count, grad_scale, dz_dtype, sample_w, logits, dz_hi, dz_lo, dz_ns, partial, loss, s_));
   TTA_REQUIRE(y && partial && loss, "tta_head_entropy: null pointer");
   TTA_REQUIRE(R >= 1 && R <= 8, "tta_head_entropy: R=%d unsupported (1..8 region channels)", R);
   TTA_REQUIRE(mode == 0 || mode == 1, "tta_head_entropy: mode %d", mode);
@@ -373,6 +375,7 @@ int tta_head_entropy(const float* y, long long y_ns, int N, int R, long long V, 
 
 int tta_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float b1,
                   float b2, float eps, float gscale, int* step_dev, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_adam_step(p, g, m, v, n, lr, b1, b2, eps, gscale, step_dev, s_));
   TTA_REQUIRE(p && g && m && v && step_dev, "tta_adam_step: null pointer");
   TTA_REQUIRE(n >= 0, "tta_adam_step: n=%d", n);
   if (n == 0) return TTA_OK;
@@ -384,6 +387,7 @@ int tta_sw_blend(const float* logits, int NB, int R, int D, int H, int W, const 
                  const float* sample_w, const float* gd, const float* gh, const float* gw,
                  float wmin, float* acc, float* wsum, int n_vol, int Ds, int Hs, int Ws,
                  cudaStream_t stream) {
+  TTA_RECORDABLE(tta_sw_blend(logits, NB, R, D, H, W, win, sample_w, gd, gh, gw, wmin, acc, wsum, n_vol, Ds, Hs, Ws, s_));
   TTA_REQUIRE(logits && win && gd && gh && gw && acc && wsum, "tta_sw_blend: null pointer");
   TTA_REQUIRE(R >= 1 && R <= 8, "tta_sw_blend: R=%d unsupported", R);
   const long long Vs = (long long)Ds * Hs * Ws;
@@ -394,6 +398,7 @@ int tta_sw_blend(const float* logits, int NB, int R, int D, int H, int W, const 
 
 int tta_sw_normalise(const float* acc, const float* wsum, int n_vol, int R, long long Vs, float* out,
                      cudaStream_t stream) {
+  TTA_RECORDABLE(tta_sw_normalise(acc, wsum, n_vol, R, Vs, out, s_));
   TTA_REQUIRE(acc && wsum && out, "tta_sw_normalise: null pointer");
   tta_launch(sw_normalise_kernel, dim3(xblocks(Vs, n_vol), n_vol), kThreads, 0, stream, tta_pdl_family(4), acc, wsum, R, Vs, out);
   return tta_check_launch("tta_sw_normalise");
@@ -401,6 +406,7 @@ int tta_sw_normalise(const float* acc, const float* wsum, int n_vol, int R, long
 
 int tta_dice_counts(const float* logits, const float* label, int BR, long long V, float thr,
                     unsigned long long* counts, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_dice_counts(logits, label, BR, V, thr, counts, s_));
   TTA_REQUIRE(logits && label && counts, "tta_dice_counts: null pointer");
   tta_launch(dice_counts_kernel, dim3(xblocks(V, BR), BR), kThreads, 0, stream, tta_pdl_family(4), logits, label, V, thr, counts);
   return tta_check_launch("tta_dice_counts");

@@ -290,6 +290,35 @@ class Plan:
     chan_scale: Optional[torch.Tensor] = None
     x_static: Optional[torch.Tensor] = None
     stats_ops: list = field(default_factory=list)
+    c_plans: dict = field(default_factory=dict)       # model.training -> CPlan (the launch list recorded in C)
+
+
+class CPlan:
+    """Handle of a ``tta_plan`` (include/tta_b200.h): the launch list of one shape, recorded once by running the
+    Python closures while the C library is in recording mode; a step is then ONE C call (``tta_step``)."""
+    SEC_FWD, SEC_HEAD_TRAIN, SEC_HEAD_INFER, SEC_BWD = 0, 1, 2, 3
+
+    def __init__(self, lib, plan: "Plan"):
+        self.lib = lib
+        self.h = ctypes.c_void_p()
+        check(lib.tta_plan_create(ctypes.byref(self.h)), "plan_create")
+        for sec, ops in ((self.SEC_FWD, plan.fwd), (self.SEC_HEAD_TRAIN, [plan.head_train]),
+                         (self.SEC_HEAD_INFER, [plan.head_infer]), (self.SEC_BWD, plan.bwd)):
+            check(lib.tta_plan_begin(self.h, sec), "plan_begin")
+            try:
+                for op in ops:
+                    op()
+            finally:
+                check(lib.tta_plan_end(), "plan_end")
+        self.launches = [lib.tta_plan_num_launches(self.h, s_) for s_ in range(4)]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.tta_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 class TTAEngine:
@@ -1233,20 +1262,36 @@ class TTAEngine:
             plan = self.get_plan(*[int(s) for s in (x.shape[0], *x.shape[2:])])
             self._load_running_stats(plan)
             self._pack_input(plan, x)
-            for op in plan.fwd:
-                op()
-            plan.head_infer()
+            if self.model.c_plan:
+                cp = self.c_plan(plan)
+                check(self.lib.tta_plan_run(cp.h, CPlan.SEC_FWD, _stream()), "plan_run(forward)")
+                check(self.lib.tta_plan_run(cp.h, CPlan.SEC_HEAD_INFER, _stream()), "plan_run(head)")
+            else:
+                for op in plan.fwd:
+                    op()
+                plan.head_infer()
             self._update_running_stats(plan)
             return plan.logits.clone()
+
+    def c_plan(self, plan: Plan) -> CPlan:
+        """The plan's launch list as a C object; the closures branch on train / eval mode (BatchNorm running
+        statistics), so one recording per mode."""
+        key = bool(self.model.training)
+        if key not in plan.c_plans:
+            plan.c_plans[key] = CPlan(self.lib, plan)
+        return plan.c_plans[key]
 
     def run_step(self, plan: Plan, adam: bool = True, gscale: float = 1.0):
         """forward + fused head + backward (+ Adam) on whatever is in plan.x."""
         self.last_inv_scale = 1.0 / plan.loss_scale
-        for op in plan.fwd:
-            op()
-        plan.head_train()
-        for op in plan.bwd:
-            op()
+        if self.model.c_plan:
+            check(self.lib.tta_step(self.c_plan(plan).h, _stream()), "tta_step")
+        else:
+            for op in plan.fwd:
+                op()
+            plan.head_train()
+            for op in plan.bwd:
+                op()
         if adam:
             self.adam_step(gscale)
 

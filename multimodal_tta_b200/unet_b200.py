@@ -175,6 +175,9 @@ class B200Model(nn.Module):
     def _backend_options(self, get) -> None:
         """Backend options (not in the reference): conv kernel family, whole-step CUDA graph, A/B switches."""
         self.conv_backend = str(get("conv_backend", "auto"))
+        # the launch list of a shape is recorded into a C object (tta_plan) and a step is one C call (tta_step);
+        # false: the Python closures are called one by one (debugging)
+        self.c_plan = bool(get("c_plan", True))
         self.use_cuda_graph = bool(get("cuda_graph", True))
         # deterministic=True disables split-K (float atomics) in the deep, SM-starved conv layers
         self.deterministic = bool(get("deterministic", False))

@@ -48,3 +48,27 @@ def test_bad_arguments_are_reported_not_crashed(lib):
     assert rc == 1 and b"null pointer" in lib.tta_last_error()
     rc = lib.tta_head_entropy(0, 0, 1, 9, 8, 1, 1.0, 1.0, 1, 0, 0, 0, 0, 0, 0, 0, 0)
     assert rc == 1
+
+
+def test_plan_recorder_lifecycle_without_gpu(lib):
+    """tta_plan (plan_create / tta_step): while a section is being recorded the launching entry points
+    store themselves instead of touching the device -- which is why this runs on a CPU-only host."""
+    import ctypes
+    h = ctypes.c_void_p()
+    assert lib.tta_plan_create(ctypes.byref(h)) == 0 and h.value
+    assert lib.tta_plan_num_launches(h, 0) == 0 and lib.tta_plan_num_launches(h, 99) == -1
+    assert lib.tta_plan_end() == 1 and b"no recording" in lib.tta_last_error()
+    assert lib.tta_plan_begin(h, 3) == 0
+    assert lib.tta_plan_begin(h, 0) == 1 and b"already active" in lib.tta_last_error()
+    # recorded, not validated or launched: argument checks happen at replay, like the launch itself
+    assert lib.tta_adam_step(0, 0, 0, 0, 10, 1e-3, 0.9, 0.999, 1e-8, 1.0, 0, 0) == 0
+    assert lib.tta_norm_stats(0, 0, 1, 1, 8, 0, 1e-5, 0, 0, 0, 1, 0) == 0
+    assert lib.tta_plan_end() == 0
+    assert lib.tta_plan_num_launches(h, 3) == 2 and lib.tta_plan_num_launches(h, 0) == 0
+    # replaying surfaces the recorded call's own argument error (nothing reaches the device)
+    assert lib.tta_plan_run(h, 3, 0) == 1 and b"null pointer" in lib.tta_last_error()
+    assert lib.tta_plan_begin(h, 3) == 0 and lib.tta_plan_end() == 0        # re-recording drops the old content
+    assert lib.tta_plan_num_launches(h, 3) == 0 and lib.tta_plan_run(h, 3, 0) == 0 and lib.tta_step(h, 0) == 0
+    assert lib.tta_plan_run(h, 8, 0) == 1
+    assert lib.tta_workspace_bytes(2, 4, 64 ** 3) == 4 * lib.tta_norm_workspace_floats(2, 4, 64 ** 3)
+    assert lib.tta_plan_destroy(h) == 0
