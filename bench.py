@@ -330,8 +330,9 @@ def run_product(args):
     loss_host = torch.zeros(max(K, 4)).pin_memory()
     counts_host = torch.zeros((max(K, 4), BATCH, 3, 3), dtype=torch.int64).pin_memory()
 
-    def e2e_loop(n, non_blocking):
-        for j, logits in enumerate(tent.adapt_stream([xs_host[i % NROT] for i in range(n)])):
+    def e2e_loop(n, non_blocking, hosts=None):
+        hosts = xs_host if hosts is None else hosts
+        for j, logits in enumerate(tent.adapt_stream([hosts[i % NROT] for i in range(n)])):
             loss_host[j:j + 1].copy_(tent.last_loss, non_blocking=non_blocking)
             counts_host[j].copy_(device_dice_counts(logits, labels[j % NROT], 0.5), non_blocking=non_blocking)
     e2e_loop(4, False)
@@ -350,6 +351,21 @@ def run_product(args):
     e2e_value = world * BATCH * K / (float(t.item()) / 1e3)
     h2d = xs_host[0].numel() * 4
     d2h = 4 + counts_host[0].numel() * 8
+
+    # ---- the same end-to-end loop with the host batches staged as fp16 (TentB200 accepts fp16 batches: the gather
+    # kernel reads them directly): half the host -> device bytes.  Reported next to the fp32 number, not instead of
+    # it -- fp32 is the reference's batch dtype; fp16 staging rounds the input to 11 bits.
+    xs_host16 = [x.half().pin_memory() for x in xs_host]
+    e2e_loop(4, False, xs_host16)
+    barrier()
+    e0.record()
+    e2e_loop(K, True, xs_host16)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e16_value = world * BATCH * K / (float(t.item()) / 1e3)
 
     # ---- sustained: the same device-resident loop for >= args.sustain_s seconds (the 20-step headline region
     # lasts ~50 ms: a burst number), clocks and power sampled over exactly that region
@@ -410,6 +426,9 @@ def run_product(args):
                     "note": "pinned host batch -> H2D (prefetched on a copy stream) -> TentB200.adapt_stream -> "
                             "tta_dice_counts on the pre-update logits -> async D2H of every step's loss and "
                             "[B,R,3] Dice counts; all copies inside the timed region", "numa": numa},
+            "e2e_fp16_staging": {"value": e2e16_value, "unit": UNIT, "h2d_bytes_per_step": h2d // 2,
+                                 "d2h_bytes_per_step": d2h,
+                                 "note": "same loop, host batches staged as fp16 (input rounded to 11 bits)"},
             "sustained": sustained,
             "gpu_launches": launches,
             "clocks": clocks,

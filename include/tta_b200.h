@@ -54,6 +54,10 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
 int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                          const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
                          uint16_t* lo, long long o_n_stride, int C8, int wsplit, tta_stream_t stream);
+/* same, the volume staged as IEEE fp16 (half the host -> device bytes of an fp32 batch) */
+int tta_gather_pack_norm_f16(const uint16_t* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                             const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
+                             uint16_t* lo, long long o_n_stride, int C8, int wsplit, tta_stream_t stream);
 
 /* ---- convolution (forward and input gradient): replaces nn.Conv3d / nn.ConvTranspose3d inside
  * monai.networks.blocks.Convolution reached from src/models/unet.py:56-66, and autograd's

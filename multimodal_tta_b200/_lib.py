@@ -68,6 +68,7 @@ _SIGNATURES = {
     "tta_split_f32": (I, [P, L, P, L, I, I, L, P, P, L, I, P]),
     "tta_gather_pack": (I, [P, I, I, I, I, I, P, P, I, I, I, I, P, P, L, I, I, P]),
     "tta_gather_pack_norm": (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, P, P, L, I, I, P]),
+    "tta_gather_pack_norm_f16": (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, P, P, L, I, I, P]),
     "tta_head_entropy_blocks": (I, [I, L]),
     "tta_head_entropy": (I, [P, L, I, I, L, I, F, F, I, P, P, P, P, L, P, P, P]),
     "tta_head_fused_supported": (I, [I, I, I, I]),

@@ -27,8 +27,12 @@ __device__ __forceinline__ void load_affine(const float* affine, int vi, int C, 
 // ---------------------------------------------------------------- gather / pack
 // win[b*4 + {0,1,2,3}] = {volume index, d0, h0, w0} of window b (origins may be negative or
 // run past the volume: those voxels read 0 = MONAI's constant pad).
+__device__ __forceinline__ float src_val(const float* p) { return *p; }
+__device__ __forceinline__ float src_val(const __half* p) { return __half2float(*p); }
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
+gather_pack_kernel(const T* vol, int C, int Ds, int Hs, int Ws,
                    const int* win, const float* chan_scale, const float* affine, int D, int H,
                    int W, int C8, uint16_t* hi, uint16_t* lo,
                    long long o_ns, int wsplit) {
@@ -38,7 +42,7 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
   const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
   const long long V = (long long)D * H * W;
   const long long Vs = (long long)Ds * Hs * Ws;
-  const float* src = vol + (long long)vi * C * Vs;
+  const T* src = vol + (long long)vi * C * Vs;
   float sc[8], alo[8], ahi[8], amu[8], ainv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -58,7 +62,7 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = chunk * 8 + i;
-      x[i] = (inside && c < C) ? (fminf(fmaxf(src[(long long)c * Vs + so], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i] : 0.f;
+      x[i] = (inside && c < C) ? (fminf(fmaxf(src_val(src + (long long)c * Vs + so), alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i] : 0.f;
     }
     // wsplit: the first conv is a stride-2 tcgen05 conv -> w-parity-split rows (tta_common.cuh)
     const long long vo = wsplit ? v - w + (w & 1) * (W >> 1) + (w >> 1) : v;
@@ -69,8 +73,9 @@ gather_pack_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
 // Same, four consecutive-w voxels per thread (W % 4 == 0): one 128-bit load per real channel instead of
 // four scalar ones, 32-bit index arithmetic with two divisions per FOUR voxels.  Measured in-stream on
 // the 2 x 4 x 128^3 input: 87 us for the per-voxel kernel above (200 MB moved).
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
+gather_pack4_kernel(const T* vol, int C, int Ds, int Hs, int Ws,
                     const int* win, const float* chan_scale, const float* affine, int D, int H,
                     int W, int C8, uint16_t* hi, uint16_t* lo,
                     long long o_ns, int wsplit) {
@@ -80,7 +85,7 @@ gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
   const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
   const long long V = (long long)D * H * W;
   const long long Vs = (long long)Ds * Hs * Ws;
-  const float* src = vol + (long long)vi * C * Vs;
+  const T* src = vol + (long long)vi * C * Vs;
   float sc[8], alo[8], ahi[8], amu[8], ainv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -99,22 +104,30 @@ gather_pack4_kernel(const float* vol, int C, int Ds, int Hs, int Ws,
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[k][i] = 0.f;
     if (sd >= 0 && sd < Ds && sh >= 0 && sh < Hs && sw > -4 && sw < Ws) {
-      const float* rowp = src + ((long long)sd * Hs + sh) * Ws + sw;
+      const T* rowp = src + ((long long)sd * Hs + sh) * Ws + sw;
       const bool whole = sw >= 0 && sw + 3 < Ws;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = chunk * 8 + i;
         if (c < C) {
-          const float* p = rowp + (long long)c * Vs;
-          if (whole && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0ull) {
-            const float4 v = *reinterpret_cast<const float4*>(p);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
+          const T* p = rowp + (long long)c * Vs;
+          if (whole && (reinterpret_cast<unsigned long long>(p) & (4ull * sizeof(T) - 1ull)) == 0ull) {
+            float vv[4];
+            if (sizeof(T) == 4) {
+              const float4 v = *reinterpret_cast<const float4*>(p);
+              vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
+            } else {   // fp16 staging: four values = one 64-bit load
+              const uint2 v = *reinterpret_cast<const uint2*>(p);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+              const float2 bq = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+              vv[0] = a.x; vv[1] = a.y; vv[2] = bq.x; vv[3] = bq.y;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) x[k][i] = (fminf(fmaxf(vv[k], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (sw + k >= 0 && sw + k < Ws) x[k][i] = (fminf(fmaxf(p[k], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
+              if (sw + k >= 0 && sw + k < Ws) x[k][i] = (fminf(fmaxf(src_val(p + k), alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
           }
         }
       }
@@ -332,22 +345,43 @@ int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, 
                               wsplit, stream);
 }
 
-// same with the intensity policy applied on the fly: affine [n_vol][C][4] from tta_intensity_stats (or null)
-int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
-                         const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
-                         uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
-  TTA_RECORDABLE(tta_gather_pack_norm(vol, n_vol, C, Ds, Hs, Ws, win, chan_scale, affine, NB, D, H, W, hi, lo, o_ns, C8, wsplit, s_));
+}  // extern "C"
+
+template <typename T>
+static int gather_impl(const T* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win, const float* chan_scale,
+                       const float* affine, int NB, int D, int H, int W, uint16_t* hi, uint16_t* lo, long long o_ns, int C8,
+                       int wsplit, cudaStream_t stream) {
   TTA_REQUIRE(vol && win && hi && lo, "tta_gather_pack: null pointer");
   TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
   const long long V = (long long)D * H * W;
   if (W % 4 == 0 && V / 4 < 0x7fffffffLL)
-    tta_launch(gather_pack4_kernel, dim3(xblocks(V / 4, (long long)NB * C8), C8, NB), kThreads, 0, stream,
+    tta_launch(gather_pack4_kernel<T>, dim3(xblocks(V / 4, (long long)NB * C8), C8, NB), kThreads, 0, stream,
                tta_pdl_family(4), vol, C, Ds, Hs, Ws, win, chan_scale, affine, D, H, W, C8, hi, lo, o_ns, wsplit);
   else
-    tta_launch(gather_pack_kernel, dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream, tta_pdl_family(4),
+    tta_launch(gather_pack_kernel<T>, dim3(xblocks(V, (long long)NB * C8), C8, NB), kThreads, 0, stream, tta_pdl_family(4),
                vol, C, Ds, Hs, Ws, win, chan_scale, affine, D, H, W, C8, hi, lo, o_ns, wsplit);
   return tta_check_launch("tta_gather_pack");
+}
+
+extern "C" {
+
+// same with the intensity policy applied on the fly: affine [n_vol][C][4] from tta_intensity_stats (or null)
+int tta_gather_pack_norm(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                         const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
+                         uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_gather_pack_norm(vol, n_vol, C, Ds, Hs, Ws, win, chan_scale, affine, NB, D, H, W, hi, lo, o_ns, C8, wsplit, s_));
+  return gather_impl<float>(vol, n_vol, C, Ds, Hs, Ws, win, chan_scale, affine, NB, D, H, W, hi, lo, o_ns, C8, wsplit, stream);
+}
+
+// FP16 staging: the volume arrives as IEEE half (half the host -> device bytes of the fp32 batch); everything
+// downstream is unchanged (the lo operand plane is exactly zero unless an affine rescales the values)
+int tta_gather_pack_norm_f16(const uint16_t* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
+                             const float* chan_scale, const float* affine, int NB, int D, int H, int W, uint16_t* hi,
+                             uint16_t* lo, long long o_ns, int C8, int wsplit, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_gather_pack_norm_f16(vol, n_vol, C, Ds, Hs, Ws, win, chan_scale, affine, NB, D, H, W, hi, lo, o_ns, C8, wsplit, s_));
+  return gather_impl<__half>(reinterpret_cast<const __half*>(vol), n_vol, C, Ds, Hs, Ws, win, chan_scale, affine, NB, D,
+                             H, W, hi, lo, o_ns, C8, wsplit, stream);
 }
 
 int tta_head_entropy_blocks(int N, long long V) { return xblocks(V, N); }

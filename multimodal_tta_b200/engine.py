@@ -1227,8 +1227,9 @@ class TTAEngine:
             win = plan.win
             vol_dims, n_vol = (D, H, W), N
         a = plan.x
+        gather = self.lib.tta_gather_pack_norm_f16 if x.dtype == torch.float16 else self.lib.tta_gather_pack_norm
         # affine [n_vol][C][4] (IntensityPolicy.stats): clip + z-score applied while gathering
-        check(self.lib.tta_gather_pack_norm(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
+        check(gather(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
                                             chan_scale.data_ptr() if chan_scale is not None else 0,
                                             affine.data_ptr() if affine is not None else 0, N, D, H, W,
                                             a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8,
@@ -1238,10 +1239,10 @@ class TTAEngine:
         if x2 is not None:
             # a second consumer wants the other layout (multimodal model: the last decoder stage concatenates the
             # input in plain layout while the encoder stems read it w-parity-split)
-            check(self.lib.tta_gather_pack_norm(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
-                                                chan_scale.data_ptr() if chan_scale is not None else 0,
-                                                affine.data_ptr() if affine is not None else 0, N, D, H, W,
-                                                x2.hi, x2.lo, x2.ns, x2.C8, 0, _stream()),
+            check(gather(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
+                         chan_scale.data_ptr() if chan_scale is not None else 0,
+                         affine.data_ptr() if affine is not None else 0, N, D, H, W,
+                         x2.hi, x2.lo, x2.ns, x2.C8, 0, _stream()),
                   "gather_pack")
 
     def _check_input(self, x: torch.Tensor):
@@ -1251,8 +1252,12 @@ class TTAEngine:
             raise ValueError(f"expected {self.model.in_channels} input channels, got {x.shape[1]}")
         if not x.is_cuda:
             raise RuntimeError("multimodal_tta_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.contiguous().float()
+        # fp32 (the reference's batch dtype) or fp16 staging (half the host -> device bytes; the gather reads it
+        # directly); anything else is converted to fp32 on the device
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        if not x.is_contiguous():
+            x = x.contiguous()
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

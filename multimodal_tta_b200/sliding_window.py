@@ -172,7 +172,7 @@ class SlidingWindowTTA:
         padded, pad_lo = sched["padded"], sched["pad_lo"]
         # the captured step bakes the volume pointer in: keep ONE resident volume buffer per shape and copy
         # the caller's tensor into it (143 MB for a BraTS volume, ~50 us) instead of re-capturing per volume
-        vkey = ("vol", dev, tuple(vol.shape))
+        vkey = ("vol", dev, tuple(vol.shape), vol.dtype)
         if vkey not in self._bufs:
             self._bufs[vkey] = torch.empty_like(vol)
         if vol.data_ptr() != self._bufs[vkey].data_ptr():

@@ -166,7 +166,7 @@ class TentB200:
         if persistent_input:
             self._run(eng, plan, lambda: eng._pack_input(plan, x), input_key=("staging", x.data_ptr()))
             return plan.logits_out
-        if plan.x_static is None or plan.x_static.shape != x.shape:
+        if plan.x_static is None or plan.x_static.shape != x.shape or plan.x_static.dtype != x.dtype:
             plan.x_static = torch.empty_like(x)
         if x.data_ptr() != plan.x_static.data_ptr():
             plan.x_static.copy_(x, non_blocking=True)
@@ -220,7 +220,9 @@ class TentB200:
             return
         dev = self.model.engine.device or torch.device("cuda", torch.cuda.current_device())
         copy_stream = torch.cuda.Stream(device=dev)
-        staging = [torch.empty(first.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        # fp16 host batches are staged as fp16 (half the PCIe bytes; the gather kernel reads them directly)
+        sdt = torch.float16 if first.dtype == torch.float16 else torch.float32
+        staging = [torch.empty(first.shape, dtype=sdt, device=dev) for _ in range(2)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
 

@@ -199,6 +199,23 @@ def test_adapt_stream_equals_step_by_step(cuda):
     assert list(tb.adapt_stream([])) == []
 
 
+def test_fp16_staged_input(cuda):
+    """Host batches staged as fp16 (half the host -> device bytes): the gather reads them directly; the step equals
+    the oracle's step on the same fp16-rounded input, and adapt_stream keeps the staging buffers in fp16."""
+    oracle, prod = make_pair(dict(BRATS_MODEL_CFG, deterministic=True), seed=14)
+    to, tp = TentOracle(oracle, mode="sigmoid"), TentB200(prod, {"cuda_graph": True})
+    hosts = [brats_volume(2, (32, 48, 32), seed=s).half().pin_memory() for s in (1, 2, 3)]
+    ref = [to.step(h.float())[0] for h in hosts]
+    got = [o.clone().cpu() for o in tp.adapt_stream(hosts)]
+    for a, b in zip(got, ref):
+        assert rel_l2(a, b) < 1e-3 and ((a >= 0) == (b >= 0)).float().mean().item() >= 0.999
+    assert rel_l2(got[0], ref[0]) < 1e-4                       # first step: identical parameters
+    # the same values staged as fp32 give bit-identical logits (fp16 -> fp32 is exact; lo plane is zero either way)
+    _, prod2 = make_pair(dict(BRATS_MODEL_CFG, deterministic=True), seed=14)
+    tp2 = TentB200(prod2, {"cuda_graph": True})
+    assert torch.equal(tp2.step(hosts[0].float().cuda()).cpu(), got[0])
+
+
 def test_rejects_bad_inputs(cuda):
     _, prod = make_pair(BRATS_MODEL_CFG, seed=5)
     tp = TentB200(prod, {})
