@@ -44,7 +44,8 @@ int tta_device_sm(void); /* compute capability major*10+minor of the current dev
  * MONAI sliding_window_inference's window slicing + constant pad (not in tree).
  * vol: fp32 NCDHW [n_vol][C][Ds][Hs][Ws]; win: int32 [NB][4] = (volume, d0, h0, w0), origins may
  * lie outside the volume (zero fill); chan_scale: optional fp32 [NB][C] (missing-modality dropout).
- * Output: fp16 hi/lo planes [NB][C8][D][H][W][8]; wsplit != 0 stores every w-row parity-split
+ * Output: fp16 hi/lo planes [NB][C8][D][H][W][8]; wsplit = 2: the COMPACT layout [NB][D][H][W][4] (<= 4 channels,
+ * C8 = 1, out_n_stride = D*H*W*4) read by tta_conv_tc with flags bit 15; wsplit = 1 stores every w-row parity-split
  * ([H][2][W/2][8]: even-w voxels first), the operand layout of a stride-2 tcgen05 conv (flags bit3). */
 int tta_gather_pack(const float* vol, int n_vol, int C, int Ds, int Hs, int Ws, const int* win,
                     const float* chan_scale, int NB, int D, int H, int W, uint16_t* hi, uint16_t* lo,
@@ -87,6 +88,10 @@ int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int spli
 int tta_conv_tc_t2s(int mode, int K, int stride, int cin, int cout, int split);
 /* 1 when a stride-2 conv reads a one-chunk input (<= 8 channels): taps are packed and issued in pairs. */
 int tta_conv_tc_s2pair(int mode, int K, int stride, int cin);
+/* 1 when a stride-2 conv may read a COMPACT <= 4-channel input ([N][D][H][W][4] 16-bit values per plane, in_n_stride
+ * in elements; tta_conv_tc flags bit 15): weights packed with layout.pack_weights_tc(s2c4=True).  Producers of the
+ * compact layout: tta_gather_pack_norm(_f16) with wsplit = 2, tta_norm_bwd_apply_c4 with dy_c4 = 1. */
+int tta_conv_tc_s2c4(int mode, int K, int stride, int cin);
 int tta_conv_tc_gmax(int mode, int K, int stride);
 int tta_conv_tc_ngroups(int mode, int K, int stride);
 long long tta_conv_tc_packed_bytes(int mode, int K, int stride, int cin, int cout);
@@ -227,7 +232,7 @@ int tta_head_fused_bwd(const float* dlogits, int N, int C, int D, int H, int W, 
 int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_n_stride, const float* y, long long y_n_stride, int N,
                           int Creal, long long V, const float* mean, const float* rstd, const float* gamma,
                           const float* beta, int batch_mode, const float* sums, uint16_t* dy_hi, uint16_t* dy_lo,
-                          long long dy_n_stride, int out_dtype, int dy_wsplit_w, tta_stream_t stream);
+                          long long dy_n_stride, int out_dtype, int dy_wsplit_w, int dy_c4, tta_stream_t stream);
 
 /* ---- fused head: logits + entropy loss + dlogits in one pass.  Replaces the loss + backward
  * entry of src/core/trainers/seg_trainer.py:141-142 with the TENT entropy (mode 0 softmax,

@@ -76,7 +76,7 @@ _SIGNATURES = {
     "tta_head_fused_workspace_floats": (L, [I, I, I, I]),
     "tta_head_fused_fwd": (I, [P, L, I, I, I, I, I, I, P, P, P, P, I, P, P, I, F, F, P, P, P, P, P, P]),
     "tta_head_fused_bwd": (I, [P, I, I, I, I, I, P, P, L, I, P, P, P, P, I, I, P, L, P, P, P, P, P]),
-    "tta_norm_bwd_apply_c4": (I, [P, L, P, L, I, I, L, P, P, P, P, I, P, P, P, L, I, I, P]),
+    "tta_norm_bwd_apply_c4": (I, [P, L, P, L, I, I, L, P, P, P, P, I, P, P, P, L, I, I, I, P]),
     "tta_adam_step": (I, [P, P, P, P, I, F, F, F, F, F, P, P]),
     "tta_sw_blend": (I, [P, I, I, I, I, I, P, P, P, P, P, F, P, P, I, I, I, I, P]),
     "tta_sw_normalise": (I, [P, P, I, I, L, P, P]),
@@ -92,6 +92,7 @@ _SIGNATURES = {
     "tta_conv_tc_stacked": (I, [I, I, I, I, I, I]),
     "tta_conv_tc_t2s": (I, [I, I, I, I, I, I]),
     "tta_conv_tc_s2pair": (I, [I, I, I, I]),
+    "tta_conv_tc_s2c4": (I, [I, I, I, I]),
     "tta_conv_tc_gmax": (I, [I, I, I]),
     "tta_conv_tc_ngroups": (I, [I, I, I]),
     "tta_conv_tc_packed_bytes": (L, [I, I, I, I, I]),

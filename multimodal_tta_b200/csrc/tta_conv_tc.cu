@@ -47,7 +47,7 @@ constexpr int kMaxLoads = 4;
 constexpr int kMaxAcc = 8;
 constexpr int kMaxStages = 8;
 
-enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2, GEOM_S1P, GEOM_S1TP, GEOM_S1K, GEOM_S1TK };
+enum { GEOM_NONE = 0, GEOM_S1, GEOM_K1, GEOM_S1T, GEOM_S2, GEOM_T2, GEOM_S1P, GEOM_S1TP, GEOM_S1K, GEOM_S1TK, GEOM_S2C4 };
 
 struct TcLoad {
   int map, dw, dh, dd, smem_off, bytes, chunk_pitch, pad;  // bytes / pitch are per k-chunk (8 channels)
@@ -354,6 +354,23 @@ __device__ __forceinline__ void issue_group(const TcParams& P, uint32_t leader, 
       const uint32_t ao = (uint32_t)(p * 128);
       mma_pair<SPLIT>(leader, tmem_acc0 + p * acc_cols, ah + ao, al + ao, a_w1, b_w0, b_w1, i2n, in_, first ? 0u : 1u);
     }
+  } else if (GEOM == GEOM_S2C4) {
+    // Stride-2 conv over a COMPACT <= 4-channel input ([N][D][H][W][4] 16-bit values, 8 B per voxel: the network
+    // input, the gradient of the head norm).  Two consecutive-w input voxels are one 16-byte K row, and the rows of
+    // 8 consecutive OUTPUT voxels (input voxels 2w-1, 2w+1, ...) are 16 B apart -- a dense core matrix without any
+    // parity splitting.  k-chunk 0 = taps (kw 0, kw 1), k-chunk 1 = (kw 2, a zero-weight fourth tap) = the same row
+    // 16 B further (LBO = 16 B: overlapping windows of ONE loaded halo row).  A group = kd; its three (kh) boxes
+    // [16 rows][18 voxels] (input rows 2h+kh-1 through an h-parity tensor map) are three K = 16 MMAs: 9 per tile
+    // instead of 15 tap pairs, on a quarter of the operand bytes of the 8-channel chunk layout.
+    const uint32_t a_w1 = 9u | (1u << 14);                 // SBO = 144 B: next output row h
+    const uint32_t lbo = 1u << 16;                         // LBO = 16 B
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const uint32_t ao = (uint32_t)(kh * 144);            // 2304-byte boxes
+      const uint32_t bo = b_w0 + (uint32_t)kh * b_ent;
+      const uint32_t accum = (first && g == 0 && kh == 0) ? 0u : 1u;
+      mma_pair<SPLIT>(leader, tmem_acc0, (a_hi0 + ao) | lbo, (a_lo0 + ao) | lbo, a_w1, bo, b_w1, i2n, in_, accum);
+    }
   } else if (GEOM == GEOM_S2) {
     // parity sub-tiles [ph][pw] at fixed 128-aligned offsets: 16x8, 16x9, 17x8, 17x9 voxels
     constexpr int off16[4] = {0, 4096 / 16, 8704 / 16, 13056 / 16};
@@ -649,7 +666,11 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
           const TcLoad& L = G.ld[my_l];
           const int cw = wi.w0 + L.dw, chh = wi.h0 + L.dh, cd = wi.d0 * P.d_mul + L.dd;
           const uint32_t dst = stage + L.smem_off + my_kc * L.chunk_pitch + my_plane * P.a_plane_bytes;
-          if (GEOM == GEOM_S2) {
+          if (GEOM == GEOM_S2C4) {
+            // map = h parity of the input row; coordinates (element of the W*4 row, h / 2, d, n)
+            // (the box starts at the EVEN voxel 2*w0 - 2: TMA box rows and UMMA operand rows must start on 16 bytes)
+            tma_load_4d(dst, &P.amap[L.map * 2 + my_plane], full, (2 * wi.w0 - 2) * 4, wi.h0 + L.dh, cd, wi.n);
+          } else if (GEOM == GEOM_S2) {
             const CUtensorMap* m = &P.amap[L.map * 2 + my_plane];
             if (P.s2_rows) tma_load_4d(dst, m, full, cw * 8, chh, cd, c4 + my_kc);
             else tma_load_5d(dst, m, full, 0, cw, chh, cd, c4 + my_kc);
@@ -1335,6 +1356,10 @@ int tta_conv_tc_stacked(int mode, int K, int stride, int cin, int cout, int spli
 
 int tta_conv_tc_s2pair(int mode, int K, int stride, int cin) { return s2pair_of(geom_of(mode, K, stride), cin) ? 1 : 0; }
 
+// 1 when a stride-2 conv may read a COMPACT <= 4-channel input ([N][D][H][W][4], flags bit 15): pack its weights
+// with layout.pack_weights_tc(s2c4=True)
+int tta_conv_tc_s2c4(int mode, int K, int stride, int cin) { return geom_of(mode, K, stride) == GEOM_S2 && cin <= 4 ? 1 : 0; }
+
 int tta_conv_tc_t2s(int mode, int K, int stride, int cin, int cout, int split) {
   return t2s_of(geom_of(mode, K, stride), cin, cout, split) ? 1 : 0;
 }
@@ -1483,6 +1508,11 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     return conv_t2s_impl(in_hi, in_lo, in_ns, N, C8in, Di, Hi, Wi, wpacked, bias, out, out_ns, t2s_small_cout, Do, Ho,
                          Wo, accumulate, stats_ws, stats_c8, (flags & 16384) ? 4 : 8, q_ksplit, q_grid, q_nbuf, stream);
   }
+  // flags bit 15: the input planes are COMPACT ([N][D][H][W][4], in_n_stride in 16-bit elements, C8in == 1): stride-2
+  // convs only (the stem, the dgrad of the head convT); weights packed with layout.pack_weights_tc(s2c4=True)
+  const bool c4in = (flags & 32768) != 0;
+  TTA_REQUIRE(!c4in || (geom == GEOM_S2 && C8in == 1), "tta_conv_tc: flags bit 15 (compact input) needs a stride-2 conv over one chunk");
+  if (c4in) geom = GEOM_S2C4;
   const bool stacked = stacked_of(geom, C8in * 8, C8out * 8, in_dtype == TTA_F16_HI ? 0 : 1);
   if (stacked) geom = geom == GEOM_S1 ? GEOM_S1K : GEOM_S1TK;
   const bool pl2 = (geom == GEOM_S1 || geom == GEOM_S1T) && Ho <= 8 && Do >= 2 && !(flags & 32);
@@ -1497,9 +1527,9 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const bool pl2t = geom == GEOM_T2 && Hi <= 8 && Di >= 2 && !(flags & 32);
   const int ppa = (pl2 || pl2t) ? 2 : 1;  // d-planes per accumulator
   const long long Vi = (long long)Di * Hi * Wi;
-  TTA_REQUIRE(in_ns % (Vi * 8) == 0, "tta_conv_tc: n_stride must be a whole number of channel chunks");
-  const int c8_pitch = (int)(in_ns / (Vi * 8));
-  if (geom == GEOM_S2) {
+  TTA_REQUIRE(c4in || in_ns % (Vi * 8) == 0, "tta_conv_tc: n_stride must be a whole number of channel chunks");
+  const int c8_pitch = c4in ? 1 : (int)(in_ns / (Vi * 8));
+  if (geom == GEOM_S2 || geom == GEOM_S2C4) {
     TTA_REQUIRE(Di % 2 == 0 && Hi % 2 == 0 && Wi % 2 == 0 && Do == Di / 2 && Ho == Hi / 2 && Wo == Wi / 2,
                 "tta_conv_tc: stride-2 conv needs even input dims");
   } else if (geom == GEOM_T2) {
@@ -1520,7 +1550,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.c8in = C8in;
   P.single_chunk = C8in == 1;
   P.out_mul = geom == GEOM_T2 ? 2 : 1;
-  P.d_mul = geom == GEOM_S2 ? 2 : 1;
+  P.d_mul = (geom == GEOM_S2 || geom == GEOM_S2C4) ? 2 : 1;
   P.Do = Do; P.Ho = Ho; P.Wo = Wo; P.C8out = C8out; P.accumulate = accumulate;
   P.out_ns = out_ns; P.wpacked = (const uint8_t*)wpacked; P.bias = bias; P.out = out;
   const int fmt = in_dtype == TTA_BF16 ? 1 : 0;
@@ -1534,10 +1564,10 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   int hx, wx;      // halo extents of the single-box geometries
   if (geom == GEOM_K1) { hx = 16; wx = 8; } else if (pl2t) { hx = 8; wx = 9; } else if (geom == GEOM_T2) { hx = 17; wx = 9; } else if (pl2) { hx = 8; wx = 10; } else if (g9w) { hx = 16; wx = 10; } else { hx = 18; wx = 10; }
   // small-plane tiles regroup the SAME packed weights: 9 (kd, kh) groups of 3 kw entries instead of 3 kd groups of 9
-  const int gmax = g9 ? 3 : tta_conv_tc_gmax(mode, K, stride);
+  const int gmax = (g9 || c4in) ? 3 : tta_conv_tc_gmax(mode, K, stride);
   P.ngroups = g9 ? 9 : tta_conv_tc_ngroups(mode, K, stride);
   P.pl2 = (pl2 || pl2t) ? 1 : 0;
-  P.s2pair = s2pair_of(geom, C8in * 8) ? 1 : 0;
+  P.s2pair = s2pair_of(geom, C8in * 8) ? 1 : 0;   // (GEOM_S2 only: the compact geometry has its own pairing)
   P.t2_jh16 = pl2t ? 144 : 9;
   const int acc_cols = split ? 2 * P.ntile : P.ntile;
   P.b_entry_bytes = 2 * acc_cols * 16;  // [kchunk 2][hi NT (| lo NT) rows][16 B]
@@ -1592,6 +1622,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   auto a_plane_of = [&](int td_) {
     if (pl2t) return 2 * 4608;  // [kchunk 2][jh 2][2 planes][8 rows][9 w][16 B]
     if (stacked) return 2 * round128(hx * wx * pps_of(td_) * 16);  // a stage is pps halo planes
+    if (geom == GEOM_S2C4) return round128(3 * 2304);   // three (kh) boxes [16 rows][144 B]; no second k-chunk copy
     return geom == GEOM_S2 ? 18176 : 2 * round128(hx * wx * td_ * ppa * 16);
   };
   const int a_planes = split ? 2 : 1;
@@ -1766,7 +1797,20 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   };
   bool ok = true;
   P.s2_rows = (geom == GEOM_S2 && (flags & 8)) ? 1 : 0;
-  if (geom == GEOM_S2) {
+  if (geom == GEOM_S2C4) {
+    // one 4-D map per input-row parity and operand plane: rows h = 2*i + par of the compact tensor, a row =
+    // W*4 contiguous 16-bit values; box = 18 voxels x 16 rows (OOB -> zero = the conv's padding)
+    for (int par = 0; par < 2; ++par)
+      for (int pl = 0; pl < (split ? 2 : 1); ++pl) {
+        const uint16_t* base = (pl ? in_lo : in_hi) + (long long)par * Wi * 4;
+        cuuint64_t gdim[4] = {(cuuint64_t)Wi * 4, (cuuint64_t)((Hi - par + 1) / 2), (cuuint64_t)Di, (cuuint64_t)N};
+        cuuint64_t gstr[3] = {(cuuint64_t)16 * Wi, (cuuint64_t)8 * Wi * Hi, (cuuint64_t)2 * in_ns};
+        cuuint32_t box[4] = {72, 16, 1, 1};
+        ok = ok && enc(&P.amap[par * 2 + pl], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, (void*)base, gdim, gstr, box, es5,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+  } else if (geom == GEOM_S2) {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
         const int m = ph * 2 + pw;
@@ -1818,6 +1862,16 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     G.ld[0] = {0, 0, 0, 0, 0, 16 * 8 * td * 16, P.lbo16[0] * 16, 0};
     G.tx_bytes = 2 * G.ld[0].bytes;
     for (int p = 0; p < td; ++p) P.acc_pd[p] = (signed char)p;
+  } else if (geom == GEOM_S2C4) {
+    for (int kd = 0; kd < 3; ++kd) {
+      TcGroup& G = P.grp[kd];
+      G.nloads = 3; G.nmma = 3;
+      for (int kh = 0; kh < 3; ++kh)   // input row 2h + kh - 1: kh = 1 -> parity 0, row h; kh = 0 / 2 -> parity 1, row h - 1 / h
+        G.ld[kh] = {kh == 1 ? 0 : 1, 0, kh == 0 ? -1 : 0, kd - 1, kh * 2304, 2304, 0, 0};
+      G.tx_bytes = 2 * 3 * 2304;
+    }
+    P.lbo16[0] = 1;
+    P.acc_pd[0] = 0;
   } else if (geom == GEOM_S2) {
     int off[4], o = 0;
     const int hxs[2] = {16, 17}, wxs[2] = {8, 9};
@@ -1925,6 +1979,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
     case GEOM_S1P: TTA_TC_LAUNCH_TD(GEOM_S1P); break;
     case GEOM_S1TP: TTA_TC_LAUNCH_TD(GEOM_S1TP); break;
     case GEOM_S2: TTA_TC_LAUNCH(GEOM_S2, 1); break;
+    case GEOM_S2C4: TTA_TC_LAUNCH(GEOM_S2C4, 1); break;
     default: TTA_TC_LAUNCH(GEOM_T2, 1); break;
   }
 #undef TTA_TC_LAUNCH_TD

@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 norm_bwd_apply_c4_kernel(const uint16_t* dz, long long dz_ns, const float* y, long long y_ns, long long V,
                          const float* mean, const float* rstd, const float* gamma, const float* beta,
                          const float* sums, float inv_m, int Creal, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
-                         int dy_wsplit_w) {
+                         int dy_wsplit_w, int dy_c4) {
   pdl_trigger();
   pdl_wait();
   const int n = blockIdx.y;
@@ -570,6 +570,20 @@ norm_bwd_apply_c4_kernel(const uint16_t* dz, long long dz_ns, const float* y, lo
       const float xh = (xv[c] - mu[c]) * rs[c];
       x[c] = fmaf(k0[c], dzv[c], -k1[c]) - xh * k2[c];
       x[4 + c] = 0.f;
+    }
+    if (dy_c4) {   // compact gradient planes [N][V][4] for a GEOM_S2C4 dgrad (dy_ns in 16-bit elements)
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        h[c] = f32_to_u16<ODT>(x[c]);
+        l[c] = ODT == TTA_F16_HI ? (uint16_t)0 : f32_to_u16<ODT>(x[c] - u16_to_f32<ODT>(h[c]));
+      }
+      *reinterpret_cast<uint2*>(dy_hi + ob + v * 4) =
+          make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+      if (ODT != TTA_F16_HI)
+        *reinterpret_cast<uint2*>(dy_lo + ob + v * 4) =
+            make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+      continue;
     }
     store_split8<ODT>(dy_hi, dy_lo, ob + (dy_wsplit_w > 0 ? wsplit_index(v, dy_wsplit_w) : v) * 8, x);
   }
@@ -849,8 +863,9 @@ int tta_norm_bwd_small(const float* g0, long long g0_ns, const float* g1, long l
 int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_ns, const float* y, long long y_ns, int N, int Creal,
                           long long V, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           int batch_mode, const float* sums, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns,
-                          int out_dtype, int dy_wsplit_w, cudaStream_t stream) {
-  TTA_RECORDABLE(tta_norm_bwd_apply_c4(dz, dz_ns, y, y_ns, N, Creal, V, mean, rstd, gamma, beta, batch_mode, sums, dy_hi, dy_lo, dy_ns, out_dtype, dy_wsplit_w, s_));
+                          int out_dtype, int dy_wsplit_w, int dy_c4, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_norm_bwd_apply_c4(dz, dz_ns, y, y_ns, N, Creal, V, mean, rstd, gamma, beta, batch_mode, sums, dy_hi, dy_lo, dy_ns, out_dtype, dy_wsplit_w, dy_c4, s_));
+  TTA_REQUIRE(!(dy_c4 && dy_wsplit_w), "tta_norm_bwd_apply_c4: compact dy is never w-parity-split");
   TTA_REQUIRE(dz && y && mean && rstd && gamma && beta && sums && dy_hi && (dy_lo || out_dtype == TTA_F16_HI),
               "tta_norm_bwd_apply_c4: null pointer");
   TTA_REQUIRE(Creal >= 1 && Creal <= 4 && N > 0 && V > 0, "tta_norm_bwd_apply_c4: bad shape C=%d", Creal);
@@ -864,7 +879,7 @@ int tta_norm_bwd_apply_c4(const uint16_t* dz, long long dz_ns, const float* y, l
   const dim3 grid((unsigned)xb, N);
 #define LAUNCH(DT)                                                                                                   \
   tta_launch(norm_bwd_apply_c4_kernel<DT>, grid, kThreads, 0, stream, tta_pdl_family(2), dz, dz_ns, y, y_ns, V, mean, \
-             rstd, gamma, beta, sums, inv_m, Creal, dy_hi, dy_lo, dy_ns, dy_wsplit_w)
+             rstd, gamma, beta, sums, inv_m, Creal, dy_hi, dy_lo, dy_ns, dy_wsplit_w, dy_c4)
   if (out_dtype == TTA_F16) LAUNCH(TTA_F16); else if (out_dtype == TTA_F16_HI) LAUNCH(TTA_F16_HI); else LAUNCH(TTA_BF16);
 #undef LAUNCH
   return tta_check_launch("tta_norm_bwd_apply_c4");

@@ -27,6 +27,18 @@ __device__ __forceinline__ void load_affine(const float* affine, int vi, int C, 
 // ---------------------------------------------------------------- gather / pack
 // win[b*4 + {0,1,2,3}] = {volume index, d0, h0, w0} of window b (origins may be negative or
 // run past the volume: those voxels read 0 = MONAI's constant pad).
+// first four of eight values -> (hi, lo) fp16, 8 bytes per plane (compact <= 4-channel layout)
+__device__ __forceinline__ void store_split4_f16(uint16_t* hi, uint16_t* lo, long long off, const float (&x)[8]) {
+  uint16_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = f32_to_u16<TTA_F16>(x[i]);
+    l[i] = f32_to_u16<TTA_F16>(x[i] - u16_to_f32<TTA_F16>(h[i]));
+  }
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  *reinterpret_cast<uint2*>(lo + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
 __device__ __forceinline__ float src_val(const float* p) { return *p; }
 __device__ __forceinline__ float src_val(const __half* p) { return __half2float(*p); }
 
@@ -63,6 +75,10 @@ gather_pack_kernel(const T* vol, int C, int Ds, int Hs, int Ws,
     for (int i = 0; i < 8; ++i) {
       const int c = chunk * 8 + i;
       x[i] = (inside && c < C) ? (fminf(fmaxf(src_val(src + (long long)c * Vs + so), alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i] : 0.f;
+    }
+    if (wsplit == 2) {   // compact layout [N][D][H][W][4] (<= 4 channels): 8 B per voxel and plane
+      store_split4_f16(hi, lo, (long long)b * o_ns + v * 4, x);
+      continue;
     }
     // wsplit: the first conv is a stride-2 tcgen05 conv -> w-parity-split rows (tta_common.cuh)
     const long long vo = wsplit ? v - w + (w & 1) * (W >> 1) + (w >> 1) : v;
@@ -132,6 +148,12 @@ gather_pack4_kernel(const T* vol, int C, int Ds, int Hs, int Ws,
         }
       }
     }
+    if (wsplit == 2) {   // compact layout: four voxels x 4 channels = 32 contiguous bytes per plane
+      const long long o4 = (long long)b * o_ns + ((long long)row * W + (long long)w4 * 4) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) store_split4_f16(hi, lo, o4 + k * 4, x[k]);
+      continue;
+    }
     const long long rowbase = (long long)b * o_ns + ((long long)chunk * V + (long long)row * W) * 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -140,6 +162,83 @@ gather_pack4_kernel(const T* vol, int C, int Ds, int Hs, int Ws,
       const int wo = wsplit ? (w & 1) * (W >> 1) + (w >> 1) : w;
       store_split8<TTA_F16>(hi, lo, rowbase + (long long)wo * 8, x[k]);
     }
+  }
+}
+
+// Compact output ([N][D][H][W][4], <= 4 channels), W % 4 == 0: one thread = four consecutive-w voxels of all (<= 4)
+// channels: one 128-bit (fp32) / 64-bit (fp16) load per channel, two 32-byte stores; 16 live values instead of the
+// 32 of the 8-channel kernel above -> more resident warps on a pass that is pure latency x bandwidth.
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4)
+gather_pack_c4_kernel(const T* vol, int C, int Ds, int Hs, int Ws, const int* win, const float* chan_scale,
+                      const float* affine, int D, int H, int W, uint16_t* hi, uint16_t* lo, long long o_ns) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int vi = win[b * 4 + 0], d0 = win[b * 4 + 1], h0 = win[b * 4 + 2], w0 = win[b * 4 + 3];
+  const long long V = (long long)D * H * W;
+  const long long Vs = (long long)Ds * Hs * Ws;
+  const T* src = vol + (long long)vi * C * Vs;
+  float sc[4], alo[4], ahi[4], amu[4], ainv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sc[i] = (i < C) ? (chan_scale ? chan_scale[b * C + i] : 1.f) : 0.f;
+    load_affine(affine, vi, C, i, alo[i], ahi[i], amu[i], ainv[i]);
+  }
+  const unsigned W4 = (unsigned)W >> 2, G = (unsigned)(V >> 2);
+  for (unsigned g = blockIdx.x * kThreads + threadIdx.x; g < G; g += gridDim.x * kThreads) {
+    const unsigned row = g / W4, w4 = g - row * W4;
+    const unsigned d = row / (unsigned)H, h = row - d * (unsigned)H;
+    const int sd = (int)d + d0, sh = (int)h + h0, sw = (int)(w4 * 4) + w0;
+    float x[4][4];   // [voxel][channel]
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[k][i] = 0.f;
+    if (sd >= 0 && sd < Ds && sh >= 0 && sh < Hs && sw > -4 && sw < Ws) {
+      const T* rowp = src + ((long long)sd * Hs + sh) * Ws + sw;
+      const bool whole = sw >= 0 && sw + 3 < Ws;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < C) {
+          const T* p = rowp + (long long)i * Vs;
+          float vv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (whole && (reinterpret_cast<unsigned long long>(p) & (4ull * sizeof(T) - 1ull)) == 0ull) {
+            if (sizeof(T) == 4) {
+              const float4 v = *reinterpret_cast<const float4*>(p);
+              vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
+            } else {
+              const uint2 v = *reinterpret_cast<const uint2*>(p);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+              const float2 bq = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+              vv[0] = a.x; vv[1] = a.y; vv[2] = bq.x; vv[3] = bq.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k][i] = (fminf(fmaxf(vv[k], alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (sw + k >= 0 && sw + k < Ws) x[k][i] = (fminf(fmaxf(src_val(p + k), alo[i]), ahi[i]) - amu[i]) * ainv[i] * sc[i];
+          }
+        }
+      }
+    }
+    uint32_t hw[8], lw[8];   // 4 voxels x 4 channels x 16 bit = 8 words per plane
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; i += 2) {
+        const uint16_t h0_ = f32_to_u16<TTA_F16>(x[k][i]), h1_ = f32_to_u16<TTA_F16>(x[k][i + 1]);
+        const uint16_t l0_ = f32_to_u16<TTA_F16>(x[k][i] - u16_to_f32<TTA_F16>(h0_));
+        const uint16_t l1_ = f32_to_u16<TTA_F16>(x[k][i + 1] - u16_to_f32<TTA_F16>(h1_));
+        hw[k * 2 + i / 2] = (uint32_t)h0_ | ((uint32_t)h1_ << 16);
+        lw[k * 2 + i / 2] = (uint32_t)l0_ | ((uint32_t)l1_ << 16);
+      }
+    const long long o4 = (long long)b * o_ns + ((long long)row * W + (long long)w4 * 4) * 4;
+    uint4* ph = reinterpret_cast<uint4*>(hi + o4);
+    uint4* pl = reinterpret_cast<uint4*>(lo + o4);
+    ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
   }
 }
 
@@ -352,9 +451,16 @@ static int gather_impl(const T* vol, int n_vol, int C, int Ds, int Hs, int Ws, c
                        const float* affine, int NB, int D, int H, int W, uint16_t* hi, uint16_t* lo, long long o_ns, int C8,
                        int wsplit, cudaStream_t stream) {
   TTA_REQUIRE(vol && win && hi && lo, "tta_gather_pack: null pointer");
-  TTA_REQUIRE(!wsplit || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
+  TTA_REQUIRE(wsplit != 1 || W % 2 == 0, "tta_gather_pack: w-parity-split output needs an even W (got %d)", W);
+  TTA_REQUIRE(wsplit >= 0 && wsplit <= 2 && (wsplit != 2 || (C <= 4 && C8 == 1)),
+              "tta_gather_pack: layout %d (0 plain, 1 w-parity-split, 2 compact: <= 4 channels, one chunk)", wsplit);
   TTA_REQUIRE(NB > 0 && C > 0 && C8 * 8 >= C && n_vol > 0, "tta_gather_pack: bad shape");
   const long long V = (long long)D * H * W;
+  if (wsplit == 2 && W % 4 == 0 && V / 4 < 0x7fffffffLL) {
+    tta_launch(gather_pack_c4_kernel<T>, dim3(xblocks(V / 4, NB), NB), kThreads, 0, stream, tta_pdl_family(4), vol, C, Ds,
+               Hs, Ws, win, chan_scale, affine, D, H, W, hi, lo, o_ns);
+    return tta_check_launch("tta_gather_pack");
+  }
   if (W % 4 == 0 && V / 4 < 0x7fffffffLL)
     tta_launch(gather_pack4_kernel<T>, dim3(xblocks(V / 4, (long long)NB * C8), C8, NB), kThreads, 0, stream,
                tta_pdl_family(4), vol, C, Ds, Hs, Ws, win, chan_scale, affine, D, H, W, C8, hi, lo, o_ns, wsplit);

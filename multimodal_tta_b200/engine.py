@@ -63,6 +63,7 @@ class Act:
         # the producing norm (`ws_planes`, skip tensors that also feed the concat)
         self.writers: list = []         # dgrad launches that wrote .grad: (c8_begin, c8_end, record, accumulate)
         self.wsplit = False
+        self.compact = False            # <= 4 channels stored [N][D][H][W][4] (8 B per voxel and plane): network input
         self.ws_planes: Optional[torch.Tensor] = None
         self.device = device
         self.peers: List["Act"] = []    # other shapes of the SAME storage (batched aliases): written-state is shared
@@ -146,6 +147,7 @@ class Res:
         self.ns = self.C8 * self.V * 8
         self.dy: Optional[torch.Tensor] = None
         self.dy_wsplit = False  # dY feeds a stride-2 tcgen05 dgrad: stored w-parity-split
+        self.dy_c4 = False      # ... or compact ([N][D][H][W][4], <= 4 channels: the head norm's gradient)
         self.stats_c8 = 0       # > 0: the producing tcgen05 conv also emits norm statistics partials
         self.stats_grid = 0     #      ... with this many slots (= its CTA count) per (n, chunk)
         self.tc_query = None    # (ksplit, grid) of the producing tcgen05 launch, None for other backends
@@ -254,9 +256,16 @@ class ConvLayer:
                 self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16,
                                                         t2s=use_t2s).to(device)
                 self.tc_fwd_flags = (self.cout << 8) if use_t2s else 0
+                # stride-2 conv over <= 4 input channels: also the variant for a COMPACT input (network input)
+                if lib.tta_conv_tc_s2c4(self.mode, self.K, self.stride, self.cin):
+                    self.packed["tc_fwd_c4"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16,
+                                                               s2c4=True).to(device)
             bmode = 1 - self.mode
             if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.dgrad_cin or self.cin):
                 self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype).to(device)
+                if lib.tta_conv_tc_s2c4(bmode, self.K, self.stride, self.cout):   # dgrad of a <= 4-channel convT
+                    self.packed["tc_bwd_c4"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype,
+                                                               s2c4=True).to(device)
 
 
 class NormLayer:
@@ -483,7 +492,7 @@ class TTAEngine:
 
     def _conv_call(self, plan: Plan, cl: ConvLayer, backward: bool, src, src_dtype, N, cin8, idims,
                    dst_ptr, dst_ns, cout8, odims, accumulate: bool, wsplit_in: bool = False,
-                   stats_res: Optional["Res"] = None, bwd_rec: Optional[dict] = None):
+                   stats_res: Optional["Res"] = None, bwd_rec: Optional[dict] = None, c4_in: bool = False):
         """Returns a closure launching one conv (tcgen05 kernel when the geometry is supported,
         otherwise the fp32 CUDA-core kernel)."""
         lib = self.lib
@@ -509,9 +518,11 @@ class TTAEngine:
             raise RuntimeError(f"conv_backend=tc but {cl.name} ({key}) is not supported by the tcgen05 kernel")
         plan.conv_backends[f"{cl.name}:{key}"] = "tc" if use_tc else "simt"
         if use_tc:
-            wp = cl.packed["tc_" + key]
+            wp = cl.packed["tc_" + key + ("_c4" if c4_in else "")]
             plan.keep.append(wp)
-            flags = (2 if self.model.deterministic else 0) | (8 if wsplit_in else 0) | self.model.tc_flags
+            flags = (2 if self.model.deterministic else 0) | (8 if (wsplit_in and not c4_in) else 0) | self.model.tc_flags
+            if c4_in:
+                flags |= 32768
             if not backward:
                 flags |= getattr(cl, "tc_fwd_flags", 0)
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
@@ -604,7 +615,19 @@ class TTAEngine:
                 if prev is not None and prev != ws_in:
                     raise ValueError("unet_b200: the network input feeds both a strided and an unstrided conv")
                 plan.x_layout = ws_in
-            if ws_in:
+            c4_in = False
+            if ws_in and inp.parent is plan.x and model.input_compact and "tc_fwd_c4" in cl.packed \
+                    and model.conv_backend in ("auto", "tc") and d % 2 == 0 and h % 2 == 0:
+                # <= 4 input channels: the packed input in the compact layout (8 B per voxel and plane)
+                c4_in = True
+                plan.x.compact = True
+                src = (plan.x.planes[0].data_ptr(), plan.x.planes[1].data_ptr(), plan.x.V * 4)
+                prev_c = getattr(plan, "x_compact", None)
+                if prev_c is False:
+                    raise ValueError("unet_b200: the network input feeds convs that disagree on its layout")
+            if inp.parent is plan.x:
+                plan.x_compact = c4_in
+            if ws_in and not c4_in:
                 par = inp.parent
                 if par is plan.x:
                     par.wsplit = True          # gather_pack writes the only copy parity-split
@@ -612,7 +635,7 @@ class TTAEngine:
                     par.need_ws_copy()         # the producing norm writes a second, parity-split copy
                     src = (inp.ws_hi, inp.ws_lo, inp.ns)
             run = self._conv_call(plan, cl, False, src, TTA_F16, N, inp.C8, inp.dims,
-                                  y.ptr, y.ns, y.C8, (od, oh, ow), False, wsplit_in=ws_in, stats_res=y)
+                                  y.ptr, y.ns, y.C8, (od, oh, ow), False, wsplit_in=ws_in, stats_res=y, c4_in=c4_in)
             plan.fwd.append(run)
             ops.append(("conv", cl, inp, y))
             return y
@@ -975,10 +998,11 @@ class TTAEngine:
                     continue
                 y.alloc_dy(nplanes)
                 crec = dict(segs=[], info=None)
+                dyc4 = y.root.dy_c4
                 plan.bwd.append(self._conv_call(
-                    plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.ns), bdt, N, y.C8,
+                    plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.V * 4 if dyc4 else y.ns), bdt, N, y.C8,
                     (y.D, y.H, y.W), inp.g, inp.ns, c8o, inp.dims, acc, wsplit_in=y.root.dy_wsplit,
-                    bwd_rec=crec))
+                    bwd_rec=crec, c4_in=dyc4))
                 par.writers.append((inp.c8_off, inp.c8_off + c8o, crec, acc))
             else:
                 rec = op[1]
@@ -1049,9 +1073,13 @@ class TTAEngine:
                 skip_reduce = fused_head is not None and rec is fused_head[1]   # done by tta_head_fused_bwd
                 c4_args = None
                 if skip_reduce and head_c4 and do_apply:
+                    pcl_ = self._producer_conv(ops, y)
+                    if (model.input_compact and "tc_bwd_c4" in pcl_.packed and self._uses_tc_s2(pcl_, True)
+                            and y.root is y and y.D % 2 == 0 and y.H % 2 == 0 and y.W % 2 == 0):
+                        y.dy_c4, y.dy_wsplit = True, False       # its dgrad reads the compact gradient planes
                     c4_args = (g0, y.V * 4, y.ptr, y.V * 4, N, nl.C, y.V, rec["mean"].data_ptr(), rec["rstd"].data_ptr(),
-                               rec["gptr"], rec["bptr"], nl.batch, rec["sums"].data_ptr(), y.dy_ptr(0), y.dy_ptr(1), y.ns,
-                               bdt, dy_ws)
+                               rec["gptr"], rec["bptr"], nl.batch, rec["sums"].data_ptr(), y.dy_ptr(0), y.dy_ptr(1),
+                               y.V * 4 if y.dy_c4 else y.ns, bdt, 0 if y.dy_c4 else dy_ws, int(y.dy_c4))
                 fin_args = None
                 if fuse_bwd is not None:
                     fin_args = (fuse_bwd[0].data_ptr(), N, y.C8, nl.C, fuse_bwd[1], nl.batch, rec["sums"].data_ptr(),
@@ -1232,8 +1260,8 @@ class TTAEngine:
         check(gather(x.data_ptr(), n_vol, self.model.in_channels, *vol_dims, win.data_ptr(),
                                             chan_scale.data_ptr() if chan_scale is not None else 0,
                                             affine.data_ptr() if affine is not None else 0, N, D, H, W,
-                                            a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.ns, a.C8,
-                                            int(a.wsplit), _stream()),
+                                            a.planes[0].data_ptr(), a.planes[1].data_ptr(), a.V * 4 if a.compact else a.ns,
+                                            a.C8, 2 if a.compact else int(a.wsplit), _stream()),
               "gather_pack")
         x2 = getattr(plan, "x2", None)
         if x2 is not None:

@@ -154,7 +154,8 @@ def pack_weights_t2s(wg: torch.Tensor) -> torch.Tensor:
     return out.contiguous()
 
 
-def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int, t2s: bool = False) -> torch.Tensor:
+def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag: int, t2s: bool = False,
+                    s2c4: bool = False) -> torch.Tensor:
     """Wg[T][ci][co] -> per-(n_tile, cblk, group) contiguous blobs
     [ntile][cblk][group][entry][kchunk 2][hi NT rows | lo NT rows][8 ci] of 16-bit values.
     A blob is what one pipeline stage of the tcgen05 kernel bulk-copies into shared memory as
@@ -203,6 +204,19 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
                 blk = sel.permute(5, 2, 3, 1, 0, 6, 4).reshape(nnt, ncb, -1)     # [nt][cb][kc][k][P][n][8]
                 flat[:, :, gi, pos: pos + blk.shape[-1]] = blk
                 pos += blk.shape[-1]
+        return out.contiguous()
+    if s2c4:
+        # stride-2 conv over a COMPACT <= 4-channel input (csrc/tta_conv_tc.cu GEOM_S2C4): group = kd, entry = kh,
+        # k-chunk 0 = [zeros | kw 0: 4 ch], k-chunk 1 = [kw 1: 4 ch | kw 2: 4 ch] (rows start at the even voxel 2w - 2)
+        assert K == 3 and mode == 0 and stride == 2 and ci <= 4
+        out = torch.zeros((nnt, 1, 3, 3, 2, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+        for kd in range(3):
+            for kh in range(3):
+                for pi, plane in enumerate(planes):
+                    for kw in range(3):
+                        sel = plane[kd * 9 + kh * 3 + kw][:4].reshape(4, nnt, ntile)      # [ci 4][nt][n]
+                        j = kw + 1
+                        out[:, 0, kd, kh, j // 2, pi, :, (j % 2) * 4:(j % 2) * 4 + 4] = sel.permute(1, 2, 0)
         return out.contiguous()
     if K == 3 and lib.tta_conv_tc_s2pair(mode, K, stride, ci):
         # stride-2 conv over a one-chunk input: entry = a PAIR of taps of one parity class, tap a in

@@ -193,6 +193,9 @@ class B200Model(nn.Module):
         # the <= 4-channel tensors of the fused head (convT result, masked gradient) in a compact 4-channel layout
         # instead of 8-channel chunks: -0.4 GB of DRAM traffic per 2x4x128^3 step
         self.head_compact = bool(get("head_compact", True))
+        # <= 4-channel operands of stride-2 convs (the packed network input, the head norm's gradient) in the compact
+        # 4-channel layout: half the bytes of the 8-channel chunk planes and 9 instead of 15 MMAs per stem tile
+        self.input_compact = bool(get("input_compact", True))
         # norm statistics (sum y, sum y^2) come out of the producing tcgen05 conv's epilogue instead of
         # a separate pass over y (only where the conv runs without split-K)
         self.fuse_stats = bool(get("fuse_stats", True))

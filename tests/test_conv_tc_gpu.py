@@ -354,3 +354,38 @@ def test_conv_tc_small_cout_transposed_gemm_col2im(lib, cuda, cin, cout, dims):
     out_g = torch.zeros_like(out)
     _tc(lib, hi, lo, c8i * Vi * 8, TTA_F16, N, c8i, dims, wpg, bias, out_g, Vo * 8, 1, odims, 1, 3, 2)
     assert rel_l2(out.cpu(), out_g.cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,dims,dt", [(4, 64, (8, 32, 16), TTA_F16), (3, 64, (6, 20, 12), TTA_F16_HI),
+                                              (2, 32, (4, 36, 24), TTA_F16), (1, 16, (2, 16, 16), TTA_BF16)])
+def test_stride2_conv_over_compact_input(lib, cuda, cin, cout, dims, dt):
+    """GEOM_S2C4 (flags bit 15): stride-2 3x3x3 conv whose <= 4-channel input is stored [N][D][H][W][4] (network
+    input; gradient of the head norm): against torch on the same rounded operands, and against the 8-channel chunk
+    path (different MMA grouping -> same value up to fp32 summation order)."""
+    torch.manual_seed(9)
+    N = 2
+    x = torch.randn(N, cin, *dims)
+    w = torch.randn(cout, cin, 3, 3, 3) * 0.1
+    b = torch.randn(cout)
+    hi8, lo8, xv = planes_from(x.to(cuda), dt)
+    whi, wlo = split_planes(w, dt)
+    wv = join_planes(whi, wlo, dt)
+    ref = F.conv3d(xv.cpu(), wv, b, stride=2, padding=1)
+    odims = tuple(ref.shape[2:])
+    V, Vo = dims[0] * dims[1] * dims[2], odims[0] * odims[1] * odims[2]
+    c8o = (cout + 7) // 8
+    hi4 = hi8[:, 0, ..., :4].contiguous(); lo4 = lo8[:, 0, ..., :4].contiguous()      # [N][D][H][W][4]
+    wg = wg_forward(w.to(cuda), False)
+    wp4 = pack_weights_tc(wg, 0, 3, 2, dt, s2c4=True)
+    out4 = torch.zeros((N, c8o, *odims, 8), device=cuda)
+    _tc(lib, hi4, lo4, V * 4, dt, N, 1, dims, wp4, pack_bias(b.to(cuda)), out4, c8o * Vo * 8, c8o, odims, 0, 3, 2,
+        flags=32768)
+    got = from_chunked(out4, cout).cpu()
+    tol = {TTA_F16: 2e-5, TTA_F16_HI: 2e-5, TTA_BF16: 1e-4}[dt]
+    assert rel_l2(got, ref) < tol, rel_l2(got, ref)
+    out8 = torch.zeros_like(out4)
+    _tc(lib, hi8, lo8, V * 8, dt, N, 1, dims, pack_weights_tc(wg, 0, 3, 2, dt), pack_bias(b.to(cuda)), out8,
+        c8o * Vo * 8, c8o, odims, 0, 3, 2, flags=2)
+    assert rel_l2(out4.cpu(), out8.cpu()) < 2e-6
+    assert lib.tta_conv_tc_s2c4(0, 3, 2, cin) == 1 and lib.tta_conv_tc_s2c4(0, 3, 2, 8) == 0
+    assert lib.tta_conv_tc_s2c4(0, 3, 1, 4) == 0 and lib.tta_conv_tc_s2c4(1, 3, 2, 4) == 0

@@ -295,6 +295,22 @@ def test_gather_pack_windows_and_padding(lib, cuda, vw, roi):
                               sd.data_ptr(), 3, *roi, hw.data_ptr(), lw.data_ptr(),
                               roi[0] * roi[1] * roi[2] * 8, 1, 1, stream()))
     assert torch.equal(hw, wsplit(hi)) and torch.equal(lw, wsplit(lo))   # w-parity-split variant
+    # compact variant (wsplit = 2: [NB][D][H][W][4], what a GEOM_S2C4 stem reads) = the first four channels, and the
+    # same from an fp16-staged volume (values exactly representable in fp16 here: identical planes)
+    V = roi[0] * roi[1] * roi[2]
+    hc = torch.full((3, *roi, 4), 7, dtype=torch.int16, device=cuda); lc = torch.full_like(hc, 7)
+    check(lib.tta_gather_pack(vd.data_ptr(), 2, 3, 9, 10, vw, wd.data_ptr(), sd.data_ptr(), 3, *roi, hc.data_ptr(),
+                              lc.data_ptr(), V * 4, 1, 2, stream()))
+    assert torch.equal(hc, hi[:, 0, ..., :4]) and torch.equal(lc, lo[:, 0, ..., :4])
+    v16 = vd.half()
+    h16 = torch.zeros_like(hc); l16 = torch.zeros_like(hc)
+    check(lib.tta_gather_pack_norm_f16(v16.data_ptr(), 2, 3, 9, 10, vw, wd.data_ptr(), sd.data_ptr(), 0, 3, *roi,
+                                       h16.data_ptr(), l16.data_ptr(), V * 4, 1, 2, stream()))
+    r16 = torch.zeros_like(hc); q16 = torch.zeros_like(hc)
+    v32 = v16.float()
+    check(lib.tta_gather_pack(v32.data_ptr(), 2, 3, 9, 10, vw, wd.data_ptr(), sd.data_ptr(), 3, *roi, r16.data_ptr(),
+                              q16.data_ptr(), V * 4, 1, 2, stream()))
+    assert torch.equal(h16, r16) and torch.equal(l16, q16) and int(l16.abs().max()) == 0
     got = from_chunked(join_planes(hi, lo, TTA_F16), 3).cpu()
     pv = F.pad(vol, (8, 8, 8, 8, 8, 8))
     for b, (vi, d0, h0, w0) in enumerate(wins.tolist()):
@@ -407,10 +423,16 @@ def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode, c
     else:
         check(lib.tta_norm_bwd_apply_c4(dz4.data_ptr(), V * 4, ych.data_ptr(), ns_y, N, C, V, mean.data_ptr(),
                                         rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), batch_mode, sums.data_ptr(),
-                                        dhi.data_ptr(), dlo.data_ptr(), ns, TTA_BF16, 0, stream()))
+                                        dhi.data_ptr(), dlo.data_ptr(), ns, TTA_BF16, 0, 0, stream()))
         dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu() / S
         assert rel_l2(dy, yr.grad) < 6e-4                # dz went through fp16 (11 bits) first
         assert float(join_planes(dhi, dlo, TTA_BF16)[..., C:].abs().max()) == 0.0
+        # compact gradient planes [N][V][4] (what a GEOM_S2C4 dgrad reads): the same values, 8 B per voxel
+        chi = torch.zeros((N, *dims, 4), dtype=torch.int16, device=cuda); clo = torch.zeros_like(chi)
+        check(lib.tta_norm_bwd_apply_c4(dz4.data_ptr(), V * 4, ych.data_ptr(), ns_y, N, C, V, mean.data_ptr(),
+                                        rstd.data_ptr(), gp.data_ptr(), bp.data_ptr(), batch_mode, sums.data_ptr(),
+                                        chi.data_ptr(), clo.data_ptr(), V * 4, TTA_BF16, 0, 1, stream()))
+        assert torch.equal(chi, dhi[:, 0, ..., :4]) and torch.equal(clo, dlo[:, 0, ..., :4])
         return
     dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu() / S
     assert rel_l2(dy, yr.grad) < 5e-5                # bf16x2 storage (~16 bits)
