@@ -290,6 +290,19 @@ int tta_upsample_fwd(const float* in, long long in_n_stride, int N, int C8, int 
 int tta_upsample_bwd(const float* g, long long g_n_stride, int N, int C8, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
                      uint16_t* dy_hi, uint16_t* dy_lo, long long dy_n_stride, int out_dtype, tta_stream_t stream);
 
+/* ---- supervised step (loss.backward() of src/core/trainers/seg_trainer.py:142 for EVERY parameter):
+ * weight / bias gradients of Conv3d and ConvTranspose3d from the operands the forward and backward passes hold.
+ * x: forward operand planes (fp16 hi + lo) of the conv's input view; dy: the 16-bit gradient planes of its output
+ * (dy_dtype TTA_F16_HI: one loss-scaled plane).  dw (+=) scale * dL/dW in the PARAMETER layout: layout 0 = Conv3d
+ * [Cout][Cin][k^3] (couts >= co_split go to dw2: fused unit0 || shortcut convs), layout 1 = ConvTranspose3d
+ * [Cin][Cout][k^3]; fp32 atomics, the caller zeroes dw / db once per step. */
+int tta_conv_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, long long x_n_stride, int Dx, int Hx, int Wx, int x_wsplit,
+                   const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_n_stride, int dy_dtype, int Dy, int Hy,
+                   int Wy, int dy_wsplit, int N, int mode, int K, int stride, int Cin, int Cout, float scale, float* dw,
+                   int layout, int co_split, float* dw2, tta_stream_t stream);
+int tta_bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_n_stride, int dy_dtype, int N, int Cout,
+                  long long V, float scale, float* db, int co_split, float* db2, tta_stream_t stream);
+
 /* ---- the step as a C object (plan_create / tta_step / workspace_bytes).  Build the launch list once
  * per input shape by calling the ordinary tta_* entry points between tta_plan_begin(plan, section) and tta_plan_end():
  * while a recording is active on the calling thread those calls store themselves (arguments by value; host pointer

@@ -1,0 +1,329 @@
+// Weight and bias gradients of Conv3d / ConvTranspose3d (k in {1, 3}, stride in {1, 2}) for the SUPERVISED step
+// (reference: loss.backward() in src/core/trainers/seg_trainer.py:142 for every parameter of the
+// model, not only the norm affines TENT touches).  fp32 CUDA-core kernel -- exact arithmetic on the operands the
+// forward / backward passes already hold:
+//     conv      (mode 0): dW[co][ci][k] = sum_{n,o} x[n][s*o - p + k][ci] * dy[n][o][co]
+//     transposed (mode 1): dW[ci][co][k] = sum_{n,i} x[n][i][ci] * dy[n][s*i - p + k][co]
+// x = the forward operand planes (fp16 hi + lo, chunk layout, optionally w-parity-split rows), dy = the 16-bit
+// gradient planes the dgrad convs read (one scaled fp16 plane or bf16 hi + lo).
+//
+// A CTA owns a (CI_T x CO_T) channel tile of dW for all taps and walks a range of spatial tiles: the "centre" tensor
+// (dy for a conv, x for a transposed conv) and the halo of the other one are staged in shared memory as fp32; thread
+// (kd, kh | ci group of 4 | co group of 4 | position slice) keeps 3 (kw) x 4 x 4 accumulators and per position does
+// one 128-bit load of the centre values, three of the halo and 48 FMAs.  Partial sums leave through fp32 atomics
+// once per CTA (a few thousand per layer).  This is a first, exact implementation of the row: a tensor-core wgrad
+// (MN-major UMMA operands: both x and dy are channel-contiguous) is the next step for it.
+#include <cstring>
+
+#include "tta_common.cuh"
+
+namespace tta {
+
+constexpr int kWgThreads = 288;
+
+struct WgParams {
+  const uint16_t* x_hi; const uint16_t* x_lo; long long x_ns; int Dx, Hx, Wx, x_wsplit;
+  const uint16_t* dy_hi; const uint16_t* dy_lo; long long dy_ns; int dy_dtype, Dy, Hy, Wy, dy_wsplit;
+  int N, stride, Cin, Cout, ci0, co0;   // ci0 / co0: first channel of this launch's channel tiles (set per block)
+  int tiles_d, tiles_h, tiles_w, tiles_per_n, tiles_total, tiles_per_block;
+  float scale;
+  float* dw; int layout; int co_split; float* dw2;
+};
+
+__device__ __forceinline__ long long vox_index(int d, int h, int w, int H, int W, int wsplit) {
+  const long long row = ((long long)d * H + h) * W;
+  return row + (wsplit ? (w & 1) * (W >> 1) + (w >> 1) : w);
+}
+
+// MODE 0: centre = dy (CO_T channels), halo = x (CI_T);  MODE 1: centre = x (CI_T), halo = dy (CO_T)
+template <int MODE, int K, int S, int CI_T, int CO_T, int TD, int TH, int TW>
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_kernel(const WgParams P) {
+  constexpr int NKK = K * K;                       // (kd, kh) pairs
+  constexpr int CG = CI_T / 4, OG = CO_T / 4;
+  constexpr int PS = kWgThreads / (NKK * CG * OG); // position slices
+  static_assert(PS >= 1 && NKK * CG * OG * PS == kWgThreads, "thread mapping");
+  constexpr int HD = S * (TD - 1) + K, HH = S * (TH - 1) + K, HW = S * (TW - 1) + K;
+  constexpr int NC = TD * TH * TW, NH = HD * HH * HW;
+  constexpr int CC = MODE == 0 ? CO_T : CI_T;      // centre channels
+  constexpr int HC = MODE == 0 ? CI_T : CO_T;      // halo channels
+  extern __shared__ __align__(16) float smem[];
+  float* cen = smem;                               // [NC][CC]
+  float* hal = smem + NC * CC;                     // [NH][HC]
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int ps = tid % PS;
+  const int og = (tid / PS) % OG;
+  const int cg = (tid / (PS * OG)) % CG;
+  const int kk = tid / (PS * OG * CG);             // kd * K + kh
+  const int kd = kk / K, kh = kk % K;
+  const int ci0 = blockIdx.y * CI_T, co0 = blockIdx.z * CO_T;
+  const int pad = (K - 1) / 2;
+  // centre / halo tensor descriptions
+  const uint16_t* c_hi = MODE == 0 ? P.dy_hi : P.x_hi;
+  const uint16_t* c_lo = MODE == 0 ? P.dy_lo : P.x_lo;
+  const uint16_t* h_hi = MODE == 0 ? P.x_hi : P.dy_hi;
+  const uint16_t* h_lo = MODE == 0 ? P.x_lo : P.dy_lo;
+  const long long c_ns = MODE == 0 ? P.dy_ns : P.x_ns, h_ns = MODE == 0 ? P.x_ns : P.dy_ns;
+  const int cD = MODE == 0 ? P.Dy : P.Dx, cH = MODE == 0 ? P.Hy : P.Hx, cW = MODE == 0 ? P.Wy : P.Wx;
+  const int hD = MODE == 0 ? P.Dx : P.Dy, hH = MODE == 0 ? P.Hx : P.Hy, hW = MODE == 0 ? P.Wx : P.Wy;
+  const int c_ws = MODE == 0 ? P.dy_wsplit : P.x_wsplit, h_ws = MODE == 0 ? P.x_wsplit : P.dy_wsplit;
+  const int c_dt = MODE == 0 ? P.dy_dtype : TTA_F16, h_dt = MODE == 0 ? TTA_F16 : P.dy_dtype;
+  const int c_c0 = MODE == 0 ? co0 : ci0, h_c0 = MODE == 0 ? ci0 : co0;
+  const int c_cmax = MODE == 0 ? (P.Cout + 7) / 8 * 8 : (P.Cin + 7) / 8 * 8;
+  const int h_cmax = MODE == 0 ? (P.Cin + 7) / 8 * 8 : (P.Cout + 7) / 8 * 8;
+  const long long cV = (long long)cD * cH * cW, hV = (long long)hD * hH * hW;
+
+  float acc[K][4][4];
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[a][i][j] = 0.f;
+
+  auto load8 = [&](const uint16_t* hi, const uint16_t* lo, long long off, int dt, float (&v)[8]) {
+    const U16x8 h = *reinterpret_cast<const U16x8*>(hi + off);
+    if (dt == TTA_F16_HI) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = u16_to_f32<TTA_F16>(h.v[i]);
+    } else {
+      const U16x8 l = *reinterpret_cast<const U16x8*>(lo + off);
+      if (dt == TTA_F16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = u16_to_f32<TTA_F16>(h.v[i]) + u16_to_f32<TTA_F16>(l.v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = u16_to_f32<TTA_BF16>(h.v[i]) + u16_to_f32<TTA_BF16>(l.v[i]);
+      }
+    }
+  };
+
+  const int t_begin = blockIdx.x * P.tiles_per_block;
+  const int t_end = min(P.tiles_total, t_begin + P.tiles_per_block);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int n = t / P.tiles_per_n;
+    int r = t - n * P.tiles_per_n;
+    const int tw = r % P.tiles_w; r /= P.tiles_w;
+    const int th = r % P.tiles_h;
+    const int td = r / P.tiles_h;
+    const int d0 = td * TD, h0 = th * TH, w0 = tw * TW;           // centre origin
+    const int hd0 = S * d0 - pad, hh0 = S * h0 - pad, hw0 = S * w0 - pad;   // halo origin
+    __syncthreads();                                              // previous tile's readers are done
+    // ---- stage the centre tile [NC][CC] and the halo tile [NH][HC] as fp32 (zero outside the tensors)
+    for (int e = tid; e < NC * (CC / 8); e += kWgThreads) {
+      const int ch = e % (CC / 8), p = e / (CC / 8);
+      const int pw = p % TW, ph = (p / TW) % TH, pd = p / (TW * TH);
+      const int d = d0 + pd, h = h0 + ph, w = w0 + pw;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      const int c = c_c0 + ch * 8;
+      if (d < cD && h < cH && w < cW && c < c_cmax)
+        load8(c_hi, c_lo, (long long)n * c_ns + ((long long)(c >> 3) * cV + vox_index(d, h, w, cH, cW, c_ws)) * 8, c_dt, v);
+      float4* dst = reinterpret_cast<float4*>(cen + p * CC + ch * 8);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    for (int e = tid; e < NH * (HC / 8); e += kWgThreads) {
+      const int ch = e % (HC / 8), p = e / (HC / 8);
+      const int pw = p % HW, ph = (p / HW) % HH, pd = p / (HW * HH);
+      const int d = hd0 + pd, h = hh0 + ph, w = hw0 + pw;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      const int c = h_c0 + ch * 8;
+      if (d >= 0 && d < hD && h >= 0 && h < hH && w >= 0 && w < hW && c < h_cmax)
+        load8(h_hi, h_lo, (long long)n * h_ns + ((long long)(c >> 3) * hV + vox_index(d, h, w, hH, hW, h_ws)) * 8, h_dt, v);
+      float4* dst = reinterpret_cast<float4*>(hal + p * HC + ch * 8);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    // ---- accumulate: this thread's (kd, kh), ci group, co group over its slice of the centre positions
+    for (int p = ps; p < NC; p += PS) {
+      const int pw = p % TW, ph = (p / TW) % TH, pd = p / (TW * TH);
+      const float4 cv = *reinterpret_cast<const float4*>(cen + p * CC + (MODE == 0 ? og : cg) * 4);
+      const int hb = ((S * pd + kd) * HH + (S * ph + kh)) * HW + S * pw;
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const float4 hv = *reinterpret_cast<const float4*>(hal + (hb + kw) * HC + (MODE == 0 ? cg : og) * 4);
+        const float xs[4] = {MODE == 0 ? hv.x : cv.x, MODE == 0 ? hv.y : cv.y, MODE == 0 ? hv.z : cv.z, MODE == 0 ? hv.w : cv.w};
+        const float ys[4] = {MODE == 0 ? cv.x : hv.x, MODE == 0 ? cv.y : hv.y, MODE == 0 ? cv.z : hv.z, MODE == 0 ? cv.w : hv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[kw][i][j] = fmaf(xs[i], ys[j], acc[kw][i][j]);
+      }
+    }
+  }
+  // ---- flush: fp32 atomics into the weight gradient (reference parameter layout)
+  constexpr int T = K * K * K;
+#pragma unroll
+  for (int kw = 0; kw < K; ++kw) {
+    const int tap = (kd * K + kh) * K + kw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ci = ci0 + cg * 4 + i;
+      if (ci >= P.Cin) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = co0 + og * 4 + j;
+        if (co >= P.Cout) continue;
+        const float v = acc[kw][i][j] * P.scale;
+        if (v == 0.f) continue;
+        float* dst;
+        if (P.layout == 1) {                                   // ConvTranspose3d weight [ci][co][T]
+          dst = P.dw + ((long long)ci * P.Cout + co) * T + tap;
+        } else if (co < P.co_split) {                          // Conv3d weight [co][ci][T]
+          dst = P.dw + ((long long)co * P.Cin + ci) * T + tap;
+        } else {                                               // second half of a fused unit0 || shortcut conv
+          dst = P.dw2 + ((long long)(co - P.co_split) * P.Cin + ci) * T + tap;
+        }
+        atomicAdd(dst, v);
+      }
+    }
+  }
+}
+
+// db[c] += scale * sum_{n, v} dy[n][v][c]
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_ns, int dy_dtype, long long V, int Cout,
+                 int co_split, float scale, float* db, float* db2) {
+  pdl_trigger();
+  pdl_wait();
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const long long base = (long long)n * dy_ns + (long long)chunk * V * 8;
+  for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < V; v += (long long)gridDim.x * 256) {
+    float x[8];
+    const U16x8 h = *reinterpret_cast<const U16x8*>(dy_hi + base + v * 8);
+    if (dy_dtype == TTA_F16_HI) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = u16_to_f32<TTA_F16>(h.v[i]);
+    } else {
+      const U16x8 l = *reinterpret_cast<const U16x8*>(dy_lo + base + v * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        x[i] = dy_dtype == TTA_F16 ? u16_to_f32<TTA_F16>(h.v[i]) + u16_to_f32<TTA_F16>(l.v[i])
+                                   : u16_to_f32<TTA_BF16>(h.v[i]) + u16_to_f32<TTA_BF16>(l.v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += x[i];
+  }
+  __shared__ float red[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int c = chunk * 8 + threadIdx.x;
+    if (c < Cout && s != 0.f) atomicAdd(c < co_split ? db + c : db2 + (c - co_split), s * scale);
+  }
+}
+
+template <int MODE, int K, int S, int CI_T, int CO_T, int TD, int TH, int TW>
+static int launch_wgrad(WgParams P, int cD, int cH, int cW, cudaStream_t stream) {
+  constexpr int HD = S * (TD - 1) + K, HH = S * (TH - 1) + K, HW = S * (TW - 1) + K;
+  constexpr int CC = MODE == 0 ? CO_T : CI_T, HC = MODE == 0 ? CI_T : CO_T;
+  constexpr size_t smem = (size_t)(TD * TH * TW * CC + HD * HH * HW * HC) * sizeof(float);
+  static_assert(smem <= 200 * 1024, "wgrad tile does not fit shared memory");
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_kernel<MODE, K, S, CI_T, CO_T, TD, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return tta_check_launch("tta_conv_wgrad(cudaFuncSetAttribute)");
+    configured = true;
+  }
+  P.tiles_d = (cD + TD - 1) / TD; P.tiles_h = (cH + TH - 1) / TH; P.tiles_w = (cW + TW - 1) / TW;
+  P.tiles_per_n = P.tiles_d * P.tiles_h * P.tiles_w;
+  P.tiles_total = P.tiles_per_n * P.N;
+  const int nci = (P.Cin + CI_T - 1) / CI_T, nco = (P.Cout + CO_T - 1) / CO_T;
+  int splits = (3 * 148 + nci * nco - 1) / (nci * nco);      // ~3 CTAs per SM over the whole launch
+  if (splits > P.tiles_total) splits = P.tiles_total;
+  if (splits < 1) splits = 1;
+  P.tiles_per_block = (P.tiles_total + splits - 1) / splits;
+  splits = (P.tiles_total + P.tiles_per_block - 1) / P.tiles_per_block;
+  tta_launch(wgrad_kernel<MODE, K, S, CI_T, CO_T, TD, TH, TW>, dim3(splits, nci, nco), kWgThreads, smem, stream,
+             tta_pdl_family(32), P);
+  return tta_check_launch("tta_conv_wgrad");
+}
+
+template <int MODE, int K, int S, int TD, int TH, int TW>
+static int dispatch_tiles(const WgParams& P, int cD, int cH, int cW, cudaStream_t stream) {
+  const bool small_ci = P.Cin <= 8, small_co = P.Cout <= 8;
+  if (small_ci && small_co) return launch_wgrad<MODE, K, S, 8, 8, TD, TH, TW>(P, cD, cH, cW, stream);
+  if (small_ci) return launch_wgrad<MODE, K, S, 8, 32, TD, TH, TW>(P, cD, cH, cW, stream);
+  if (small_co) return launch_wgrad<MODE, K, S, 16, 8, TD, TH, TW>(P, cD, cH, cW, stream);
+  return launch_wgrad<MODE, K, S, 16, 32, TD, TH, TW>(P, cD, cH, cW, stream);
+}
+
+}  // namespace tta
+
+using namespace tta;
+
+extern "C" {
+
+// x: forward operand planes (fp16 hi + lo) of the conv's INPUT view [N][C8][Dx][Hx][Wx][8] (x_wsplit: rows stored
+// w-parity-split); dy: gradient planes of the conv's OUTPUT [N][C8][Dy][Hy][Wy][8] (dy_dtype TTA_F16_HI: one plane,
+// dy_lo unused; TTA_BF16 / TTA_F16: hi + lo).  dw (+=) scale * dL/dW in the PARAMETER layout: layout 0 = nn.Conv3d
+// [Cout][Cin][k^3] (couts >= co_split go to dw2, a second Conv3d weight [Cout - co_split][Cin][k^3]: the fused
+// unit0 || shortcut convs), layout 1 = nn.ConvTranspose3d [Cin][Cout][k^3].  The caller zeroes dw once per step.
+int tta_conv_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, long long x_ns, int Dx, int Hx, int Wx, int x_wsplit,
+                   const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_ns, int dy_dtype, int Dy, int Hy, int Wy,
+                   int dy_wsplit, int N, int mode, int K, int stride, int Cin, int Cout, float scale, float* dw,
+                   int layout, int co_split, float* dw2, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_conv_wgrad(x_hi, x_lo, x_ns, Dx, Hx, Wx, x_wsplit, dy_hi, dy_lo, dy_ns, dy_dtype, Dy, Hy, Wy, dy_wsplit, N, mode, K, stride, Cin, Cout, scale, dw, layout, co_split, dw2, s_));
+  TTA_REQUIRE(x_hi && x_lo && dy_hi && (dy_lo || dy_dtype == TTA_F16_HI) && dw, "tta_conv_wgrad: null pointer");
+  TTA_REQUIRE((mode == 0 || mode == 1) && (K == 1 || K == 3) && (stride == 1 || stride == 2) && !(K == 1 && stride != 1),
+              "tta_conv_wgrad: unsupported geometry mode=%d K=%d stride=%d", mode, K, stride);
+  TTA_REQUIRE(dy_dtype >= 0 && dy_dtype <= 2 && N > 0 && Cin > 0 && Cout > 0, "tta_conv_wgrad: bad argument");
+  TTA_REQUIRE(layout == 0 || layout == 1, "tta_conv_wgrad: layout %d", layout);
+  if (co_split <= 0 || co_split > Cout) co_split = Cout;
+  TTA_REQUIRE(co_split == Cout || (dw2 != nullptr && layout == 0), "tta_conv_wgrad: a split output needs dw2 and layout 0");
+  WgParams P;
+  memset(&P, 0, sizeof(P));
+  P.x_hi = x_hi; P.x_lo = x_lo; P.x_ns = x_ns; P.Dx = Dx; P.Hx = Hx; P.Wx = Wx; P.x_wsplit = x_wsplit;
+  P.dy_hi = dy_hi; P.dy_lo = dy_lo; P.dy_ns = dy_ns; P.dy_dtype = dy_dtype; P.Dy = Dy; P.Hy = Hy; P.Wy = Wy;
+  P.dy_wsplit = dy_wsplit;
+  P.N = N; P.stride = stride; P.Cin = Cin; P.Cout = Cout; P.scale = scale;
+  P.dw = dw; P.layout = layout; P.co_split = co_split; P.dw2 = dw2;
+  // centre tensor: dy for a conv (mode 0), x for a transposed conv (mode 1)
+  const int cD = mode == 0 ? Dy : Dx, cH = mode == 0 ? Hy : Hx, cW = mode == 0 ? Wy : Wx;
+  if (mode == 0) {
+    if (K == 1) return dispatch_tiles<0, 1, 1, 4, 4, 8>(P, cD, cH, cW, stream);
+    if (stride == 1) return dispatch_tiles<0, 3, 1, 4, 4, 8>(P, cD, cH, cW, stream);
+    return dispatch_tiles<0, 3, 2, 2, 4, 8>(P, cD, cH, cW, stream);
+  }
+  if (K == 1) return dispatch_tiles<1, 1, 1, 4, 4, 8>(P, cD, cH, cW, stream);
+  if (stride == 1) return dispatch_tiles<1, 3, 1, 4, 4, 8>(P, cD, cH, cW, stream);
+  return dispatch_tiles<1, 3, 2, 2, 2, 8>(P, cD, cH, cW, stream);
+}
+
+// db (+=) scale * sum over batch and voxels of dy (channels >= co_split go to db2)
+int tta_bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_ns, int dy_dtype, int N, int Cout, long long V,
+                  float scale, float* db, int co_split, float* db2, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_bias_grad(dy_hi, dy_lo, dy_ns, dy_dtype, N, Cout, V, scale, db, co_split, db2, s_));
+  TTA_REQUIRE(dy_hi && (dy_lo || dy_dtype == TTA_F16_HI) && db && N > 0 && Cout > 0 && V > 0, "tta_bias_grad: bad argument");
+  if (co_split <= 0 || co_split > Cout) co_split = Cout;
+  TTA_REQUIRE(co_split == Cout || db2 != nullptr, "tta_bias_grad: a split output needs db2");
+  const int C8 = (Cout + 7) / 8;
+  long long xb = (V + 255) / 256;
+  const long long want = (4LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
+  if (xb > want) xb = want;
+  tta_launch(bias_grad_kernel, dim3((unsigned)xb, C8, N), 256, 0, stream, tta_pdl_family(32), dy_hi, dy_lo, dy_ns, dy_dtype, V,
+             Cout, co_split, scale, db, db2);
+  return tta_check_launch("tta_bias_grad");
+}
+
+}  // extern "C"

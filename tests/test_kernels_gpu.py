@@ -436,3 +436,56 @@ def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode, c
         return
     dy = from_chunked(join_planes(dhi, dlo, TTA_BF16), C).cpu() / S
     assert rel_l2(dy, yr.grad) < 5e-5                # bf16x2 storage (~16 bits)
+
+
+@pytest.mark.parametrize("cin,cout,K,s,tr,dims,dyt", [
+    (32, 32, 3, 1, False, (5, 9, 11), TTA_F16_HI), (4, 64, 3, 2, False, (8, 12, 16), TTA_F16_HI),
+    (64, 128, 3, 2, False, (4, 8, 8), TTA_BF16), (48, 16, 3, 2, True, (3, 6, 5), TTA_F16_HI),
+    (64, 3, 3, 2, True, (4, 8, 8), TTA_BF16), (3, 3, 3, 1, False, (6, 10, 12), TTA_F16_HI),
+    (256, 512, 1, 1, False, (2, 4, 4), TTA_F16_HI), (96, 40, 3, 1, False, (3, 5, 7), TTA_BF16)])
+def test_conv_weight_and_bias_gradients(lib, cuda, cin, cout, K, s, tr, dims, dyt):
+    """tta_conv_wgrad / tta_bias_grad (supervised step) against torch autograd on the same rounded
+    operands: Conv3d and ConvTranspose3d, strides 1 / 2, 1x1, ragged tiles, channel counts that are not multiples of
+    the channel tiles, scaled single-plane fp16 and bf16x2 gradients, w-parity-split operands, split outputs."""
+    torch.manual_seed(13)
+    N, pad, S = 2, (K - 1) // 2, 64.0
+    x = torch.randn(N, cin, *dims)
+    w = (torch.randn((cin, cout, K, K, K) if tr else (cout, cin, K, K, K)) * 0.1).requires_grad_(True)
+    b = torch.zeros(cout, requires_grad=True)
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    y = F.conv_transpose3d(xv.cpu(), w, b, stride=s, padding=pad, output_padding=s - 1) if tr else \
+        F.conv3d(xv.cpu(), w, b, stride=s, padding=pad)
+    dy = torch.randn_like(y)
+    odims = tuple(y.shape[2:])
+    if dyt == TTA_F16_HI:
+        dch = to_chunked((dy * S).to(cuda))
+        dhi = dch.half().view(torch.int16).contiguous(); dlo = dhi
+        dyv = from_chunked(dhi.view(torch.float16).float(), cout).cpu() / S
+        scale = 1.0 / S
+    else:
+        dhi, dlo, dv = planes_from(dy.to(cuda), TTA_BF16)
+        dyv, scale = dv.cpu(), 1.0
+    y.backward(dyv)
+    c8i, c8o = (cin + 7) // 8, (cout + 7) // 8
+    Vi, Vo = dims[0] * dims[1] * dims[2], odims[0] * odims[1] * odims[2]
+    mode = 1 if tr else 0
+    for ws in ((False, False), (True, True)):
+        xw, dw_ = ws[0] and dims[2] % 2 == 0, ws[1] and odims[2] % 2 == 0
+        xh, xl = (wsplit(hi), wsplit(lo)) if xw else (hi, lo)
+        gh, gl = (wsplit(dhi), wsplit(dlo)) if dw_ else (dhi, dlo)
+        gw = torch.zeros_like(w.detach()).to(cuda); gb = torch.zeros(cout, device=cuda)
+        check(lib.tta_conv_wgrad(xh.data_ptr(), xl.data_ptr(), c8i * Vi * 8, *dims, int(xw), gh.data_ptr(), gl.data_ptr(),
+                                 c8o * Vo * 8, dyt, *odims, int(dw_), N, mode, K, s, cin, cout, scale, gw.data_ptr(),
+                                 1 if tr else 0, 0, 0, stream()), "wgrad")
+        check(lib.tta_bias_grad(dhi.data_ptr(), dlo.data_ptr(), c8o * Vo * 8, dyt, N, cout, Vo, scale, gb.data_ptr(), 0, 0,
+                                stream()), "bias_grad")
+        assert rel_l2(gw.cpu(), w.grad) < 2e-5, rel_l2(gw.cpu(), w.grad)
+        assert rel_l2(gb.cpu(), b.grad) < 2e-5
+    if not tr and cout % 16 == 0:
+        # split output (fused unit0 || shortcut conv): the two halves land in two Conv3d weight gradients
+        h = cout // 2
+        ga = torch.zeros((h, cin, K, K, K), device=cuda); gb2 = torch.zeros((cout - h, cin, K, K, K), device=cuda)
+        check(lib.tta_conv_wgrad(hi.data_ptr(), lo.data_ptr(), c8i * Vi * 8, *dims, 0, dhi.data_ptr(), dlo.data_ptr(),
+                                 c8o * Vo * 8, dyt, *odims, 0, N, mode, K, s, cin, cout, scale, ga.data_ptr(), 0, h,
+                                 gb2.data_ptr(), stream()), "wgrad")
+        assert rel_l2(torch.cat([ga, gb2]).cpu(), w.grad) < 2e-5
