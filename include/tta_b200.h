@@ -300,6 +300,14 @@ int tta_conv_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, long long x_n_str
                    const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_n_stride, int dy_dtype, int Dy, int Hy,
                    int Wy, int dy_wsplit, int N, int mode, int K, int stride, int Cin, int Cout, float scale, float* dw,
                    int layout, int co_split, float* dw2, tta_stream_t stream);
+/* dL/dlogits (NCDHW fp32, from the reference's own loss through autograd) -> the 16-bit gradient plane(s) of the
+ * last conv's result, times the power-of-two loss scale */
+int tta_pack_grad(const float* g, int N, int R, long long V, float scale, uint16_t* dy_hi, uint16_t* dy_lo,
+                  long long dy_n_stride, int out_dtype, tta_stream_t stream);
+/* packed operand blob <- flat parameter buffer after an optimizer step: map[e] = +-(1 + source index) (sign = hi / lo
+ * plane of the 16-bit formats, 0 = padding), add[e] != 0 adds the folded identity shortcut; kind 0 fp32, 1 fp16, 2 bf16 */
+int tta_repack_weights(const float* src, const int* map, const signed char* add, long long n, void* out, int kind,
+                       tta_stream_t stream);
 int tta_bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_n_stride, int dy_dtype, int N, int Cout,
                   long long V, float scale, float* db, int co_split, float* db2, tta_stream_t stream);
 

@@ -327,3 +327,89 @@ int tta_bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_ns,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- dL/dlogits -> gradient planes
+// g: NCDHW fp32 (what autograd hands to the model's backward) -> the 16-bit gradient plane(s) of the last conv's
+// result in the chunk layout, multiplied by the (power-of-two) loss scale
+namespace tta {
+
+template <int ODT>
+__global__ void __launch_bounds__(256)
+pack_grad_kernel(const float* g, int R, long long V, float scale, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns) {
+  pdl_trigger();
+  pdl_wait();
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const float* gb = g + (long long)n * R * V;
+  for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < V; v += (long long)gridDim.x * 256) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = chunk * 8 + i;
+      x[i] = c < R ? gb[(long long)c * V + v] * scale : 0.f;
+    }
+    store_split8<ODT>(dy_hi, dy_lo, (long long)n * dy_ns + ((long long)chunk * V + v) * 8, x);
+  }
+}
+
+}  // namespace tta
+
+extern "C" int tta_pack_grad(const float* g, int N, int R, long long V, float scale, uint16_t* dy_hi, uint16_t* dy_lo,
+                             long long dy_ns, int out_dtype, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_pack_grad(g, N, R, V, scale, dy_hi, dy_lo, dy_ns, out_dtype, s_));
+  TTA_REQUIRE(g && dy_hi && (dy_lo || out_dtype == TTA_F16_HI) && N > 0 && R > 0 && V > 0 && out_dtype >= 0 && out_dtype <= 2,
+              "tta_pack_grad: bad argument");
+  const int C8 = (R + 7) / 8;
+  long long xb = (V + 255) / 256;
+  const long long want = (8LL * 148 + (long long)N * C8 - 1) / ((long long)N * C8);
+  if (xb > want) xb = want;
+  const dim3 grid((unsigned)xb, C8, N);
+  if (out_dtype == TTA_F16) tta::tta_launch(tta::pack_grad_kernel<TTA_F16>, grid, 256, 0, stream, tta_pdl_family(32), g, R, V, scale, dy_hi, dy_lo, dy_ns);
+  else if (out_dtype == TTA_F16_HI) tta::tta_launch(tta::pack_grad_kernel<TTA_F16_HI>, grid, 256, 0, stream, tta_pdl_family(32), g, R, V, scale, dy_hi, dy_lo, dy_ns);
+  else tta::tta_launch(tta::pack_grad_kernel<TTA_BF16>, grid, 256, 0, stream, tta_pdl_family(32), g, R, V, scale, dy_hi, dy_lo, dy_ns);
+  return tta_check_launch("tta_pack_grad");
+}
+
+// ---------------------------------------------------------------- device-side weight repack
+// After an optimizer step the packed operand blobs of the conv kernels (fp16 hi / lo planes in the tcgen05 blob
+// layouts, fp32 for the CUDA-core kernels, padded biases) are rebuilt FROM THE FLAT PARAMETER BUFFER by one gather
+// per blob: map[e] = +-(1 + source index), sign = hi / lo plane, 0 = padding; add[e] != 0 adds the folded identity
+// shortcut's 1.0 (layout.index_mode builds the maps once by running the host packers on index tensors).
+namespace tta {
+
+template <int KIND>   // 0: fp32, 1: fp16 planes, 2: bf16 planes
+__global__ void __launch_bounds__(256)
+repack_kernel(const float* src, const int* map, const signed char* add, long long n, void* out) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+    const int m = map[e];
+    const int a = add ? (int)add[e] : 0;
+    float v = 0.f;
+    if (m != 0) v = src[(m > 0 ? m : -m) - 1];
+    if (a) v += 1.f;
+    if (KIND == 0) {
+      reinterpret_cast<float*>(out)[e] = v;
+    } else {
+      constexpr int DT = KIND == 1 ? TTA_F16 : TTA_BF16;
+      const uint16_t h = f32_to_u16<DT>(v);
+      uint16_t r = h;
+      if (m < 0) r = f32_to_u16<DT>(v - u16_to_f32<DT>(h));
+      if (m == 0 && !a) r = 0;
+      reinterpret_cast<uint16_t*>(out)[e] = r;
+    }
+  }
+}
+
+}  // namespace tta
+
+extern "C" int tta_repack_weights(const float* src, const int* map, const signed char* add, long long n, void* out,
+                                  int kind, cudaStream_t stream) {
+  TTA_RECORDABLE(tta_repack_weights(src, map, add, n, out, kind, s_));
+  TTA_REQUIRE(src && map && out && n > 0 && kind >= 0 && kind <= 2, "tta_repack_weights: bad argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8 * 148) blocks = 8 * 148;
+  if (kind == 0) tta::tta_launch(tta::repack_kernel<0>, dim3((unsigned)blocks), 256, 0, stream, tta_pdl_family(32), src, map, add, n, out);
+  else if (kind == 1) tta::tta_launch(tta::repack_kernel<1>, dim3((unsigned)blocks), 256, 0, stream, tta_pdl_family(32), src, map, add, n, out);
+  else tta::tta_launch(tta::repack_kernel<2>, dim3((unsigned)blocks), 256, 0, stream, tta_pdl_family(32), src, map, add, n, out);
+  return tta_check_launch("tta_repack_weights");
+}

@@ -209,43 +209,38 @@ class ConvLayer:
         self.w_map: Optional[Callable[[torch.Tensor], torch.Tensor]] = None
         self.dgrad_cin: Optional[int] = None    # input gradient only for the leading channels (rest needs none)
 
-    def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16, t2s: bool = True):
-        """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05.
-        Packing runs on the HOST (a few hundred small index ops per layer, once per weight load) and every
-        blob reaches the device as one H2D copy -- the device only ever executes this library's kernels."""
-        host = torch.device("cpu")
-        w = self.h.weight.detach().to(device=host, dtype=torch.float32)
+    def _canonical(self, w, b, w2=None, b2=None, add_identity=None):
+        """Parameter tensors (or tensors of the same shapes holding source indices / additive constants) -> the
+        canonical forward / dgrad weights Wg[T][ci][co] and the bias vector this launch uses."""
         if self.w_map is not None:
             w = self.w_map(w)
+            if w2 is not None:
+                w2 = self.w_map(w2)
         wf = wg_forward(w, self.h.transposed)
         wd = wg_dgrad(w, self.h.transposed)
-        b = self.h.bias.detach().to(device=host, dtype=torch.float32) if self.h.bias is not None else \
-            torch.zeros(self.h.cout, dtype=torch.float32)        # nn.Conv3d(bias=False)
-        if self.extra is not None:
-            w2 = self.extra.weight.detach().to(device=host, dtype=torch.float32)
-            if self.w_map is not None:
-                w2 = self.w_map(w2)
+        if w2 is not None:
             wf = torch.cat([wf, wg_forward(w2, False)], dim=2)      # [T][ci][co0 + co1]
             wd = torch.cat([wd, wg_dgrad(w2, False)], dim=1)        # [T][ci = dy0 || dy1][co = cin]
-            b = torch.cat([b, self.extra.bias.detach().to(device=host, dtype=torch.float32)])
-        if self.fold_identity:
+            b = torch.cat([b, b2])
+        if add_identity is not None:
             c = self.K ** 3 // 2
-            eye = torch.eye(self.cin)
+            eye = torch.eye(self.cin, dtype=wf.dtype) * add_identity
             wf = wf.clone(); wd = wd.clone()
             wf[c] += eye
             wd[c] += eye
         if self.dgrad_cin is not None:
             wd = wd[:, :, : self.dgrad_cin].contiguous()
-        self.wg_fwd_host = wf          # canonical Wg[T][ci][co] (fp32, host): weight-gradient tests, diagnostics
-        self.packed = {
-            "simt_fwd": pack_weights_simt(wf).to(device), "simt_bwd": pack_weights_simt(wd).to(device),
-            "bias": pack_bias(b).to(device),
-        }
+        return wf, wd, b
+
+    def _pack_all(self, wf, wd, b, want_tc: bool, bwd_dtype: int, t2s: bool, small: bool = True) -> dict:
+        """Every device format of the launch from the canonical tensors (values, or -- inside layout.index_mode() --
+        source indices: the packers are pure rearrangements)."""
+        out = {"simt_fwd": pack_weights_simt(wf), "simt_bwd": pack_weights_simt(wd), "bias": pack_bias(b)}
         lib = _lib.lib()
-        if lib.tta_conv_small_supported(self.K, self.stride, self.cin, self.cout):
-            # tiny-channel stride-1 convs (UNet head): direct CUDA-core kernel, HBM-bound
-            self.packed["small_fwd"] = pack_weights_small(wf, self.mode)
-            self.packed["small_bwd"] = pack_weights_small(wd, 1 - self.mode)
+        if small and lib.tta_conv_small_supported(self.K, self.stride, self.cin, self.cout):
+            # tiny-channel stride-1 convs (UNet head): direct CUDA-core kernel, HBM-bound (HOST weights = kernel params)
+            out["small_fwd"] = pack_weights_small(wf, self.mode)
+            out["small_bwd"] = pack_weights_small(wd, 1 - self.mode)
         if want_tc:
             self.tc_fwd_flags = 0
             if lib.tta_conv_tc_supported(self.mode, self.K, self.stride, self.cin, self.cout):
@@ -253,19 +248,68 @@ class ConvLayer:
                 # layout, real Cout in flags bits 8..10 (include/tta_b200.h)
                 use_t2s = t2s and self.extra is None and bool(
                     lib.tta_conv_tc_t2s(self.mode, self.K, self.stride, self.cin, self.cout, 1))
-                self.packed["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16,
-                                                        t2s=use_t2s).to(device)
+                out["tc_fwd"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16, t2s=use_t2s)
                 self.tc_fwd_flags = (self.cout << 8) if use_t2s else 0
                 # stride-2 conv over <= 4 input channels: also the variant for a COMPACT input (network input)
                 if lib.tta_conv_tc_s2c4(self.mode, self.K, self.stride, self.cin):
-                    self.packed["tc_fwd_c4"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16,
-                                                               s2c4=True).to(device)
+                    out["tc_fwd_c4"] = pack_weights_tc(wf, self.mode, self.K, self.stride, TTA_F16, s2c4=True)
             bmode = 1 - self.mode
             if lib.tta_conv_tc_supported(bmode, self.K, self.stride, self.cout, self.dgrad_cin or self.cin):
-                self.packed["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype).to(device)
+                out["tc_bwd"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype)
                 if lib.tta_conv_tc_s2c4(bmode, self.K, self.stride, self.cout):   # dgrad of a <= 4-channel convT
-                    self.packed["tc_bwd_c4"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype,
-                                                               s2c4=True).to(device)
+                    out["tc_bwd_c4"] = pack_weights_tc(wd, bmode, self.K, self.stride, bwd_dtype, s2c4=True)
+        return out
+
+    def pack(self, device, want_tc: bool, bwd_dtype: int = TTA_BF16, t2s: bool = True, trainable: bool = False):
+        """(Re)pack weights: fp32 for the CUDA-core kernels, split fp16 / single fp16 for tcgen05.
+        Packing runs on the HOST (a few hundred small index ops per layer, once per weight load) and every
+        blob reaches the device as one H2D copy -- the device only ever executes this library's kernels.
+        ``trainable`` (supervised step): no host-parameter kernels (their weights could not follow the optimizer
+        without a device -> host copy per step)."""
+        host = torch.device("cpu")
+        f32 = lambda t: t.detach().to(device=host, dtype=torch.float32)
+        w = f32(self.h.weight)
+        b = f32(self.h.bias) if self.h.bias is not None else torch.zeros(self.h.cout, dtype=torch.float32)  # bias=False
+        w2 = f32(self.extra.weight) if self.extra is not None else None
+        b2 = f32(self.extra.bias) if self.extra is not None else None
+        wf, wd, bb = self._canonical(w, b, w2, b2, 1.0 if self.fold_identity else None)
+        self.wg_fwd_host = wf          # canonical Wg[T][ci][co] (fp32, host): weight-gradient tests, diagnostics
+        self.packed = {k: (v if k.startswith("small_") else v.to(device))
+                       for k, v in self._pack_all(wf, wd, bb, want_tc, bwd_dtype, t2s, small=not trainable).items()}
+
+    def index_maps(self, offsets: dict, device, want_tc: bool, bwd_dtype: int, t2s: bool) -> dict:
+        """For every packed blob: (int32 map, optional int8 additive map, kind) with map[e] = +-(1 + flat index of the
+        source parameter element) (sign = hi / lo plane, 0 = padding) -- what tta_repack_weights turns back into the
+        blob from the flat parameter buffer after an optimizer step.  ``offsets[id(holder)] = (w_off, b_off)``."""
+        from .layout import index_mode
+        if self.w_map is not None:
+            raise NotImplementedError("supervised step: layers with effective-weight maps (multimodal stems) are not supported")
+
+        def idx(t, off):
+            return torch.arange(t.numel(), dtype=torch.float64).view(t.shape) + (off + 1)
+        wo, bo = offsets[id(self.h)]
+        w = idx(self.h.weight, wo)
+        b = idx(self.h.bias, bo) if self.h.bias is not None else torch.zeros(self.h.cout, dtype=torch.float64)
+        w2 = b2 = None
+        if self.extra is not None:
+            wo2, bo2 = offsets[id(self.extra)]
+            w2, b2 = idx(self.extra.weight, wo2), idx(self.extra.bias, bo2)
+        maps = {}
+        with index_mode():
+            wf, wd, bb = self._canonical(w, b, w2, b2, None)
+            pm = self._pack_all(wf, wd, bb, want_tc, bwd_dtype, t2s, small=False)
+            pa = None
+            if self.fold_identity:   # the additive identity of the folded shortcut, through the same rearrangement
+                z = lambda t: torch.zeros(t.shape, dtype=torch.float64)
+                af, ad, ab = self._canonical(z(self.h.weight), z(b), None, None, 1.0)
+                pa = self._pack_all(af, ad, ab, want_tc, bwd_dtype, t2s, small=False)
+        for k, m in pm.items():
+            kind = 0 if k in ("simt_fwd", "simt_bwd", "bias") else (2 if (k.startswith("tc_bwd") and bwd_dtype == TTA_BF16) else 1)
+            add = None
+            if pa is not None and k != "bias" and bool((pa[k] != 0).any()):
+                add = (pa[k] != 0).to(torch.int8).contiguous().to(device)
+            maps[k] = (m.to(torch.int32).contiguous().to(device), add, kind)
+        return maps
 
 
 class NormLayer:
@@ -346,6 +390,11 @@ class TTAEngine:
         self.adam = dict(lr=1e-3, b1=0.9, b2=0.999, eps=1e-8)
         self.bwd_dtype = TTA_F16_HI if model.bwd_precision == "fp16" else TTA_BF16
         self.last_inv_scale = 1.0
+        # supervised step (model.trainable): every conv weight / bias lives in ONE flat fp32 buffer (the holders'
+        # Parameters are views of it, their gradients views of gflat), so that the weight-gradient kernels write
+        # into .grad directly and the packed operand blobs are rebuilt on the device after an optimizer step
+        self.wflat = self.gflat = None
+        self.w_off: dict = {}
         self._collect()
 
     # ---------------------------------------------------------------- structure
@@ -384,6 +433,66 @@ class TTAEngine:
     def invalidate(self):
         self.model._params_dirty = True
 
+    def active_layers(self) -> List["ConvLayer"]:
+        fused_members = set()
+        for fl in self.fused_layers.values():
+            fused_members |= {id(fl.h), id(fl.extra)}
+        return [cl for k, cl in self.conv_layers.items() if k not in fused_members] + list(self.fused_layers.values())
+
+    def _bind_conv_params(self):
+        """model.trainable: move every conv weight / bias into the flat buffer and rebind the Parameters as views
+        (same Parameter objects: an optimizer built earlier keeps working)."""
+        holders = self.model.conv_holders()
+        n = sum(h.weight.numel() + (h.bias.numel() if h.bias is not None else 0) for h in holders)
+        if self.wflat is not None and self.wflat.device == self.device and self.wflat.numel() == n:
+            return
+        wflat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.gflat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        self.w_off = {}
+        for h in holders:
+            nw = h.weight.numel()
+            wflat[off: off + nw].copy_(h.weight.detach().reshape(-1).to(self.device))
+            h.weight.data = wflat[off: off + nw].view(h.weight.shape)
+            bo = -1
+            if h.bias is not None:
+                bo = off + nw
+                nb = h.bias.numel()
+                wflat[bo: bo + nb].copy_(h.bias.detach().reshape(-1).to(self.device))
+                h.bias.data = wflat[bo: bo + nb]
+            self.w_off[id(h)] = (off, bo)
+            off += nw + (h.bias.numel() if h.bias is not None else 0)
+        self.wflat = wflat
+
+    def repack_on_device(self):
+        """Rebuild every packed operand blob from the flat parameter buffer (one gather per blob)."""
+        with self.on_device():
+            for cl in self.active_layers():
+                for k, (mp, add, kind) in cl.maps.items():
+                    out = cl.packed[k]
+                    check(self.lib.tta_repack_weights(self.wflat.data_ptr(), mp.data_ptr(), add.data_ptr() if add is not None else 0,
+                                                      mp.numel(), out.data_ptr(), kind, _stream()), "repack_weights")
+
+    def param_grads(self, params) -> list:
+        """Gradient tensors (fresh copies) for the given Parameters after a supervised backward: conv weights /
+        biases from gflat, norm affines from the [dgamma || dbeta] buffer (loss scale divided out), None otherwise."""
+        look = {}
+        for h in self.model.conv_holders():
+            wo, bo = self.w_off[id(h)]
+            look[id(h.weight)] = self.gflat[wo: wo + h.weight.numel()].view(h.weight.shape)
+            if h.bias is not None:
+                look[id(h.bias)] = self.gflat[bo: bo + h.bias.numel()]
+        P = self.P
+        for nl in self.norm_layers:
+            if nl.h.weight is not None:
+                look[id(nl.h.weight)] = self.dgb[nl.off: nl.off + nl.C] * self.last_inv_scale
+                look[id(nl.h.bias)] = self.dgb[P + nl.off: P + nl.off + nl.C] * self.last_inv_scale
+        out = []
+        for p_ in params:
+            g = look.get(id(p_))
+            out.append(None if g is None or not p_.requires_grad else g.clone())
+        return out
+
     @contextlib.contextmanager
     def on_device(self):
         """Every launch of this engine runs with ITS device current and on that device's current stream, whatever
@@ -421,8 +530,13 @@ class TTAEngine:
             self.v = torch.zeros(2 * P, dtype=torch.float32, device=device)
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)
             self.model._params_dirty = True
+        trainable = bool(getattr(self.model, "trainable", False)) and not dry
+        if trainable:
+            self.model._params_dirty = True      # an optimizer updates the weights in place: check every time
         if self.model._params_dirty:
             self._bind_params()
+            if trainable:
+                self._bind_conv_params()
             # conv weights are baked into the plans (packed device blobs, host kernel parameters of the small /
             # head kernels, captured CUDA graphs): repack only when a weight tensor really changed
             # (storage, in-place version, device) and then drop every plan built on the old blobs
@@ -430,20 +544,29 @@ class TTAEngine:
                         h.bias.data_ptr() if h.bias is not None else 0, h.bias._version if h.bias is not None else 0,
                         str(h.weight.device)) for h in self.model.conv_holders())
             fp = (fp, self.model.conv_backend, self.model.t2s_head, self.bwd_dtype)
-            if fp == getattr(self, "_packed_fp", None):
+            fp = (fp, trainable)
+            prev = getattr(self, "_packed_fp", None)
+            if fp == prev:
                 self.model._params_dirty = False
                 return
-            self._packed_fp = fp
-            self.plans.clear()
             want_tc = self.model.conv_backend in ("auto", "tc")
-            fused_members = set()
-            for fl in self.fused_layers.values():
-                fused_members |= {id(fl.h), id(fl.extra)}
-            for key, cl in self.conv_layers.items():
-                if key not in fused_members:
-                    cl.pack(device, want_tc, self.bwd_dtype, t2s=self.model.t2s_head)
-            for fl in self.fused_layers.values():
-                fl.pack(device, want_tc, self.bwd_dtype, t2s=self.model.t2s_head)
+            # same storages, only in-place versions moved (an optimizer step, an in-place load_state_dict) and the
+            # index maps exist: rebuild the blobs on the device, at their old addresses -- plans and graphs stay valid
+            # fp = ((per-holder tuples, backend, t2s, bwd dtype), trainable)
+            same_storage = (prev is not None and trainable and prev[1:] == fp[1:] and prev[0][1:] == fp[0][1:]
+                            and len(prev[0][0]) == len(fp[0][0])
+                            and all(a[:2] == b[:2] and a[3] == b[3] and a[5] == b[5] for a, b in zip(prev[0][0], fp[0][0]))
+                            and all(hasattr(cl, "maps") for cl in self.active_layers()))
+            self._packed_fp = fp
+            if same_storage:
+                self.repack_on_device()
+                self.model._params_dirty = False
+                return
+            self.plans.clear()
+            for cl in self.active_layers():
+                cl.pack(device, want_tc, self.bwd_dtype, t2s=self.model.t2s_head, trainable=trainable)
+                if trainable:
+                    cl.maps = cl.index_maps(self.w_off, device, want_tc, self.bwd_dtype, self.model.t2s_head)
             self.model._params_dirty = False
 
     def _bind_params(self):
@@ -616,7 +739,7 @@ class TTAEngine:
                     raise ValueError("unet_b200: the network input feeds both a strided and an unstrided conv")
                 plan.x_layout = ws_in
             c4_in = False
-            if ws_in and inp.parent is plan.x and model.input_compact and "tc_fwd_c4" in cl.packed \
+            if ws_in and inp.parent is plan.x and model.input_compact and not model.trainable and "tc_fwd_c4" in cl.packed \
                     and model.conv_backend in ("auto", "tc") and d % 2 == 0 and h % 2 == 0:
                 # <= 4 input channels: the packed input in the compact layout (8 B per voxel and plane)
                 c4_in = True
@@ -848,6 +971,7 @@ class TTAEngine:
                 fused_head = (hcl, hrec, hinp)
                 max_ws[0] = max(max_ws[0], lib.tta_head_fused_workspace_floats(N, *final_dims(final)))
         plan.fused_head = fused_head is not None
+        plan.final = final
         # compact layout of the head's tensors (conv result fp32 x4, masked gradient fp16 x4 per voxel instead of
         # 8-channel chunks): when the small-Cout transposed kernel produces the result AND its statistics (no pass
         # of the generic 8-channel norm kernels ever touches it)
@@ -968,9 +1092,41 @@ class TTAEngine:
                 continue
             if op[0] == "conv":
                 _, cl, inp, y = op
+                N = y.N
+                if model.trainable:
+                    # supervised step: weight / bias gradients from the operands both passes hold (forward input
+                    # planes, the output's gradient planes), straight into the parameters' .grad storage
+                    if cl.w_map is not None or cl.dgrad_cin is not None:
+                        raise NotImplementedError("supervised step: effective-weight layers are not supported")
+                    y.alloc_dy(nplanes)
+                    xpar = inp.parent
+                    if xpar.compact:
+                        raise RuntimeError("supervised step: compact input layout")
+                    wo, bo = self.w_off[id(cl.h)]
+                    wo2, bo2 = self.w_off[id(cl.extra)] if cl.extra is not None else (0, -1)
+                    gbase = self.gflat.data_ptr()
+                    wg_args = (inp.hi, inp.lo, inp.ns, *inp.dims, int(xpar.wsplit and xpar is plan.x),
+                               y.dy_ptr(0), y.dy_ptr(1), y.ns, bdt, y.D, y.H, y.W, 0, N, cl.mode, cl.K, cl.stride,
+                               cl.h.cin, cl.cout, 1.0 / plan.loss_scale, gbase + wo * 4, 1 if cl.h.transposed else 0,
+                               cl.h.cout if cl.extra is not None else 0, gbase + wo2 * 4)
+                    bg_args = None
+                    if bo >= 0:
+                        bg_args = (y.dy_ptr(0), y.dy_ptr(1), y.ns, bdt, N, cl.cout, y.V, 1.0 / plan.loss_scale,
+                                   gbase + bo * 4, cl.h.cout if cl.extra is not None else 0,
+                                   gbase + bo2 * 4 if bo2 >= 0 else 0)
+
+                    def run_wgrad(wg_args=wg_args, bg_args=bg_args, yroot=y.root, name=cl.name):
+                        a = list(wg_args)
+                        a[14] = int(yroot.dy_wsplit)          # resolved at launch time, like the dgrad's flag
+                        check(lib.tta_conv_wgrad(*a, _stream()), f"conv_wgrad {name}")
+                        if bg_args is not None:
+                            check(lib.tta_bias_grad(*bg_args, _stream()), f"bias_grad {name}")
+                    run_wgrad.label = f"wgrad {cl.name} {cl.h.cin}->{cl.cout}"
+                    run_wgrad.launches = 2 if bg_args is not None else 1
+                    plan.bwd.append(run_wgrad)
+                    plan.n_wgrad = getattr(plan, "n_wgrad", 0) + run_wgrad.launches
                 if not inp.parent.needs_grad:
                     continue
-                N = y.N
                 par = inp.parent
                 c8o = (cl.dgrad_cin + 7) // 8 if cl.dgrad_cin is not None else inp.C8
                 chunks = set(range(inp.c8_off, inp.c8_off + c8o))
@@ -1039,10 +1195,11 @@ class TTAEngine:
                                                     rec["mean"].data_ptr(), rec["rstd"].data_ptr(), rec["gptr"],
                                                     rec["bptr"], pbuf.data_ptr()))
                             fuse_bwd = (pbuf, info[1])
-                conv_in_needs = self._producer_input_needs_grad(ops, y)
+                # (supervised step: every conv needs its output gradient for the weight gradient)
+                conv_in_needs = self._producer_input_needs_grad(ops, y) or model.trainable
                 res = rec["residual"]
                 aux = None
-                if isinstance(res, (Res, ResView)) and self._producer_input_needs_grad(ops, res):
+                if isinstance(res, (Res, ResView)) and (self._producer_input_needs_grad(ops, res) or model.trainable):
                     res.alloc_dy(nplanes)
                     aux = res
                 elif isinstance(res, ActView):
@@ -1182,7 +1339,7 @@ class TTAEngine:
         plan.launches_bwd += sum(2 * (o[1]["per_sample_bwd"] - 1) for o in ops if o[0] == "norm" and o[1].get("per_sample_bwd"))
         n_extra = sum(1 for o in ops if o[0] in ("mean", "upsample", "cast"))   # one launch each way
         plan.launches_fwd += n_extra + (1 if getattr(plan, "x2", None) is not None else 0)
-        plan.launches_bwd += n_extra
+        plan.launches_bwd += n_extra + getattr(plan, "n_wgrad", 0)
         return plan
 
     def _nl(self, holder: NormHolder) -> NormLayer:
@@ -1327,6 +1484,49 @@ class TTAEngine:
                 op()
         if adam:
             self.adam_step(gscale)
+
+    def forward_train(self, x: torch.Tensor):
+        """Forward of the supervised path (model.trainable): train-mode norm statistics, logits only.  Returns
+        (logits copy, plan); the plan's operand / result buffers are what backward_from_logits_grad reads."""
+        x = self._check_input(x)
+        self._ensure_device(x.device)
+        with self.on_device():
+            plan = self.get_plan(*[int(s_) for s_ in (x.shape[0], *x.shape[2:])])
+            if plan.fused_head:
+                raise RuntimeError("supervised step: the fused head holds host-side weights (internal error)")
+            self._pack_input(plan, x)
+            if self.model.c_plan:
+                cp = self.c_plan(plan)
+                check(self.lib.tta_plan_run(cp.h, CPlan.SEC_FWD, _stream()), "plan_run(forward)")
+                check(self.lib.tta_plan_run(cp.h, CPlan.SEC_HEAD_INFER, _stream()), "plan_run(head)")
+            else:
+                for op in plan.fwd:
+                    op()
+                plan.head_infer()
+            self._update_running_stats(plan)
+            return plan.logits.clone(), plan
+
+    def backward_from_logits_grad(self, plan: Plan, grad_logits: torch.Tensor):
+        """dL/dlogits [N,R,D,H,W] fp32 (from ANY loss: the reference's DiceCELoss through autograd) -> gradients of every
+        conv weight / bias (gflat) and norm affine (dgb, loss-scaled).  The gradient enters the 16-bit gradient planes
+        of the last conv through tta_pack_grad (NCDHW -> chunk layout), times the plan's power-of-two loss scale."""
+        if not self.model.trainable:
+            raise RuntimeError("backward needs model.trainable = true")
+        g = grad_logits.contiguous().float()
+        R = self.model.out_channels
+        N, (D, H, W) = plan.N, plan.dims
+        final = plan.final
+        with self.on_device():
+            self.last_inv_scale = 1.0 / plan.loss_scale
+            self.gflat.zero_()
+            self.dgb.zero_()
+            check(self.lib.tta_pack_grad(g.data_ptr(), N, R, final.V, float(plan.loss_scale), final.dy_ptr(0),
+                                         final.dy_ptr(1), final.ns, self.bwd_dtype, _stream()), "pack_grad")
+            if self.model.c_plan:
+                check(self.lib.tta_plan_run(self.c_plan(plan).h, CPlan.SEC_BWD, _stream()), "plan_run(backward)")
+            else:
+                for op in plan.bwd:
+                    op()
 
     def adam_step(self, gscale: float = 1.0):
         """``gscale`` multiplies the gradient (1/world for the all-reduced sum); the loss scale of

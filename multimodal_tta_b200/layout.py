@@ -13,6 +13,33 @@ import torch
 from ._lib import TTA_BF16, TTA_F16, TTA_F16_HI
 
 
+# ---- index mode: the packers below are pure rearrangements (+ the hi/lo split) of the canonical weights.  Run on a
+# tensor of SOURCE INDICES instead of values they yield, for every packed element, which parameter element it comes
+# from -- the map the device-side repack kernel (tta_repack_weights) needs after every optimizer step of the
+# supervised path, where re-running the host packers (1.3 s) is not an option.  In index mode values are float64
+# (exact integers up to 2^53), packed outputs int64, and split_planes returns (+idx, -idx): the sign tells the
+# repack kernel which plane (hi / lo) an element is.
+_IDX = False
+
+
+class index_mode:
+    def __enter__(self):
+        global _IDX
+        self.prev, _IDX = _IDX, True
+
+    def __exit__(self, *a):
+        global _IDX
+        _IDX = self.prev
+
+
+def _i16():
+    return torch.int64 if _IDX else torch.int16
+
+
+def _f32():
+    return torch.float64 if _IDX else torch.float32
+
+
 def wg_forward(w: torch.Tensor, transposed: bool) -> torch.Tensor:
     """nn.Conv3d weight [co][ci][k,k,k] or nn.ConvTranspose3d weight [ci][co][k,k,k] -> Wg[T][ci][co]."""
     k = w.shape[-1]
@@ -39,9 +66,10 @@ def pack_weights_simt(wg: torch.Tensor) -> torch.Tensor:
     """Wg[T][ci][co] -> Wp[T][C8in][C8out][8 ci][8 co] fp32 (zero padded)."""
     T, ci, co = wg.shape
     cip, cop = _pad8(ci), _pad8(co)
-    p = torch.zeros((T, cip, cop), dtype=torch.float32, device=wg.device)
+    p = torch.zeros((T, cip, cop), dtype=_f32(), device=wg.device)
     p[:, :ci, :co] = wg
-    return p.reshape(T, cip // 8, 8, cop // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+    p = p.reshape(T, cip // 8, 8, cop // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+    return p.round().long() if _IDX else p
 
 
 def pack_weights_small(wg: torch.Tensor, mode: int) -> torch.Tensor:
@@ -56,13 +84,18 @@ def pack_weights_small(wg: torch.Tensor, mode: int) -> torch.Tensor:
 
 
 def pack_bias(b: torch.Tensor) -> torch.Tensor:
-    p = torch.zeros(_pad8(b.numel()), dtype=torch.float32, device=b.device)
+    p = torch.zeros(_pad8(b.numel()), dtype=_f32(), device=b.device)
     p[: b.numel()] = b
+    if _IDX:
+        return p.round().long()
     return p
 
 
 def split_planes(x: torch.Tensor, dtype_tag: int) -> tuple[torch.Tensor, torch.Tensor]:
     """fp32 -> (hi, lo) 16-bit planes stored as int16, hi = rn16(x), lo = rn16(x - hi)."""
+    if _IDX:
+        h = x.round().long()
+        return h, -h
     dt = torch.bfloat16 if dtype_tag == TTA_BF16 else torch.float16
     if dtype_tag != TTA_BF16:
         x = x.clamp(-65504.0, 65504.0)
@@ -146,8 +179,8 @@ def pack_weights_t2s(wg: torch.Tensor) -> torch.Tensor:
     T, ci, co = wg.shape
     assert T == 27 and ci % 16 == 0 and 1 <= co <= 4
     npad = (27 * co + 15) // 16 * 16
-    hi, lo = split_planes(wg.float(), TTA_F16)                       # [27][ci][co]
-    out = torch.zeros((ci // 16, 2, 2, npad, 8), dtype=torch.int16, device=wg.device)
+    hi, lo = split_planes(wg.to(_f32()), TTA_F16)                    # [27][ci][co]
+    out = torch.zeros((ci // 16, 2, 2, npad, 8), dtype=_i16(), device=wg.device)
     for pi, plane in enumerate((hi, lo)):
         rows = plane.permute(0, 2, 1).reshape(27 * co, ci // 16, 2, 8)   # [tap*co + c][ks][kc][8]
         out[:, :, pi, : 27 * co] = rows.permute(1, 2, 0, 3)
@@ -170,20 +203,20 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
     ntile = lib.tta_conv_tc_ntile(mode, K, stride, co, int(split))
     cip = (ci + 15) // 16 * 16
     cop = (co + ntile - 1) // ntile * ntile
-    w = torch.zeros((T, cip, cop), dtype=torch.float32, device=wg.device)
+    w = torch.zeros((T, cip, cop), dtype=_f32(), device=wg.device)
     w[:, :ci, :co] = wg
     hi, lo = split_planes(w, dtype_tag)
     planes = (hi, lo) if split else (hi,)
     groups = tc_groups(mode, K, stride)
     gmax = max(len(g) for g in groups)
     ncb, nnt = cip // 16, cop // ntile
-    out = torch.zeros((nnt, ncb, len(groups), gmax, 2, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+    out = torch.zeros((nnt, ncb, len(groups), gmax, 2, len(planes), ntile, 8), dtype=_i16(), device=wg.device)
     if K == 3 and stride == 1 and lib.tta_conv_tc_stacked(mode, K, stride, ci, co, int(split)):
         # kd-stacked stride-1 conv (small n-tile, resident weights; csrc/tta_conv_tc.cu GEOM_S1K): one
         # blob per channel block, entry (kh, kw) = [kchunk][slot 0..2][hi NT | lo NT][8].  Slot s feeds
         # the accumulator of output plane j - 2 + s from input plane j: kd = 2 - s for a conv, kd = s
         # for its input-gradient dual (mirrored offsets).
-        st = torch.zeros((1, ncb, 9, 2, 3, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+        st = torch.zeros((1, ncb, 9, 2, 3, len(planes), ntile, 8), dtype=_i16(), device=wg.device)
         for sl in range(3):
             kd = 2 - sl if mode == 0 else sl
             for pi, plane in enumerate(planes):
@@ -209,7 +242,7 @@ def pack_weights_tc(wg: torch.Tensor, mode: int, K: int, stride: int, dtype_tag:
         # stride-2 conv over a COMPACT <= 4-channel input (csrc/tta_conv_tc.cu GEOM_S2C4): group = kd, entry = kh,
         # k-chunk 0 = [zeros | kw 0: 4 ch], k-chunk 1 = [kw 1: 4 ch | kw 2: 4 ch] (rows start at the even voxel 2w - 2)
         assert K == 3 and mode == 0 and stride == 2 and ci <= 4
-        out = torch.zeros((nnt, 1, 3, 3, 2, len(planes), ntile, 8), dtype=torch.int16, device=wg.device)
+        out = torch.zeros((nnt, 1, 3, 3, 2, len(planes), ntile, 8), dtype=_i16(), device=wg.device)
         for kd in range(3):
             for kh in range(3):
                 for pi, plane in enumerate(planes):

@@ -115,6 +115,24 @@ class SkipConnectionH(nn.Module):
         self.submodule = submodule
 
 
+class _SupervisedFunction(torch.autograd.Function):
+    """Autograd bridge of the supervised path: the reference's trainer computes its own loss on the logits (MONAI
+    DiceCELoss) and calls ``loss.backward()``; this node turns dL/dlogits into the gradients of every parameter with
+    the CUDA backward.  The input needs no gradient (it is data)."""
+
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        logits, plan = model.engine.forward_train(x)
+        ctx.model, ctx.plan, ctx.params = model, plan, params
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        eng = ctx.model.engine
+        eng.backward_from_logits_grad(ctx.plan, grad_logits)
+        return (None, None, *eng.param_grads(ctx.params))
+
+
 class B200Model(nn.Module):
     """Common part of the B200 model classes: backend options, holder plumbing, the lazily built TTAEngine.
     A subclass builds its holder tree, then implements ``build_graph(G)`` (walk the tree with the engine's
@@ -169,11 +187,20 @@ class B200Model(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Raw logits [B,R,D,H,W].  train(): test-batch norm statistics; eval(): BatchNorm uses its
-        running statistics (InstanceNorm always uses instance statistics, as in the reference)."""
+        running statistics (InstanceNorm always uses instance statistics, as in the reference).
+        With ``trainable: true`` and gradients enabled the logits carry a grad_fn: ``loss.backward()`` of the
+        reference's supervised step (src/core/trainers/seg_trainer.py:141-143) runs the CUDA backward (input
+        gradients, norm backward, weight / bias gradients) and fills every parameter's ``.grad``."""
+        if self.trainable and torch.is_grad_enabled() and self.training:
+            params = [p for p in self.parameters() if p.requires_grad]
+            if params:
+                return _SupervisedFunction.apply(x, self, *params)
         return self.engine.forward(x)
 
     def _backend_options(self, get) -> None:
         """Backend options (not in the reference): conv kernel family, whole-step CUDA graph, A/B switches."""
+        # supervised step (SURVEY 8f-4): forward keeps an autograd edge, backward computes ALL parameter gradients
+        self.trainable = bool(get("trainable", False))
         self.conv_backend = str(get("conv_backend", "auto"))
         # the launch list of a shape is recorded into a C object (tta_plan) and a step is one C call (tta_step);
         # false: the Python closures are called one by one (debugging)
