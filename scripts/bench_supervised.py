@@ -59,3 +59,16 @@ for tf32 in (False, True):
     ms_r, _ = timed(ref, make_optimizer(ref), n=3)
     print(f"torch eager ({'TF32' if tf32 else 'fp32, TF32 off = reference setting'}): {ms_r:.2f} ms per step = {B * 1e3 / ms_r:.1f} volumes/s")
     del ref
+# ---- in-stream duration of the backward ops (top 12)
+ops = list(plan.bwd)
+torch.cuda._sleep(40_000_000)
+evs = []
+for op in ops:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); op(); e1.record(); evs.append((e0, e1))
+torch.cuda.synchronize()
+rows = sorted(((a.elapsed_time(b) * 1e3, getattr(op, "label", "?")) for (a, b), op in zip(evs, ops)), reverse=True)
+print("backward ops, top 12 (us):")
+for us, lab in rows[:12]:
+    print(f"  {us:8.1f}  {lab}")
+print(f"  wgrad total {sum(u for u, l in rows if l.startswith('wgrad')) / 1e3:.2f} ms")
