@@ -76,7 +76,10 @@ int tta_gather_pack_norm_f16(const uint16_t* vol, int n_vol, int C, int Ds, int 
  bit12 CTA pairs: 2-CTA clusters with multicast weight blobs (opt-in; measured neutral), bit13 nine (kd, kh)
  * pipeline groups for ordinary planes (opt-in; measured slower),
  * bits 8..10 real Cout of a small-Cout transposed conv
- * packed for the dense-GEMM + col2im kernel (tta_conv_tc_t2s). */
+ * packed for the dense-GEMM + col2im kernel (tta_conv_tc_t2s),
+ * bit16 `out` is ONE fp16 plane in the chunk layout (16 B per voxel-chunk; out_n_stride in elements): the loss-scaled
+ * input gradient of a dgrad, consumed by tta_norm_bwd_* with the fp16-source bits; implies bit1, accumulate becomes a
+ * 16-byte read-modify-write. */
 int tta_conv_tc_supported(int mode, int K, int stride, int cin, int cout);
 int tta_conv_tc_ntile(int mode, int K, int stride, int cout, int split);
 /* 1 when this layer runs kd-stacked (stride-1, single small n-tile, resident weights): its packed
@@ -165,7 +168,10 @@ int tta_norm_apply(const float* y, long long y_n_stride, int N, int C8, long lon
 /* mean/rstd from the partial sums in a workspace with `splits` slots per (n, chunk) */
 int tta_norm_stats_finalize(const float* workspace, int N, int C8, int splits, long long V, int batch_mode,
                             float eps, float* mean, float* rstd, tta_stream_t stream);
-/* partial sums of dz and dz*xhat (dz = (g0+g1)*[z>0]); finalize != 0 also writes sums[N][C][2] and
+/* Gradient sources of the three norm-backward entry points: g0 / g1 are fp32 chunk tensors, or -- when bit 1 / bit 2
+ * of the `relu` argument is set (bit 0 stays the ReLU switch) -- ONE loss-scaled fp16 plane each, as a tcgen05 dgrad
+ * writes it with tta_conv_tc flags bit 16 (n strides stay in elements).
+ * partial sums of dz and dz*xhat (dz = (g0+g1)*[z>0]); finalize != 0 also writes sums[N][C][2] and
  * dgamma/dbeta[C] (accumulate_dgb != 0: adds to them -- a layer processed sample by sample, each call
  * with N = 1 and pointers advanced by one sample, so that the apply pass re-reads g and y from L2) */
 int tta_norm_bwd_reduce(const float* g0, long long g0_n_stride, const float* g1, long long g1_n_stride,
@@ -300,6 +306,16 @@ int tta_conv_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, long long x_n_str
                    const uint16_t* dy_hi, const uint16_t* dy_lo, long long dy_n_stride, int dy_dtype, int Dy, int Hy,
                    int Wy, int dy_wsplit, int N, int mode, int K, int stride, int Cin, int Cout, float scale, float* dw,
                    int layout, int co_split, float* dw2, tta_stream_t stream);
+/* The same weight gradient on the tensor cores (tcgen05, csrc/tta_wgrad_tc.cu) for the 3x3x3 layers whose output
+ * gradient is ONE loss-scaled fp16 plane (dy_dtype TTA_F16_HI): conv stride 1 / 2 and transposed conv stride 2.
+ * Operand layouts: stride 1 -- x and dy plain; stride-2 conv -- x w-parity-split (x_wsplit = 1: the copy its forward
+ * conv reads), dy plain; transposed -- x plain, dy w-parity-split (dy_wsplit = 1: what its dgrad reads).
+ * flags bit 0: use only the hi plane of x (one fp16 product instead of two). */
+int tta_conv_wgrad_tc_supported(int mode, int K, int stride, int Cin, int Cout, int dy_dtype);
+int tta_conv_wgrad_tc(const uint16_t* x_hi, const uint16_t* x_lo, long long x_n_stride, int Dx, int Hx, int Wx,
+                      int x_wsplit, const uint16_t* dy_hi, long long dy_n_stride, int Dy, int Hy, int Wy, int dy_wsplit,
+                      int N, int mode, int stride, int Cin, int Cout, float scale, float* dw, int layout, int co_split,
+                      float* dw2, int flags, tta_stream_t stream);
 /* dL/dlogits (NCDHW fp32, from the reference's own loss through autograd) -> the 16-bit gradient plane(s) of the
  * last conv's result, times the power-of-two loss scale */
 int tta_pack_grad(const float* g, int N, int R, long long V, float scale, uint16_t* dy_hi, uint16_t* dy_lo,

@@ -100,6 +100,8 @@ _SIGNATURES = {
     "tta_conv_tc_bwd_norm": (I, [P, P, L, I, I, I, I, I, I, P, P, L, I, I, I, I, I, I, I, I, I, P, I, P]),
     "tta_norm_bwd_finalize": (I, [P, I, I, I, I, I, P, P, P, P]),
     "tta_conv_wgrad": (I, [P, P, L, I, I, I, I, P, P, L, I, I, I, I, I, I, I, I, I, I, I, F, P, I, I, P, P]),
+    "tta_conv_wgrad_tc_supported": (I, [I, I, I, I, I, I]),
+    "tta_conv_wgrad_tc": (I, [P, P, L, I, I, I, I, P, L, I, I, I, I, I, I, I, I, I, F, P, I, I, P, I, P]),
     "tta_pack_grad": (I, [P, I, I, L, F, P, P, L, I, P]),
     "tta_repack_weights": (I, [P, P, P, L, P, I, P]),
     "tta_bias_grad": (I, [P, P, L, I, I, I, L, F, P, I, P, P]),

@@ -72,6 +72,7 @@ struct TcParams {
   // and each fetches HALF of every weight blob, multicast into both; cl2 = 2 when active
   int cl2, pair_items;
   int pps;      // kd-stacked convs: halo planes per pipeline stage
+  int out_f16;  // flags bit 16: the result is ONE fp16 plane (16 B per voxel-chunk): loss-scaled input gradients
   int s2pair;   // GEOM_S2 with a one-chunk input: tap pairs share one K = 16 MMA (see issue_group)
   int t2_jh16;  // GEOM_T2: offset (16 B units) of the h+1 halo rows inside a k-chunk: 9 = next row, or a second box
   int pl2;      // small-plane tiles (H <= 8): the 128 rows are 2 d-planes x 8 h x 8 w (GEOM_S1P / GEOM_S1TP)
@@ -755,7 +756,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
               if (valid[k] && co_chunk < P.C8out) {
                 const float* src = obase[k] + (long long)co_chunk * Vo * 8;
                 float ov[8];
-                load_f32x8(src, ov);  // one 256-bit load per 32-byte voxel-chunk
+                if (P.out_f16) {
+                  const U16x8 h = *reinterpret_cast<const U16x8*>(reinterpret_cast<const uint16_t*>(P.out) + (src - P.out));
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) ov[i] = u16_to_f32<TTA_F16>(h.v[i]);
+                } else {
+                  load_f32x8(src, ov);  // one 256-bit load per 32-byte voxel-chunk
+                }
                 old[k][hlf][0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
                 old[k][hlf][1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
               } else {
@@ -805,7 +812,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P) {
                   r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
                 }
                 const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                store_f32x8(dst, rv);  // whole 32-byte sector in one store
+                if (P.out_f16) {
+                  U16x8 h;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) h.v[i] = f32_to_u16<TTA_F16>(rv[i]);
+                  *reinterpret_cast<U16x8*>(reinterpret_cast<uint16_t*>(P.out) + (dst - P.out)) = h;
+                } else {
+                  store_f32x8(dst, rv);  // whole 32-byte sector in one store
+                }
               }
             }
             if (STATS == 2) {
@@ -1362,6 +1376,13 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
                         int* q_nbuf, cudaStream_t stream) {
   const int split = in_dtype == TTA_F16_HI ? 0 : 1;
   const bool query = q_ksplit != nullptr;  // shape the launch only: report split-K factor and grid
+  // flags bit 16: `out` is one fp16 plane in the chunk layout (out_n_stride in ELEMENTS as always): the scaled
+  // input gradient of a dgrad goes to the norm backward in 2 instead of 4 bytes.  fp16 has no vector atomics:
+  // no split-K; gradient fan-in (accumulate) is a 16-byte read-modify-write
+  const bool out_f16 = (flags & 65536) != 0;
+  if (out_f16) flags |= 2;
+  TTA_REQUIRE(!out_f16 || (stats_ws == nullptr && segs == nullptr && !(flags & 16384) && ((flags >> 8) & 7) == 0),
+              "tta_conv_tc: flags bit 16 (fp16 result) excludes fused statistics and the small-Cout transposed kernel");
   TTA_REQUIRE(query || (in_hi && (in_lo || !split) && wpacked && out), "tta_conv_tc: null pointer");
   int geom = geom_of(mode, K, stride);
   TTA_REQUIRE(geom != GEOM_NONE, "tta_conv_tc: unsupported geometry mode=%d K=%d stride=%d", mode, K, stride);
@@ -1427,6 +1448,7 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   P.d_mul = (geom == GEOM_S2 || geom == GEOM_S2C4) ? 2 : 1;
   P.Do = Do; P.Ho = Ho; P.Wo = Wo; P.C8out = C8out; P.accumulate = accumulate;
   P.out_ns = out_ns; P.wpacked = (const uint8_t*)wpacked; P.bias = bias; P.out = out;
+  P.out_f16 = out_f16 ? 1 : 0;
   const int fmt = in_dtype == TTA_BF16 ? 1 : 0;
   const int idesc0 = (1 << 4) | (fmt << 7) | (fmt << 10) | ((128 >> 4) << 24);
   P.idesc0 = idesc0;

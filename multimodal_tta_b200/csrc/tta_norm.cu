@@ -284,6 +284,18 @@ norm_apply_kernel(const float* y, long long y_ns, int C8, long long V,
   }
 }
 
+// incoming gradient of a norm backward: fp32 chunks, or ONE loss-scaled fp16 plane (a dgrad that ran with
+// tta_conv_tc flags bit 16) -- `g` is the base pointer, `off` the element offset of the voxel-chunk
+__device__ __forceinline__ void load_grad8(const float* g, long long off, bool f16, float (&o)[8]) {
+  if (f16) {
+    const U16x8 h = *reinterpret_cast<const U16x8*>(reinterpret_cast<const uint16_t*>(g) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = u16_to_f32<TTA_F16>(h.v[i]);
+  } else {
+    load_f32x8(g + off, o);
+  }
+}
+
 // ---------------------------------------------------------------- backward reductions
 // partial[..][0..7] = sum dz, [8..15] = sum dz*xhat     (dz = (g0+g1) * [z>0])
 __global__ void __launch_bounds__(kThreads, 4)
@@ -291,12 +303,14 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
                         const float* g1, long long g1_ns,
                         const float* y, long long y_ns, int C8, long long V,
                         const float* mean, const float* rstd,
-                        const float* gamma, const float* beta, int relu,
+                        const float* gamma, const float* beta, int relu_flags,
                         int splits, float* partial, unsigned int* counters, int N,
                         int batch_mode, int Creal, float* sums, float* dgamma,
                         float* dbeta, int acc_dgb, int rev) {
   pdl_trigger();
   pdl_wait();
+  const int relu = relu_flags & 1;
+  const bool g0h = (relu_flags & 2) != 0, g1h = (relu_flags & 4) != 0;
   const int split = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int chunk = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int n = rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
@@ -311,8 +325,7 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
   }
   const long long slab = (long long)chunk * V * 8;
   const float* yb = y + (long long)n * y_ns + slab;
-  const float* g0b = g0 + (long long)n * g0_ns + slab;
-  const float* g1b = g1 ? g1 + (long long)n * g1_ns + slab : nullptr;
+  const long long g0o = (long long)n * g0_ns + slab, g1o = (long long)n * g1_ns + slab;
   const long long per = (V + splits - 1) / splits;
   const long long v0 = (long long)split * per;
   const long long v1 = min(V, v0 + per);
@@ -323,10 +336,10 @@ norm_bwd_partial_kernel(const float* g0, long long g0_ns,
   for (long long v = v0 + threadIdx.x; v < v1; v += kThreads) {
     float x[8], g[8];
     load_f32x8(yb + v * 8, x);
-    load_f32x8(g0b + v * 8, g);
-    if (g1b) {
+    load_grad8(g0, g0o + v * 8, g0h, g);
+    if (g1) {
       float h[8];
-      load_f32x8(g1b + v * 8, h);
+      load_grad8(g1, g1o + v * 8, g1h, h);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] += h[i];
     }
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
                       long long g1_ns, const float* y, long long y_ns, int C8,
                       long long V, const float* mean, const float* rstd,
-                      const float* gamma, const float* beta, int relu,
+                      const float* gamma, const float* beta, int relu_flags,
                       const float* sums, float inv_m, uint16_t* dy_hi,
                       uint16_t* dy_lo, long long dy_ns, uint16_t* aux_hi,
                       uint16_t* aux_lo, long long aux_ns, const float* partial,
@@ -399,6 +412,8 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
                       float* sums_w, int rev) {
   pdl_trigger();
   pdl_wait();
+  const int relu = relu_flags & 1;
+  const bool g0h = (relu_flags & 2) != 0, g1h = (relu_flags & 4) != 0;
   // rev: reverse of the reduction pass's order -> the tail of g / y it just streamed is still in L2
   const bool rv = rev && splits >= 0;
   const int chunk = rv ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
@@ -422,16 +437,15 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     const long long sl = (long long)chunk * V * 8;
     const float* ys = y + (long long)n * y_ns + sl;
-    const float* gs0 = g0 + (long long)n * g0_ns + sl;
-    const float* gs1 = g1 ? g1 + (long long)n * g1_ns + sl : nullptr;
+    const long long gs0 = (long long)n * g0_ns + sl, gs1 = (long long)n * g1_ns + sl;
 #pragma unroll 2
     for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V; v += (long long)gridDim.x * kThreads) {
       float x[8], g[8];
       load_f32x8(ys + v * 8, x);
-      load_f32x8(gs0 + v * 8, g);
-      if (gs1) {
+      load_grad8(g0, gs0 + v * 8, g0h, g);
+      if (g1) {
         float h[8];
-        load_f32x8(gs1 + v * 8, h);
+        load_grad8(g1, gs1 + v * 8, g1h, h);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] += h[i];
       }
@@ -497,8 +511,7 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
   }
   const long long slab = (long long)chunk * V * 8;
   const float* yb = y + (long long)n * y_ns + slab;
-  const float* g0b = g0 + (long long)n * g0_ns + slab;
-  const float* g1b = g1 ? g1 + (long long)n * g1_ns + slab : nullptr;
+  const long long g0o = (long long)n * g0_ns + slab, g1o = (long long)n * g1_ns + slab;
   const long long ob = (long long)n * dy_ns + slab;
   const long long ab = (long long)n * aux_ns + slab;
   const long long vstride = (long long)gridDim.x * kThreads, vfirst = (long long)bx * kThreads + threadIdx.x;
@@ -509,10 +522,10 @@ norm_bwd_apply_kernel(const float* g0, long long g0_ns, const float* g1,
   for (long long it = 0; it <= vlast_it; ++it, v += vstep) {
     float x[8], g[8];
     load_f32x8(yb + v * 8, x);
-    load_f32x8(g0b + v * 8, g);
-    if (g1b) {
+    load_grad8(g0, g0o + v * 8, g0h, g);
+    if (g1) {
       float h[8];
-      load_f32x8(g1b + v * 8, h);
+      load_grad8(g1, g1o + v * 8, g1h, h);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] += h[i];
     }

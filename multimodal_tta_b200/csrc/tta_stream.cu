@@ -388,6 +388,18 @@ sw_normalise_kernel(const float* acc, const float* wsum, int R,
 // ---------------------------------------------------------------- Dice counts
 // counts[(b*R + r)*3 + {0,1,2}] += {sum pred*gt, sum pred, sum gt} with
 // pred = sigmoid(z) >= thr, gt = label > 0.5 (integer atomics: order-independent, exact).
+// Four voxels per 128-bit load, four loads of each tensor in flight per thread (the scalar version waited for one
+// 4-byte load at a time: 78 us for 50 MB); the sigmoid keeps the reference's arithmetic (1 / (1 + exp(-z)) in fp32
+// compared against thr), so the counts stay bit exact.
+__device__ __forceinline__ void dice_acc(float z, float y, float thr, unsigned int& inter, unsigned int& ps,
+                                         unsigned int& gs) {
+  const float p = 1.f / (1.f + expf(-z));
+  const unsigned int pr = p >= thr, gt = y > 0.5f;
+  inter += pr & gt;
+  ps += pr;
+  gs += gt;
+}
+
 __global__ void __launch_bounds__(kThreads)
 dice_counts_kernel(const float* logits, const float* label, long long V,
                    float thr, unsigned long long* counts) {
@@ -397,14 +409,40 @@ dice_counts_kernel(const float* logits, const float* label, long long V,
   const float* z = logits + (long long)br * V;
   const float* y = label + (long long)br * V;
   unsigned int inter = 0, ps = 0, gs = 0;
-  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V;
-       v += (long long)gridDim.x * kThreads) {
-    const float p = 1.f / (1.f + expf(-z[v]));
-    const unsigned int pr = p >= thr, gt = y[v] > 0.5f;
-    inter += pr & gt;
-    ps += pr;
-    gs += gt;
+  const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x, nthr = (long long)gridDim.x * kThreads;
+  // rows start 16-byte aligned when V % 4 == 0 and the bases are (cudaMalloc / torch allocations are)
+  const bool vec = (V & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(label)) & 15) == 0;
+  long long done = 0;
+  if (vec) {
+    const long long V4 = V >> 2;
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    long long v = tid;
+    for (; v + 3 * nthr < V4; v += 4 * nthr) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = z4[v + u * nthr];
+        b[u] = y4[v + u * nthr];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dice_acc(a[u].x, b[u].x, thr, inter, ps, gs);
+        dice_acc(a[u].y, b[u].y, thr, inter, ps, gs);
+        dice_acc(a[u].z, b[u].z, thr, inter, ps, gs);
+        dice_acc(a[u].w, b[u].w, thr, inter, ps, gs);
+      }
+    }
+    for (; v < V4; v += nthr) {
+      const float4 a = z4[v], b = y4[v];
+      dice_acc(a.x, b.x, thr, inter, ps, gs);
+      dice_acc(a.y, b.y, thr, inter, ps, gs);
+      dice_acc(a.z, b.z, thr, inter, ps, gs);
+      dice_acc(a.w, b.w, thr, inter, ps, gs);
+    }
+    done = V;
   }
+  for (long long v = done + tid; v < V; v += nthr) dice_acc(z[v], y[v], thr, inter, ps, gs);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     inter += __shfl_xor_sync(0xffffffffu, inter, o);

@@ -44,17 +44,25 @@ class NormBwdSeg(ctypes.Structure):
                 ("partial", ctypes.c_void_p)]
 
 
+class _NoGrad16(Exception):
+    """A gradient tensor planned as one fp16 plane met a writer / reader that needs fp32: the plan is rebuilt
+    with fp32 gradients."""
+
+
 # ------------------------------------------------------------------------------ tensors
 class Act:
     """Conv-operand activation: split fp16 planes [2][N][C8][D][H][W][8] (+ fp32 grad)."""
 
-    def __init__(self, N, C, D, H, W, device, needs_grad: bool, name: str = ""):
+    def __init__(self, N, C, D, H, W, device, needs_grad: bool, name: str = "", g16: bool = False):
         self.N, self.C, self.C8, self.D, self.H, self.W = N, C, (C + 7) // 8, D, H, W
         self.V = D * H * W
         self.name, self.needs_grad = name, needs_grad
         self.planes = torch.zeros((2, N, self.C8, D, H, W, 8), dtype=torch.int16, device=device)
-        self.grad = (torch.zeros((N, self.C8, D, H, W, 8), dtype=torch.float32, device=device)
-                     if needs_grad else None)
+        # g16: the gradient is ONE loss-scaled fp16 plane (written by tcgen05 dgrads with flags bit 16, read by the
+        # norm backward with its fp16-source bits): 2 instead of 4 bytes per element through three passes
+        self.g16 = bool(g16 and needs_grad)
+        self.grad = (torch.zeros((N, self.C8, D, H, W, 8), dtype=torch.int16 if self.g16 else torch.float32,
+                                 device=device) if needs_grad else None)
         self.ns = self.C8 * self.V * 8  # elements between samples
         self.written: set = set()       # chunks of .grad written so far in this backward
         self.extra: List["ActView"] = []  # identity-residual gradient contributions
@@ -78,6 +86,7 @@ class Act:
         a.N, a.C8, a.D, a.H, a.W, a.V = self.N * factor, self.C8 // factor, self.D, self.H, self.W, self.V
         a.C = a.C8 * 8
         a.name, a.needs_grad = name or self.name + "/batched", self.needs_grad
+        a.g16 = self.g16
         a.planes = self.planes.view(2, a.N, a.C8, self.D, self.H, self.W, 8)
         a.grad = self.grad.view(a.N, a.C8, self.D, self.H, self.W, 8) if self.grad is not None else None
         a.ns = a.C8 * a.V * 8
@@ -129,7 +138,7 @@ class ActView:
 
     @property
     def g(self) -> int:
-        return self.parent.grad.data_ptr() + self.c8_off * self.parent.V * 8 * 4
+        return self.parent.grad.data_ptr() + self.c8_off * self.parent.V * 8 * (2 if self.parent.g16 else 4)
 
     @property
     def ns(self) -> int:
@@ -615,7 +624,8 @@ class TTAEngine:
 
     def _conv_call(self, plan: Plan, cl: ConvLayer, backward: bool, src, src_dtype, N, cin8, idims,
                    dst_ptr, dst_ns, cout8, odims, accumulate: bool, wsplit_in: bool = False,
-                   stats_res: Optional["Res"] = None, bwd_rec: Optional[dict] = None, c4_in: bool = False):
+                   stats_res: Optional["Res"] = None, bwd_rec: Optional[dict] = None, c4_in: bool = False,
+                   out16: bool = False):
         """Returns a closure launching one conv (tcgen05 kernel when the geometry is supported,
         otherwise the fp32 CUDA-core kernel)."""
         lib = self.lib
@@ -624,6 +634,8 @@ class TTAEngine:
         bias = 0 if backward else cl.packed["bias"].data_ptr()
         hi, lo, ns = src
         if ("small_" + key) in cl.packed and self.model.conv_backend != "simt":
+            if out16:
+                raise _NoGrad16(cl.name)
             wp = cl.packed["small_" + key]
             plan.keep.append(wp)
             plan.conv_backends[f"{cl.name}:{key}"] = "small"
@@ -640,12 +652,16 @@ class TTAEngine:
         if self.model.conv_backend == "tc" and not use_tc:
             raise RuntimeError(f"conv_backend=tc but {cl.name} ({key}) is not supported by the tcgen05 kernel")
         plan.conv_backends[f"{cl.name}:{key}"] = "tc" if use_tc else "simt"
+        if out16 and not use_tc:
+            raise _NoGrad16(cl.name)
         if use_tc:
             wp = cl.packed["tc_" + key + ("_c4" if c4_in else "")]
             plan.keep.append(wp)
             flags = (2 if self.model.deterministic else 0) | (8 if (wsplit_in and not c4_in) else 0) | self.model.tc_flags
             if c4_in:
                 flags |= 32768
+            if out16:
+                flags |= 65536
             if not backward:
                 flags |= getattr(cl, "tc_fwd_flags", 0)
             args = (hi, lo, ns, src_dtype, N, cin8, *idims, wp.data_ptr(), bias, dst_ptr, dst_ns, cout8,
@@ -705,6 +721,18 @@ class TTAEngine:
         return run
 
     def build_plan(self, N: int, D: int, H: int, W: int) -> Plan:
+        model = self.model
+        want = (getattr(model, "grad_f16", False) and getattr(model, "supports_grad_f16", True) and not model.trainable and self.bwd_dtype == TTA_F16_HI
+                and model.conv_backend in ("auto", "tc") and not model.fuse_bwd_stats
+                and not model.per_sample_norm_bwd and model.norm_bwd_l2_mb <= 0)
+        if want:
+            try:
+                return self._build_plan(N, D, H, W, True)
+            except _NoGrad16:
+                pass
+        return self._build_plan(N, D, H, W, False)
+
+    def _build_plan(self, N: int, D: int, H: int, W: int, grad16: bool) -> Plan:
         dev = self.device
         lib = self.lib
         model = self.model
@@ -717,6 +745,11 @@ class TTAEngine:
                     loss=torch.zeros(1, dtype=torch.float32, device=dev))
         ops: list = []  # forward op records, replayed in reverse to emit the backward
         max_ws = [1]
+        plan.grad16 = grad16
+
+        def g16_for(V_: int) -> bool:
+            # levels whose dgrads run without split-K anyway; the full-resolution tensors belong to the fused head
+            return grad16 and model.grad_f16_min_voxels <= V_ < D * H * W
 
         def conv(cl: ConvLayer, inp: ActView) -> Res:
             N = inp.parent.N            # instances of THIS tensor (a batched alias has N * modalities)
@@ -766,7 +799,7 @@ class TTAEngine:
         def normact(nl: NormLayer, y: Res, relu: bool, residual, out: Optional[ActView]) -> ActView:
             N = y.N
             if out is None:
-                a = Act(N, y.C, y.D, y.H, y.W, dev, needs_grad=True, name=nl.name)
+                a = Act(N, y.C, y.D, y.H, y.W, dev, needs_grad=True, name=nl.name, g16=g16_for(y.V))
                 plan.keep.append(a)
                 out = a.view()
             if (out.C8, *out.dims) != (y.C8, y.D, y.H, y.W) or out.parent.N != N:
@@ -893,7 +926,8 @@ class TTAEngine:
 
         # ---- ops beyond the plain UNet (multimodal model): modality mean, trilinear upsample, fp32 -> operand cast
         def new_act(C, dims, needs_grad=True, name="", n=None) -> Act:
-            a = Act(N if n is None else n, C, *dims, dev, needs_grad=needs_grad, name=name)
+            a = Act(N if n is None else n, C, *dims, dev, needs_grad=needs_grad, name=name,
+                    g16=g16_for(dims[0] * dims[1] * dims[2]))
             plan.keep.append(a)
             return a
 
@@ -1045,6 +1079,8 @@ class TTAEngine:
                 # sources: its own grad slice (written by the dgrads of its consumers) and identity-residual extras
                 _, inputs, dst, rep = op
                 par = dst.parent
+                if par.g16 or any(v.parent.g16 for v in inputs):
+                    raise _NoGrad16("mean")
                 chunks = set(range(dst.c8_off, dst.c8_off + dst.C8))
                 srcs = []
                 if chunks <= par.written:
@@ -1072,6 +1108,8 @@ class TTAEngine:
                 # gradient of the operand tensor (fp32, complete) -> 16-bit gradient plane(s) of the conv-only result
                 _, y, dst = op
                 par = dst.parent
+                if par.g16:
+                    raise _NoGrad16(op[0])
                 chunks = set(range(dst.c8_off, dst.c8_off + dst.C8))
                 if not chunks <= par.written or any((ev[2], ev[3]) == (dst.c8_off, dst.C8) for ev in par.extra):
                     raise RuntimeError(f"{op[0]}: the destination's gradient must come from dgrads only")
@@ -1115,10 +1153,41 @@ class TTAEngine:
                                    gbase + bo * 4, cl.h.cout if cl.extra is not None else 0,
                                    gbase + bo2 * 4 if bo2 >= 0 else 0)
 
-                    def run_wgrad(wg_args=wg_args, bg_args=bg_args, yroot=y.root, name=cl.name):
-                        a = list(wg_args)
-                        a[14] = int(yroot.dy_wsplit)          # resolved at launch time, like the dgrad's flag
-                        check(lib.tta_conv_wgrad(*a, _stream()), f"conv_wgrad {name}")
+                    # tensor-core variant (tta_conv_wgrad_tc): 3x3x3 layers with one scaled fp16 gradient plane; the
+                    # finer operand of a stride-2 layer must be the w-parity-split copy its forward / dgrad conv reads
+                    tc_args = None
+                    if (model.wgrad_backend == "auto" and model.conv_backend in ("auto", "tc") and
+                            lib.tta_conv_wgrad_tc_supported(cl.mode, cl.K, cl.stride, cl.h.cin, cl.cout, bdt)):
+                        x_ws = self._uses_tc_s2(cl, False) and inp.dims[2] % 2 == 0
+                        xp = None
+                        if cl.mode == 0 and cl.stride == 2:
+                            if x_ws and xpar is plan.x and xpar.wsplit:
+                                xp = (inp.hi, inp.lo)
+                            elif x_ws and xpar.ws_planes is not None:
+                                xp = (inp.ws_hi, inp.ws_lo)
+                        elif not (xpar.wsplit and xpar is plan.x):
+                            xp = (inp.hi, inp.lo)
+                        if xp is not None:
+                            tc_args = (xp[0], xp[1], inp.ns, *inp.dims, int(cl.mode == 0 and cl.stride == 2),
+                                       y.dy_ptr(0), y.ns, y.D, y.H, y.W, 0, N, cl.mode, cl.stride, cl.h.cin, cl.cout,
+                                       1.0 / plan.loss_scale, gbase + wo * 4, 1 if cl.h.transposed else 0,
+                                       cl.h.cout if cl.extra is not None else 0, gbase + wo2 * 4,
+                                       0 if model.wgrad_x_lo else 1)
+                    plan.wgrad_backends = getattr(plan, "wgrad_backends", {})
+
+                    def run_wgrad(wg_args=wg_args, bg_args=bg_args, yroot=y.root, name=cl.name, tc_args=tc_args,
+                                  tr=cl.mode == 1):
+                        dyw = int(yroot.dy_wsplit)            # resolved at launch time, like the dgrad's flag
+                        if tc_args is not None and dyw == int(tr):
+                            a = list(tc_args)
+                            a[12] = dyw
+                            plan.wgrad_backends[name] = "tc"
+                            check(lib.tta_conv_wgrad_tc(*a, _stream()), f"conv_wgrad_tc {name}")
+                        else:
+                            a = list(wg_args)
+                            a[14] = dyw
+                            plan.wgrad_backends[name] = "simt"
+                            check(lib.tta_conv_wgrad(*a, _stream()), f"conv_wgrad {name}")
                         if bg_args is not None:
                             check(lib.tta_bias_grad(*bg_args, _stream()), f"bias_grad {name}")
                     run_wgrad.label = f"wgrad {cl.name} {cl.h.cin}->{cl.cout}"
@@ -1158,7 +1227,7 @@ class TTAEngine:
                 plan.bwd.append(self._conv_call(
                     plan, cl, True, (y.dy_ptr(0), y.dy_ptr(1), y.V * 4 if dyc4 else y.ns), bdt, N, y.C8,
                     (y.D, y.H, y.W), inp.g, inp.ns, c8o, inp.dims, acc, wsplit_in=y.root.dy_wsplit,
-                    bwd_rec=crec, c4_in=dyc4))
+                    bwd_rec=crec, c4_in=dyc4, out16=par.g16))
                 par.writers.append((inp.c8_off, inp.c8_off + c8o, crec, acc))
             else:
                 rec = op[1]
@@ -1168,20 +1237,22 @@ class TTAEngine:
                 chunks = set(range(out.c8_off, out.c8_off + out.C8))
                 srcs = []
                 if chunks <= par.written:
-                    srcs.append((out.g, out.ns))
+                    srcs.append((out.g, out.ns, par.g16))
                 for ev in par.extra:
                     if (ev[2], ev[3]) == (out.c8_off, out.C8):
-                        srcs.append((ev[0], ev[1]))
+                        srcs.append((ev[0], ev[1], len(ev) > 4 and ev[4]))
                 if not srcs or len(srcs) > 2:
                     raise RuntimeError(f"{nl.name}: {len(srcs)} gradient sources (supported: 1 or 2)")
-                g0, g0ns = srcs[0]
-                g1, g1ns = srcs[1] if len(srcs) > 1 else (0, 0)
+                g0, g0ns, g0h = srcs[0]
+                g1, g1ns, g1h = srcs[1] if len(srcs) > 1 else (0, 0, False)
+                # gradient source formats ride in the relu argument: bit 1 / bit 2 = g0 / g1 is one fp16 plane
+                relu_flags = int(rec["relu"]) | (2 if g0h else 0) | (4 if g1h else 0)
                 # backward reductions from the epilogue of the dgrad that COMPLETES this gradient: single
                 # source (the parent's grad slice), every writer of the slice covers it, the last one is
                 # a tcgen05 launch without split-K on one fp16 plane
                 fuse_bwd = None
                 cb0, cb1 = out.c8_off, out.c8_off + out.C8
-                if (model.fuse_bwd_stats and bdt == TTA_F16_HI and len(srcs) == 1 and chunks <= par.written
+                if (model.fuse_bwd_stats and not par.g16 and bdt == TTA_F16_HI and len(srcs) == 1 and chunks <= par.written
                         and not (fused_head is not None and rec is fused_head[1])):
                     touching = [w for w in par.writers if w[0] < cb1 and w[1] > cb0]
                     if touching and all(w[0] <= cb0 and w[1] >= cb1 for w in touching):
@@ -1206,11 +1277,11 @@ class TTAEngine:
                     # identity shortcut: this op's incoming gradient also flows into `res`
                     if len(srcs) != 1:
                         raise RuntimeError("identity residual with two incoming gradients is unsupported")
-                    res.parent.extra.append((g0, g0ns, res.c8_off, res.C8))
+                    res.parent.extra.append((g0, g0ns, res.c8_off, res.C8, g0h))
                 dg = self.dgb.data_ptr() + nl.off * 4
                 db = self.dgb.data_ptr() + (P + nl.off) * 4
                 rd_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, nl.C, y.V, rec["mean"].data_ptr(),
-                           rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
+                           rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], relu_flags, nl.batch,
                            rec["sums"].data_ptr(), dg, db)
                 do_apply = conv_in_needs or aux is not None
                 bwd_apply_flags.append(do_apply)
@@ -1222,7 +1293,7 @@ class TTAEngine:
                         y.dy_wsplit = True
                         dy_ws = y.W
                     ap_args = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, y.V, rec["mean"].data_ptr(),
-                               rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]), nl.batch,
+                               rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], relu_flags, nl.batch,
                                rec["sums"].data_ptr(), y.dy_ptr(0), y.dy_ptr(1), y.ns,
                                aux.dy_ptr(0) if aux else 0, aux.dy_ptr(1) if aux else 0,
                                aux.ns if aux else 0, bdt)
@@ -1248,7 +1319,7 @@ class TTAEngine:
                         and y.V <= model.small_norm_max_voxels
                         and lib.tta_norm_small_supported(N, y.V, nl.batch)):
                     sm_bwd = (g0, g0ns, g1, g1ns, y.ptr, y.ns, N, y.C8, nl.C, y.V, rec["mean"].data_ptr(),
-                              rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], int(rec["relu"]),
+                              rec["rstd"].data_ptr(), rec["gptr"], rec["bptr"], relu_flags,
                               rec["sums"].data_ptr(), dg, db, y.dy_ptr(0), y.dy_ptr(1), y.ns,
                               aux.dy_ptr(0) if aux else 0, aux.dy_ptr(1) if aux else 0, aux.ns if aux else 0, bdt,
                               dy_ws)

@@ -84,6 +84,8 @@ class _BiaslessConvHolder(ConvHolder):
 @register_model("unet_multimodal_deepfusion_b200")
 @register_model("unet_multimodal_midfusion_b200")
 class MultimodalUNetB200(B200Model):
+    supports_grad_f16 = False     # its mean / upsample backward read fp32 gradient tensors
+
     def __init__(self, cfg: DictConfig | Dict[str, Any]):
         super().__init__()
         if not isinstance(cfg, DictConfig):

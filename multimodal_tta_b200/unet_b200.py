@@ -263,6 +263,19 @@ class B200Model(nn.Module):
         # the fp16 gradient planes carry the loss times 2^ceil(log2(4 * voxels * loss_scale_mult)): large enough that
         # the deep layers' gradients stay out of the fp16 subnormals, small enough that the head's do not saturate
         self.loss_scale_mult = float(get("loss_scale_mult", 1.0))
+        # activation gradients between a dgrad conv and the norm backward that consumes them as ONE loss-scaled fp16
+        # plane instead of fp32 (tta_conv_tc flags bit 16 / the fp16-source bits of tta_norm_bwd_*), at the levels with
+        # at least grad_f16_min_voxels voxels per instance (their dgrads run without split-K anyway).  Same-box A/B at
+        # 2x4x128^3, ms per step: fp32 2.189, fp16 at the 64^3 and 32^3 levels 2.177, at the 64^3 level only 2.165
+        self.grad_f16 = bool(get("grad_f16", True))
+        self.grad_f16_min_voxels = int(get("grad_f16_min_voxels", 100000))
+        # supervised step: weight gradients of the 3x3x3 layers on the tensor cores (tta_conv_wgrad_tc) where the
+        # operand layouts allow it ("auto"), or always on the exact fp32 CUDA-core kernel ("simt")
+        self.wgrad_backend = str(get("wgrad_backend", "auto"))
+        # ... with x = fp16 hi + lo planes (two products, default) or the hi plane only (one product)
+        self.wgrad_x_lo = bool(get("wgrad_x_lo", True))
+        if self.wgrad_backend not in ("auto", "simt"):
+            raise ValueError("unet_b200: wgrad_backend must be 'auto' or 'simt'")
         if self.bwd_precision not in ("fp16", "bf16x2"):
             raise ValueError("unet_b200: bwd_precision must be 'fp16' or 'bf16x2'")
 

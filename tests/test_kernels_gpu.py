@@ -489,3 +489,49 @@ def test_conv_weight_and_bias_gradients(lib, cuda, cin, cout, K, s, tr, dims, dy
                                  c8o * Vo * 8, dyt, *odims, 0, N, mode, K, s, cin, cout, scale, ga.data_ptr(), 0, h,
                                  gb2.data_ptr(), stream()), "wgrad")
         assert rel_l2(torch.cat([ga, gb2]).cpu(), w.grad) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,s,tr,dims,flags", [
+    (32, 32, 1, False, (5, 9, 11), 0), (32, 32, 1, False, (6, 16, 16), 1), (64, 128, 2, False, (4, 8, 8), 0),
+    (128, 256, 2, False, (4, 16, 8), 0), (8, 64, 2, False, (8, 12, 16), 0), (48, 16, 2, True, (3, 6, 5), 0),
+    (64, 8, 2, True, (4, 8, 8), 0), (256, 64, 2, True, (3, 4, 4), 0), (12, 9, 1, False, (6, 10, 12), 0),
+    (160, 40, 1, False, (3, 5, 7), 0), (512, 512, 1, False, (2, 4, 4), 0), (128, 128, 1, False, (4, 20, 24), 0)])
+def test_conv_weight_gradients_tensor_core(lib, cuda, cin, cout, s, tr, dims, flags):
+    """tta_conv_wgrad_tc (tcgen05, MN-major operands, M = 64 / 128 row tiles, N = 8 / 16 / 32 column tiles, parity
+    sub-tiles of the finer tensor for stride 2) against torch autograd on the same rounded operands (x = fp16 hi + lo,
+    dy = one scaled fp16 plane); flags = 1 uses the hi plane of x only and is compared on hi-rounded operands."""
+    torch.manual_seed(17)
+    N, K, pad, S = 2, 3, 1, 64.0
+    x = torch.randn(N, cin, *dims)
+    w = (torch.randn((cin, cout, K, K, K) if tr else (cout, cin, K, K, K)) * 0.1).requires_grad_(True)
+    hi, lo, xv = planes_from(x.to(cuda), TTA_F16)
+    if flags & 1:
+        xv = from_chunked(hi.view(torch.float16).float(), cin)
+    y = F.conv_transpose3d(xv.cpu(), w, None, stride=s, padding=pad, output_padding=s - 1) if tr else \
+        F.conv3d(xv.cpu(), w, None, stride=s, padding=pad)
+    dy = torch.randn_like(y)
+    odims = tuple(y.shape[2:])
+    dch = to_chunked((dy * S).to(cuda))
+    dhi = dch.half().view(torch.int16).contiguous()
+    dyv = from_chunked(dhi.view(torch.float16).float(), cout).cpu() / S
+    y.backward(dyv)
+    c8i, c8o = (cin + 7) // 8, (cout + 7) // 8
+    Vi, Vo = dims[0] * dims[1] * dims[2], odims[0] * odims[1] * odims[2]
+    mode = 1 if tr else 0
+    assert lib.tta_conv_wgrad_tc_supported(mode, K, s, cin, cout, TTA_F16_HI) == 1
+    xw, dw_ = (s == 2 and not tr), (s == 2 and tr)
+    xh, xl = (wsplit(hi), wsplit(lo)) if xw else (hi, lo)
+    gh = wsplit(dhi) if dw_ else dhi
+    gw = torch.zeros_like(w.detach()).to(cuda)
+    check(lib.tta_conv_wgrad_tc(xh.data_ptr(), xl.data_ptr(), c8i * Vi * 8, *dims, int(xw), gh.data_ptr(), c8o * Vo * 8,
+                                *odims, int(dw_), N, mode, s, cin, cout, 1.0 / S, gw.data_ptr(), 1 if tr else 0, 0, 0,
+                                flags, stream()), "wgrad_tc")
+    torch.cuda.synchronize()
+    assert rel_l2(gw.cpu(), w.grad) < 3e-5, rel_l2(gw.cpu(), w.grad)
+    if not tr and cout % 16 == 0:
+        h = cout // 2
+        ga = torch.zeros((h, cin, K, K, K), device=cuda); gb2 = torch.zeros((cout - h, cin, K, K, K), device=cuda)
+        check(lib.tta_conv_wgrad_tc(xh.data_ptr(), xl.data_ptr(), c8i * Vi * 8, *dims, int(xw), gh.data_ptr(),
+                                    c8o * Vo * 8, *odims, int(dw_), N, mode, s, cin, cout, 1.0 / S, ga.data_ptr(), 0, h,
+                                    gb2.data_ptr(), flags, stream()), "wgrad_tc")
+        assert rel_l2(torch.cat([ga, gb2]).cpu(), w.grad) < 3e-5
