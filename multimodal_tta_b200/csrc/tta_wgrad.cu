@@ -268,6 +268,115 @@ static int dispatch_tiles(const WgParams& P, int cD, int cH, int cW, cudaStream_
   return launch_wgrad<MODE, K, S, 16, 32, TD, TH, TW>(P, cD, cH, cW, stream);
 }
 
+
+// ---------------------------------------------------------------- <= 4 x <= 4 channels, stride-1 conv (the UNet's
+// full-resolution 3 -> 3 residual unit: 4.2 M voxels, 81 weights).  The generic kernel above tiles CHANNELS (16 x 32
+// per CTA) and would carry 13 zero channels per real one; on the tensor cores the layer fills 3 of 64 rows.  Here a
+// thread owns one (h, w) position of a 16 x 16 tile, a CTA one kd and a segment of d-planes: per plane the x tile
+// (+ halo) is staged in shared memory as fp32, every thread reads its 9 neighbours x CI channels and does 9 * CI * CO
+// FMAs with its own dy voxel into 9 * CI * CO register accumulators; one shuffle + shared-memory reduction and
+// 9 * CI * CO atomics per CTA.
+constexpr int kWsTile = 16, kWsThreads = kWsTile * kWsTile;
+
+struct WsParams {
+  const uint16_t* x_hi; const uint16_t* x_lo; long long x_ns;
+  const uint16_t* dy_hi; const uint16_t* dy_lo; long long dy_ns;
+  int D, H, W, N, Cin, Cout, dseg, nseg, tiles_h, tiles_w;
+  float scale;
+  float* dw;
+};
+
+template <int CI, int CO, int DT>
+__global__ void __launch_bounds__(kWsThreads)
+wgrad_small_kernel(const WsParams P) {
+  constexpr int HT = kWsTile + 2, PW = HT + 1;               // halo tile, padded rows
+  __shared__ float xs[CI][HT][PW];
+  __shared__ float red[kWsThreads / 32][9 * CI * CO];
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x, tw = tid % kWsTile, th = tid / kWsTile;
+  int b = blockIdx.x;
+  const int tile_w = b % P.tiles_w; b /= P.tiles_w;
+  const int tile_h = b % P.tiles_h; b /= P.tiles_h;
+  const int seg = b % P.nseg, n = b / P.nseg;
+  const int kd = blockIdx.y;
+  const int h0 = tile_h * kWsTile, w0 = tile_w * kWsTile;
+  const int h = h0 + th, w = w0 + tw;
+  const bool inside = h < P.H && w < P.W;
+  const long long plane = (long long)P.H * P.W;
+  const uint16_t* xh = P.x_hi + (long long)n * P.x_ns;
+  const uint16_t* xl = P.x_lo + (long long)n * P.x_ns;
+  const uint16_t* gh = P.dy_hi + (long long)n * P.dy_ns;
+  const uint16_t* gl = P.dy_lo ? P.dy_lo + (long long)n * P.dy_ns : nullptr;
+  float acc[9][CI][CO];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < CI; ++i)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[t][i][o] = 0.f;
+  const int d_begin = seg * P.dseg, d_end = min(P.D, d_begin + P.dseg);
+  for (int d = d_begin; d < d_end; ++d) {
+    const int dx = d + kd - 1;                               // x plane of this tap
+    if (dx < 0 || dx >= P.D) continue;                       // block-uniform: zero padding contributes nothing
+    __syncthreads();                                         // previous plane's readers are done
+    for (int e = tid; e < HT * HT; e += kWsThreads) {
+      const int ey = e / HT, ex = e % HT;
+      const int hh = h0 + ey - 1, ww = w0 + ex - 1;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (hh >= 0 && hh < P.H && ww >= 0 && ww < P.W)
+        load_split8<TTA_F16>(xh, xl, ((long long)dx * plane + (long long)hh * P.W + ww) * 8, v);
+#pragma unroll
+      for (int i = 0; i < CI; ++i) xs[i][ey][ex] = v[i];
+    }
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    if (inside) load_split8<DT>(gh, gl, ((long long)d * plane + (long long)h * P.W + w) * 8, g);
+    __syncthreads();
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int i = 0; i < CI; ++i) {
+          const float xv = xs[i][th + kh][tw + kw];
+#pragma unroll
+          for (int o = 0; o < CO; ++o) acc[kh * 3 + kw][i][o] = fmaf(xv, g[o], acc[kh * 3 + kw][i][o]);
+        }
+  }
+  // ---- CTA reduction: warp shuffles, then one row per warp in shared memory
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < CI; ++i)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const float s = warp_sum(acc[t][i][o]);
+        if (lane == 0) red[warp][(t * CI + i) * CO + o] = s;
+      }
+  __syncthreads();
+  for (int e = tid; e < 9 * CI * CO; e += kWsThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kWsThreads / 32; ++wv) s += red[wv][e];
+    const int o = e % CO, i = (e / CO) % CI, t = e / (CO * CI);
+    if (i < P.Cin && o < P.Cout && s != 0.f)
+      atomicAdd(P.dw + ((long long)o * P.Cin + i) * 27 + kd * 9 + t, s * P.scale);   // Conv3d layout [Cout][Cin][27]
+  }
+}
+
+template <int CI, int CO>
+static int launch_wgrad_small(const WsParams& P, int dy_dtype, cudaStream_t stream) {
+  const dim3 grid((unsigned)(P.N * P.nseg * P.tiles_h * P.tiles_w), 3);
+  if (dy_dtype == TTA_F16_HI) tta_launch(wgrad_small_kernel<CI, CO, TTA_F16_HI>, grid, kWsThreads, 0, stream, tta_pdl_family(32), P);
+  else if (dy_dtype == TTA_F16) tta_launch(wgrad_small_kernel<CI, CO, TTA_F16>, grid, kWsThreads, 0, stream, tta_pdl_family(32), P);
+  else tta_launch(wgrad_small_kernel<CI, CO, TTA_BF16>, grid, kWsThreads, 0, stream, tta_pdl_family(32), P);
+  return tta_check_launch("tta_conv_wgrad (small channels)");
+}
 }  // namespace tta
 
 using namespace tta;
@@ -291,6 +400,24 @@ int tta_conv_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, long long x_ns, i
   TTA_REQUIRE(layout == 0 || layout == 1, "tta_conv_wgrad: layout %d", layout);
   if (co_split <= 0 || co_split > Cout) co_split = Cout;
   TTA_REQUIRE(co_split == Cout || (dw2 != nullptr && layout == 0), "tta_conv_wgrad: a split output needs dw2 and layout 0");
+  if (mode == 0 && K == 3 && stride == 1 && Cin <= 4 && Cout <= 4 && !x_wsplit && !dy_wsplit && layout == 0 &&
+      co_split == Cout) {
+    // <= 4 x <= 4 channels at (typically) full resolution: one thread per voxel, no channel tiles
+    WsParams S;
+    memset(&S, 0, sizeof(S));
+    S.x_hi = x_hi; S.x_lo = x_lo; S.x_ns = x_ns; S.dy_hi = dy_hi; S.dy_lo = dy_dtype == TTA_F16_HI ? nullptr : dy_lo;
+    S.dy_ns = dy_ns; S.D = Dx; S.H = Hx; S.W = Wx; S.N = N; S.Cin = Cin; S.Cout = Cout; S.scale = scale; S.dw = dw;
+    S.tiles_h = (Hx + kWsTile - 1) / kWsTile; S.tiles_w = (Wx + kWsTile - 1) / kWsTile;
+    // d-segments: ~4 CTAs per SM over the grid, at least 8 planes each (the reduction costs about 4 planes' work)
+    const long long cols = (long long)N * S.tiles_h * S.tiles_w * 3;
+    int nseg = (int)((4LL * 148 + cols - 1) / cols);
+    if (nseg > (Dx + 7) / 8) nseg = (Dx + 7) / 8;
+    if (nseg < 1) nseg = 1;
+    S.dseg = (Dx + nseg - 1) / nseg;
+    S.nseg = (Dx + S.dseg - 1) / S.dseg;
+    if (Cin <= 3 && Cout <= 3) return launch_wgrad_small<3, 3>(S, dy_dtype, stream);
+    return launch_wgrad_small<4, 4>(S, dy_dtype, stream);
+  }
   WgParams P;
   memset(&P, 0, sizeof(P));
   P.x_hi = x_hi; P.x_lo = x_lo; P.x_ns = x_ns; P.Dx = Dx; P.Hx = Hx; P.Wx = Wx; P.x_wsplit = x_wsplit;

@@ -442,7 +442,8 @@ def test_fused_head_forward_and_backward(lib, cuda, mode, C, dims, batch_mode, c
     (32, 32, 3, 1, False, (5, 9, 11), TTA_F16_HI), (4, 64, 3, 2, False, (8, 12, 16), TTA_F16_HI),
     (64, 128, 3, 2, False, (4, 8, 8), TTA_BF16), (48, 16, 3, 2, True, (3, 6, 5), TTA_F16_HI),
     (64, 3, 3, 2, True, (4, 8, 8), TTA_BF16), (3, 3, 3, 1, False, (6, 10, 12), TTA_F16_HI),
-    (256, 512, 1, 1, False, (2, 4, 4), TTA_F16_HI), (96, 40, 3, 1, False, (3, 5, 7), TTA_BF16)])
+    (256, 512, 1, 1, False, (2, 4, 4), TTA_F16_HI), (96, 40, 3, 1, False, (3, 5, 7), TTA_BF16),
+    (4, 4, 3, 1, False, (5, 18, 20), TTA_BF16), (2, 3, 3, 1, False, (9, 17, 33), TTA_F16_HI)])
 def test_conv_weight_and_bias_gradients(lib, cuda, cin, cout, K, s, tr, dims, dyt):
     """tta_conv_wgrad / tta_bias_grad (supervised step) against torch autograd on the same rounded
     operands: Conv3d and ConvTranspose3d, strides 1 / 2, 1x1, ragged tiles, channel counts that are not multiples of
@@ -492,10 +493,14 @@ def test_conv_weight_and_bias_gradients(lib, cuda, cin, cout, K, s, tr, dims, dy
 
 
 @pytest.mark.parametrize("cin,cout,s,tr,dims,flags", [
-    (32, 32, 1, False, (5, 9, 11), 0), (32, 32, 1, False, (6, 16, 16), 1), (64, 128, 2, False, (4, 8, 8), 0),
-    (128, 256, 2, False, (4, 16, 8), 0), (8, 64, 2, False, (8, 12, 16), 0), (48, 16, 2, True, (3, 6, 5), 0),
-    (64, 8, 2, True, (4, 8, 8), 0), (256, 64, 2, True, (3, 4, 4), 0), (12, 9, 1, False, (6, 10, 12), 0),
-    (160, 40, 1, False, (3, 5, 7), 0), (512, 512, 1, False, (2, 4, 4), 0), (128, 128, 1, False, (4, 20, 24), 0)])
+    (32, 32, 1, False, (5, 9, 11), 0), (32, 32, 1, False, (6, 16, 16), 1), (32, 32, 1, False, (5, 9, 11), 2),
+    (64, 128, 2, False, (4, 8, 8), 0), (128, 256, 2, False, (4, 16, 8), 0), (4, 64, 2, False, (8, 12, 16), 0),
+    (4, 64, 2, False, (8, 12, 16), 2), (32, 128, 2, False, (6, 32, 16), 0), (32, 128, 2, False, (6, 32, 16), 2),
+    (48, 16, 2, True, (3, 6, 5), 0), (48, 16, 2, True, (3, 6, 5), 2), (64, 3, 2, True, (4, 8, 8), 0),
+    (256, 64, 2, True, (3, 4, 4), 0), (128, 32, 2, True, (4, 16, 8), 0), (768, 128, 2, True, (2, 4, 4), 0),
+    (3, 8, 1, False, (6, 10, 12), 0), (8, 3, 1, False, (6, 20, 12), 2), (24, 200, 1, False, (3, 5, 7), 0),
+    (160, 40, 1, False, (3, 5, 7), 0), (64, 64, 1, False, (3, 18, 9), 0), (512, 512, 1, False, (2, 4, 4), 0),
+    (128, 128, 1, False, (4, 20, 24), 0), (40, 24, 2, True, (2, 3, 4), 0)])
 def test_conv_weight_gradients_tensor_core(lib, cuda, cin, cout, s, tr, dims, flags):
     """tta_conv_wgrad_tc (tcgen05, MN-major operands, M = 64 / 128 row tiles, N = 8 / 16 / 32 column tiles, parity
     sub-tiles of the finer tensor for stride 2) against torch autograd on the same rounded operands (x = fp16 hi + lo,
