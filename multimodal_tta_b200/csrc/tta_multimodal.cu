@@ -158,7 +158,7 @@ __device__ __forceinline__ void out_range(float scale, int i, int out, int& lo, 
 }
 
 template <int ODT>
-__global__ void __launch_bounds__(kMmThreads, 4)
+__global__ void __launch_bounds__(kMmThreads, 3)
 upsample_bwd_kernel(const float* g, long long g_ns, const UpGeom G, uint16_t* dy_hi, uint16_t* dy_lo, long long dy_ns) {
   pdl_trigger();
   pdl_wait();
@@ -175,20 +175,55 @@ upsample_bwd_kernel(const float* g, long long g_ns, const UpGeom G, uint16_t* dy
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int od = dlo; od <= dhi; ++od) {
-      const float wd = axis_weight(G.sd, od, G.Di, d);
-      if (wd == 0.f) continue;
-      for (int oh = hlo; oh <= hhi; ++oh) {
-        const float wh = axis_weight(G.sh, oh, G.Hi, h) * wd;
-        if (wh == 0.f) continue;
-        const float* p = gb + ((long long)od * G.Ho + oh) * G.Wo * 8;
-        for (int ow = wlo; ow <= whi; ++ow) {
-          const float ww = axis_weight(G.sw, ow, G.Wi, w) * wh;
-          if (ww == 0.f) continue;
-          float x[8];
-          load_f32x8(p + (long long)ow * 8, x);
+    // per-axis weights once per voxel (the candidate ranges hold <= kUpMax outputs for scale factors >= 1.5; a longer
+    // range falls back to evaluating the weight inside the loops): 3 x ~7 evaluations instead of ~7^3
+    constexpr int kUpMax = 8;
+    const bool tab = dhi - dlo < kUpMax && hhi - hlo < kUpMax && whi - wlo < kUpMax;
+    float whv[kUpMax], wwv[kUpMax];
+    if (tab) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(ww, x[i], acc[i]);
+      for (int j = 0; j < kUpMax; ++j) {
+        whv[j] = hlo + j <= hhi ? axis_weight(G.sh, hlo + j, G.Hi, h) : 0.f;
+        wwv[j] = wlo + j <= whi ? axis_weight(G.sw, wlo + j, G.Wi, w) : 0.f;
+      }
+    }
+    if (tab) {
+#pragma unroll 1
+      for (int jd = 0; jd <= dhi - dlo; ++jd) {
+        const float wd = axis_weight(G.sd, dlo + jd, G.Di, d);
+        if (wd == 0.f) continue;
+#pragma unroll
+        for (int jh = 0; jh < kUpMax; ++jh) {
+          const float wh = whv[jh] * wd;
+          if (wh == 0.f) continue;
+          const float* p = gb + (((long long)(dlo + jd) * G.Ho + (hlo + jh)) * G.Wo + wlo) * 8;
+#pragma unroll
+          for (int jw = 0; jw < kUpMax; ++jw) {
+            const float ww = wwv[jw] * wh;
+            if (ww == 0.f) continue;
+            float x[8];
+            load_f32x8(p + (long long)jw * 8, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(ww, x[i], acc[i]);
+          }
+        }
+      }
+    } else {
+      for (int od = dlo; od <= dhi; ++od) {
+        const float wd = axis_weight(G.sd, od, G.Di, d);
+        if (wd == 0.f) continue;
+        for (int oh = hlo; oh <= hhi; ++oh) {
+          const float wh = axis_weight(G.sh, oh, G.Hi, h) * wd;
+          if (wh == 0.f) continue;
+          const float* p = gb + ((long long)od * G.Ho + oh) * G.Wo * 8;
+          for (int ow = wlo; ow <= whi; ++ow) {
+            const float ww = axis_weight(G.sw, ow, G.Wi, w) * wh;
+            if (ww == 0.f) continue;
+            float x[8];
+            load_f32x8(p + (long long)ow * 8, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(ww, x[i], acc[i]);
+          }
         }
       }
     }
