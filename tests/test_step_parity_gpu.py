@@ -9,7 +9,8 @@ is a property of the recipe, not of the kernels: the fp32 CPU oracle run with 3 
 threads flips 1 of 4870 scalars, and the fp32-exact CUDA-core backend flips 6 at 64^3
 (scripts/diag_parity.py).  The check is therefore: (a) every sign flip sits on
 a scalar whose oracle gradient is < 5 % of the median magnitude, (b) at most 1 % (first step) /
-3 % (later steps) of the scalars differ by more than 1e-4, (c) the median difference is < 1e-5,
+3 % (later steps) of the scalars differ by more than 1e-4 in the tight case and 1 % / 4 % / 8 % after one / two /
+three steps in the 32^3 cases, (c) the median difference is < 1e-5,
 (d) the gradient itself matches in relative L2.  Spatial sizes: 64^3 for the tight check (the
 bottom level then normalises over 4^3 voxels); the 32^3 cases normalise over 2^3 = 8 voxels at the
 bottom and are kept as looser structural checks.
@@ -49,7 +50,7 @@ def _check_step(cfg, x, mode, steps, use_graph, backend="auto", tight=False):
             agree = ((lp >= 0) == (lo >= 0)).float().mean().item()
         else:
             agree = (lp.argmax(1) == lo.argmax(1)).float().mean().item()
-        assert agree >= (0.9999 if (tight or it == 0) else 0.999), (it, agree)
+        assert agree >= 0.9999, (it, agree)          # north star: >= 99.99 % on EVERY step (measured minimum 0.99996)
         # --- gradients
         assert rel_l2(g_p, g_o) < (1e-3 if tight else 3e-3), (it, rel_l2(g_p, g_o))
         med = g_o.abs().median()
@@ -61,7 +62,8 @@ def _check_step(cfg, x, mode, steps, use_graph, backend="auto", tight=False):
         frac_bad = float((perr > 1e-4).float().mean())
         print(f"[{mode} {tuple(x.shape)} {backend} step {it}] logits {rel_l2(lp, lo):.1e} agree {agree:.6f} grad "
               f"{rel_l2(g_p, g_o):.1e} flips {int(flip.sum())} params>1e-4 {100 * frac_bad:.2f} % median {float(perr.median()):.1e}")
-        assert frac_bad < ((0.01 if it == 0 else 0.03) if tight else 0.12), (it, frac_bad)
+        # (measured maxima, round 2: tight 1.6 %, 32^3 cases 0.4 % / 2.1 % / 4.1 % after 1 / 2 / 3 steps)
+        assert frac_bad < ((0.01 if it == 0 else 0.03) if tight else (0.01, 0.04, 0.08)[min(it, 2)]), (it, frac_bad)
         assert float(perr.median()) < 1e-5, (it, float(perr.median()))
     return to, tp, prod
 
@@ -93,6 +95,22 @@ def test_bare_default_batchnorm_no_res_units(cuda):
     cfg = dict(BARE_DEFAULT_MODEL_CFG, in_channels=4)
     x = brats_volume(2, (32, 32, 32), seed=44)
     _check_step(cfg, x, "sigmoid", steps=3, use_graph=True)
+
+
+def test_fp16_activation_gradients_at_every_level(cuda):
+    """grad_f16 (DESIGN.md 3) is on by default only for levels of >= 100 000 voxels (covered by the full-size tests);
+    here EVERY level below the full resolution carries its activation gradient as one scaled fp16 plane: fp16 stores
+    and read-modify-write fan-in in the dgrad epilogues, fp16 sources (own slice and identity-shortcut extras) in the
+    streaming, small-slab and cluster norm-backward kernels."""
+    x = brats_volume(2, (32, 32, 32), seed=42)
+    _, _, prod = _check_step(dict(BRATS_MODEL_CFG, grad_f16_min_voxels=1), x, "sigmoid", steps=2, use_graph=True)
+    plan = prod.engine.plans[(2, 32, 32, 32)]
+    assert plan.grad16
+    x = brats_volume(1, (64, 64, 64), seed=43)
+    _check_step(dict(BRATS_MODEL_CFG, grad_f16_min_voxels=1, deterministic=True), x, "sigmoid", steps=2, use_graph=False,
+                tight=True)
+    _, _, prod = _check_step(dict(BRATS_MODEL_CFG, grad_f16=False), x, "sigmoid", steps=1, use_graph=False, tight=True)
+    assert not prod.engine.plans[(1, 64, 64, 64)].grad16
 
 
 def test_simt_backend_alone(cuda):
