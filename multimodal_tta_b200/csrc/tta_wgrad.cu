@@ -316,35 +316,57 @@ wgrad_small_kernel(const WsParams P) {
 #pragma unroll
       for (int o = 0; o < CO; ++o) acc[t][i][o] = 0.f;
   const int d_begin = seg * P.dseg, d_end = min(P.D, d_begin + P.dseg);
-  for (int d = d_begin; d < d_end; ++d) {
-    const int dx = d + kd - 1;                               // x plane of this tap
-    if (dx < 0 || dx >= P.D) continue;                       // block-uniform: zero padding contributes nothing
-    __syncthreads();                                         // previous plane's readers are done
-    for (int e = tid; e < HT * HT; e += kWsThreads) {
+  // software pipeline: the next plane's values (<= 2 halo positions and the thread's own dy voxel) are in flight in
+  // registers while the current plane is consumed from shared memory
+  constexpr int NE = (HT * HT + kWsThreads - 1) / kWsThreads;
+  float xv[NE][CI], g[CO], gn[CO];
+  auto fetch = [&](int d) {
+    const int dx = d + kd - 1;
+    const bool live = d < d_end && dx >= 0 && dx < P.D;     // block-uniform
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+      const int e = tid + k * kWsThreads;
       const int ey = e / HT, ex = e % HT;
       const int hh = h0 + ey - 1, ww = w0 + ex - 1;
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (hh >= 0 && hh < P.H && ww >= 0 && ww < P.W)
+      if (live && e < HT * HT && hh >= 0 && hh < P.H && ww >= 0 && ww < P.W)
         load_split8<TTA_F16>(xh, xl, ((long long)dx * plane + (long long)hh * P.W + ww) * 8, v);
 #pragma unroll
-      for (int i = 0; i < CI; ++i) xs[i][ey][ex] = v[i];
+      for (int i = 0; i < CI; ++i) xv[k][i] = v[i];
     }
-    float g[8];
+    float gv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = 0.f;
-    if (inside) load_split8<DT>(gh, gl, ((long long)d * plane + (long long)h * P.W + w) * 8, g);
+    for (int i = 0; i < 8; ++i) gv[i] = 0.f;
+    if (live && inside) load_split8<DT>(gh, gl, ((long long)d * plane + (long long)h * P.W + w) * 8, gv);
+#pragma unroll
+    for (int o = 0; o < CO; ++o) gn[o] = gv[o];
+  };
+  fetch(d_begin);
+  for (int d = d_begin; d < d_end; ++d) {
+    __syncthreads();                                         // previous plane's readers are done
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+      const int e = tid + k * kWsThreads;
+      if (e < HT * HT) {
+#pragma unroll
+        for (int i = 0; i < CI; ++i) xs[i][e / HT][e % HT] = xv[k][i];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CO; ++o) g[o] = gn[o];
     __syncthreads();
+    fetch(d + 1);                                            // zero padding planes arrive as zeros (g = 0: no contribution)
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
         for (int i = 0; i < CI; ++i) {
-          const float xv = xs[i][th + kh][tw + kw];
+          const float xval = xs[i][th + kh][tw + kw];
 #pragma unroll
-          for (int o = 0; o < CO; ++o) acc[kh * 3 + kw][i][o] = fmaf(xv, g[o], acc[kh * 3 + kw][i][o]);
+          for (int o = 0; o < CO; ++o) acc[kh * 3 + kw][i][o] = fmaf(xval, g[o], acc[kh * 3 + kw][i][o]);
         }
   }
   // ---- CTA reduction: warp shuffles, then one row per warp in shared memory

@@ -38,11 +38,18 @@ def dice_iou_from_counts(counts: torch.Tensor, eps: float = 1e-7):
     return dice, iou, valid
 
 
-def device_dice_counts(logits: torch.Tensor, labels: torch.Tensor, threshold: float) -> torch.Tensor:
-    """One kernel: sigmoid >= threshold, label > 0.5, intersection / sums per (b, r)."""
+def device_dice_counts(logits: torch.Tensor, labels: torch.Tensor, threshold: float,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One kernel: sigmoid >= threshold, label > 0.5, intersection / sums per (b, r).  ``out``: a ZEROED contiguous
+    int64 [B, R, 3] device tensor to add into (a slot of a caller-owned ring: no allocation / memset per call)."""
     B, R = int(logits.shape[0]), int(logits.shape[1])
     V = logits[0, 0].numel()
-    counts = torch.zeros((B, R, 3), dtype=torch.int64, device=logits.device)
+    if out is not None:
+        if out.dtype != torch.int64 or tuple(out.shape) != (B, R, 3) or not out.is_contiguous() or out.device != logits.device:
+            raise ValueError("device_dice_counts: out must be a contiguous int64 [B, R, 3] tensor on the logits' device")
+        counts = out
+    else:
+        counts = torch.zeros((B, R, 3), dtype=torch.int64, device=logits.device)
     lab = labels.to(device=logits.device, dtype=torch.float32).contiguous()
     if not logits.is_cuda:
         raise RuntimeError("multimodal_tta_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")

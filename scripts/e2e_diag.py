@@ -77,3 +77,25 @@ timed("adapt_stream (H2D prefetch) only", stream_only)
 timed("adapt_stream + loss D2H", stream_loss)
 timed("adapt_stream + loss D2H + dice counts (bench e2e)", stream_full)
 timed("resident steps + dice counts", resident_dice)
+
+side = torch.cuda.Stream()
+counts_dev = torch.zeros((K, B, 3, 3), dtype=torch.int64, device=dev)
+loss_dev = torch.zeros(K, device=dev)
+events = [torch.cuda.Event() for _ in range(K)]
+
+
+def stream_full_side(n):
+    cur = torch.cuda.current_stream()
+    counts_dev.zero_()
+    for j, logits in enumerate(tent.adapt_stream([xs_host[i % NROT] for i in range(n)])):
+        loss_dev[j:j + 1].copy_(tent.last_loss.reshape(1))
+        device_dice_counts(logits, labels[j % NROT], 0.5, out=counts_dev[j])
+        events[j].record(cur)
+        with torch.cuda.stream(side):
+            side.wait_event(events[j])
+            loss_host[j:j + 1].copy_(loss_dev[j:j + 1], non_blocking=True)
+            counts_host[j].copy_(counts_dev[j], non_blocking=True)
+    cur.wait_stream(side)
+
+
+timed("bench e2e with side-stream read-back", stream_full_side)
