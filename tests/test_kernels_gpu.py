@@ -332,6 +332,33 @@ def test_dice_counts_match_reference_golden(lib, cuda):
         assert torch.equal(valid, torch.from_numpy(gold[f"valid{i}"]))
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 9, 10, 37), (1, 1, 5, 17, 6), (2, 3, 16, 16, 64), (1, 2, 33, 40, 48)])
+def test_dice_counts_vector_and_scalar_paths(lib, cuda, shape):
+    """tta_dice_counts: four voxels per 128-bit load when every row starts 16-byte aligned (V % 4 == 0), the scalar
+    loop otherwise and for misaligned views; random logits around the threshold, thresholds 0.5 and 0.3
+    (seg_eval.py:41-68, hecktor21.yaml:80); `out=` adds into a caller-owned zeroed slot."""
+    from multimodal_tta_b200.evaluation import device_dice_counts
+    torch.manual_seed(3)
+    logits = torch.randn(shape) * 2
+    labels = (torch.rand(shape) > 0.6).float()
+    for thr in (0.5, 0.3):
+        pred = (torch.sigmoid(logits) >= thr).long()
+        gt = (labels > 0.5).long()
+        ref = torch.stack([(pred * gt).flatten(2).sum(-1), pred.flatten(2).sum(-1), gt.flatten(2).sum(-1)], dim=-1)
+        got = device_dice_counts(logits.to(cuda), labels.to(cuda), thr).cpu()
+        assert torch.equal(got, ref)
+        ring = torch.zeros((3, shape[0], shape[1], 3), dtype=torch.int64, device=cuda)
+        device_dice_counts(logits.to(cuda), labels.to(cuda), thr, out=ring[1])
+        assert torch.equal(ring[1].cpu(), ref) and int(ring[0].abs().sum()) == 0 and int(ring[2].abs().sum()) == 0
+    # a view that starts 4 bytes into an allocation: rows are no longer 16-byte aligned
+    flat = torch.zeros(logits.numel() + 1)
+    flat[1:] = logits.flatten()
+    lview = flat.to(cuda)[1:].view(shape)
+    pred = (torch.sigmoid(logits) >= 0.5).long()
+    ref = torch.stack([(pred * gt).flatten(2).sum(-1), pred.flatten(2).sum(-1), gt.flatten(2).sum(-1)], dim=-1)
+    assert torch.equal(device_dice_counts(lview, labels.to(cuda), 0.5).cpu(), ref)
+
+
 @pytest.mark.parametrize("cpv", [8, 4])
 @pytest.mark.parametrize("mode,C,dims,batch_mode", [(1, 3, (9, 10, 37), 0), (0, 3, (8, 8, 32), 0), (1, 1, (5, 17, 6), 0),
                                                      (1, 2, (16, 8, 40), 1), (0, 4, (3, 9, 33), 0)])

@@ -111,6 +111,13 @@ def test_fp16_activation_gradients_at_every_level(cuda):
                 tight=True)
     _, _, prod = _check_step(dict(BRATS_MODEL_CFG, grad_f16=False), x, "sigmoid", steps=1, use_graph=False, tight=True)
     assert not prod.engine.plans[(1, 64, 64, 64)].grad16
+    # other architectures: BatchNorm without residual units, the single-channel HECKTOR head, unfused shortcuts, no
+    # fused head (the full-resolution tensors keep fp32 gradients either way) -- a plan that meets a writer without
+    # fp16 support is rebuilt with fp32 gradients instead of failing
+    for cfg, xx in ((dict(BARE_DEFAULT_MODEL_CFG, in_channels=4), brats_volume(2, (32, 32, 32), seed=44)),
+                    (HECKTOR_MODEL_CFG, torch.randn(1, 2, 48, 32, 32)),
+                    (dict(BRATS_MODEL_CFG, fuse_shortcut=False, fuse_head=False), brats_volume(1, (32, 32, 32), seed=46))):
+        _check_step(dict(cfg, grad_f16_min_voxels=1), xx, "sigmoid", steps=1, use_graph=True)
 
 
 def test_simt_backend_alone(cuda):
