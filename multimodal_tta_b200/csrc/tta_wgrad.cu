@@ -11,8 +11,10 @@
 // (dy for a conv, x for a transposed conv) and the halo of the other one are staged in shared memory as fp32; thread
 // (kd, kh | ci group of 4 | co group of 4 | position slice) keeps 3 (kw) x 4 x 4 accumulators and per position does
 // one 128-bit load of the centre values, three of the halo and 48 FMAs.  Partial sums leave through fp32 atomics
-// once per CTA (a few thousand per layer).  This is a first, exact implementation of the row: a tensor-core wgrad
-// (MN-major UMMA operands: both x and dy are channel-contiguous) is the next step for it.
+// once per CTA (a few thousand per layer).  This is the exact reference implementation of the row and the path for
+// 1x1 convs, bf16x2 gradients and operand layouts the tensor-core kernel does not take (csrc/tta_wgrad_tc.cu runs the
+// 3x3x3 layers with one scaled fp16 gradient plane); <= 4 x <= 4 channel stride-1 convs have their own per-voxel
+// kernel below.
 #include <cstring>
 
 #include "tta_common.cuh"

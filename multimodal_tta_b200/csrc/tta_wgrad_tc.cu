@@ -578,11 +578,11 @@ int tta_conv_wgrad_tc(const uint16_t* x_hi, const uint16_t* x_lo, long long x_ns
   P.tiles_per_n = Dc * P.tiles_h * P.tiles_w;
   P.tiles_total = N * P.tiles_per_n;
   const int gy = 3 * P.nkh * P.ci_tiles, gz = co_tiles;
-  // ~2 CTAs per SM over the whole grid (one resident at a time: the second wave hides the first one's flush), at
-  // least 2 tiles per CTA so that the pipeline has something to overlap; every CTA flushes nacc x M x N atomics:
-  // where the (kd, kh, ci, co) tiles alone fill the GPU, one CTA per tile
-  int gx = gy * gz >= 148 ? 1 : (2 * 148 + gy * gz - 1) / (gy * gz);
-  if (gx > (P.tiles_total + 1) / 2) gx = (P.tiles_total + 1) / 2;
+  // every CTA flushes nacc x M x N atomics into dW, so the tile ranges are as long as filling the GPU once allows
+  // (ncu, profiles/wgrad_tc_r2.md: the 8^3 / 16^3 layers were bound by their flush -- 432 CTAs x 49 152 scattered
+  // atomics for 512 -> 512 -- so: ONE wave of CTAs, at least four tiles each)
+  int gx = 148 / (gy * gz);
+  if (gx > (P.tiles_total + 3) / 4) gx = (P.tiles_total + 3) / 4;
   if (gx < 1) gx = 1;
   P.tiles_per_block = (P.tiles_total + gx - 1) / gx;
   gx = (P.tiles_total + P.tiles_per_block - 1) / P.tiles_per_block;
