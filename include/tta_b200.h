@@ -77,6 +77,8 @@ int tta_gather_pack_norm_f16(const uint16_t* vol, int n_vol, int C, int Ds, int 
  * pipeline groups for ordinary planes (opt-in; measured slower),
  * bits 8..10 real Cout of a small-Cout transposed conv
  * packed for the dense-GEMM + col2im kernel (tta_conv_tc_t2s),
+ * bit17 EXPERIMENT: two products instead of three (A_hi * [B_hi | B_lo] only; measured: logits 1.2e-5 -> 6.8e-4, agreement
+ * below 99.99 %, 0.8 % faster -- not used),
  * bit16 `out` is ONE fp16 plane in the chunk layout (16 B per voxel-chunk; out_n_stride in elements): the loss-scaled
  * input gradient of a dgrad, consumed by tta_norm_bwd_* with the fp16-source bits; implies bit1, accumulate becomes a
  * 16-byte read-modify-write. */
