@@ -229,10 +229,11 @@ class B200Model(nn.Module):
         # OPT-IN: statistics from a conv epilogue finalized inside the apply pass's prologue instead of a separate
         # launch.  Measured slower (2.337 vs 2.326 ms per step: every apply block re-reduces 148 slots)
         self.stats_finalize_in_apply = bool(get("stats_finalize_in_apply", False))
-        # OPT-IN: also when the conv has a single TMEM accumulator buffer (the reduction is then not hidden
-        # behind the next item's MMAs, but a statistics pass over the conv result disappears).  Same-box A/B:
-        # 2.2936 vs 2.2968 ms per step -- within noise, so the default stays off
-        self.fuse_stats_single_buffer = bool(get("fuse_stats_single_buffer", False))
+        # ... also when the conv has a single TMEM accumulator buffer (the reduction is then not hidden behind the next
+        # item's MMAs, but a statistics pass over the conv result disappears).  Same-box A/B: 2.2936 vs 2.2968 ms per
+        # step in round 1 (within noise, default off); on the final round-2 build 2.1190 vs 2.1335 (two rounds each,
+        # spread 0.002): default on
+        self.fuse_stats_single_buffer = bool(get("fuse_stats_single_buffer", True))
         # ... and, OPT-IN, the norm-BACKWARD reductions (sum dz, sum dz*xhat) out of the epilogue of
         # the dgrad conv that completes the layer's incoming gradient.  Measured on B200 (2x4x128^3):
         # the four 64^3 / 32^3 layers it applies to lose 162 us in their dgrads (the epilogue has
