@@ -1817,7 +1817,8 @@ static int conv_tc_impl(const uint16_t* in_hi, const uint16_t* in_lo, long long 
   const size_t smem = (size_t)P.nstages * P.stage_bytes + (P.b_res ? b_total : 0) + 1024;
   const bool pdl_ok = !(P.ksplit > 1 && !accumulate);  // a memset precedes the split-K launch
   if (P.ksplit > 1 && !accumulate) {
-    // partial sums are combined with float4 atomics: start from zero
+    // partial sums are combined with float4 atomics: start from zero (timing experiment, round 2: skipping all 14
+    // memset nodes of a step -- wrong results -- gains 0.5 %, so a shared pre-zeroed arena is not worth building)
     const long long Vo = (long long)Do * Ho * Wo;
     const long long per_n = (long long)C8out * Vo * 8;
     static const bool per_sample_memset = getenv("TTA_MEMSET_PER_SAMPLE") != nullptr;   // A/B switch
